@@ -1,0 +1,131 @@
+/*
+ * winnowmap_b200.h -- C ABI of the B200-native seed-chain-align path of Winnowmap v2.03.
+ *
+ * Plain pointers and sizes only (no torch / CUDA types).  Every entry point cites the
+ * reference interface it replaces (paths relative to the reference repository root).
+ * All functions return 0 on success; on a CUDA failure they print a message to stderr
+ * and exit(1), mirroring the reference's fatal-error convention (src/misc.c:123-151).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef WINNOWMAP_B200_H
+#define WINNOWMAP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- flags, identical values to src/ksw2.h:8-17 ---- */
+#define WM_KSW_EZ_SCORE_ONLY  0x01
+#define WM_KSW_EZ_RIGHT       0x02
+#define WM_KSW_EZ_GENERIC_SC  0x04
+#define WM_KSW_EZ_APPROX_MAX  0x08
+#define WM_KSW_EZ_APPROX_DROP 0x10
+#define WM_KSW_EZ_EXTZ_ONLY   0x40
+#define WM_KSW_EZ_REV_CIGAR   0x80
+#define WM_KSW_NEG_INF (-0x40000000)
+
+/* (x,y) pair, same layout as mm128_t (src/minimap.h:55) */
+typedef struct { uint64_t x, y; } wm128_t;
+
+/* result of one extension DP; same fields as ksw_extz_t (src/ksw2.h:23-32) without the
+ * heap pointer: the CIGAR of task i lives at cigar[cigar_off[i] .. +n_cigar) */
+typedef struct {
+	int32_t max, zdropped;
+	int32_t max_q, max_t;
+	int32_t mqe, mqe_t;
+	int32_t mte, mte_q;
+	int32_t score;
+	int32_t reach_end;
+	int32_t n_cigar;
+	int32_t reserved;
+} wm_extz_t;
+
+/* library / device */
+const char *wm_version(void);
+int wm_device_count(void);                 /* number of visible CUDA devices (0 if none) */
+int wm_set_device(int device);
+
+/* ------------------------------------------------------------------------------------
+ * Kernel-level batch entry points (used by the parity tests and by bench.py to time one
+ * stage in isolation).  Host buffers in, host buffers out.
+ * ---------------------------------------------------------------------------------- */
+
+/* Batched ksw_extd2_sse (src/ksw2_extd2_sse.c:26; prototype src/ksw2.h:60-61), m = 5,
+ * scoring matrix `mat` (25 entries, src/align.c:9-22).  Sequences are 0..4 codes.
+ * qoff/toff: n+1 offsets into qseq/tseq.  w/zdrop/end_bonus/flag: per task.
+ * cigar_off: n+1 offsets (capacity per task); a task whose CIGAR does not fit reports the
+ * needed length in n_cigar and writes nothing beyond its capacity. */
+int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qoff, const uint8_t *tseq, const int64_t *toff,
+                       const int8_t *mat, int q, int e, int q2, int e2,
+                       const int32_t *w, const int32_t *zdrop, const int32_t *end_bonus, const int32_t *flag,
+                       wm_extz_t *ez, uint32_t *cigar, const int64_t *cigar_off);
+
+/* Batched ksw_ll_qinit + ksw_ll_i16 (src/ksw2_ll_sse.c:32,80): score, query end, target end. */
+int wm_ksw_ll_batch(int n, const uint8_t *qseq, const int64_t *qoff, const uint8_t *tseq, const int64_t *toff,
+                    const int8_t *mat, int gapo, int gape, int32_t *score, int32_t *qe, int32_t *te);
+
+/* Down-weighted k-mer filter: replaces the bloom_filter built in mm_idx_gen
+ * (src/index.c:404-432; ext/bloom/bloom_filter.hpp).  `canon_kmers` are the values of
+ * encodeKmer() (src/index.c:362-376) for each line of the -W file. */
+typedef struct wm_bloom_s wm_bloom_t;
+wm_bloom_t *wm_bloom_build(const uint64_t *canon_kmers, int64_t n);
+uint64_t wm_bloom_bits(const wm_bloom_t *b);
+const uint8_t *wm_bloom_table(const wm_bloom_t *b);
+void wm_bloom_destroy(wm_bloom_t *b);
+
+/* Batched mm_sketch (src/sketch.c:128; prototype src/mmpriv.h:57), is_hpc = 0.
+ * seq: concatenated ASCII sequences, off: n+1 offsets, rid: per sequence.
+ * Output: minimizers of sequence i at out[out_off[i] .. out_off[i+1]); *out / *out_off are
+ * malloc()ed by the callee and owned by the caller (free()). */
+int wm_sketch_batch(const wm_bloom_t *bloom, int n, const char *seq, const int64_t *off, const uint32_t *rid,
+                    int w, int k, wm128_t **out, int64_t **out_off);
+
+/* radix_sort_128x (src/misc.c:156; src/ksort.h:116-151) on n_arr independent arrays:
+ * array i is a[off[i] .. off[i+1]); sorted in place with the reference's tie order. */
+int wm_radix_sort_128x_batch(int n_arr, wm128_t *a, const int64_t *off);
+
+/* Batched mm_chain_dp (src/chain.c:22; prototype src/mmpriv.h:67) for n_segs = 1,
+ * is_cdna = 0.  Anchors of task i: a[off[i] .. off[i+1]) (sorted as by collect_seed_hits).
+ * Outputs: n_u[i]; u at u[off[i] .. +n_u[i]); chained anchors at b[off[i] .. +n_b[i]). */
+int wm_chain_dp_batch(int n_tasks, const wm128_t *a, const int64_t *off,
+                      int max_dist_x, int min_dist_x, int max_dist_y, int bw, int max_skip, int max_iter,
+                      int min_cnt, int min_sc, float gap_scale,
+                      int32_t *n_u, uint64_t *u, wm128_t *b, int64_t *n_b);
+
+/* ------------------------------------------------------------------------------------
+ * Drop-in boundary: what the reference's batch driver binds.
+ * ---------------------------------------------------------------------------------- */
+
+/* Flattened view of an mm_idx_t (src/minimap.h:66-77, src/index.c:33-38): the caller walks
+ * its buckets once and hands over plain arrays.  keys[i] (minimizer hash, i.e. mm128_t.x>>8)
+ * owns the occurrence list pos[pos_off[i] .. pos_off[i+1]) sorted ascending exactly as
+ * mm_idx_get() (src/index.c:88-105) would return it. */
+typedef struct {
+	int32_t k, w, n_seq;
+	const char *const *seq_name;   /* n_seq names (mm_idx_seq_t.name) */
+	const uint32_t *seq_len;       /* mm_idx_seq_t.len */
+	const uint64_t *seq_offset;    /* mm_idx_seq_t.offset into S */
+	const uint32_t *S;             /* 4-bit packed reference (mm_idx_t.S) */
+	uint64_t S_words;              /* number of uint32 words in S */
+	int64_t n_keys;
+	const uint64_t *keys;
+	const uint64_t *pos_off;       /* n_keys + 1 */
+	const uint64_t *pos;
+	uint64_t bloom_bits;           /* bloom_filter::size() */
+	const uint8_t *bloom_table;    /* bloom_filter::table() */
+} wm_idx_view_t;
+
+typedef struct wm_gpu_ctx_s wm_gpu_ctx;
+
+/* Upload (replicate) the index to `n_gpus` devices starting at device 0, or to the single
+ * device `device` when n_gpus == 1.  Call site in the reference: after main.c:403. */
+wm_gpu_ctx *wm_gpu_idx_upload(const wm_idx_view_t *idx, int device);
+void wm_gpu_destroy(wm_gpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,63 @@
+"""GPU parity: the CUDA ksw_extd2 (through the C ABI) against the CPU oracle, bit-exact on
+the full ksw_extz_t and the CIGAR."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from test_oracle_vs_ref import FLAGS, rand_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(queries, targets, mat, prm, w, zdrop, eb, flag):
+    from winnowmap_b200 import kernels
+    ez, cigs = kernels.ksw_extd2_batch(queries, targets, mat, *prm, w, zdrop, eb, flag)
+    for i in range(len(queries)):
+        e0, c0 = ol.oracle_extd2(queries[i], targets[i], mat, *prm, int(w[i]), int(zdrop[i]), int(eb[i]), int(flag[i]))
+        assert np.array_equal(e0, ez[i]), (i, len(queries[i]), len(targets[i]), int(w[i]), int(flag[i]), e0, ez[i])
+        assert np.array_equal(c0, cigs[i]), (i, len(queries[i]), len(targets[i]), int(w[i]), int(flag[i]))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_extd2_random_batch(seed):
+    rng = np.random.default_rng(900 + seed)
+    mat = ol.simple_mat()
+    Q, T, W, Z, E, F = [], [], [], [], [], []
+    for it in range(400):
+        tlen = int(rng.choice([1, 5, 16, 17, 33, 100, 250, 300, 700, 1100, 2500]))
+        q, t = rand_pair(rng, tlen, err=float(rng.choice([0.02, 0.1, 0.3])), drift=int(rng.choice([0, 0, 30, 120, 400])),
+                         n_runs=int(rng.integers(0, 3)))
+        Q.append(q); T.append(t)
+        W.append(int(rng.choice([5, 20, 50, 100, 751, 3001]))); Z.append(int(rng.choice([400, 200, 50, -1])))
+        E.append(int(rng.choice([-1, 0, 10]))); F.append(FLAGS[int(rng.integers(0, len(FLAGS)))])
+    _check(Q, T, mat, (4, 2, 24, 1), np.array(W), np.array(Z), np.array(E), np.array(F))
+
+
+def test_extd2_asm_scoring_and_swapped_gaps():
+    rng = np.random.default_rng(77)
+    for a, b, q, e, q2, e2 in [(1, 4, 6, 2, 26, 1), (2, 4, 24, 1, 4, 2)]:
+        mat = ol.simple_mat(a, b, 1)
+        Q, T = zip(*[rand_pair(rng, int(rng.integers(20, 900)), err=0.05, drift=int(rng.choice([0, 50]))) for _ in range(64)])
+        n = len(Q)
+        _check(list(Q), list(T), mat, (q, e, q2, e2), np.full(n, 200), np.full(n, 200), np.full(n, -1),
+               np.array([FLAGS[i % 4] for i in range(n)]))
+
+
+def test_extd2_long_end_extension_and_empty():
+    rng = np.random.default_rng(5)
+    mat = ol.simple_mat()
+    q, t = rand_pair(rng, 9000, err=0.08, drift=300)
+    Q = [q, q[:1], np.zeros(0, np.uint8), q[:300]]
+    T = [t, t[:1], t[:10], np.zeros(0, np.uint8)]
+    n = len(Q)
+    _check(Q, T, mat, (4, 2, 24, 1), np.array([3001, 751, 751, 751]), np.full(n, 400), np.full(n, -1), np.array([0x40, 0x40, 0, 0]))
+
+
+def test_cigar_capacity_overflow_is_reported():
+    from winnowmap_b200 import kernels
+    rng = np.random.default_rng(6)
+    mat = ol.simple_mat()
+    q, t = rand_pair(rng, 800, err=0.2)
+    e0, c0 = ol.oracle_extd2(q, t, mat, 4, 2, 24, 1, 751, 400, -1, 0)
+    ez, cigs = kernels.ksw_extd2_batch([q], [t], mat, 4, 2, 24, 1, 751, 400, -1, 0, cigar_cap=4)
+    assert ez[0, 10] == len(c0) and len(c0) > 4

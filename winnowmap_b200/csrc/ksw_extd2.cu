@@ -1,0 +1,363 @@
+// Banded dual-affine extension DP with traceback on sm_100a.
+//
+// Computes exactly what ksw_extd2_sse (reference src/ksw2_extd2_sse.c:26-393) computes,
+// including the artefacts of its SSE formulation that reach the output:
+// the band is processed in whole 16-cell blocks (:139), the per-diagonal score refresh runs
+// in unaligned 16-cell groups past the band end (:158-172), state arrays are int8 with
+// wrap-around arithmetic, and the backtrack uses block bounds (src/ksw2.h:119-151).
+//
+// Mapping to the GPU: one warp owns one DP job and sweeps anti-diagonals r = i + j; lanes
+// own consecutive target positions t of the diagonal (32 cells per step), the t-1 operand
+// of the recurrence comes from the neighbouring lane by shuffle (the SSE code shifts a
+// vector by one byte instead).  The seven int8 state rows (u,v,x,y,x2,y2,s) and the int32
+// H row live in shared memory for jobs up to WM_SMEM_CELLS target bases and in an
+// L2-resident global scratch slice otherwise.  Direction bytes are streamed to HBM, one
+// row of the rotated matrix per diagonal; a second kernel walks them back (one thread per
+// job) and emits the CIGAR.
+#include "wm_common.cuh"
+
+#define WM_FILL_WARPS 4
+#define WM_SMEM_CELLS 1024   // per-warp shared-memory slice covers tlen <= 1024
+
+__device__ __forceinline__ int wm_band_st(int r, int qlen, int w)
+{
+	int st = 0;
+	if (st < r - qlen + 1) st = r - qlen + 1;
+	if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
+	return st;
+}
+__device__ __forceinline__ int wm_band_en(int r, int tlen, int w)
+{
+	int en = tlen - 1;
+	if (en > r) en = r;
+	if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+	return en;
+}
+
+__device__ __forceinline__ int wm_ncol16(int qlen, int tlen, int w)
+{ // src/ksw2_extd2_sse.c:84-86, in bytes
+	int n = qlen < tlen ? qlen : tlen;
+	n = ((n < w + 1 ? n : w + 1) + 15) / 16 + 1;
+	return n * 16;
+}
+
+// ksw_apply_zdrop (src/ksw2.h:160-176), rotated coordinates
+__device__ __forceinline__ bool wm_apply_zdrop(wm_extz_dev &ez, int32_t H, int r, int t, int zdrop, int e)
+{
+	if (H > ez.max) {
+		ez.max = H, ez.max_t = t, ez.max_q = r - t;
+	} else if (t >= ez.max_t && r - t >= ez.max_q) {
+		int tl = t - ez.max_t, ql = (r - t) - ez.max_q, l;
+		l = tl > ql ? tl - ql : ql - tl;
+		if (zdrop >= 0 && ez.max - H > zdrop + l * e) { ez.zdropped = 1; return true; }
+	}
+	return false;
+}
+
+__device__ void wm_extd2_fill_job(const wm_dp_job &J, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
+                                  wm_extz_dev *out, const wm_dp_params &P, int8_t *S, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	const uint8_t *query = seq + J.q_off, *target = seq + J.t_off;
+	const int qlen = J.qlen, tlen = J.tlen, flag = J.flag;
+	int w = J.w;
+	wm_extz_dev ez;
+	ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+	ez.max = 0, ez.score = ez.mqe = ez.mte = WM_NEG_INF;
+	ez.n_cigar = 0, ez.zdropped = 0, ez.reach_end = 0, ez.reserved = 0;
+	if (qlen <= 0 || tlen <= 0 || P.early_out) { if (lane == 0) *out = ez; return; }
+
+	const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2, qe = q + e, qe2 = q2 + e2;
+	const bool approx_max = (flag & 0x08) != 0, right = (flag & 0x02) != 0;
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	const int tlen16 = (tlen + 15) / 16 * 16;
+	const int n_col16 = wm_ncol16(qlen, tlen, w);
+	int8_t *u = S, *v = u + tlen16, *x = v + tlen16, *y = x + tlen16, *x2 = y + tlen16, *y2 = x2 + tlen16, *s = y2 + tlen16;
+	int32_t *H = (int32_t*)(s + tlen16);
+	for (int i = lane; i < tlen16; i += 32) {
+		u[i] = v[i] = x[i] = y[i] = (int8_t)(-q - e);
+		x2[i] = y2[i] = (int8_t)(-q2 - e2);
+		s[i] = 0;
+		if (!approx_max) H[i] = WM_NEG_INF;
+	}
+	__syncwarp();
+
+	int32_t H0 = 0, last_H0_t = 0;
+	int last_st = -1, last_en = -1;
+	const int n_diag = qlen + tlen - 1;
+	for (int r = 0; r < n_diag; ++r) {
+		const int st0 = wm_band_st(r, qlen, w), en0 = wm_band_en(r, tlen, w);
+		if (st0 > en0) { ez.zdropped = 1; break; }
+		const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
+		// boundary operands (src/ksw2_extd2_sse.c:141-151)
+		int x1, x21, v1;
+		const int bnd = r == 0 ? -q - e : r < P.long_thres ? -e : r == P.long_thres ? P.long_diff : -e2;
+		if (st > 0) {
+			if (st - 1 >= last_st && st - 1 <= last_en) x1 = x[st - 1], x21 = x2[st - 1], v1 = v[st - 1];
+			else x1 = -q - e, x21 = -q2 - e2, v1 = -q - e;
+		} else x1 = -q - e, x21 = -q2 - e2, v1 = bnd;
+		if (en >= r && lane == 0) { // :152-155
+			y[r] = (int8_t)(-q - e), y2[r] = (int8_t)(-q2 - e2);
+			u[r] = (int8_t)bnd;
+		}
+		// score refresh in unaligned 16-cell groups starting at st0 (:158-172)
+		{
+			const int lim = st0 + ((en0 - st0) / 16 + 1) * 16;
+			for (int i = st0 + lane; i < lim; i += 32) {
+				if (i < tlen16) { // writes past the s[] row land in sf[] in the reference and are never read back
+					int sq = i < tlen ? target[i] : 0;             // sf[] is zero padded up to tlen16
+					int j = r - i;                                  // qrr[i] = qr[qlen-1-r+i] = query[r-i]; zero padded
+					int sr = (j >= 0 && j < qlen) ? query[j] : 0;
+					s[i] = (int8_t)((sq == 4 || sr == 4) ? P.sc_N : (sq == sr ? P.sc_mch : P.sc_mis));
+				}
+			}
+		}
+		__syncwarp();
+		// the cells of this diagonal, whole 16-cell blocks [st, en]
+		{
+			int cx = x1, cv = v1, cx2 = x21;
+			uint8_t *pr = bt + J.p_off + (size_t)r * n_col16;
+			for (int c = st; c <= en; c += 32) {
+				const int t = c + lane;
+				const bool act = t <= en;
+				int z = 0, xo = 0, vo = 0, x2o = 0, uo = 0, yo = 0, y2o = 0;
+				if (act) z = s[t], xo = x[t], vo = v[t], x2o = x2[t], uo = u[t], yo = y[t], y2o = y2[t];
+				int xl = __shfl_up_sync(FULL, xo, 1), vl = __shfl_up_sync(FULL, vo, 1), x2l = __shfl_up_sync(FULL, x2o, 1);
+				if (lane == 0) xl = cx, vl = cv, x2l = cx2;
+				cx = __shfl_sync(FULL, xo, 31), cv = __shfl_sync(FULL, vo, 31), cx2 = __shfl_sync(FULL, x2o, 31);
+				if (act) {
+					int a = (int8_t)(xl + vl), b = (int8_t)(yo + uo), a2 = (int8_t)(x2l + vl), b2 = (int8_t)(y2o + uo), d, tmp;
+					if (!right) { // :227-234
+						d = 0;
+						if (a > z) d = 1, z = a;
+						if (b > z) d = 2, z = b;
+						if (a2 > z) d = 3, z = a2;
+						if (b2 > z) d = 4, z = b2;
+					} else { // :274-281
+						d = z > a ? 0 : 1; z = max(z, a);
+						d = z > b ? d : 2; z = max(z, b);
+						d = z > a2 ? d : 3; z = max(z, a2);
+						d = z > b2 ? d : 4; z = max(z, b2);
+					}
+					z = min(z, P.sc_mch);
+					u[t] = (int8_t)(z - vl); v[t] = (int8_t)(z - uo);
+					tmp = (int8_t)(z - q);  a = (int8_t)(a - tmp);  b = (int8_t)(b - tmp);
+					tmp = (int8_t)(z - q2); a2 = (int8_t)(a2 - tmp); b2 = (int8_t)(b2 - tmp);
+					if (!right) { // :253-264
+						x[t]  = (int8_t)((a  > 0 ? a  : 0) - qe);  d |= a  > 0 ? 0x08 : 0;
+						y[t]  = (int8_t)((b  > 0 ? b  : 0) - qe);  d |= b  > 0 ? 0x10 : 0;
+						x2[t] = (int8_t)((a2 > 0 ? a2 : 0) - qe2); d |= a2 > 0 ? 0x20 : 0;
+						y2[t] = (int8_t)((b2 > 0 ? b2 : 0) - qe2); d |= b2 > 0 ? 0x40 : 0;
+					} else { // :300-311
+						x[t]  = (int8_t)((a  < 0 ? 0 : a ) - qe);  d |= a  < 0 ? 0 : 0x08;
+						y[t]  = (int8_t)((b  < 0 ? 0 : b ) - qe);  d |= b  < 0 ? 0 : 0x10;
+						x2[t] = (int8_t)((a2 < 0 ? 0 : a2) - qe2); d |= a2 < 0 ? 0 : 0x20;
+						y2[t] = (int8_t)((b2 < 0 ? 0 : b2) - qe2); d |= b2 < 0 ? 0 : 0x40;
+					}
+					pr[t - st] = (uint8_t)d;
+				}
+			}
+		}
+		__syncwarp();
+		if (!approx_max) { // exact max with the 32-bit H row (:315-358)
+			int32_t max_H, max_t;
+			if (r > 0) {
+				const int32_t Hm1 = en0 > 0 ? H[en0 - 1] : 0, Hen = H[en0];
+				__syncwarp();
+				const int en1 = st0 + (en0 - st0) / 4 * 4;
+				long long best = (long long)0x8000000000000000LL;
+				for (int t = st0 + lane; t < en0; t += 32) {
+					int32_t h = H[t] + v[t];
+					H[t] = h;
+					uint32_t prio = t < en1 ? 1u + ((uint32_t)((t - st0) & 3) << 24) + (uint32_t)((t - st0) >> 2 << 2)
+					                        : (1u << 27) + (uint32_t)(t - st0);
+					long long key = ((long long)h << 32) | (long long)(0xffffffffu - prio);
+					best = key > best ? key : best;
+				}
+				const int32_t Hn = en0 > 0 ? Hm1 + u[en0] : Hen + v[en0]; // special-cased last element (:319)
+				if (lane == 0) H[en0] = Hn;
+				{
+					long long key = ((long long)Hn << 32) | (long long)0xffffffffu; // prio 0: H[en0] seeds the max
+					best = key > best ? key : best;
+				}
+				#pragma unroll
+				for (int o = 16; o; o >>= 1) {
+					long long other = __shfl_xor_sync(FULL, best, o);
+					best = other > best ? other : best;
+				}
+				max_H = (int32_t)(best >> 32);
+				uint32_t prio = 0xffffffffu - (uint32_t)(best & 0xffffffffLL);
+				if (prio == 0) max_t = en0;
+				else if (prio < (1u << 27)) max_t = st0 + (int)((prio - 1) & 0xffffffu) + (int)((prio - 1) >> 24); // block base + lane (:342)
+				else max_t = st0 + (int)(prio - (1u << 27));
+				__syncwarp();
+			} else {
+				max_H = (int32_t)v[0] - P.qe_h, max_t = 0; // :351
+				if (lane == 0) H[0] = max_H;
+				__syncwarp();
+			}
+			const int32_t Hen0 = H[en0], Hst0 = H[st0];
+			if (en0 == tlen - 1 && Hen0 > ez.mte) ez.mte = Hen0, ez.mte_q = r - en;
+			if (r - st0 == qlen - 1 && Hst0 > ez.mqe) ez.mqe = Hst0, ez.mqe_t = st0;
+			if (wm_apply_zdrop(ez, max_H, r, max_t, J.zdrop, e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
+		} else { // approximate max (:359-375)
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					int32_t d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
+					H0 += v[last_H0_t];
+				} else {
+					++last_H0_t, H0 += u[last_H0_t];
+				}
+			} else H0 = (int32_t)v[0] - P.qe_h, last_H0_t = 0;
+			if ((flag & 0x10) && wm_apply_zdrop(ez, H0, r, last_H0_t, J.zdrop, e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+	if (lane == 0) *out = ez;
+}
+
+__global__ void __launch_bounds__(WM_FILL_WARPS * 32)
+wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
+                     wm_extz_dev *__restrict__ ez, wm_dp_params P, int8_t *gscratch, size_t gscratch_stride, int *counter)
+{
+	extern __shared__ __align__(16) int8_t smem[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	int8_t *my_smem = smem + (size_t)wid * (WM_SMEM_CELLS * 11);
+	int8_t *my_g = gscratch + (size_t)(blockIdx.x * WM_FILL_WARPS + wid) * gscratch_stride;
+	for (;;) {
+		int j = 0;
+		if (lane == 0) j = atomicAdd(counter, 1);
+		j = __shfl_sync(0xffffffffu, j, 0);
+		if (j >= n_jobs) break;
+		const wm_dp_job J = jobs[j];
+		const int tlen16 = (J.tlen + 15) / 16 * 16;
+		wm_extd2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane);
+		__syncwarp();
+	}
+}
+
+// ksw_backtrack (src/ksw2.h:119-151, is_rot = 1, min_intron_len = 0) + the start-cell choice of
+// src/ksw2_extd2_sse.c:379-391.  One thread per job; the band bounds off[]/off_end[] the
+// reference stores per diagonal are recomputed from r.
+// CIGAR run-length accumulator with ksw_push_cigar semantics (src/ksw2.h:103-113); the pending
+// run stays in registers so that the count stays exact even if the buffer is too small.
+struct wm_cigar_acc {
+	uint32_t *cig; int cap, n, cur_len; uint32_t cur_op; bool pending;
+	__device__ __forceinline__ void init(uint32_t *c, int cap_) { cig = c, cap = cap_, n = 0, cur_len = 0, cur_op = 0, pending = false; }
+	__device__ __forceinline__ void flush() { if (pending) { if (n < cap) cig[n] = (uint32_t)cur_len << 4 | cur_op; ++n; pending = false; } }
+	__device__ __forceinline__ void push(uint32_t op, int len) {
+		if (pending && op == cur_op) cur_len += len;
+		else { flush(); cur_op = op, cur_len = len, pending = true; }
+	}
+};
+
+__global__ void wm_extd2_backtrack_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ bt,
+                                          wm_extz_dev *__restrict__ ezs, uint32_t *__restrict__ cigar_pool)
+{
+	int jid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (jid >= n_jobs) return;
+	const wm_dp_job J = jobs[jid];
+	wm_extz_dev ez = ezs[jid];
+	const int qlen = J.qlen, tlen = J.tlen;
+	int w = J.w;
+	if (qlen <= 0 || tlen <= 0) return;
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	int i0 = -1, j0 = -1;
+	if (!ez.zdropped && !(J.flag & 0x40)) i0 = tlen - 1, j0 = qlen - 1;
+	else if (!ez.zdropped && (J.flag & 0x40) && ez.mqe + J.end_bonus > ez.max) ez.reach_end = 1, i0 = ez.mqe_t, j0 = qlen - 1;
+	else if (ez.max_t >= 0 && ez.max_q >= 0) i0 = ez.max_t, j0 = ez.max_q;
+	int n = 0;
+	if (i0 >= 0 && j0 >= 0) {
+		const int n_col16 = wm_ncol16(qlen, tlen, w);
+		const uint8_t *p = bt + J.p_off;
+		uint32_t *cig = cigar_pool + J.cig_off;
+		const int cap = J.cig_cap;
+		wm_cigar_acc acc; acc.init(cig, cap);
+		int i = i0, j = j0, state = 0;
+		while (i >= 0 && j >= 0) {
+			int r = i + j, force_state = -1;
+			int off = wm_band_st(r, qlen, w) / 16 * 16, off_end = (wm_band_en(r, tlen, w) + 16) / 16 * 16 - 1;
+			if (i < off) force_state = 2;
+			if (i > off_end) force_state = 1;
+			uint32_t tmp = force_state < 0 ? p[(size_t)r * n_col16 + i - off] : 0;
+			if (state == 0) state = tmp & 7;
+			else if (!(tmp >> (state + 2) & 1)) state = 0;
+			if (state == 0) state = tmp & 7;
+			if (force_state >= 0) state = force_state;
+			if (state == 0) acc.push(0, 1), --i, --j;
+			else if (state == 1 || state == 3) acc.push(2, 1), --i;
+			else acc.push(1, 1), --j;
+		}
+		if (i >= 0) acc.push(2, i + 1);
+		if (j >= 0) acc.push(1, j + 1);
+		acc.flush();
+		n = acc.n;
+		if (!(J.flag & 0x80) && n <= cap)
+			for (int k = 0; k < n >> 1; ++k) { uint32_t t2 = cig[k]; cig[k] = cig[n - 1 - k]; cig[n - 1 - k] = t2; }
+	}
+	ez.n_cigar = n;
+	ezs[jid] = ez;
+}
+
+// ---- host-side launcher on device-resident jobs ----
+struct wm_extd2_ws { wm_dbuf scratch, counter; };
+
+void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2)
+{ // src/ksw2_extd2_sse.c:61-97
+	P->qe_h = q + e;
+	if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
+	P->q = q, P->e = e, P->q2 = q2, P->e2 = e2;
+	P->sc_mch = mat[0], P->sc_mis = mat[1];
+	P->sc_N = mat[24] == 0 ? -e2 : mat[24];
+	int max_sc = mat[0], min_sc = mat[1];
+	for (int t = 1; t < 25; ++t) { max_sc = max_sc > mat[t] ? max_sc : mat[t]; min_sc = min_sc < mat[t] ? min_sc : mat[t]; }
+	P->early_out = -min_sc > 2 * (q + e);
+	int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+	if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
+	P->long_thres = long_thres;
+	P->long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+}
+
+size_t wm_extd2_bt_bytes(int qlen, int tlen, int w)
+{
+	if (qlen <= 0 || tlen <= 0) return 16;
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	int n = qlen < tlen ? qlen : tlen;
+	n = ((n < w + 1 ? n : w + 1) + 15) / 16 + 1;
+	return ((size_t)(qlen + tlen - 1) * n + 1) * 16;
+}
+
+// jobs/seq/bt/ez/cigar are device pointers; max_tlen = largest tlen among the jobs.
+void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, const uint8_t *d_seq, uint8_t *d_bt,
+                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream)
+{
+	if (n_jobs <= 0) return;
+	int dev = 0, n_sm = 148;
+	WM_CUDA_CHECK(cudaGetDevice(&dev));
+	WM_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+	const size_t smem = (size_t)WM_FILL_WARPS * WM_SMEM_CELLS * 11;
+	int per_sm = 4; // 45 KB of shared memory per block
+	int grid = n_sm * per_sm;
+	int need = (n_jobs + WM_FILL_WARPS - 1) / WM_FILL_WARPS;
+	if (grid > need) grid = need;
+	size_t stride = 0;
+	int tlen16 = (max_tlen + 15) / 16 * 16;
+	if (tlen16 > WM_SMEM_CELLS) stride = (size_t)tlen16 * 11;
+	int8_t *gs = (int8_t*)ws->scratch.need(stride * grid * WM_FILL_WARPS + 16);
+	int *counter = (int*)ws->counter.need(sizeof(int));
+	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+	static bool attr_set = false;
+	if (!attr_set) {
+		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_extd2_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
+	wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, stream>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, counter);
+	WM_CUDA_CHECK(cudaGetLastError());
+	wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar);
+	WM_CUDA_CHECK(cudaGetLastError());
+}

@@ -1,0 +1,63 @@
+// Shared helpers for the sm_100a kernels of the Winnowmap seed-chain-align path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+// Fatal-error convention of the reference (src/misc.c:123-151): message on stderr, exit(1).
+#define WM_CUDA_CHECK(call) do { \
+	cudaError_t wm_e_ = (call); \
+	if (wm_e_ != cudaSuccess) { \
+		fprintf(stderr, "[ERROR] CUDA failure at %s:%d: %s: %s\n", __FILE__, __LINE__, #call, cudaGetErrorString(wm_e_)); \
+		exit(1); \
+	} \
+} while (0)
+
+#define WM_NEG_INF (-0x40000000)
+
+// One extension-DP job; sequences live in a device byte pool (0..4 codes).
+struct wm_dp_job {
+	int64_t q_off, t_off;   // byte offsets of query / target codes in the sequence pool
+	int64_t p_off;          // byte offset of this job's backtrack matrix
+	int64_t cig_off;        // uint32 offset of this job's CIGAR buffer
+	int32_t qlen, tlen, w, zdrop, end_bonus, flag;
+	int32_t cig_cap, pad;
+};
+
+// Scoring parameters shared by a batch (src/ksw2_extd2_sse.c:61-97)
+struct wm_dp_params {
+	int32_t q, e, q2, e2;      // after the swap at :70
+	int32_t qe_h;              // q+e BEFORE the swap (:61), used only for H[0]/H0 (:351,:371)
+	int32_t sc_mch, sc_mis, sc_N;
+	int32_t long_thres, long_diff;
+	int32_t early_out;         // -min_sc > 2*(q+e) (:92)
+};
+
+struct wm_extz_dev {
+	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar, reserved;
+};
+
+template <typename T>
+static inline T *wm_dev_alloc(size_t n)
+{
+	T *p = 0;
+	WM_CUDA_CHECK(cudaMalloc((void**)&p, (n > 0 ? n : 1) * sizeof(T)));
+	return p;
+}
+
+// Growable device buffer (never shrinks): pre-sized pools instead of a per-call allocator.
+struct wm_dbuf {
+	void *p; size_t cap;
+	wm_dbuf() : p(0), cap(0) {}
+	void *need(size_t bytes) {
+		if (bytes > cap) {
+			if (p) WM_CUDA_CHECK(cudaFree(p));
+			size_t nc = bytes + bytes / 4 + 256;
+			WM_CUDA_CHECK(cudaMalloc(&p, nc));
+			cap = nc;
+		}
+		return p;
+	}
+	void release() { if (p) cudaFree(p); p = 0; cap = 0; }
+};
