@@ -36,5 +36,16 @@ def lib():
         L.wm_set_device.argtypes = [C.c_int]
         L.wm_ksw_extd2_batch.argtypes = [C.c_int, u8p, i64p, u8p, i64p, i8p, C.c_int, C.c_int, C.c_int, C.c_int,
                                          i32p, i32p, i32p, i32p, C.POINTER(ExtZ), u32p, i64p]
+        L.wm_bloom_build.restype = C.c_void_p
+        L.wm_bloom_build.argtypes = [u64p, C.c_int64]
+        L.wm_bloom_bits.restype = C.c_uint64
+        L.wm_bloom_bits.argtypes = [C.c_void_p]
+        L.wm_bloom_table.restype = C.c_void_p
+        L.wm_bloom_table.argtypes = [C.c_void_p]
+        L.wm_bloom_destroy.argtypes = [C.c_void_p]
+        L.wm_sketch_batch.argtypes = [C.c_void_p, C.c_int, C.c_char_p, i64p, u32p, C.c_int, C.c_int,
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.wm_radix_sort_128x_batch.argtypes = [C.c_int, u64p, i64p]
+        L.wm_chain_dp_batch.argtypes = [C.c_int, u64p, i64p] + [C.c_int] * 8 + [C.c_float, i32p, u64p, u64p, i64p]
         _lib = L
     return _lib

@@ -1,0 +1,307 @@
+// Anchor chaining on sm_100a: mm_chain_dp (reference src/chain.c:22-167) for n_segs == 1 and
+// is_cdna == 0, one warp per task.
+//
+// Forward pass (:45-90): anchors are taken in order; for anchor i the 32 lanes score 32 predecessors
+// j = i-1, i-2, ... at a time.  The reference's inner loop is order dependent (running maximum with
+// strict ">", the n_skip counter fed by t[j]==i marks, "break" above max_skip, and the t[p[j]] = i side
+// effects); a chunk is resolved exactly by (1) letting every candidate lane publish t[p[j]] = i, which
+// can only touch indices below every j still to be examined, (2) a prefix maximum over the lanes to
+// find the record-setting lanes, and (3) replaying the n_skip arithmetic over the ballot masks.
+// Backtracking (:92-165) is a second warp-per-task kernel: the data-parallel sweeps use all lanes, the
+// greedy claim walk (:118-135) is inherently serial and runs on lane 0.
+#include <vector>
+#include <algorithm>
+#include <limits.h>
+#include "wm_common.cuh"
+#include "sketch.cuh"
+#include "rsort.cuh"
+#include "chain.cuh"
+
+#define WM_CHAIN_WARPS 4
+
+__device__ __forceinline__ int wm_warp_incl_max(int v, int lane)
+{
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, v, o);
+		if (lane >= o) v = max(v, t);
+	}
+	return v;
+}
+
+__global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
+wm_chain_fill_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ order, int n_tasks,
+                     wm_chain_params P, int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
+                     int *counter)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	for (;;) {
+		int ti = 0;
+		if (lane == 0) ti = atomicAdd(counter, 1);
+		ti = __shfl_sync(FULL, ti, 0);
+		if (ti >= n_tasks) break;
+		const int task = order ? order[ti] : ti;
+		const int64_t base = off[task];
+		const int n = (int)(off[task + 1] - base);
+		if (n <= 0) continue;
+		const wm128_dev *a = a_all + base;
+		int32_t *f = f_all + base, *p = p_all + base, *t = t_all + base, *v = v_all + base;
+		// avg_qspan (src/chain.c:41-42)
+		unsigned long long sum = 0;
+		for (int i = lane; i < n; i += 32) { sum += a[i].y >> 32 & 0xff; t[i] = 0; }
+		for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+		const float avg_qspan = __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n));
+		const double avg_d = (double)avg_qspan, scale_d = (double)P.gap_scale;
+		__syncwarp();
+		int st = 0;
+		for (int i = 0; i < n; ++i) {
+			const uint64_t ri = a[i].x;
+			const int32_t qi = (int32_t)a[i].y, q_span = (int32_t)(a[i].y >> 32 & 0xff);
+			while (st < i && ri > a[st].x + (uint64_t)(int64_t)P.max_dist_x) ++st;
+			if (i - st > P.max_iter) // the relaxed window of Winnowmap (src/chain.c:52-55)
+				while (i - st > P.max_iter && ri > a[st].x + (uint64_t)(int64_t)P.min_dist_x) ++st;
+			int max_f = q_span, max_j = -1, n_skip = 0;
+			for (int jb = i - 1; jb >= st; jb -= 32) {
+				const int j = jb - lane;
+				bool cand = false;
+				int sc = INT_MIN, pj = -1;
+				if (j >= st) {
+					const wm128_dev aj = a[j];
+					const int64_t dr = (int64_t)(ri - aj.x);
+					const int32_t dq = qi - (int32_t)aj.y;
+					if (!(dr == 0 || dq <= 0) && !(dq > P.max_dist_y || dq > P.max_dist_x)) {
+						const int32_t dd = (int32_t)(dr > dq ? dr - dq : dq - dr);
+						if (dd <= P.bw) {
+							const int32_t min_d = dq < dr ? dq : (int32_t)dr;
+							sc = min_d > q_span ? q_span : min_d;
+							const int log_dd = dd ? 31 - __clz(dd) : 0;
+							const int gap_cost = (int)__dmul_rn(__dmul_rn((double)dd, .01), avg_d) + (log_dd >> 1);
+							sc -= (int)__dadd_rn(__dmul_rn((double)gap_cost, scale_d), .499);
+							sc += f[j];
+							pj = p[j];
+							cand = true;
+						}
+					}
+				}
+				if (cand && pj >= 0) t[pj] = i; // src/chain.c:87 (only indices below every j still to be visited)
+				__syncwarp();
+				const bool marked = cand && t[j] == i;
+				const int incl = wm_warp_incl_max(cand ? sc : INT_MIN, lane);
+				int excl = __shfl_up_sync(FULL, incl, 1);
+				if (lane == 0) excl = INT_MIN;
+				excl = max(excl, max_f);
+				const bool rec = cand && sc > excl;
+				unsigned R = __ballot_sync(FULL, rec), K = __ballot_sync(FULL, marked && !rec);
+				int brk = 32; // first lane at which the reference breaks out of the j loop
+				if (K == 0) {
+					n_skip -= __popc(R); if (n_skip < 0) n_skip = 0;
+				} else {
+					unsigned ev = R | K;
+					while (ev) {
+						const int l = __ffs(ev) - 1;
+						ev &= ev - 1;
+						if (R >> l & 1) { if (n_skip > 0) --n_skip; }
+						else if (++n_skip > P.max_skip) { brk = l; break; }
+					}
+				}
+				const unsigned Rv = brk < 32 ? (R & ((1u << brk) - 1u)) : R;
+				if (Rv) {
+					const int top = 31 - __clz(Rv);
+					max_f = __shfl_sync(FULL, sc, top);
+					max_j = jb - top;
+				}
+				if (brk < 32) break;
+			}
+			if (lane == 0) {
+				f[i] = max_f, p[i] = max_j;
+				const int vj = max_j >= 0 ? v[max_j] : INT_MIN;
+				v[i] = (max_j >= 0 && vj > max_f) ? vj : max_f; // src/chain.c:89
+			}
+			__syncwarp();
+		}
+	}
+}
+
+// descending bitonic sort of m (power of two) uint64 keys by one warp
+__device__ void wm_warp_bitonic_desc(uint64_t *x, int m, int lane)
+{
+	for (int k = 2; k <= m; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int i = lane; i < m; i += 32) {
+				const int l = i ^ j;
+				if (l > i) {
+					const uint64_t a = x[i], b = x[l];
+					const bool up = (i & k) == 0; // first half of each k-block sorted descending
+					if (up ? a < b : a > b) x[i] = b, x[l] = a;
+				}
+			}
+			__syncwarp();
+		}
+}
+
+__global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
+wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, int n_tasks, wm_chain_params P,
+                          int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
+                          uint64_t *__restrict__ u_all, uint64_t *__restrict__ u2_all, wm128_dev *__restrict__ w_all, wm128_dev *__restrict__ b_all,
+                          int32_t *__restrict__ n_u_out, int64_t *__restrict__ n_b_out, wm_rs_stack *__restrict__ stacks, int *counter)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const int wslot = blockIdx.x * WM_CHAIN_WARPS + (threadIdx.x >> 5);
+	for (;;) {
+		int task = 0;
+		if (lane == 0) task = atomicAdd(counter, 1);
+		task = __shfl_sync(FULL, task, 0);
+		if (task >= n_tasks) break;
+		const int64_t base = off[task];
+		const int n = (int)(off[task + 1] - base);
+		if (lane == 0) n_u_out[task] = 0, n_b_out[task] = 0;
+		if (n <= 0) continue;
+		wm128_dev *a = a_all + base, *b = b_all + base, *w = w_all + base;
+		int32_t *f = f_all + base, *p = p_all + base, *t = t_all + base, *v = v_all + base;
+		uint64_t *u = u_all + 2 * base, *u2 = u2_all + base; // u has room for the power-of-two padding of the bitonic sort
+		// chain ends (src/chain.c:93-98): anchors that are nobody's predecessor and whose peak score passes
+		for (int i = lane; i < n; i += 32) t[i] = 0;
+		__syncwarp();
+		for (int i = lane; i < n; i += 32) if (p[i] >= 0) t[p[i]] = 1;
+		__syncwarp();
+		int n_u = 0;
+		for (int ib = 0; ib < n; ib += 32) {
+			const int i = ib + lane;
+			const bool is_end = i < n && t[i] == 0 && v[i] >= P.min_sc;
+			const unsigned m = __ballot_sync(FULL, is_end);
+			if (is_end) { // :104-110: walk back to the peak that maximises f[]
+				int j = i;
+				while (j >= 0 && f[j] < v[j]) j = p[j];
+				if (j < 0) j = i;
+				u[n_u + __popc(m & ((1u << lane) - 1u))] = (uint64_t)(uint32_t)f[j] << 32 | (uint32_t)j;
+			}
+			n_u += __popc(m);
+		}
+		__syncwarp();
+		if (n_u == 0) continue; // :99-102
+		{ // :112-116 sort by (score, index) descending; keys are distinct so any correct sort gives the reference order
+			int m = 1; while (m < n_u) m <<= 1;
+			for (int i = n_u + lane; i < m; i += 32) u[i] = 0;
+			__syncwarp();
+			wm_warp_bitonic_desc(u, m, lane);
+		}
+		for (int i = lane; i < n; i += 32) t[i] = 0;
+		__syncwarp();
+		int n_v = 0, k = 0;
+		if (lane == 0) { // :118-135 greedy claim walk, serial by construction
+			for (int i = 0; i < n_u; ++i) {
+				const int n_v0 = n_v, k0 = k;
+				int j = (int32_t)u[i];
+				do { v[n_v++] = j; t[j] = 1; j = p[j]; } while (j >= 0 && t[j] == 0);
+				if (j < 0) {
+					if (n_v - n_v0 >= P.min_cnt) u[k++] = u[i] >> 32 << 32 | (uint32_t)(n_v - n_v0);
+				} else if ((int32_t)(u[i] >> 32) - f[j] >= P.min_sc) {
+					if (n_v - n_v0 >= P.min_cnt) u[k++] = ((u[i] >> 32) - (uint64_t)f[j]) << 32 | (uint32_t)(n_v - n_v0);
+				}
+				if (k0 == k) n_v = n_v0;
+			}
+		}
+		n_v = __shfl_sync(FULL, n_v, 0); k = __shfl_sync(FULL, k, 0);
+		n_u = k;
+		__syncwarp();
+		// :141-147 write chains to b[] in ascending anchor order; :150-154 build the re-sort keys
+		{
+			int kk = 0;
+			for (int i = 0; i < n_u; ++i) {
+				const int ni = (int32_t)u[i];
+				for (int j = lane; j < ni; j += 32) b[kk + j] = a[v[kk + (ni - j - 1)]];
+				kk += ni;
+			}
+			__syncwarp();
+			if (lane == 0) {
+				int k2 = 0;
+				for (int i = 0; i < n_u; ++i) { w[i].x = b[k2].x, w[i].y = (uint64_t)k2 << 32 | (uint32_t)i; k2 += (int32_t)u[i]; }
+				wm_radix_sort_emul(w, n_u, stacks + wslot); // :155, tie order matters
+			}
+			__syncwarp();
+		}
+		{ // :156-164 chains re-ordered by the position of their first anchor
+			int kk = 0;
+			for (int i = 0; i < n_u; ++i) {
+				const int j = (int32_t)w[i].y, nn = (int32_t)u[j];
+				const wm128_dev *src = b + (w[i].y >> 32);
+				if (lane == 0) u2[i] = u[j];
+				for (int l = lane; l < nn; l += 32) a[kk + l] = src[l];
+				kk += nn;
+			}
+			__syncwarp();
+			if (lane == 0) n_u_out[task] = n_u, n_b_out[task] = kk;
+		}
+		__syncwarp();
+	}
+}
+
+// Chains for n_tasks anchor arrays a[off[t]..off[t+1]) (device, sorted).  Results are left in place:
+// d_a holds the chained anchors of task t at off[t].. (n_b[t] of them), ws->u2 the (score<<32|cnt) words
+// at off[t].. (n_u[t] of them).
+void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_tasks, const wm_chain_params &P, cudaStream_t st)
+{
+	if (n_tasks <= 0) return;
+	const int64_t n_a = h_off[n_tasks];
+	int32_t *f = (int32_t*)ws->f.need(sizeof(int32_t) * (n_a + 1)), *p = (int32_t*)ws->p.need(sizeof(int32_t) * (n_a + 1));
+	int32_t *t = (int32_t*)ws->t.need(sizeof(int32_t) * (n_a + 1)), *v = (int32_t*)ws->v.need(sizeof(int32_t) * (n_a + 1));
+	uint64_t *u = (uint64_t*)ws->u.need(sizeof(uint64_t) * (2 * n_a + 2)), *u2 = (uint64_t*)ws->u2.need(sizeof(uint64_t) * (n_a + 1));
+	wm128_dev *w = (wm128_dev*)ws->w.need(sizeof(wm128_dev) * (n_a + 1)), *b = (wm128_dev*)ws->b.need(sizeof(wm128_dev) * (n_a + 1));
+	int32_t *n_u = (int32_t*)ws->n_u.need(sizeof(int32_t) * (n_tasks + 1));
+	int64_t *n_b = (int64_t*)ws->n_b.need(sizeof(int64_t) * (n_tasks + 1));
+	int *counter = (int*)ws->counter.need(2 * sizeof(int));
+	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));
+	// largest tasks first
+	std::vector<int32_t> order(n_tasks);
+	for (int i = 0; i < n_tasks; ++i) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return h_off[x + 1] - h_off[x] > h_off[y + 1] - h_off[y]; });
+	int32_t *d_order = (int32_t*)ws->order.need(sizeof(int32_t) * n_tasks);
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_order, order.data(), sizeof(int32_t) * n_tasks, cudaMemcpyHostToDevice, st));
+	int dev = 0, n_sm = 148;
+	WM_CUDA_CHECK(cudaGetDevice(&dev));
+	WM_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+	int grid = n_sm * 8;
+	const int need = (n_tasks + WM_CHAIN_WARPS - 1) / WM_CHAIN_WARPS;
+	if (grid > need) grid = need;
+	wm_rs_stack *stk = (wm_rs_stack*)ws->stacks.need(sizeof(wm_rs_stack) * (size_t)grid * WM_CHAIN_WARPS);
+	wm_chain_fill_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, P, f, p, t, v, counter);
+	WM_CUDA_CHECK(cudaGetLastError());
+	wm_chain_backtrack_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, n_tasks, P, f, p, t, v, u, u2, w, b, n_u, n_b, stk, counter + 1);
+	WM_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- C ABI ----
+extern "C" int wm_chain_dp_batch(int n_tasks, const wm128_dev *a, const int64_t *off,
+                                 int max_dist_x, int min_dist_x, int max_dist_y, int bw, int max_skip, int max_iter,
+                                 int min_cnt, int min_sc, float gap_scale,
+                                 int32_t *n_u, uint64_t *u, wm128_dev *b, int64_t *n_b)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+		fprintf(stderr, "[ERROR] wm_chain_dp_batch: no CUDA device visible; winnowmap-b200 has no CPU fallback\n");
+		exit(1);
+	}
+	if (n_tasks <= 0) return 0;
+	const int64_t n = off[n_tasks];
+	wm128_dev *d_a = wm_dev_alloc<wm128_dev>(n + 1);
+	int64_t *d_off = wm_dev_alloc<int64_t>(n_tasks + 1);
+	WM_CUDA_CHECK(cudaMemcpy(d_a, a, sizeof(wm128_dev) * n, cudaMemcpyHostToDevice));
+	WM_CUDA_CHECK(cudaMemcpy(d_off, off, sizeof(int64_t) * (n_tasks + 1), cudaMemcpyHostToDevice));
+	wm_chain_params P;
+	P.max_dist_x = max_dist_x, P.min_dist_x = min_dist_x, P.max_dist_y = max_dist_y, P.bw = bw, P.max_skip = max_skip, P.max_iter = max_iter;
+	P.min_cnt = min_cnt, P.min_sc = min_sc, P.gap_scale = gap_scale;
+	wm_chain_ws ws;
+	wm_chain_run(&ws, d_a, d_off, off, n_tasks, P, 0);
+	WM_CUDA_CHECK(cudaDeviceSynchronize());
+	WM_CUDA_CHECK(cudaMemcpy(n_u, ws.n_u.p, sizeof(int32_t) * n_tasks, cudaMemcpyDeviceToHost));
+	WM_CUDA_CHECK(cudaMemcpy(n_b, ws.n_b.p, sizeof(int64_t) * n_tasks, cudaMemcpyDeviceToHost));
+	if (n > 0) {
+		WM_CUDA_CHECK(cudaMemcpy(u, ws.u2.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+		WM_CUDA_CHECK(cudaMemcpy(b, d_a, sizeof(wm128_dev) * n, cudaMemcpyDeviceToHost));
+	}
+	ws.release();
+	cudaFree(d_a); cudaFree(d_off);
+	return 0;
+}

@@ -1,0 +1,17 @@
+#pragma once
+#include "wm_common.cuh"
+#include "sketch.cuh"
+
+// arguments of mm_chain_dp (reference src/chain.c:22)
+struct wm_chain_params {
+	int32_t max_dist_x, min_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc;
+	float gap_scale;
+};
+
+struct wm_chain_ws {
+	wm_dbuf f, p, t, v, u, u2, w, b, n_u, n_b, counter, order, stacks;
+	void release() { f.release(); p.release(); t.release(); v.release(); u.release(); u2.release(); w.release(); b.release();
+	                 n_u.release(); n_b.release(); counter.release(); order.release(); stacks.release(); }
+};
+
+void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_tasks, const wm_chain_params &P, cudaStream_t st);

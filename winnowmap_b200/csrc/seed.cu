@@ -1,0 +1,240 @@
+// Seed lookup and anchor generation on sm_100a: mm_idx_get (reference src/index.c:88-105),
+// collect_matches (src/map.c:97-130) and collect_seed_hits (src/map.c:222-254) for a batch of
+// sketched query windows, followed by the tie-exact anchor sort (rsort.cuh).
+//
+// Index layout in HBM (replicated per GPU): sorted unique minimizer hashes `keys`, CSR offsets
+// `pos_off` into the occurrence array `pos` (each list ascending, as src/index.c:239 leaves it) and an
+// open-addressing hash table key -> key index for O(1) probes.  The bucket/khash structure of the
+// reference is an implementation detail; the contract "hash -> (sorted list, n)" is what is kept.
+#include <vector>
+#include "wm_common.cuh"
+#include "scan.cuh"
+#include "sketch.cuh"
+#include "rsort.cuh"
+#include "seed.cuh"
+
+#define WM_HT_EMPTY 0xffffffffffffffffULL
+
+__device__ __forceinline__ uint64_t wm_ht_mix(uint64_t k)
+{
+	k ^= k >> 31; k *= 0x9E3779B97F4A7C15ULL; k ^= k >> 29;
+	return k;
+}
+
+__global__ void wm_ht_fill_kernel(const uint64_t *__restrict__ keys, int64_t n_keys, uint64_t *ht_key, uint32_t *ht_val, uint64_t mask)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_keys) return;
+	const uint64_t key = keys[i];
+	uint64_t slot = wm_ht_mix(key) & mask;
+	for (;;) {
+		unsigned long long old = atomicCAS((unsigned long long*)&ht_key[slot], (unsigned long long)WM_HT_EMPTY, (unsigned long long)key);
+		if (old == WM_HT_EMPTY || old == key) { ht_val[slot] = (uint32_t)i; return; }
+		slot = (slot + 1) & mask;
+	}
+}
+
+// mm_idx_get: returns the number of occurrences and the offset of the list in pos[]
+__device__ __forceinline__ int wm_idx_get(const wm_idx_dev &ix, uint64_t minier, uint64_t *off)
+{
+	uint64_t slot = wm_ht_mix(minier) & ix.ht_mask;
+	for (;;) {
+		const uint64_t k = ix.ht_key[slot];
+		if (k == minier) {
+			const uint32_t i = ix.ht_val[slot];
+			const uint64_t o = ix.pos_off[i];
+			*off = o;
+			return (int)(ix.pos_off[i + 1] - o);
+		}
+		if (k == WM_HT_EMPTY) { *off = 0; return 0; }
+		slot = (slot + 1) & ix.ht_mask;
+	}
+}
+
+// pass 1: one thread per query minimizer
+__global__ void wm_seed_lookup_kernel(wm_idx_dev ix, const wm128_dev *__restrict__ mz, const int64_t *__restrict__ mz_off, int n_tasks, int64_t n_mz,
+                                      int max_occ, int32_t *__restrict__ n_occ, int32_t *__restrict__ cnt, uint64_t *__restrict__ list_off,
+                                      uint8_t *__restrict__ tandem, int32_t *__restrict__ mz_task)
+{
+	const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= n_mz) return;
+	int lo = 0, hi = n_tasks; // task of this minimizer: last t with mz_off[t] <= m
+	while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (mz_off[mid] <= m) lo = mid; else hi = mid; }
+	const uint64_t h = mz[m].x >> 8;
+	uint64_t off;
+	const int t = wm_idx_get(ix, h, &off);
+	n_occ[m] = t;
+	cnt[m] = t >= max_occ ? 0 : t; // src/map.c:111
+	list_off[m] = off;
+	int td = 0; // src/map.c:121-122
+	if (m > mz_off[lo] && mz[m - 1].x >> 8 == h) td = 1;
+	if (m < mz_off[lo + 1] - 1 && mz[m + 1].x >> 8 == h) td = 1;
+	tandem[m] = (uint8_t)td;
+	mz_task[m] = lo;
+}
+
+// pass 2: one thread per anchor (src/map.c:233-249; skip_seed() is a no-op without -D/-X/--for-only/--rev-only)
+__global__ void wm_seed_expand_kernel(wm_idx_dev ix, const wm128_dev *__restrict__ mz, int64_t n_mz, const int64_t *__restrict__ a_off,
+                                      const uint64_t *__restrict__ list_off, const uint8_t *__restrict__ tandem, const int32_t *__restrict__ mz_task,
+                                      const int32_t *__restrict__ qlen, int64_t n_a, wm128_dev *__restrict__ a)
+{
+	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n_a) return;
+	int64_t lo = 0, hi = n_mz; // last m with a_off[m] <= j
+	while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (a_off[mid] <= j) lo = mid; else hi = mid; }
+	const wm128_dev p = mz[lo];
+	const uint64_t r = ix.pos[list_off[lo] + (uint64_t)(j - a_off[lo])];
+	const uint32_t q_pos = (uint32_t)p.y, q_span = (uint32_t)(p.x & 0xff);
+	const int32_t rpos = (uint32_t)r >> 1;
+	wm128_dev o;
+	if ((r & 1) == (q_pos & 1)) { // forward strand
+		o.x = (r & 0xffffffff00000000ULL) | (uint32_t)rpos;
+		o.y = (uint64_t)q_span << 32 | q_pos >> 1;
+	} else { // reverse strand
+		o.x = 1ULL << 63 | (r & 0xffffffff00000000ULL) | (uint32_t)rpos;
+		o.y = (uint64_t)q_span << 32 | (uint32_t)(qlen[mz_task[lo]] - ((q_pos >> 1) + 1 - q_span) - 1);
+	}
+	o.y |= (uint64_t)(p.y >> 32) << 48; // MM_SEED_SEG_SHIFT
+	if (tandem[lo]) o.y |= 1ULL << 42;   // MM_SEED_TANDEM
+	a[j] = o;
+}
+
+// pass 3: one thread per task: rep_len (src/map.c:106-127), kept-minimizer count, anchor offsets
+__global__ void wm_seed_task_kernel(const wm128_dev *__restrict__ mz, const int64_t *__restrict__ mz_off, const int64_t *__restrict__ a_off,
+                                    const int32_t *__restrict__ n_occ, int max_occ, int n_tasks, int32_t *__restrict__ rep_len,
+                                    int32_t *__restrict__ n_mini_pos, int64_t *__restrict__ task_a_off, uint32_t *__restrict__ mini_pos)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t > n_tasks) return;
+	if (t == n_tasks) { task_a_off[t] = a_off[mz_off[t]]; return; }
+	int rep_st = 0, rep_en = 0, rl = 0, nk = 0;
+	for (int64_t m = mz_off[t]; m < mz_off[t + 1]; ++m) {
+		const uint32_t q_pos = (uint32_t)mz[m].y, q_span = (uint32_t)(mz[m].x & 0xff);
+		if (n_occ[m] >= max_occ) {
+			int en = (int)(q_pos >> 1) + 1, st = en - (int)q_span;
+			if (st > rep_en) { rl += rep_en - rep_st; rep_st = st, rep_en = en; }
+			else rep_en = en;
+			mini_pos[m] = q_pos >> 1;
+		} else { ++nk; mini_pos[m] = (q_pos >> 1) | 0x80000000u; }
+	}
+	rl += rep_en - rep_st;
+	rep_len[t] = rl, n_mini_pos[t] = nk;
+	task_a_off[t] = a_off[mz_off[t]];
+}
+
+// tie-exact radix_sort_128x of each task's anchors (src/map.c:252)
+__global__ void wm_anchor_sort_small_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__ off, int n_arr)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_arr) return;
+	const int64_t n = off[t + 1] - off[t];
+	if (n <= WM_RS_MIN_SIZE) wm_rs_insertsort(a + off[t], a + off[t] + n);
+}
+
+__global__ void wm_anchor_sort_big_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__ off, const int32_t *__restrict__ big_ids, int n_big,
+                                          wm_rs_stack *__restrict__ stacks)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_big) return;
+	const int t = big_ids[i];
+	wm_radix_sort_emul(a + off[t], (int)(off[t + 1] - off[t]), stacks + i);
+}
+
+// sort n_arr arrays (device); h_off is the host copy of the offsets
+void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_arr, cudaStream_t st)
+{
+	if (n_arr <= 0) return;
+	std::vector<int32_t> big;
+	for (int i = 0; i < n_arr; ++i) if (h_off[i + 1] - h_off[i] > WM_RS_MIN_SIZE) big.push_back(i);
+	wm_anchor_sort_small_kernel<<<(n_arr + 127) / 128, 128, 0, st>>>(d_a, d_off, n_arr);
+	WM_CUDA_CHECK(cudaGetLastError());
+	if (!big.empty()) {
+		int32_t *d_big = (int32_t*)ws->big_ids.need(sizeof(int32_t) * big.size());
+		wm_rs_stack *d_stk = (wm_rs_stack*)ws->rs_stacks.need(sizeof(wm_rs_stack) * big.size());
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_big, big.data(), sizeof(int32_t) * big.size(), cudaMemcpyHostToDevice, st));
+		wm_anchor_sort_big_kernel<<<((int)big.size() + 31) / 32, 32, 0, st>>>(d_a, d_off, d_big, (int)big.size(), d_stk);
+		WM_CUDA_CHECK(cudaGetLastError());
+	}
+}
+
+// Collect sorted anchors for all sketched tasks.  Inputs are the outputs of wm_sketch_run.
+// On return: ws->a (anchors), ws->task_a_off (device, n_tasks+1), ws->rep_len, ws->n_mini_pos, ws->mini_pos;
+// h_task_a_off (host, n_tasks+1) receives the anchor offsets.
+void wm_seed_run(wm_seed_ws *ws, const wm_idx_dev &ix, const wm128_dev *d_mz, const int64_t *d_mz_off, int64_t n_mz, int n_tasks,
+                 const int32_t *d_qlen, int max_occ, int64_t *h_task_a_off, cudaStream_t st)
+{
+	for (int i = 0; i <= n_tasks; ++i) h_task_a_off[i] = 0;
+	int64_t *d_task_a_off = (int64_t*)ws->task_a_off.need(sizeof(int64_t) * (n_tasks + 1));
+	int32_t *d_rep = (int32_t*)ws->rep_len.need(sizeof(int32_t) * (n_tasks + 1));
+	int32_t *d_nmp = (int32_t*)ws->n_mini_pos.need(sizeof(int32_t) * (n_tasks + 1));
+	WM_CUDA_CHECK(cudaMemsetAsync(d_task_a_off, 0, sizeof(int64_t) * (n_tasks + 1), st));
+	WM_CUDA_CHECK(cudaMemsetAsync(d_rep, 0, sizeof(int32_t) * (n_tasks + 1), st));
+	WM_CUDA_CHECK(cudaMemsetAsync(d_nmp, 0, sizeof(int32_t) * (n_tasks + 1), st));
+	ws->n_a = 0;
+	if (n_tasks <= 0) return;
+	int32_t *d_nocc = (int32_t*)ws->n_occ.need(sizeof(int32_t) * (n_mz + 1));
+	int32_t *d_cnt = (int32_t*)ws->cnt.need(sizeof(int32_t) * (n_mz + 1));
+	uint64_t *d_loff = (uint64_t*)ws->list_off.need(sizeof(uint64_t) * (n_mz + 1));
+	uint8_t *d_td = (uint8_t*)ws->tandem.need(n_mz + 1);
+	int32_t *d_mtask = (int32_t*)ws->mz_task.need(sizeof(int32_t) * (n_mz + 1));
+	int64_t *d_aoff = (int64_t*)ws->a_off.need(sizeof(int64_t) * (n_mz + 2));
+	int64_t *d_tmp = (int64_t*)ws->scan_tmp.need(sizeof(int64_t) * wm_scan_tmp_elems(n_mz));
+	uint32_t *d_mpos = (uint32_t*)ws->mini_pos.need(sizeof(uint32_t) * (n_mz + 1));
+	if (n_mz > 0) {
+		wm_seed_lookup_kernel<<<(unsigned)((n_mz + 127) / 128), 128, 0, st>>>(ix, d_mz, d_mz_off, n_tasks, n_mz, max_occ, d_nocc, d_cnt, d_loff, d_td, d_mtask);
+		WM_CUDA_CHECK(cudaGetLastError());
+	}
+	wm_exclusive_scan(d_cnt, n_mz, d_aoff, d_tmp, st);
+	int64_t n_a = 0;
+	WM_CUDA_CHECK(cudaMemcpyAsync(&n_a, d_aoff + n_mz, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	ws->n_a = n_a;
+	wm128_dev *d_a = (wm128_dev*)ws->a.need(sizeof(wm128_dev) * (n_a + 1));
+	if (n_a > 0) {
+		wm_seed_expand_kernel<<<(unsigned)((n_a + 127) / 128), 128, 0, st>>>(ix, d_mz, n_mz, d_aoff, d_loff, d_td, d_mtask, d_qlen, n_a, d_a);
+		WM_CUDA_CHECK(cudaGetLastError());
+	}
+	wm_seed_task_kernel<<<(n_tasks + 1 + 127) / 128, 128, 0, st>>>(d_mz, d_mz_off, d_aoff, d_nocc, max_occ, n_tasks, d_rep, d_nmp, d_task_a_off, d_mpos);
+	WM_CUDA_CHECK(cudaGetLastError());
+	WM_CUDA_CHECK(cudaMemcpyAsync(h_task_a_off, d_task_a_off, sizeof(int64_t) * (n_tasks + 1), cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	wm_anchor_sort_run(ws, d_a, d_task_a_off, h_task_a_off, n_tasks, st);
+}
+
+// ---- index upload ----
+void wm_idx_dev_build_ht(wm_idx_dev *ix, cudaStream_t st)
+{
+	uint64_t cap = 1024;
+	while (cap < (uint64_t)ix->n_keys * 2) cap <<= 1;
+	uint64_t *hk = wm_dev_alloc<uint64_t>(cap);
+	uint32_t *hv = wm_dev_alloc<uint32_t>(cap);
+	WM_CUDA_CHECK(cudaMemsetAsync(hk, 0xff, cap * 8, st));
+	if (ix->n_keys > 0) {
+		wm_ht_fill_kernel<<<(unsigned)((ix->n_keys + 255) / 256), 256, 0, st>>>(ix->keys, ix->n_keys, hk, hv, cap - 1);
+		WM_CUDA_CHECK(cudaGetLastError());
+	}
+	ix->ht_key = hk, ix->ht_val = hv, ix->ht_mask = cap - 1;
+}
+
+// ---- C ABI: standalone tie-exact sort (for the parity tests) ----
+extern "C" int wm_radix_sort_128x_batch(int n_arr, wm128_dev *a, const int64_t *off)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+		fprintf(stderr, "[ERROR] wm_radix_sort_128x_batch: no CUDA device visible; winnowmap-b200 has no CPU fallback\n");
+		exit(1);
+	}
+	if (n_arr <= 0) return 0;
+	const int64_t n = off[n_arr];
+	wm128_dev *d_a = wm_dev_alloc<wm128_dev>(n + 1);
+	int64_t *d_off = wm_dev_alloc<int64_t>(n_arr + 1);
+	WM_CUDA_CHECK(cudaMemcpy(d_a, a, sizeof(wm128_dev) * n, cudaMemcpyHostToDevice));
+	WM_CUDA_CHECK(cudaMemcpy(d_off, off, sizeof(int64_t) * (n_arr + 1), cudaMemcpyHostToDevice));
+	wm_seed_ws ws;
+	wm_anchor_sort_run(&ws, d_a, d_off, off, n_arr, 0);
+	WM_CUDA_CHECK(cudaDeviceSynchronize());
+	WM_CUDA_CHECK(cudaMemcpy(a, d_a, sizeof(wm128_dev) * n, cudaMemcpyDeviceToHost));
+	ws.release();
+	cudaFree(d_a); cudaFree(d_off);
+	return 0;
+}

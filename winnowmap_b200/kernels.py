@@ -45,3 +45,77 @@ def ksw_extd2_batch(queries, targets, mat, q, e, q2, e2, w, zdrop, end_bonus, fl
     out = np.array([[getattr(ez[i], f) for f in EZ_FIELDS] for i in range(n)], dtype=np.int32).reshape(n, len(EZ_FIELDS))
     cigs = [cig[coff[i]: coff[i] + min(out[i, 10], cap[i])].copy() for i in range(n)]
     return out, cigs
+
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
+
+class Bloom:
+    """Down-weighted k-mer filter (reference: bloom_filter built at src/index.c:404-432)."""
+
+    def __init__(self, canon_kmers):
+        k = np.ascontiguousarray(canon_kmers, dtype=np.uint64)
+        self._k = k
+        self.h = lib().wm_bloom_build(_p(k, u64p) if len(k) else None, len(k))
+
+    def bits(self):
+        return lib().wm_bloom_bits(self.h)
+
+    def table(self):
+        n = self.bits() // 8
+        return np.ctypeslib.as_array(C.cast(lib().wm_bloom_table(self.h), u8p), shape=(n,)).copy()
+
+    def __del__(self):
+        try:
+            lib().wm_bloom_destroy(self.h)
+        except Exception:
+            pass
+
+
+def sketch_batch(bloom, seqs, w, k, rids=None):
+    """Batched mm_sketch (reference src/sketch.c:128).  seqs: list of bytes.  Returns list of (n,2) uint64."""
+    n = len(seqs)
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        off[1:] = np.cumsum([len(s) for s in seqs])
+    buf = b"".join(seqs) + b"\0"
+    rid = np.ascontiguousarray(rids if rids is not None else np.zeros(n), dtype=np.uint32)
+    out, out_off = C.c_void_p(), C.c_void_p()
+    rc = lib().wm_sketch_batch(bloom.h, n, buf, _p(off, i64p), _p(rid, u32p), w, k, C.byref(out), C.byref(out_off))
+    if rc != 0:
+        raise ValueError("wm_sketch_batch failed")
+    o = np.ctypeslib.as_array(C.cast(out_off, i64p), shape=(n + 1,)).copy()
+    tot = int(o[-1])
+    xy = np.ctypeslib.as_array(C.cast(out, u64p), shape=(max(tot, 1) * 2,)).copy()[: tot * 2].reshape(-1, 2)
+    _libc.free(out)
+    _libc.free(out_off)
+    return [xy[o[i]: o[i + 1]].copy() for i in range(n)]
+
+
+def radix_sort_128x_batch(arrays):
+    """radix_sort_128x (reference src/misc.c:156) on each (n,2) uint64 array, tie order included."""
+    n = len(arrays)
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        off[1:] = np.cumsum([len(a) for a in arrays])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.uint64).reshape(-1, 2) for a in arrays] + [np.zeros((1, 2), np.uint64)]))
+    lib().wm_radix_sort_128x_batch(n, _p(flat, u64p), _p(off, i64p))
+    return [flat[off[i]: off[i + 1]].copy() for i in range(n)]
+
+
+def chain_dp_batch(arrays, max_dist_x, min_dist_x, max_dist_y, bw, max_skip=25, max_iter=5000, min_cnt=3, min_sc=40, gap_scale=1.0):
+    """Batched mm_chain_dp (reference src/chain.c:22).  Returns list of (u, b)."""
+    n = len(arrays)
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        off[1:] = np.cumsum([len(a) for a in arrays])
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.uint64).reshape(-1, 2) for a in arrays] + [np.zeros((1, 2), np.uint64)]))
+    tot = int(off[-1])
+    n_u = np.zeros(max(n, 1), dtype=np.int32)
+    n_b = np.zeros(max(n, 1), dtype=np.int64)
+    u = np.zeros(max(tot, 1), dtype=np.uint64)
+    b = np.zeros((max(tot, 1), 2), dtype=np.uint64)
+    lib().wm_chain_dp_batch(n, _p(flat, u64p), _p(off, i64p), max_dist_x, min_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc,
+                            C.c_float(gap_scale), _p(n_u, i32p), _p(u, u64p), _p(b, u64p), _p(n_b, i64p))
+    return [(u[off[i]: off[i] + n_u[i]].copy(), b[off[i]: off[i] + n_b[i]].copy()) for i in range(n)]
