@@ -118,12 +118,124 @@ typedef struct {
 	const uint8_t *bloom_table;    /* bloom_filter::table() */
 } wm_idx_view_t;
 
+
+/* ---- structs that cross the boundary: field-for-field the reference's public structs ---- */
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+typedef struct { /* mm_extra_t, src/minimap.h:80-86 */
+	uint32_t capacity;
+	int32_t dp_score, dp_max, dp_max2;
+	uint32_t n_ambi:30, trans_strand:2;
+	uint32_t n_cigar;
+	uint32_t cigar[];
+} wm_extra_t;
+
+typedef struct { /* mm_reg1_t, src/minimap.h:88-103 */
+	int32_t id, cnt, rid, score;
+	int32_t qs, qe, rs, re;
+	int32_t parent, subsc;
+	int32_t as;
+	int32_t mlen, blen;
+	int32_t n_sub;
+	int32_t score0;
+	uint32_t mapq:8, split:2, rev:1, inv:1, sam_pri:1, proper_frag:1, pe_thru:1, seg_split:1, seg_id:8, split_inv:1, is_alt:1, dummy:6;
+	uint32_t hash;
+	float div;
+	wm_extra_t *p;
+} wm_reg1_t;
+
+typedef struct { /* mm_idxopt_t, src/minimap.h:106-110 */
+	short k, w, flag, bucket_bits;
+	int mini_batch_size;
+	uint64_t batch_size;
+} wm_idxopt_t;
+
+typedef struct { /* mm_mapopt_t, src/minimap.h:112-176 */
+	int64_t flag;
+	int seed;
+	int sdust_thres;
+	int max_qlen;
+	int bw;
+	int max_gap, max_gap_ref;
+	int min_gap_ref;
+	int max_frag_len;
+	int max_chain_skip, max_chain_iter;
+	int min_cnt;
+	int min_chain_score;
+	float chain_gap_scale;
+	bool SVaware;
+	int SVawareMinReadLength;
+	int suffixSampleOffset;
+	int min_mapq;
+	float min_qcov;
+	int minPrefixLength;
+	int maxPrefixLength;
+	float prefixIncrementFactor;
+	int stage2_bw;
+	int stage2_zdrop_inv;
+	int stage2_max_gap;
+	int stage2_extension_inc;
+	float mask_level;
+	int mask_len;
+	float pri_ratio;
+	int best_n;
+	int max_join_long, max_join_short;
+	int min_join_flank_sc;
+	float min_join_flank_ratio;
+	float alt_drop;
+	int a, b, q, e, q2, e2;
+	int sc_ambi;
+	int noncan;
+	int junc_bonus;
+	int zdrop, zdrop_inv;
+	int end_bonus;
+	int min_dp_max;
+	int min_ksw_len;
+	int anchor_ext_len, anchor_ext_shift;
+	float max_clip_ratio;
+	int pe_ori, pe_bonus;
+	float mid_occ_frac;
+	int32_t min_mid_occ;
+	int32_t mid_occ;
+	int32_t max_occ;
+	int mini_batch_size;
+	int64_t max_sw_mat;
+	const char *kmer_freq_filename;
+	const char *split_prefix;
+} wm_mapopt_t;
+
+
+/* mm_set_opt / mm_check_opt (src/options.c:89,133): same presets, same return codes */
+int wm_set_opt(const char *preset, wm_idxopt_t *io, wm_mapopt_t *mo);
+int wm_check_opt(const wm_idxopt_t *io, const wm_mapopt_t *mo);
+int wm_sizeof_mapopt(void);
+int wm_sizeof_reg1(void);
+
 typedef struct wm_gpu_ctx_s wm_gpu_ctx;
 
 /* Upload (replicate) the index to `n_gpus` devices starting at device 0, or to the single
  * device `device` when n_gpus == 1.  Call site in the reference: after main.c:403. */
 wm_gpu_ctx *wm_gpu_idx_upload(const wm_idx_view_t *idx, int device);
 void wm_gpu_destroy(wm_gpu_ctx *ctx);
+
+/* Index construction from FASTA (mm_idx_gen, src/index.c:378-449; reader loop main.c:384): the reference
+ * sequences are sketched by the same CUDA kernel as the reads, the -W list goes into the down-weight filter. */
+wm_gpu_ctx *wm_index_build(const char *ref_fn, const char *kmer_freq_fn, int k, int w, int device);
+
+/* Replaces kt_for(p->n_threads, worker_for, in, n_frag) (src/map.c:1162-1165; worker_for :1008-1048): one call per
+ * mini-batch, blocking; fills n_reg[i], reg[i] (malloc()ed array whose ->p are malloc()ed, freed by the caller as
+ * at src/map.c:1210-1211), rep_len[i] and frag_gap[i] (src/map.c:1025-1034).  n_threads = host threads for the glue. */
+int wm_gpu_map_batch(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_seq, const char *const *names, const char *const *seqs,
+                     const int32_t *lens, int32_t *n_reg, wm_reg1_t **reg, int32_t *rep_len, int32_t *frag_gap, int n_threads);
+
+/* mm_map_file (src/map.c:1273) for PAF output into out_fn ("-" = stdout).  rank/world shard the reads of every
+ * mini-batch round-robin over processes (one process per GPU); tag_order prefixes "<batch>\t<pos>\t" for merging. */
+int wm_map_file(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, const char *reads_fn, const char *out_fn, int n_threads, int rank, int world,
+                int tag_order, int64_t max_batch_bases);
+
+void wm_get_stats(wm_gpu_ctx *ctx, double *out, int n);
+void wm_reset_stats(wm_gpu_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,42 @@
+"""End-to-end parity on the GPU: PAF (coordinates, chaining/DP scores, MAPQ, CIGAR, every tag) must be
+byte-identical to the golden output of the real reference (tests/golden/, made by tools/make_golden.py)."""
+import gzip
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import make_golden  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+MANIFEST = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
+
+
+def _first_diff(a, b):
+    la, lb = a.split(b"\n"), b.split(b"\n")
+    for i, (x, y) in enumerate(zip(la, lb)):
+        if x != y:
+            fx, fy = x.split(b"\t"), y.split(b"\t")
+            cols = [j for j, (p, q) in enumerate(zip(fx, fy)) if p != q]
+            return f"line {i}: cols {cols}: exp {[fx[j][:60] for j in cols[:6]]} got {[fy[j][:60] for j in cols[:6]]} (name {fx[0].decode()})"
+    return f"line count {len(la)} vs {len(lb)}"
+
+
+@pytest.mark.parametrize("name", sorted(MANIFEST))
+def test_paf_matches_reference(name, tmp_path):
+    from winnowmap_b200.mapper import Mapper
+    m = MANIFEST[name]
+    ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
+    assert make_golden.md5(ref) == m["ref_md5"] and make_golden.md5(reads) == m["reads_md5"], "synthetic input generator drifted"
+    exp = gzip.open(os.path.join(ROOT, "tests", "golden", name + ".paf.gz")).read()
+    mp = Mapper(ref, wfile, preset=m["params"]["preset"], cigar=True)
+    out = str(tmp_path / "out.paf")
+    mp.map_file(reads, out)
+    got = open(out, "rb").read()
+    st = mp.stats()
+    mp.close()
+    assert st["n_dp_jobs"] > 0
+    assert got == exp, _first_diff(exp, got)

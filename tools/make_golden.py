@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Generates the end-to-end golden fixtures under tests/golden/ by running the REAL reference
+(oracle/_ref/winnowmap = /root/reference + the documented rep_len=0 init, built by oracle/build_ref.sh)
+on small deterministic synthetic inputs.  Inputs are regenerated from seeds at test time (tools/gen_data.py);
+the manifest stores their md5 so that generator drift is detected.  Run only where /root/reference exists."""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import gen_data  # noqa: E402
+import numpy as np  # noqa: E402
+
+CASES = {
+    # name: (ref_len, contigs, tandem, ref_seed, n_reads, n50, err, read_seed, min_len, preset, use_W, extra)
+    "ont_small": dict(ref_len=300000, contigs=2, tandem=False, ref_seed=1011, n_reads=60, n50=9000, err=0.05, read_seed=2011, min_len=500,
+                      preset="map-ont", use_W=False, k=15),
+    "ont_tandem": dict(ref_len=400000, contigs=2, tandem=True, ref_seed=1005, n_reads=60, n50=12000, err=0.05, read_seed=2005, min_len=1000,
+                       preset="map-ont", use_W=True, k=15),
+    "hifi_small": dict(ref_len=300000, contigs=1, tandem=True, ref_seed=1013, n_reads=40, n50=12000, err=0.005, read_seed=2013, min_len=1000,
+                       preset="map-pb", use_W=True, k=15),
+    "asm20_small": dict(ref_len=300000, contigs=1, tandem=False, ref_seed=1014, n_reads=12, n50=40000, err=0.02, read_seed=2014, min_len=5000,
+                        preset="asm20", use_W=True, k=19),
+}
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+def make_inputs(name, outdir):
+    c = CASES[name]
+    os.makedirs(outdir, exist_ok=True)
+    ref = os.path.join(outdir, name + ".ref.fa")
+    reads = os.path.join(outdir, name + ".reads.fa")
+    wfile = os.path.join(outdir, name + ".rep.txt")
+    rng = np.random.default_rng(c["ref_seed"])
+    contigs = gen_data.make_ref(rng, c["ref_len"], c["contigs"], c["tandem"])
+    gen_data.write_fasta(ref, contigs)
+    rng = np.random.default_rng(c["read_seed"])
+    recs = gen_data.make_reads(rng, contigs, c["n_reads"], c["n50"], c["err"], min_len=c["min_len"])
+    gen_data.write_fasta(reads, recs)
+    if c["use_W"]:
+        gen_data.write_top_kmers(wfile, contigs, c["k"], 0.9998)
+    else:
+        wfile = None
+    return ref, reads, wfile
+
+
+def main():
+    refbin = os.path.join(ROOT, "oracle", "_ref", "winnowmap")
+    if not os.path.exists(refbin):
+        subprocess.check_call([os.path.join(ROOT, "oracle", "build_ref.sh")])
+    gdir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(gdir, exist_ok=True)
+    tmp = "/tmp/wm_golden"
+    manifest = {}
+    for name, c in CASES.items():
+        ref, reads, wfile = make_inputs(name, tmp)
+        cmd = [refbin, "-t", "4", "-c", "-x", c["preset"]]
+        if wfile:
+            cmd += ["-W", wfile]
+        cmd += [ref, reads]
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        with gzip.GzipFile(os.path.join(gdir, name + ".paf.gz"), "wb", mtime=0) as f:
+            f.write(out)
+        manifest[name] = dict(params=c, ref_md5=md5(ref), reads_md5=md5(reads), w_md5=md5(wfile) if wfile else None,
+                              cmd=" ".join(["winnowmap"] + cmd[1:]), n_lines=out.count(b"\n"), paf_md5=hashlib.md5(out).hexdigest())
+        print(name, manifest[name]["n_lines"], "lines", len(out), "bytes")
+    json.dump(manifest, open(os.path.join(gdir, "manifest.json"), "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,7 +12,7 @@ NVCC = os.environ.get("WM_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: the reference is built without FMA contraction (Makefile:4); chaining and the
 # minimizer weights use double/float expressions whose roundings must match.
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fopenmp",
          "-ccbin", "/usr/bin/g++", "-Xptxas", "-v"]
 
 
@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         sys.stderr.write("\n".join(log))
-    cmd = [NVCC] + ARCH + ["-shared", "-o", SO] + objs + ["-ccbin", "/usr/bin/g++", "-lpthread"]
+    cmd = [NVCC] + ARCH + ["-shared", "-o", SO] + objs + ["-ccbin", "/usr/bin/g++", "-lpthread", "-lz", "-lgomp"]
     subprocess.check_call(cmd)
     return SO
 

@@ -1,0 +1,246 @@
+// C-ABI of the drop-in boundary (include/winnowmap_b200.h): index upload / construction, batch mapping
+// (the replacement of kt_for(worker_for), reference src/map.c:1162-1165) and the file-level driver that mirrors
+// mm_map_file (src/map.c:1244-1276) for PAF output.
+#include <string.h>
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <vector>
+#include "wm_common.cuh"
+#include "sketch.cuh"
+#include "gpu_backend.h"
+#include "host_io.h"
+
+using namespace wmh;
+
+
+struct wm_gpu_ctx_s {
+	wm_host_idx hidx;
+	Backend *be;
+	int device;
+	MapStats stats;
+	double t_index, t_map;
+	int64_t n_keys, n_pos;
+};
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static void require_device(const char *who)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+		fprintf(stderr, "[ERROR] %s: no CUDA device visible; winnowmap-b200 has no CPU fallback\n", who);
+		exit(1);
+	}
+}
+
+extern "C" wm_gpu_ctx_s *wm_gpu_idx_upload(const wm_idx_view_t *v, int device)
+{
+	require_device("wm_gpu_idx_upload");
+	wm_gpu_ctx_s *c = new wm_gpu_ctx_s();
+	memset(&c->stats, 0, sizeof(c->stats));
+	c->device = device; c->t_index = c->t_map = 0;
+	c->hidx.k = v->k, c->hidx.w = v->w;
+	for (int i = 0; i < v->n_seq; ++i) {
+		c->hidx.name.push_back(v->seq_name && v->seq_name[i] ? v->seq_name[i] : std::to_string(i));
+		c->hidx.len.push_back(v->seq_len[i]);
+		c->hidx.offset.push_back(v->seq_offset[i]);
+	}
+	c->hidx.S.assign(v->S, v->S + v->S_words);
+	c->n_keys = v->n_keys, c->n_pos = (int64_t)v->pos_off[v->n_keys];
+	c->be = gpu_backend_create(&c->hidx, v->keys, v->n_keys, v->pos_off, v->pos, v->bloom_bits, v->bloom_table, device);
+	return c;
+}
+
+extern "C" void wm_gpu_destroy(wm_gpu_ctx_s *c)
+{
+	if (!c) return;
+	gpu_backend_destroy(c->be);
+	delete c;
+}
+
+// Index construction from a FASTA file (mm_idx_gen, src/index.c:378-449): same minimizers as the reference
+// because the reference sequences go through the same sketch kernel as the reads.
+extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_freq_fn, int k, int w, int device)
+{
+	require_device("wm_index_build");
+	WM_CUDA_CHECK(cudaSetDevice(device));
+	const double t0 = now_s();
+	SeqReader rd;
+	if (!rd.open(ref_fn)) { fprintf(stderr, "ERROR: failed to open file '%s'\n", ref_fn); return 0; }
+	wm_gpu_ctx_s *c = new wm_gpu_ctx_s();
+	memset(&c->stats, 0, sizeof(c->stats));
+	c->device = device; c->t_index = c->t_map = 0;
+	wm_host_idx &H = c->hidx;
+	H.k = k, H.w = w;
+	std::vector<uint64_t> kmers;
+	if (read_kmer_list(kmer_freq_fn, k, kmers) < 0) abort();
+	wm_bloom_s *bloom = wm_bloom_build(kmers.empty() ? 0 : kmers.data(), (int64_t)kmers.size());
+	uint8_t *d_table = wm_dev_alloc<uint8_t>(wm_bloom_bits(bloom) / 8 + 16);
+	WM_CUDA_CHECK(cudaMemcpy(d_table, wm_bloom_table(bloom), wm_bloom_bits(bloom) / 8, cudaMemcpyHostToDevice));
+	wm_bloom_dev bf; wm_bloom_dev_from_table(&bf, d_table, wm_bloom_bits(bloom));
+	// read the reference, pack it 4 bits per base (mm_seq4_set, src/mmpriv.h:29) and sketch it in groups
+	std::vector<wm128_dev> mz;
+	wm_sketch_ws ws;
+	std::vector<wm_sk_task> tasks; std::string group; uint64_t sum_len = 0;
+	wm_dbuf d_ascii, d_codes;
+	auto flush = [&]() {
+		if (tasks.empty()) return;
+		char *da = (char*)d_ascii.need(group.size() + 16);
+		uint8_t *dc = (uint8_t*)d_codes.need(group.size() + 16);
+		WM_CUDA_CHECK(cudaMemcpy(da, group.data(), group.size(), cudaMemcpyHostToDevice));
+		wm_ascii_to_code(da, dc, (int64_t)group.size(), 0);
+		int64_t n_mz = 0;
+		wm_sketch_run(&ws, bf, dc, tasks.data(), (int)tasks.size(), w, k, &n_mz, 0);
+		WM_CUDA_CHECK(cudaDeviceSynchronize());
+		const size_t old = mz.size();
+		mz.resize(old + n_mz);
+		if (n_mz > 0) WM_CUDA_CHECK(cudaMemcpy(mz.data() + old, ws.mz.p, sizeof(wm128_dev) * n_mz, cudaMemcpyDeviceToHost));
+		tasks.clear(); group.clear();
+	};
+	wm_read r;
+	while (rd.next(r)) {
+		const uint32_t rid = (uint32_t)H.name.size();
+		H.name.push_back(r.name); H.len.push_back((uint32_t)r.seq.size()); H.offset.push_back(sum_len);
+		const uint64_t need_words = (sum_len + r.seq.size() + 7) / 8;
+		if (H.S.size() < need_words) H.S.resize(need_words, 0);
+		for (size_t j = 0; j < r.seq.size(); ++j) {
+			int cc;
+			switch (r.seq[j]) { case 'A': case 'a': cc = 0; break; case 'C': case 'c': cc = 1; break; case 'G': case 'g': cc = 2; break;
+				case 'T': case 't': cc = 3; break; default: cc = 4; }
+			const uint64_t o = sum_len + j;
+			H.S[o >> 3] |= (uint32_t)cc << ((o & 7) << 2);
+		}
+		sum_len += r.seq.size();
+		if (!r.seq.empty()) {
+			wm_sk_task t; t.seq_off = (int64_t)group.size(); t.len = (int32_t)r.seq.size(); t.rid = rid;
+			tasks.push_back(t); group += r.seq;
+		}
+		if (group.size() >= ((size_t)1 << 30)) flush();
+	}
+	flush();
+	ws.release(); d_ascii.release(); d_codes.release(); cudaFree(d_table);
+	// (hash, position) pairs sorted by hash then position: the occurrence lists mm_idx_get returns (src/index.c:239)
+	std::sort(mz.begin(), mz.end(), [](const wm128_dev &a, const wm128_dev &b) { return (a.x >> 8) != (b.x >> 8) ? (a.x >> 8) < (b.x >> 8) : a.y < b.y; });
+	std::vector<uint64_t> keys, pos_off, pos(mz.size());
+	for (size_t i = 0; i < mz.size(); ++i) {
+		if (i == 0 || (mz[i].x >> 8) != (mz[i - 1].x >> 8)) { keys.push_back(mz[i].x >> 8); pos_off.push_back(i); }
+		pos[i] = mz[i].y;
+	}
+	pos_off.push_back(mz.size());
+	c->n_keys = (int64_t)keys.size(), c->n_pos = (int64_t)pos.size();
+	c->be = gpu_backend_create(&H, keys.data(), (int64_t)keys.size(), pos_off.data(), pos.data(), wm_bloom_bits(bloom), wm_bloom_table(bloom), device);
+	wm_bloom_destroy(bloom);
+	c->t_index = now_s() - t0;
+	return c;
+}
+
+extern "C" int wm_set_opt(const char *preset, wm_idxopt_t *io, wm_mapopt_t *mo) { return set_opt(preset, io, mo); }
+extern "C" int wm_check_opt(const wm_idxopt_t *io, const wm_mapopt_t *mo) { return check_opt(io, mo); }
+extern "C" int wm_sizeof_mapopt(void) { return (int)sizeof(wm_mapopt_t); }
+extern "C" int wm_sizeof_reg1(void) { return (int)sizeof(wm_reg1_t); }
+
+// The GPU replacement of kt_for(n_threads, worker_for, ...) (src/map.c:1164): fills n_reg/reg/rep_len/frag_gap of
+// every sequence exactly as worker_for does (:1025-1034).  reg[i] and each reg[i][j].p are malloc()ed; the caller
+// frees them (src/minimap.h:355-356).
+extern "C" int wm_gpu_map_batch(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, int n_seq, const char *const *names, const char *const *seqs,
+                                const int32_t *lens, int32_t *n_reg, wm_reg1_t **reg, int32_t *rep_len, int32_t *frag_gap, int n_threads)
+{
+	require_device("wm_gpu_map_batch");
+	std::vector<wm_read> store(n_seq);
+	std::vector<const wm_read*> reads(n_seq);
+	for (int i = 0; i < n_seq; ++i) {
+		store[i].name = names && names[i] ? names[i] : "";
+		store[i].seq.assign(seqs[i], lens[i]);
+		reads[i] = &store[i];
+	}
+	std::vector<std::vector<wm_reg1_t>> regs; std::vector<int> rl, fg;
+	map_batch(c->be, &c->hidx, opt, reads, regs, rl, fg, n_threads, &c->stats);
+	for (int i = 0; i < n_seq; ++i) {
+		n_reg[i] = (int32_t)regs[i].size();
+		reg[i] = 0;
+		if (n_reg[i] > 0) {
+			reg[i] = (wm_reg1_t*)malloc(sizeof(wm_reg1_t) * n_reg[i]);
+			memcpy(reg[i], regs[i].data(), sizeof(wm_reg1_t) * n_reg[i]);
+		}
+		rep_len[i] = rl[i], frag_gap[i] = fg[i];
+	}
+	return 0;
+}
+
+// mm_map_file for PAF output.  Reads are taken in the reference's mini-batches (src/bseq.c:80-119), sorted by
+// length descending inside a batch (src/map.c:1124-1143) and printed in that order (:1173-1208).  With world > 1
+// this process maps and prints only the reads whose position in the sorted batch is rank mod world; every output
+// line is preceded by "<batch>\t<position>\t" when tag_order != 0 so that the shards can be merged back.
+extern "C" int wm_map_file(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const char *reads_fn, const char *out_fn, int n_threads, int rank, int world,
+                           int tag_order, int64_t max_batch_bases)
+{
+	require_device("wm_map_file");
+	SeqReader rd;
+	if (!rd.open(reads_fn)) { fprintf(stderr, "ERROR: failed to open file '%s': %s\n", reads_fn, strerror(errno)); return -1; }
+	FILE *out = out_fn && strcmp(out_fn, "-") ? fopen(out_fn, "wb") : stdout;
+	if (!out) return -1;
+	const double t0 = now_s();
+	std::string line;
+	wm_read pending; bool has_pending = false;
+	int64_t batch_no = 0;
+	const int64_t chunk = opt->mini_batch_size;
+	for (;;) {
+		std::vector<wm_read> batch;
+		int64_t size = 0;
+		wm_read r;
+		while (rd.next(r)) {
+			size += (int64_t)r.seq.size();
+			batch.push_back(r);
+			if (size >= chunk) break;
+		}
+		if (batch.empty()) break;
+		(void)has_pending; (void)pending;
+		// longer reads first; ties by larger input index first (std::greater on (len, index), src/map.c:1129)
+		std::vector<std::pair<int, int>> ord;
+		for (size_t i = 0; i < batch.size(); ++i) ord.emplace_back((int)batch[i].seq.size(), (int)i);
+		std::sort(ord.begin(), ord.end(), std::greater<std::pair<int, int>>());
+		std::vector<const wm_read*> mine; std::vector<int> mine_pos;
+		for (size_t p = 0; p < ord.size(); ++p)
+			if ((int)(p % (size_t)world) == rank) { mine.push_back(&batch[ord[p].second]); mine_pos.push_back((int)p); }
+		// internal sub-batches bound device memory; results do not depend on how reads are grouped
+		size_t s0 = 0;
+		while (s0 < mine.size()) {
+			size_t s1 = s0; int64_t nb = 0;
+			while (s1 < mine.size() && (s1 == s0 || nb + (int64_t)mine[s1]->seq.size() <= max_batch_bases)) nb += (int64_t)mine[s1]->seq.size(), ++s1;
+			std::vector<const wm_read*> sub(mine.begin() + s0, mine.begin() + s1);
+			std::vector<std::vector<wm_reg1_t>> regs; std::vector<int> rl, fg;
+			map_batch(c->be, &c->hidx, opt, sub, regs, rl, fg, n_threads, &c->stats);
+			for (size_t i = 0; i < sub.size(); ++i) {
+				const wm_read *t = sub[i];
+				auto emit = [&](const wm_reg1_t *rr) {
+					write_paf(line, &c->hidx, t, rr, opt->flag, rl[i]);
+					if (tag_order) fprintf(out, "%lld\t%d\t", (long long)batch_no, mine_pos[s0 + i]);
+					fwrite(line.data(), 1, line.size(), out); fputc('\n', out);
+				};
+				if (!regs[i].empty()) {
+					for (size_t j = 0; j < regs[i].size(); ++j) {
+						const wm_reg1_t *rr = &regs[i][j];
+						if ((opt->flag & WM_F_NO_PRINT_2ND) && rr->id != rr->parent) continue;
+						emit(rr);
+					}
+				} else if (opt->flag & WM_F_PAF_NO_HIT) emit(0);
+				for (auto &rr : regs[i]) free(rr.p);
+			}
+			s0 = s1;
+		}
+		++batch_no;
+	}
+	if (out != stdout) fclose(out); else fflush(out);
+	c->t_map += now_s() - t0;
+	return 0;
+}
+
+extern "C" void wm_get_stats(wm_gpu_ctx_s *c, double *o, int n)
+{
+	const MapStats &s = c->stats;
+	double v[] = { (double)s.n_reads, (double)s.n_bases, (double)s.n_minimaps, (double)s.n_chained, (double)s.n_dp_jobs, (double)s.n_ll_jobs,
+	               (double)s.n_rounds, s.t_seed, s.t_dp, s.t_host, c->t_index, c->t_map, (double)c->n_keys, (double)c->n_pos };
+	for (int i = 0; i < n && i < (int)(sizeof(v) / sizeof(v[0])); ++i) o[i] = v[i];
+}
+extern "C" void wm_reset_stats(wm_gpu_ctx_s *c) { memset(&c->stats, 0, sizeof(c->stats)); c->t_map = 0; }

@@ -31,7 +31,7 @@ __device__ __forceinline__ int wm_warp_incl_max(int v, int lane)
 
 __global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
 wm_chain_fill_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ order, int n_tasks,
-                     wm_chain_params P, int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
+                     wm_chain_params2 PP, const uint8_t *__restrict__ set_id, int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
                      int *counter)
 {
 	const unsigned FULL = 0xffffffffu;
@@ -45,6 +45,7 @@ wm_chain_fill_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restr
 		const int64_t base = off[task];
 		const int n = (int)(off[task + 1] - base);
 		if (n <= 0) continue;
+		const wm_chain_params P = PP.p[set_id ? set_id[task] : 0];
 		const wm128_dev *a = a_all + base;
 		int32_t *f = f_all + base, *p = p_all + base, *t = t_all + base, *v = v_all + base;
 		// avg_qspan (src/chain.c:41-42)
@@ -141,7 +142,7 @@ __device__ void wm_warp_bitonic_desc(uint64_t *x, int m, int lane)
 }
 
 __global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
-wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, int n_tasks, wm_chain_params P,
+wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, int n_tasks, wm_chain_params2 PP, const uint8_t *__restrict__ set_id,
                           int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
                           uint64_t *__restrict__ u_all, uint64_t *__restrict__ u2_all, wm128_dev *__restrict__ w_all, wm128_dev *__restrict__ b_all,
                           int32_t *__restrict__ n_u_out, int64_t *__restrict__ n_b_out, wm_rs_stack *__restrict__ stacks, int *counter)
@@ -158,6 +159,7 @@ wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restri
 		const int n = (int)(off[task + 1] - base);
 		if (lane == 0) n_u_out[task] = 0, n_b_out[task] = 0;
 		if (n <= 0) continue;
+		const wm_chain_params P = PP.p[set_id ? set_id[task] : 0];
 		wm128_dev *a = a_all + base, *b = b_all + base, *w = w_all + base;
 		int32_t *f = f_all + base, *p = p_all + base, *t = t_all + base, *v = v_all + base;
 		uint64_t *u = u_all + 2 * base, *u2 = u2_all + base; // u has room for the power-of-two padding of the bitonic sort
@@ -241,7 +243,7 @@ wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restri
 // Chains for n_tasks anchor arrays a[off[t]..off[t+1]) (device, sorted).  Results are left in place:
 // d_a holds the chained anchors of task t at off[t].. (n_b[t] of them), ws->u2 the (score<<32|cnt) words
 // at off[t].. (n_u[t] of them).
-void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_tasks, const wm_chain_params &P, cudaStream_t st)
+void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_tasks, const wm_chain_params2 &PP, const uint8_t *d_set_id, cudaStream_t st)
 {
 	if (n_tasks <= 0) return;
 	const int64_t n_a = h_off[n_tasks];
@@ -266,9 +268,9 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	const int need = (n_tasks + WM_CHAIN_WARPS - 1) / WM_CHAIN_WARPS;
 	if (grid > need) grid = need;
 	wm_rs_stack *stk = (wm_rs_stack*)ws->stacks.need(sizeof(wm_rs_stack) * (size_t)grid * WM_CHAIN_WARPS);
-	wm_chain_fill_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, P, f, p, t, v, counter);
+	wm_chain_fill_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
 	WM_CUDA_CHECK(cudaGetLastError());
-	wm_chain_backtrack_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, n_tasks, P, f, p, t, v, u, u2, w, b, n_u, n_b, stk, counter + 1);
+	wm_chain_backtrack_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, n_tasks, PP, d_set_id, f, p, t, v, u, u2, w, b, n_u, n_b, stk, counter + 1);
 	WM_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -289,11 +291,13 @@ extern "C" int wm_chain_dp_batch(int n_tasks, const wm128_dev *a, const int64_t 
 	int64_t *d_off = wm_dev_alloc<int64_t>(n_tasks + 1);
 	WM_CUDA_CHECK(cudaMemcpy(d_a, a, sizeof(wm128_dev) * n, cudaMemcpyHostToDevice));
 	WM_CUDA_CHECK(cudaMemcpy(d_off, off, sizeof(int64_t) * (n_tasks + 1), cudaMemcpyHostToDevice));
-	wm_chain_params P;
+	wm_chain_params2 PP;
+	wm_chain_params &P = PP.p[0];
 	P.max_dist_x = max_dist_x, P.min_dist_x = min_dist_x, P.max_dist_y = max_dist_y, P.bw = bw, P.max_skip = max_skip, P.max_iter = max_iter;
 	P.min_cnt = min_cnt, P.min_sc = min_sc, P.gap_scale = gap_scale;
+	PP.p[1] = P;
 	wm_chain_ws ws;
-	wm_chain_run(&ws, d_a, d_off, off, n_tasks, P, 0);
+	wm_chain_run(&ws, d_a, d_off, off, n_tasks, PP, 0, 0);
 	WM_CUDA_CHECK(cudaDeviceSynchronize());
 	WM_CUDA_CHECK(cudaMemcpy(n_u, ws.n_u.p, sizeof(int32_t) * n_tasks, cudaMemcpyDeviceToHost));
 	WM_CUDA_CHECK(cudaMemcpy(n_b, ws.n_b.p, sizeof(int64_t) * n_tasks, cudaMemcpyDeviceToHost));

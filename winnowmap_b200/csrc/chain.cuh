@@ -8,10 +8,12 @@ struct wm_chain_params {
 	float gap_scale;
 };
 
+struct wm_chain_params2 { wm_chain_params p[2]; }; // stage-1/fallback and stage-2 parameter sets
+
 struct wm_chain_ws {
 	wm_dbuf f, p, t, v, u, u2, w, b, n_u, n_b, counter, order, stacks;
 	void release() { f.release(); p.release(); t.release(); v.release(); u.release(); u2.release(); w.release(); b.release();
 	                 n_u.release(); n_b.release(); counter.release(); order.release(); stacks.release(); }
 };
 
-void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_tasks, const wm_chain_params &P, cudaStream_t st);
+void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_tasks, const wm_chain_params2 &PP, const uint8_t *d_set_id, cudaStream_t st);

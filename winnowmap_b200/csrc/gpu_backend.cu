@@ -1,0 +1,531 @@
+// CUDA implementation of the device boundary (host_backend.h) for one GPU: resident index, per-batch read
+// pool, and the three coarse operations the orchestrator calls.  All buffers are grow-only pools (wm_dbuf)
+// sized for a batch; nothing is allocated per read.
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "wm_common.cuh"
+#include "scan.cuh"
+#include "sketch.cuh"
+#include "seed.cuh"
+#include "chain.cuh"
+#include "gpu_backend.h"
+
+// from ksw_extd2.cu / ksw_ll.cu
+struct wm_extd2_ws { wm_dbuf scratch, counter; };
+void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2);
+size_t wm_extd2_bt_bytes(int qlen, int tlen, int w);
+void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, const uint8_t *d_seq, uint8_t *d_bt,
+                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream);
+struct wm_ll_job { int64_t q_off, t_off; int64_t s_off; int32_t qlen, tlen; };
+void wm_ksw_ll_launch(const wm_ll_job *d_jobs, int n, const uint8_t *d_seq, const int8_t *d_mat, int gapo, int gape, int32_t *d_scratch, int32_t *d_out, cudaStream_t st);
+
+using namespace wmh;
+
+// ---- small data-movement kernels ----
+__global__ void wm_revcomp_kernel(const uint8_t *__restrict__ fwd, uint8_t *__restrict__ rev, const int64_t *__restrict__ read_off, int n_reads, int64_t n)
+{ // strand 1 of every read (src/align.c:874-876): rev[L-1-i] = comp(fwd[i])
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n) return;
+	int lo = 0, hi = n_reads;
+	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (read_off[m] <= g) lo = m; else hi = m; }
+	const int64_t b = read_off[lo], L = read_off[lo + 1] - b;
+	const uint8_t c = fwd[g];
+	rev[b + (L - 1 - (g - b))] = c < 4 ? 3 - c : 4;
+}
+
+struct wm_mask_task { int64_t src_off, dst_off, mask_off; int32_t len, n_mask; };
+
+__global__ void wm_mask_copy_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ dst, const wm_mask_task *__restrict__ tasks, const int64_t *__restrict__ toff,
+                                    int n_tasks, const int32_t *__restrict__ mask_pool, int64_t n)
+{ // covered bases become ambiguous (src/map.c:795-801)
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n) return;
+	int lo = 0, hi = n_tasks;
+	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (toff[m] <= g) lo = m; else hi = m; }
+	const wm_mask_task T = tasks[lo];
+	const int p = (int)(g - toff[lo]);
+	const int32_t *iv = mask_pool + 2 * T.mask_off;
+	int a = 0, b = T.n_mask; // last interval with start <= p
+	bool covered = false;
+	while (a < b) { int m = (a + b) >> 1; if (iv[2 * m] <= p) a = m + 1; else b = m; }
+	if (a > 0) covered = p < iv[2 * (a - 1) + 1];
+	dst[T.dst_off + p] = covered ? 4 : codes[T.src_off + p];
+}
+
+struct wm_gather_job { int64_t src_off, dst_off; int32_t len, kind, reversed, pad; }; // kind 0: read strand 0, 2: read strand 1, 1: 4-bit packed reference
+
+struct wm_cat_task { int64_t pre_off, seed_off, dst_off; int32_t n_pre, n_seed; };
+
+__global__ void wm_concat_kernel(const wm_cat_task *__restrict__ tasks, const int64_t *__restrict__ toff, int n_tasks, const wm128_dev *__restrict__ pre,
+                                 const wm128_dev *__restrict__ seeds, wm128_dev *__restrict__ dst, int64_t n)
+{ // a_whole = [a ; a_remaining] (src/map.c:818-828)
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n) return;
+	int lo = 0, hi = n_tasks;
+	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (toff[m] <= g) lo = m; else hi = m; }
+	const wm_cat_task T = tasks[lo];
+	const int64_t p = g - toff[lo];
+	dst[T.dst_off + p] = p < T.n_pre ? pre[T.pre_off + p] : seeds[T.seed_off + (p - T.n_pre)];
+}
+
+__global__ void wm_compact_chain_kernel(const int64_t *__restrict__ src_off, const int64_t *__restrict__ nb_off, const int64_t *__restrict__ nu_off, int n_tasks,
+                                        const wm128_dev *__restrict__ a, const uint64_t *__restrict__ u, wm128_dev *__restrict__ b_out, uint64_t *__restrict__ u_out)
+{ // one warp per task copies the meaningful prefix of its chain output
+	const int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (task >= n_tasks) return;
+	const int64_t so = src_off[task], bo = nb_off[task], uo = nu_off[task];
+	const int64_t nb = nb_off[task + 1] - bo, nu = nu_off[task + 1] - uo;
+	for (int64_t i = lane; i < nb; i += 32) b_out[bo + i] = a[so + i];
+	for (int64_t i = lane; i < nu; i += 32) u_out[uo + i] = u[so + i];
+}
+
+__global__ void wm_compact_cigar_kernel(const wm_dp_job *__restrict__ jobs, const wm_extz_dev *__restrict__ ez, const int64_t *__restrict__ out_off, int n_jobs,
+                                        const uint32_t *__restrict__ cig, uint32_t *__restrict__ out)
+{
+	const int job = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (job >= n_jobs) return;
+	const int64_t o = out_off[job], n = out_off[job + 1] - o, s = jobs[job].cig_off;
+	for (int64_t i = lane; i < n; i += 32) out[o + i] = cig[s + i];
+}
+
+namespace wmh {
+
+struct GpuBackendImpl {
+	int device;
+	cudaStream_t st;
+	wm_idx_dev ix;
+	wm_bloom_dev bf;
+	const wm_host_idx *hidx;
+	// batch state
+	std::vector<int64_t> read_off; // host
+	wm_dbuf ascii, codes, rcodes, d_read_off;
+	int64_t n_bases;
+	// workspaces
+	wm_sketch_ws sk; wm_seed_ws sd, sd2; wm_chain_ws ch; wm_extd2_ws dpws;
+	wm_dbuf masked, mask_tasks, mask_toff, mask_pool, qlen_buf, pre_buf, cat_tasks, cat_toff, cat_a, set_id, off_buf, nb_off, nu_off, b_out, u_out;
+	wm_dbuf g_jobs, g_joff, seq_pool, dp_jobs, bt, ez, cig, cig_off, cig_out, ll_jobs, ll_scr, ll_out, mat;
+	// host result pools
+	std::vector<uint32_t> h_mzpos; std::vector<int64_t> h_mz_off; std::vector<int32_t> h_rep;
+	std::vector<uint64_t> h_u; std::vector<wm_pair_t> h_b; std::vector<int32_t> h_nu; std::vector<int64_t> h_nb;
+	std::vector<uint32_t> h_cig; std::vector<wm_extz_dev> h_ez;
+	size_t bt_budget;
+};
+
+class GpuBackend : public Backend {
+public:
+	GpuBackendImpl g;
+	GpuBackend() {}
+	~GpuBackend() {}
+	void begin_batch(const std::vector<const wm_read*> &reads) override;
+	void seed_chain(const std::vector<SeedTask> &tasks, const int32_t *mask_pool, const wm_pair_t *pre_pool, const ChainParams cp[2], int max_occ, std::vector<SeedOut> &out) override;
+	void run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<DpRes> &res) override;
+	void run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<LlRes> &res) override;
+	void end_batch() override {}
+};
+
+void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
+{
+	WM_CUDA_CHECK(cudaSetDevice(g.device));
+	const int n = (int)reads.size();
+	g.read_off.assign(n + 1, 0);
+	for (int i = 0; i < n; ++i) g.read_off[i + 1] = g.read_off[i] + (int64_t)reads[i]->seq.size();
+	g.n_bases = g.read_off[n];
+	char *d_ascii = (char*)g.ascii.need(g.n_bases + 16);
+	uint8_t *d_codes = (uint8_t*)g.codes.need(g.n_bases + 16), *d_rc = (uint8_t*)g.rcodes.need(g.n_bases + 16);
+	int64_t *d_off = (int64_t*)g.d_read_off.need(sizeof(int64_t) * (n + 1));
+	for (int i = 0; i < n; ++i)
+		if (!reads[i]->seq.empty())
+			WM_CUDA_CHECK(cudaMemcpyAsync(d_ascii + g.read_off[i], reads[i]->seq.data(), reads[i]->seq.size(), cudaMemcpyHostToDevice, g.st));
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_off, g.read_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, g.st));
+	wm_ascii_to_code(d_ascii, d_codes, g.n_bases, g.st);
+	if (g.n_bases > 0) {
+		wm_revcomp_kernel<<<(unsigned)((g.n_bases + 255) / 256), 256, 0, g.st>>>(d_codes, d_rc, d_off, n, g.n_bases);
+		WM_CUDA_CHECK(cudaGetLastError());
+	}
+}
+
+void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *mask_pool, const wm_pair_t *pre_pool, const ChainParams cp[2], int max_occ, std::vector<SeedOut> &out)
+{
+	WM_CUDA_CHECK(cudaSetDevice(g.device));
+	cudaStream_t st = g.st;
+	const int n = (int)tasks.size();
+	out.assign(n, SeedOut());
+	if (n == 0) return;
+	const uint8_t *d_codes = (const uint8_t*)g.codes.p;
+	// 1. masked copies
+	std::vector<wm_mask_task> mt; std::vector<int64_t> mtoff(1, 0);
+	int64_t n_mask_iv = 0, n_pre = 0;
+	for (int i = 0; i < n; ++i) {
+		const SeedTask &t = tasks[i];
+		if (t.flags & SEED_MASKED) {
+			wm_mask_task m;
+			m.src_off = g.read_off[t.win.read] + t.win.wb, m.dst_off = mtoff.back(), m.mask_off = t.mask_off, m.len = t.win.wl, m.n_mask = t.n_mask;
+			mt.push_back(m); mtoff.push_back(mtoff.back() + t.win.wl);
+			n_mask_iv = std::max<int64_t>(n_mask_iv, t.mask_off + t.n_mask);
+		}
+		n_pre = std::max<int64_t>(n_pre, t.pre_off + t.n_pre);
+	}
+	uint8_t *d_masked = (uint8_t*)g.masked.need(mtoff.back() + 16);
+	if (!mt.empty()) {
+		wm_mask_task *d_mt = (wm_mask_task*)g.mask_tasks.need(sizeof(wm_mask_task) * mt.size());
+		int64_t *d_mtoff = (int64_t*)g.mask_toff.need(sizeof(int64_t) * mtoff.size());
+		int32_t *d_mp = (int32_t*)g.mask_pool.need(sizeof(int32_t) * 2 * (n_mask_iv + 1));
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_mt, mt.data(), sizeof(wm_mask_task) * mt.size(), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_mtoff, mtoff.data(), sizeof(int64_t) * mtoff.size(), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_mp, mask_pool, sizeof(int32_t) * 2 * n_mask_iv, cudaMemcpyHostToDevice, st));
+		wm_mask_copy_kernel<<<(unsigned)((mtoff.back() + 255) / 256), 256, 0, st>>>(d_codes, d_masked, d_mt, d_mtoff, (int)mt.size(), d_mp, mtoff.back());
+		WM_CUDA_CHECK(cudaGetLastError());
+	}
+	// 2. sketch: tasks that sketch something.  The masked copies live in another buffer, so two passes.
+	std::vector<int> sk_of(n, -1);       // task -> index among the sketched tasks
+	std::vector<wm_sk_task> skt_plain, skt_mask;
+	std::vector<int> plain_ids, mask_ids;
+	{
+		size_t mi_ = 0;
+		for (int i = 0; i < n; ++i) {
+			const SeedTask &t = tasks[i];
+			if (t.flags & SEED_NO_SKETCH) continue;
+			wm_sk_task s; s.len = t.win.wl, s.rid = 0;
+			if (t.flags & SEED_MASKED) { s.seq_off = mt[mi_++].dst_off; skt_mask.push_back(s); mask_ids.push_back(i); }
+			else { s.seq_off = g.read_off[t.win.read] + t.win.wb; skt_plain.push_back(s); plain_ids.push_back(i); }
+		}
+	}
+	// per task results gathered into one anchor array `A` with offsets `a_off`
+	const int k = g.ix.k, w = g.ix.w;
+	std::vector<int64_t> seed_cnt(n, 0), seed_src(n, 0); // per task: number of seed anchors and their offset in the pass's anchor array
+	std::vector<int> seed_pass(n, -1);
+	std::vector<int64_t> h_mz_off_all(n + 1, 0);
+	g.h_mzpos.clear(); g.h_rep.assign(n, 0);
+	std::vector<int64_t> mz_cnt(n, 0), mz_src(n, 0);
+	wm128_dev *d_seed_a[2] = {0, 0};
+	wm_seed_ws *sdp[2] = { &g.sd, 0 };
+	sdp[1] = &g.sd2; // second seed workspace for the masked pass (kept until chaining is done)
+	std::vector<uint32_t> pass_mzpos[2]; std::vector<int64_t> pass_mzoff[2];
+	for (int pass = 0; pass < 2; ++pass) {
+		std::vector<wm_sk_task> &skt = pass == 0 ? skt_plain : skt_mask;
+		std::vector<int> &ids = pass == 0 ? plain_ids : mask_ids;
+		const int ns = (int)skt.size();
+		if (ns == 0) continue;
+		int64_t n_mz = 0;
+		wm_sketch_run(&g.sk, g.bf, pass == 0 ? d_codes : d_masked, skt.data(), ns, w, k, &n_mz, st);
+		std::vector<int32_t> qlen(ns);
+		for (int i = 0; i < ns; ++i) qlen[i] = skt[i].len;
+		int32_t *d_qlen = (int32_t*)g.qlen_buf.need(sizeof(int32_t) * ns);
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_qlen, qlen.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, st));
+		std::vector<int64_t> a_off(ns + 1);
+		wm_seed_run(sdp[pass], g.ix, (const wm128_dev*)g.sk.mz.p, (const int64_t*)g.sk.mz_off.p, n_mz, ns, d_qlen, max_occ, a_off.data(), st);
+		d_seed_a[pass] = (wm128_dev*)sdp[pass]->a.p;
+		// small per-task results
+		std::vector<int32_t> rep(ns);
+		pass_mzoff[pass].assign(ns + 1, 0); pass_mzpos[pass].resize(n_mz);
+		WM_CUDA_CHECK(cudaMemcpyAsync(rep.data(), sdp[pass]->rep_len.p, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(cudaMemcpyAsync(pass_mzoff[pass].data(), g.sk.mz_off.p, sizeof(int64_t) * (ns + 1), cudaMemcpyDeviceToHost, st));
+		if (n_mz > 0) WM_CUDA_CHECK(cudaMemcpyAsync(pass_mzpos[pass].data(), sdp[pass]->mini_pos.p, sizeof(uint32_t) * n_mz, cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(cudaStreamSynchronize(st));
+		for (int i = 0; i < ns; ++i) {
+			const int t = ids[i];
+			g.h_rep[t] = rep[i];
+			seed_cnt[t] = a_off[i + 1] - a_off[i], seed_src[t] = a_off[i], seed_pass[t] = pass;
+			mz_cnt[t] = pass_mzoff[pass][i + 1] - pass_mzoff[pass][i], mz_src[t] = pass_mzoff[pass][i];
+		}
+	}
+	// 3. final anchor arrays: [pre ; seeds] per task
+	std::vector<int64_t> f_off(n + 1, 0);
+	std::vector<wm_cat_task> ct(n);
+	std::vector<uint8_t> set_id(n);
+	bool any_pre = false, any_mask_pass = !skt_mask.empty();
+	for (int i = 0; i < n; ++i) {
+		const SeedTask &t = tasks[i];
+		f_off[i + 1] = f_off[i] + t.n_pre + seed_cnt[i];
+		set_id[i] = (uint8_t)t.chain_set;
+		any_pre |= t.n_pre > 0;
+	}
+	const int64_t n_f = f_off[n];
+	wm128_dev *d_A;
+	int64_t *d_foff = (int64_t*)g.off_buf.need(sizeof(int64_t) * (n + 1));
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_foff, f_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+	if (!any_pre && !any_mask_pass) {
+		d_A = d_seed_a[0]; // the plain pass' array already has exactly this layout (tasks in order, no gaps)
+		if (d_A == 0) d_A = (wm128_dev*)g.cat_a.need(16);
+	} else {
+		d_A = (wm128_dev*)g.cat_a.need(sizeof(wm128_dev) * (n_f + 1));
+		wm128_dev *d_pre = (wm128_dev*)g.pre_buf.need(sizeof(wm128_dev) * (n_pre + 1));
+		if (n_pre > 0) WM_CUDA_CHECK(cudaMemcpyAsync(d_pre, pre_pool, sizeof(wm128_dev) * n_pre, cudaMemcpyHostToDevice, st));
+		// tasks fed from the plain pass and from the masked pass need different source arrays: two launches
+		for (int pass = 0; pass < 2; ++pass) {
+			std::vector<wm_cat_task> c2; std::vector<int64_t> toff(1, 0);
+			for (int i = 0; i < n; ++i) {
+				const SeedTask &t = tasks[i];
+				const bool mine = seed_pass[i] == pass || (seed_pass[i] < 0 && pass == 0);
+				if (!mine) continue;
+				wm_cat_task c;
+				c.pre_off = t.pre_off, c.n_pre = t.n_pre, c.seed_off = seed_src[i], c.n_seed = (int32_t)seed_cnt[i], c.dst_off = f_off[i];
+				if (c.n_pre + c.n_seed == 0) continue;
+				c2.push_back(c); toff.push_back(toff.back() + c.n_pre + c.n_seed);
+			}
+			if (c2.empty()) continue;
+			wm_cat_task *d_ct = (wm_cat_task*)g.cat_tasks.need(sizeof(wm_cat_task) * c2.size());
+			int64_t *d_toff = (int64_t*)g.cat_toff.need(sizeof(int64_t) * toff.size());
+			WM_CUDA_CHECK(cudaMemcpyAsync(d_ct, c2.data(), sizeof(wm_cat_task) * c2.size(), cudaMemcpyHostToDevice, st));
+			WM_CUDA_CHECK(cudaMemcpyAsync(d_toff, toff.data(), sizeof(int64_t) * toff.size(), cudaMemcpyHostToDevice, st));
+			const wm128_dev *src = d_seed_a[pass] ? d_seed_a[pass] : d_A;
+			wm_concat_kernel<<<(unsigned)((toff.back() + 255) / 256), 256, 0, st>>>(d_ct, d_toff, (int)c2.size(), d_pre, src, d_A, toff.back());
+			WM_CUDA_CHECK(cudaGetLastError());
+			WM_CUDA_CHECK(cudaStreamSynchronize(st)); // c2/toff are reused by the next pass
+		}
+		// sort #3 (src/map.c:831): only arrays that really merged two sorted runs can change
+		std::vector<int64_t> s_off(n + 1);
+		{
+			// sort only the tasks with both parts; others are already sorted -> give them empty ranges via a filtered offset list
+			std::vector<int64_t> offs; std::vector<int> which;
+			for (int i = 0; i < n; ++i) if (tasks[i].n_pre > 0 && seed_cnt[i] > 0) which.push_back(i);
+			if (!which.empty()) {
+				// build a compact offset table of (begin,end) pairs by sorting each as its own array
+				std::vector<int64_t> pair_off;
+				for (int i : which) { pair_off.push_back(f_off[i]); pair_off.push_back(f_off[i + 1]); }
+				// wm_anchor_sort_run expects contiguous offsets; call it per maximal run of adjacent tasks
+				size_t a0 = 0;
+				while (a0 < which.size()) {
+					size_t a1 = a0;
+					while (a1 + 1 < which.size() && which[a1 + 1] == which[a1] + 1) ++a1;
+					const int first = which[a0], cnt = (int)(a1 - a0 + 1);
+					wm_anchor_sort_run(&g.sd, d_A, d_foff + first, f_off.data() + first, cnt, st);
+					WM_CUDA_CHECK(cudaStreamSynchronize(st));
+					a0 = a1 + 1;
+				}
+			}
+		}
+	}
+	// 4. chaining
+	uint8_t *d_set = (uint8_t*)g.set_id.need(n);
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_set, set_id.data(), n, cudaMemcpyHostToDevice, st));
+	wm_chain_params2 PP;
+	for (int s = 0; s < 2; ++s) {
+		wm_chain_params &P = PP.p[s];
+		P.max_dist_x = cp[s].max_dist_x, P.min_dist_x = cp[s].min_dist_x, P.max_dist_y = cp[s].max_dist_y, P.bw = cp[s].bw;
+		P.max_skip = cp[s].max_skip, P.max_iter = cp[s].max_iter, P.min_cnt = cp[s].min_cnt, P.min_sc = cp[s].min_sc, P.gap_scale = cp[s].gap_scale;
+	}
+	wm_chain_run(&g.ch, d_A, d_foff, f_off.data(), n, PP, d_set, st);
+	g.h_nu.assign(n, 0); g.h_nb.assign(n, 0);
+	WM_CUDA_CHECK(cudaMemcpyAsync(g.h_nu.data(), g.ch.n_u.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(cudaMemcpyAsync(g.h_nb.data(), g.ch.n_b.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	std::vector<int64_t> nb_off(n + 1, 0), nu_off(n + 1, 0);
+	for (int i = 0; i < n; ++i) nb_off[i + 1] = nb_off[i] + g.h_nb[i], nu_off[i + 1] = nu_off[i] + g.h_nu[i];
+	int64_t *d_nb = (int64_t*)g.nb_off.need(sizeof(int64_t) * (n + 1)), *d_nu = (int64_t*)g.nu_off.need(sizeof(int64_t) * (n + 1));
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_nb, nb_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_nu, nu_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+	wm128_dev *d_bo = (wm128_dev*)g.b_out.need(sizeof(wm128_dev) * (nb_off[n] + 1));
+	uint64_t *d_uo = (uint64_t*)g.u_out.need(sizeof(uint64_t) * (nu_off[n] + 1));
+	wm_compact_chain_kernel<<<(unsigned)(((int64_t)n * 32 + 127) / 128), 128, 0, st>>>(d_foff, d_nb, d_nu, n, d_A, (const uint64_t*)g.ch.u2.p, d_bo, d_uo);
+	WM_CUDA_CHECK(cudaGetLastError());
+	g.h_b.resize(nb_off[n] + 1); g.h_u.resize(nu_off[n] + 1);
+	if (nb_off[n] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_b.data(), d_bo, sizeof(wm128_dev) * nb_off[n], cudaMemcpyDeviceToHost, st));
+	if (nu_off[n] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_u.data(), d_uo, sizeof(uint64_t) * nu_off[n], cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	// 5. per task views
+	g.h_mz_off.assign(n + 1, 0);
+	for (int i = 0; i < n; ++i) g.h_mz_off[i + 1] = g.h_mz_off[i] + mz_cnt[i];
+	g.h_mzpos.resize(g.h_mz_off[n] + 1);
+	for (int i = 0; i < n; ++i)
+		if (mz_cnt[i] > 0) memcpy(&g.h_mzpos[g.h_mz_off[i]], &pass_mzpos[seed_pass[i]][mz_src[i]], sizeof(uint32_t) * mz_cnt[i]);
+	for (int i = 0; i < n; ++i) {
+		SeedOut &o = out[i];
+		o.rep_len = g.h_rep[i];
+		o.n_mz = (int32_t)mz_cnt[i], o.mz_pos = g.h_mzpos.data() + g.h_mz_off[i];
+		o.n_u = g.h_nu[i], o.u = g.h_u.data() + nu_off[i];
+		o.n_b = g.h_nb[i], o.b = g.h_b.data() + nb_off[i];
+	}
+}
+
+// query / target slices of a job -> gather descriptors
+static inline void add_gather(std::vector<wm_gather_job> &gj, std::vector<int64_t> &joff, const GpuBackendImpl &g, const SeqRef &s, const MapWin &w, int64_t *pool_off)
+{
+	wm_gather_job j;
+	j.len = s.len, j.reversed = s.reversed, j.pad = 0, j.dst_off = *pool_off;
+	const int64_t L = g.read_off[w.read + 1] - g.read_off[w.read];
+	if (s.kind == SEQ_Q0) j.kind = 0, j.src_off = g.read_off[w.read] + w.wb + s.off;
+	else if (s.kind == SEQ_Q1) j.kind = 2, j.src_off = g.read_off[w.read] + (L - w.wb - w.wl) + s.off; // strand 1 of the window is a slice of strand 1 of the read
+	else j.kind = 1, j.src_off = (int64_t)g.hidx->offset[s.rid] + s.off;
+	gj.push_back(j);
+	joff.push_back(joff.back() + s.len);
+	*pool_off += s.len;
+}
+
+__global__ void wm_gather2_kernel(const wm_gather_job *__restrict__ jobs, const int64_t *__restrict__ joff, int n_jobs, const uint8_t *__restrict__ codes,
+                                  const uint8_t *__restrict__ rcodes, const uint32_t *__restrict__ S, uint8_t *__restrict__ dst, int64_t n)
+{
+	const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gidx >= n) return;
+	int lo = 0, hi = n_jobs;
+	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (joff[m] <= gidx) lo = m; else hi = m; }
+	const wm_gather_job J = jobs[lo];
+	const int p = (int)(gidx - joff[lo]);
+	const int64_t s = J.src_off + (J.reversed ? J.len - 1 - p : p);
+	uint8_t c;
+	if (J.kind == 0) c = codes[s];
+	else if (J.kind == 2) c = rcodes[s];
+	else { c = (uint8_t)(S[s >> 3] >> ((s & 7) << 2) & 0xf); if (c > 4) c = 4; }
+	dst[J.dst_off + p] = c;
+}
+
+void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<DpRes> &res)
+{
+	WM_CUDA_CHECK(cudaSetDevice(g.device));
+	cudaStream_t st = g.st;
+	const int n = (int)jobs.size();
+	res.assign(n, DpRes());
+	g.h_cig.clear();
+	if (n == 0) return;
+	wm_dp_params P; wm_dp_params_init(&P, sc.mat, sc.q, sc.e, sc.q2, sc.e2);
+	std::vector<int64_t> cig_base(n + 1, 0); // offsets into h_cig
+	g.h_ez.resize(n);
+	std::vector<uint32_t> chunk_cig;
+	int done = 0;
+	while (done < n) {
+		// a chunk of jobs whose backtrack matrices fit the budget
+		size_t bt_bytes = 0; int end = done; int64_t cig_cap = 0, pool = 0; int max_tlen = 0;
+		while (end < n) {
+			const DpJob &J = jobs[end];
+			size_t b = wm_extd2_bt_bytes(J.q.len, J.t.len, J.w);
+			if (end > done && bt_bytes + b > g.bt_budget) break;
+			bt_bytes += b; cig_cap += J.q.len + J.t.len + 2; pool += J.q.len + J.t.len; max_tlen = std::max(max_tlen, J.t.len);
+			++end;
+		}
+		const int m = end - done;
+		std::vector<wm_gather_job> gj; std::vector<int64_t> joff(1, 0); std::vector<wm_dp_job> dj(m);
+		gj.reserve(2 * m); joff.reserve(2 * m + 1);
+		int64_t pool_off = 0, p_off = 0, c_off = 0;
+		for (int i = 0; i < m; ++i) {
+			const DpJob &J = jobs[done + i];
+			wm_dp_job &D = dj[i];
+			D.q_off = pool_off; add_gather(gj, joff, g, J.q, wins[J.task], &pool_off);
+			D.t_off = pool_off; add_gather(gj, joff, g, J.t, wins[J.task], &pool_off);
+			D.qlen = J.q.len, D.tlen = J.t.len, D.w = J.w, D.zdrop = J.zdrop, D.end_bonus = J.end_bonus, D.flag = J.flag;
+			D.p_off = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.q.len, J.t.len, J.w);
+			D.cig_off = c_off; D.cig_cap = J.q.len + J.t.len + 2; c_off += D.cig_cap; D.pad = 0;
+		}
+		wm_gather_job *d_gj = (wm_gather_job*)g.g_jobs.need(sizeof(wm_gather_job) * gj.size());
+		int64_t *d_joff = (int64_t*)g.g_joff.need(sizeof(int64_t) * joff.size());
+		uint8_t *d_pool = (uint8_t*)g.seq_pool.need(pool_off + 16);
+		wm_dp_job *d_dj = (wm_dp_job*)g.dp_jobs.need(sizeof(wm_dp_job) * m);
+		uint8_t *d_bt = (uint8_t*)g.bt.need(p_off + 16);
+		wm_extz_dev *d_ez = (wm_extz_dev*)g.ez.need(sizeof(wm_extz_dev) * m);
+		uint32_t *d_cig = (uint32_t*)g.cig.need(sizeof(uint32_t) * (c_off + 1));
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_gj, gj.data(), sizeof(wm_gather_job) * gj.size(), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_joff, joff.data(), sizeof(int64_t) * joff.size(), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_dj, dj.data(), sizeof(wm_dp_job) * m, cudaMemcpyHostToDevice, st));
+		if (pool_off > 0) {
+			wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
+			WM_CUDA_CHECK(cudaGetLastError());
+		}
+		wm_extd2_launch(&g.dpws, d_dj, m, max_tlen, d_pool, d_bt, d_ez, d_cig, P, st);
+		WM_CUDA_CHECK(cudaMemcpyAsync(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(cudaStreamSynchronize(st));
+		// compact the CIGARs on the device, then one copy
+		std::vector<int64_t> o_off(m + 1, 0);
+		for (int i = 0; i < m; ++i) {
+			int nc = g.h_ez[done + i].n_cigar;
+			if (nc > dj[i].cig_cap) { fprintf(stderr, "[ERROR] winnowmap-b200: CIGAR buffer overflow (%d > %d)\n", nc, dj[i].cig_cap); exit(1); }
+			o_off[i + 1] = o_off[i] + nc;
+		}
+		int64_t *d_ooff = (int64_t*)g.cig_off.need(sizeof(int64_t) * (m + 1));
+		uint32_t *d_cout = (uint32_t*)g.cig_out.need(sizeof(uint32_t) * (o_off[m] + 1));
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_ooff, o_off.data(), sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
+		wm_compact_cigar_kernel<<<(unsigned)(((int64_t)m * 32 + 127) / 128), 128, 0, st>>>(d_dj, d_ez, d_ooff, m, d_cig, d_cout);
+		WM_CUDA_CHECK(cudaGetLastError());
+		const size_t base = g.h_cig.size();
+		g.h_cig.resize(base + o_off[m] + 1);
+		if (o_off[m] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_cig.data() + base, d_cout, sizeof(uint32_t) * o_off[m], cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(cudaStreamSynchronize(st));
+		g.h_cig.resize(base + o_off[m]);
+		for (int i = 0; i < m; ++i) cig_base[done + i] = (int64_t)base + o_off[i];
+		done = end;
+	}
+	g.h_cig.push_back(0);
+	for (int i = 0; i < n; ++i) {
+		const wm_extz_dev &e = g.h_ez[i];
+		DpRes &r = res[i];
+		r.max = e.max, r.zdropped = e.zdropped, r.max_q = e.max_q, r.max_t = e.max_t, r.mqe = e.mqe, r.mqe_t = e.mqe_t;
+		r.mte = e.mte, r.mte_q = e.mte_q, r.score = e.score, r.reach_end = e.reach_end, r.n_cigar = e.n_cigar;
+		r.cigar = g.h_cig.data() + cig_base[i];
+	}
+}
+
+void GpuBackend::run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<LlRes> &res)
+{
+	WM_CUDA_CHECK(cudaSetDevice(g.device));
+	cudaStream_t st = g.st;
+	const int n = (int)jobs.size();
+	res.assign(n, LlRes());
+	if (n == 0) return;
+	std::vector<wm_gather_job> gj; std::vector<int64_t> joff(1, 0); std::vector<wm_ll_job> lj(n);
+	int64_t pool_off = 0, s_off = 0;
+	for (int i = 0; i < n; ++i) {
+		const LlJob &J = jobs[i];
+		lj[i].q_off = pool_off; add_gather(gj, joff, g, J.q, wins[J.task], &pool_off);
+		lj[i].t_off = pool_off; add_gather(gj, joff, g, J.t, wins[J.task], &pool_off);
+		lj[i].qlen = J.q.len, lj[i].tlen = J.t.len, lj[i].s_off = s_off;
+		s_off += 4 * (int64_t)((J.q.len + 7) / 8 * 8);
+	}
+	wm_gather_job *d_gj = (wm_gather_job*)g.g_jobs.need(sizeof(wm_gather_job) * gj.size());
+	int64_t *d_joff = (int64_t*)g.g_joff.need(sizeof(int64_t) * joff.size());
+	uint8_t *d_pool = (uint8_t*)g.seq_pool.need(pool_off + 16);
+	wm_ll_job *d_lj = (wm_ll_job*)g.ll_jobs.need(sizeof(wm_ll_job) * n);
+	int32_t *d_scr = (int32_t*)g.ll_scr.need(sizeof(int32_t) * (s_off + 4)), *d_out = (int32_t*)g.ll_out.need(sizeof(int32_t) * 3 * (size_t)n);
+	int8_t *d_mat = (int8_t*)g.mat.need(32);
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_gj, gj.data(), sizeof(wm_gather_job) * gj.size(), cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_joff, joff.data(), sizeof(int64_t) * joff.size(), cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_lj, lj.data(), sizeof(wm_ll_job) * n, cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(cudaMemcpyAsync(d_mat, sc.mat, 25, cudaMemcpyHostToDevice, st));
+	if (pool_off > 0) {
+		wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
+		WM_CUDA_CHECK(cudaGetLastError());
+	}
+	wm_ksw_ll_launch(d_lj, n, d_pool, d_mat, sc.q, sc.e, d_scr, d_out, st);
+	std::vector<int32_t> out(3 * (size_t)n);
+	WM_CUDA_CHECK(cudaMemcpyAsync(out.data(), d_out, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	for (int i = 0; i < n; ++i) res[i].score = out[3 * i], res[i].qe = out[3 * i + 1], res[i].te = out[3 * i + 2];
+}
+
+// ---- construction: upload the index to one device ----
+Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64_t n_keys, const uint64_t *pos_off, const uint64_t *pos,
+                            uint64_t bloom_bits, const uint8_t *bloom_table, int device)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+		fprintf(stderr, "[ERROR] winnowmap-b200: no CUDA device visible; there is no CPU fallback\n");
+		exit(1);
+	}
+	WM_CUDA_CHECK(cudaSetDevice(device));
+	GpuBackend *be = new GpuBackend();
+	GpuBackendImpl &g = be->g;
+	g.device = device; g.hidx = hidx; g.n_bases = 0;
+	WM_CUDA_CHECK(cudaStreamCreate(&g.st));
+	const uint64_t n_pos = pos_off[n_keys];
+	uint64_t *d_keys = wm_dev_alloc<uint64_t>(n_keys + 1), *d_poff = wm_dev_alloc<uint64_t>(n_keys + 2), *d_pos = wm_dev_alloc<uint64_t>(n_pos + 1);
+	uint32_t *d_S = wm_dev_alloc<uint32_t>(hidx->S.size() + 4);
+	uint8_t *d_bt = wm_dev_alloc<uint8_t>(bloom_bits / 8 + 16);
+	WM_CUDA_CHECK(cudaMemcpy(d_keys, keys, sizeof(uint64_t) * n_keys, cudaMemcpyHostToDevice));
+	WM_CUDA_CHECK(cudaMemcpy(d_poff, pos_off, sizeof(uint64_t) * (n_keys + 1), cudaMemcpyHostToDevice));
+	WM_CUDA_CHECK(cudaMemcpy(d_pos, pos, sizeof(uint64_t) * n_pos, cudaMemcpyHostToDevice));
+	WM_CUDA_CHECK(cudaMemcpy(d_S, hidx->S.data(), sizeof(uint32_t) * hidx->S.size(), cudaMemcpyHostToDevice));
+	WM_CUDA_CHECK(cudaMemcpy(d_bt, bloom_table, bloom_bits / 8, cudaMemcpyHostToDevice));
+	memset(&g.ix, 0, sizeof(g.ix));
+	g.ix.k = hidx->k, g.ix.w = hidx->w, g.ix.n_seq = (uint32_t)hidx->len.size();
+	g.ix.n_keys = n_keys, g.ix.keys = d_keys, g.ix.pos_off = d_poff, g.ix.pos = d_pos, g.ix.S = d_S;
+	wm_idx_dev_build_ht(&g.ix, g.st);
+	wm_bloom_dev_from_table(&g.bf, d_bt, bloom_bits);
+	WM_CUDA_CHECK(cudaStreamSynchronize(g.st));
+	size_t free_b = 0, total_b = 0;
+	WM_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+	g.bt_budget = free_b / 4; // backtrack matrices of one DP chunk
+	if (g.bt_budget > ((size_t)32 << 30)) g.bt_budget = (size_t)32 << 30;
+	return be;
+}
+
+void gpu_backend_destroy(Backend *be) { delete be; }
+
+} // namespace wmh

@@ -1,0 +1,10 @@
+#pragma once
+#include "host_backend.h"
+
+namespace wmh {
+// Uploads the flattened index (sorted unique minimizer hashes + CSR occurrence lists + packed reference +
+// down-weight filter bits) to `device` and returns the CUDA backend.  Exits with a message if no device.
+Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64_t n_keys, const uint64_t *pos_off, const uint64_t *pos,
+                            uint64_t bloom_bits, const uint8_t *bloom_table, int device);
+void gpu_backend_destroy(Backend *be);
+}
