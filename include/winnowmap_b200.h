@@ -234,6 +234,18 @@ int wm_gpu_map_batch(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_seq, const c
 int wm_map_file(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, const char *reads_fn, const char *out_fn, int n_threads, int rank, int world,
                 int tag_order, int64_t max_batch_bases);
 
+/* frees what wm_gpu_map_batch returned (the reference's output step does this itself, src/map.c:1210-1211) */
+void wm_free_regs(int n, const int32_t *n_reg, wm_reg1_t **reg);
+/* bench: upload a batch (not timed), then map it with the reads resident in HBM; *ms = CUDA-event time of the step */
+int wm_bench_upload(wm_gpu_ctx *ctx, int n_seq, const char *const *names, const char *const *seqs, const int32_t *lens);
+int wm_bench_map_resident(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_threads, double *ms);
+
+/* bench instrumentation: launch counter and CUDA-event timing of the dominant (DP fill) kernel */
+void wm_prof_enable(int on);
+void wm_prof_reset(void);
+void wm_prof_get(double *out6); /* launches, fill_ms, fill_launches, fill_algorithmic_bytes, fill_block_cells, fill_jobs */
+int wm_device_synchronize(void);
+
 void wm_get_stats(wm_gpu_ctx *ctx, double *out, int n);
 void wm_reset_stats(wm_gpu_ctx *ctx);
 

@@ -268,9 +268,9 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	const int need = (n_tasks + WM_CHAIN_WARPS - 1) / WM_CHAIN_WARPS;
 	if (grid > need) grid = need;
 	wm_rs_stack *stk = (wm_rs_stack*)ws->stacks.need(sizeof(wm_rs_stack) * (size_t)grid * WM_CHAIN_WARPS);
-	wm_chain_fill_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
+	wm_count_launch(); wm_chain_fill_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
 	WM_CUDA_CHECK(cudaGetLastError());
-	wm_chain_backtrack_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, n_tasks, PP, d_set_id, f, p, t, v, u, u2, w, b, n_u, n_b, stk, counter + 1);
+	wm_count_launch(); wm_chain_backtrack_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, n_tasks, PP, d_set_id, f, p, t, v, u, u2, w, b, n_u, n_b, stk, counter + 1);
 	WM_CUDA_CHECK(cudaGetLastError());
 }
 

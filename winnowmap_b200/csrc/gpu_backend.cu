@@ -140,7 +140,7 @@ void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
 	WM_CUDA_CHECK(cudaMemcpyAsync(d_off, g.read_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, g.st));
 	wm_ascii_to_code(d_ascii, d_codes, g.n_bases, g.st);
 	if (g.n_bases > 0) {
-		wm_revcomp_kernel<<<(unsigned)((g.n_bases + 255) / 256), 256, 0, g.st>>>(d_codes, d_rc, d_off, n, g.n_bases);
+		wm_count_launch(); wm_revcomp_kernel<<<(unsigned)((g.n_bases + 255) / 256), 256, 0, g.st>>>(d_codes, d_rc, d_off, n, g.n_bases);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 }
@@ -174,7 +174,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		WM_CUDA_CHECK(cudaMemcpyAsync(d_mt, mt.data(), sizeof(wm_mask_task) * mt.size(), cudaMemcpyHostToDevice, st));
 		WM_CUDA_CHECK(cudaMemcpyAsync(d_mtoff, mtoff.data(), sizeof(int64_t) * mtoff.size(), cudaMemcpyHostToDevice, st));
 		WM_CUDA_CHECK(cudaMemcpyAsync(d_mp, mask_pool, sizeof(int32_t) * 2 * n_mask_iv, cudaMemcpyHostToDevice, st));
-		wm_mask_copy_kernel<<<(unsigned)((mtoff.back() + 255) / 256), 256, 0, st>>>(d_codes, d_masked, d_mt, d_mtoff, (int)mt.size(), d_mp, mtoff.back());
+		wm_count_launch(); wm_mask_copy_kernel<<<(unsigned)((mtoff.back() + 255) / 256), 256, 0, st>>>(d_codes, d_masked, d_mt, d_mtoff, (int)mt.size(), d_mp, mtoff.back());
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	// 2. sketch: tasks that sketch something.  The masked copies live in another buffer, so two passes.
@@ -270,7 +270,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 			WM_CUDA_CHECK(cudaMemcpyAsync(d_ct, c2.data(), sizeof(wm_cat_task) * c2.size(), cudaMemcpyHostToDevice, st));
 			WM_CUDA_CHECK(cudaMemcpyAsync(d_toff, toff.data(), sizeof(int64_t) * toff.size(), cudaMemcpyHostToDevice, st));
 			const wm128_dev *src = d_seed_a[pass] ? d_seed_a[pass] : d_A;
-			wm_concat_kernel<<<(unsigned)((toff.back() + 255) / 256), 256, 0, st>>>(d_ct, d_toff, (int)c2.size(), d_pre, src, d_A, toff.back());
+			wm_count_launch(); wm_concat_kernel<<<(unsigned)((toff.back() + 255) / 256), 256, 0, st>>>(d_ct, d_toff, (int)c2.size(), d_pre, src, d_A, toff.back());
 			WM_CUDA_CHECK(cudaGetLastError());
 			WM_CUDA_CHECK(cudaStreamSynchronize(st)); // c2/toff are reused by the next pass
 		}
@@ -318,7 +318,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	WM_CUDA_CHECK(cudaMemcpyAsync(d_nu, nu_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
 	wm128_dev *d_bo = (wm128_dev*)g.b_out.need(sizeof(wm128_dev) * (nb_off[n] + 1));
 	uint64_t *d_uo = (uint64_t*)g.u_out.need(sizeof(uint64_t) * (nu_off[n] + 1));
-	wm_compact_chain_kernel<<<(unsigned)(((int64_t)n * 32 + 127) / 128), 128, 0, st>>>(d_foff, d_nb, d_nu, n, d_A, (const uint64_t*)g.ch.u2.p, d_bo, d_uo);
+	wm_count_launch(); wm_compact_chain_kernel<<<(unsigned)(((int64_t)n * 32 + 127) / 128), 128, 0, st>>>(d_foff, d_nb, d_nu, n, d_A, (const uint64_t*)g.ch.u2.p, d_bo, d_uo);
 	WM_CUDA_CHECK(cudaGetLastError());
 	g.h_b.resize(nb_off[n] + 1); g.h_u.resize(nu_off[n] + 1);
 	if (nb_off[n] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_b.data(), d_bo, sizeof(wm128_dev) * nb_off[n], cudaMemcpyDeviceToHost, st));
@@ -405,6 +405,22 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			D.qlen = J.q.len, D.tlen = J.t.len, D.w = J.w, D.zdrop = J.zdrop, D.end_bonus = J.end_bonus, D.flag = J.flag;
 			D.p_off = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.q.len, J.t.len, J.w);
 			D.cig_off = c_off; D.cig_cap = J.q.len + J.t.len + 2; c_off += D.cig_cap; D.pad = 0;
+			if (g_wm_prof.enabled) { // qlen + tlen + C_block + (qlen + tlen) + 4 n_cigar + 48 per call
+				const int ql = J.q.len, tl = J.t.len, w = J.w < 0 ? (tl > ql ? tl : ql) : J.w;
+				double cb = 0;
+				for (int r = 0; r < ql + tl - 1; ++r) {
+					int st = 0, en = tl - 1;
+					if (st < r - ql + 1) st = r - ql + 1;
+					if (en > r) en = r;
+					if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
+					if (en > ((r + w) >> 1)) en = (r + w) >> 1;
+					if (st > en) break;
+					cb += (en + 16) / 16 * 16 - st / 16 * 16;
+				}
+				g_wm_prof.fill_cells += cb;
+				g_wm_prof.fill_alg_bytes += 2.0 * (ql + tl) + cb + 48;
+				g_wm_prof.fill_jobs += 1;
+			}
 		}
 		wm_gather_job *d_gj = (wm_gather_job*)g.g_jobs.need(sizeof(wm_gather_job) * gj.size());
 		int64_t *d_joff = (int64_t*)g.g_joff.need(sizeof(int64_t) * joff.size());
@@ -417,7 +433,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		WM_CUDA_CHECK(cudaMemcpyAsync(d_joff, joff.data(), sizeof(int64_t) * joff.size(), cudaMemcpyHostToDevice, st));
 		WM_CUDA_CHECK(cudaMemcpyAsync(d_dj, dj.data(), sizeof(wm_dp_job) * m, cudaMemcpyHostToDevice, st));
 		if (pool_off > 0) {
-			wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
+			wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
 			WM_CUDA_CHECK(cudaGetLastError());
 		}
 		wm_extd2_launch(&g.dpws, d_dj, m, max_tlen, d_pool, d_bt, d_ez, d_cig, P, st);
@@ -433,7 +449,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		int64_t *d_ooff = (int64_t*)g.cig_off.need(sizeof(int64_t) * (m + 1));
 		uint32_t *d_cout = (uint32_t*)g.cig_out.need(sizeof(uint32_t) * (o_off[m] + 1));
 		WM_CUDA_CHECK(cudaMemcpyAsync(d_ooff, o_off.data(), sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
-		wm_compact_cigar_kernel<<<(unsigned)(((int64_t)m * 32 + 127) / 128), 128, 0, st>>>(d_dj, d_ez, d_ooff, m, d_cig, d_cout);
+		wm_count_launch(); wm_compact_cigar_kernel<<<(unsigned)(((int64_t)m * 32 + 127) / 128), 128, 0, st>>>(d_dj, d_ez, d_ooff, m, d_cig, d_cout);
 		WM_CUDA_CHECK(cudaGetLastError());
 		const size_t base = g.h_cig.size();
 		g.h_cig.resize(base + o_off[m] + 1);
@@ -441,6 +457,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		WM_CUDA_CHECK(cudaStreamSynchronize(st));
 		g.h_cig.resize(base + o_off[m]);
 		for (int i = 0; i < m; ++i) cig_base[done + i] = (int64_t)base + o_off[i];
+		if (g_wm_prof.enabled) g_wm_prof.fill_alg_bytes += 4.0 * (double)o_off[m];
 		done = end;
 	}
 	g.h_cig.push_back(0);
@@ -480,7 +497,7 @@ void GpuBackend::run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin
 	WM_CUDA_CHECK(cudaMemcpyAsync(d_lj, lj.data(), sizeof(wm_ll_job) * n, cudaMemcpyHostToDevice, st));
 	WM_CUDA_CHECK(cudaMemcpyAsync(d_mat, sc.mat, 25, cudaMemcpyHostToDevice, st));
 	if (pool_off > 0) {
-		wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
+		wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	wm_ksw_ll_launch(d_lj, n, d_pool, d_mat, sc.q, sc.e, d_scr, d_out, st);

@@ -58,6 +58,7 @@ struct MapStats { // work counters for the roofline accounting
 // mm_map_frag for every read of a batch (src/map.c:279-974 with n_segs == 1): fills regs[i] (malloc-owned, as the
 // reference returns them), rep_len[i] and frag_gap[i] exactly as worker_for does (src/map.c:1025-1034).
 void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const std::vector<const wm_read*> &reads,
-               std::vector<std::vector<wm_reg1_t>> &regs, std::vector<int> &rep_len, std::vector<int> &frag_gap, int n_threads, MapStats *stats);
+               std::vector<std::vector<wm_reg1_t>> &regs, std::vector<int> &rep_len, std::vector<int> &frag_gap, int n_threads, MapStats *stats,
+               bool reads_resident = false);
 
 } // namespace wmh

@@ -333,6 +333,8 @@ size_t wm_extd2_bt_bytes(int qlen, int tlen, int w)
 }
 
 // jobs/seq/bt/ez/cigar are device pointers; max_tlen = largest tlen among the jobs.
+wm_prof_t g_wm_prof = {0, 0, 0.0, 0, 0.0, 0.0, 0.0};
+
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream)
 {
@@ -356,8 +358,20 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_extd2_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, stream>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, counter);
+	static cudaEvent_t ev0 = 0, ev1 = 0;
+	if (g_wm_prof.enabled) {
+		if (!ev0) { WM_CUDA_CHECK(cudaEventCreate(&ev0)); WM_CUDA_CHECK(cudaEventCreate(&ev1)); }
+		WM_CUDA_CHECK(cudaEventRecord(ev0, stream));
+	}
+	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, stream>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, counter);
 	WM_CUDA_CHECK(cudaGetLastError());
-	wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar);
+	if (g_wm_prof.enabled) WM_CUDA_CHECK(cudaEventRecord(ev1, stream));
+	wm_count_launch(); wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar);
 	WM_CUDA_CHECK(cudaGetLastError());
+	if (g_wm_prof.enabled) { // bench mode: serialise to read the kernel's own duration
+		float ms = 0.f;
+		WM_CUDA_CHECK(cudaEventSynchronize(ev1));
+		WM_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+		g_wm_prof.fill_ms += ms; ++g_wm_prof.fill_launches;
+	}
 }

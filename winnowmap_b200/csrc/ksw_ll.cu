@@ -57,7 +57,7 @@ __global__ void wm_ksw_ll_kernel(const wm_ll_job *__restrict__ jobs, int n, cons
 void wm_ksw_ll_launch(const wm_ll_job *d_jobs, int n, const uint8_t *d_seq, const int8_t *d_mat, int gapo, int gape, int32_t *d_scratch, int32_t *d_out, cudaStream_t st)
 {
 	if (n <= 0) return;
-	wm_ksw_ll_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_jobs, n, d_seq, d_mat, gapo, gape, d_scratch, d_out);
+	wm_count_launch(); wm_ksw_ll_kernel<<<(n + 63) / 64, 64, 0, st>>>(d_jobs, n, d_seq, d_mat, gapo, gape, d_scratch, d_out);
 	WM_CUDA_CHECK(cudaGetLastError());
 }
 

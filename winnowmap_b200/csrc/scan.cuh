@@ -85,8 +85,8 @@ static inline void wm_exclusive_scan(const int32_t *d_in, int64_t n, int64_t *d_
 {
 	if (n <= 0) { WM_CUDA_CHECK(cudaMemsetAsync(d_out, 0, sizeof(int64_t), st)); return; }
 	int64_t nb = (n + WM_SCAN_BLOCK * WM_SCAN_ITEMS - 1) / (WM_SCAN_BLOCK * WM_SCAN_ITEMS);
-	wm_scan_block_sums<<<(unsigned)nb, WM_SCAN_BLOCK, 0, st>>>(d_in, n, d_tmp);
-	wm_scan_top<<<1, 1024, 0, st>>>(d_tmp, nb, d_out + n);
-	wm_scan_apply<<<(unsigned)nb, WM_SCAN_BLOCK, 0, st>>>(d_in, n, d_tmp, d_out);
+	wm_count_launch(); wm_scan_block_sums<<<(unsigned)nb, WM_SCAN_BLOCK, 0, st>>>(d_in, n, d_tmp);
+	wm_count_launch(); wm_scan_top<<<1, 1024, 0, st>>>(d_tmp, nb, d_out + n);
+	wm_count_launch(); wm_scan_apply<<<(unsigned)nb, WM_SCAN_BLOCK, 0, st>>>(d_in, n, d_tmp, d_out);
 	WM_CUDA_CHECK(cudaGetLastError());
 }

@@ -146,13 +146,13 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 	if (n_arr <= 0) return;
 	std::vector<int32_t> big;
 	for (int i = 0; i < n_arr; ++i) if (h_off[i + 1] - h_off[i] > WM_RS_MIN_SIZE) big.push_back(i);
-	wm_anchor_sort_small_kernel<<<(n_arr + 127) / 128, 128, 0, st>>>(d_a, d_off, n_arr);
+	wm_count_launch(); wm_anchor_sort_small_kernel<<<(n_arr + 127) / 128, 128, 0, st>>>(d_a, d_off, n_arr);
 	WM_CUDA_CHECK(cudaGetLastError());
 	if (!big.empty()) {
 		int32_t *d_big = (int32_t*)ws->big_ids.need(sizeof(int32_t) * big.size());
 		wm_rs_stack *d_stk = (wm_rs_stack*)ws->rs_stacks.need(sizeof(wm_rs_stack) * big.size());
 		WM_CUDA_CHECK(cudaMemcpyAsync(d_big, big.data(), sizeof(int32_t) * big.size(), cudaMemcpyHostToDevice, st));
-		wm_anchor_sort_big_kernel<<<((int)big.size() + 31) / 32, 32, 0, st>>>(d_a, d_off, d_big, (int)big.size(), d_stk);
+		wm_count_launch(); wm_anchor_sort_big_kernel<<<((int)big.size() + 31) / 32, 32, 0, st>>>(d_a, d_off, d_big, (int)big.size(), d_stk);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 }
@@ -181,7 +181,7 @@ void wm_seed_run(wm_seed_ws *ws, const wm_idx_dev &ix, const wm128_dev *d_mz, co
 	int64_t *d_tmp = (int64_t*)ws->scan_tmp.need(sizeof(int64_t) * wm_scan_tmp_elems(n_mz));
 	uint32_t *d_mpos = (uint32_t*)ws->mini_pos.need(sizeof(uint32_t) * (n_mz + 1));
 	if (n_mz > 0) {
-		wm_seed_lookup_kernel<<<(unsigned)((n_mz + 127) / 128), 128, 0, st>>>(ix, d_mz, d_mz_off, n_tasks, n_mz, max_occ, d_nocc, d_cnt, d_loff, d_td, d_mtask);
+		wm_count_launch(); wm_seed_lookup_kernel<<<(unsigned)((n_mz + 127) / 128), 128, 0, st>>>(ix, d_mz, d_mz_off, n_tasks, n_mz, max_occ, d_nocc, d_cnt, d_loff, d_td, d_mtask);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	wm_exclusive_scan(d_cnt, n_mz, d_aoff, d_tmp, st);
@@ -191,10 +191,10 @@ void wm_seed_run(wm_seed_ws *ws, const wm_idx_dev &ix, const wm128_dev *d_mz, co
 	ws->n_a = n_a;
 	wm128_dev *d_a = (wm128_dev*)ws->a.need(sizeof(wm128_dev) * (n_a + 1));
 	if (n_a > 0) {
-		wm_seed_expand_kernel<<<(unsigned)((n_a + 127) / 128), 128, 0, st>>>(ix, d_mz, n_mz, d_aoff, d_loff, d_td, d_mtask, d_qlen, n_a, d_a);
+		wm_count_launch(); wm_seed_expand_kernel<<<(unsigned)((n_a + 127) / 128), 128, 0, st>>>(ix, d_mz, n_mz, d_aoff, d_loff, d_td, d_mtask, d_qlen, n_a, d_a);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
-	wm_seed_task_kernel<<<(n_tasks + 1 + 127) / 128, 128, 0, st>>>(d_mz, d_mz_off, d_aoff, d_nocc, max_occ, n_tasks, d_rep, d_nmp, d_task_a_off, d_mpos);
+	wm_count_launch(); wm_seed_task_kernel<<<(n_tasks + 1 + 127) / 128, 128, 0, st>>>(d_mz, d_mz_off, d_aoff, d_nocc, max_occ, n_tasks, d_rep, d_nmp, d_task_a_off, d_mpos);
 	WM_CUDA_CHECK(cudaGetLastError());
 	WM_CUDA_CHECK(cudaMemcpyAsync(h_task_a_off, d_task_a_off, sizeof(int64_t) * (n_tasks + 1), cudaMemcpyDeviceToHost, st));
 	WM_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -210,7 +210,7 @@ void wm_idx_dev_build_ht(wm_idx_dev *ix, cudaStream_t st)
 	uint32_t *hv = wm_dev_alloc<uint32_t>(cap);
 	WM_CUDA_CHECK(cudaMemsetAsync(hk, 0xff, cap * 8, st));
 	if (ix->n_keys > 0) {
-		wm_ht_fill_kernel<<<(unsigned)((ix->n_keys + 255) / 256), 256, 0, st>>>(ix->keys, ix->n_keys, hk, hv, cap - 1);
+		wm_count_launch(); wm_ht_fill_kernel<<<(unsigned)((ix->n_keys + 255) / 256), 256, 0, st>>>(ix->keys, ix->n_keys, hk, hv, cap - 1);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	ix->ht_key = hk, ix->ht_val = hv, ix->ht_mask = cap - 1;

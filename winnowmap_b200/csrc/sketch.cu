@@ -288,7 +288,7 @@ __global__ void wm_ascii_to_code_kernel(const char *__restrict__ in, uint8_t *__
 void wm_ascii_to_code(const char *d_in, uint8_t *d_out, int64_t n, cudaStream_t st)
 {
 	if (n <= 0) return;
-	wm_ascii_to_code_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, d_out, n);
+	wm_count_launch(); wm_ascii_to_code_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, d_out, n);
 	WM_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -323,19 +323,19 @@ void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_co
 		double *d_ord = (double*)ws->ord.need(sizeof(double) * n_bases);
 		uint8_t *d_elig = (uint8_t*)ws->elig.need(n_bases);
 		const size_t smem = (size_t)(WM_SK_TN + 256) * 8 + WM_SK_TN + 256 + 32;
-		wm_sketch_order_kernel<<<(unsigned)n_tiles, WM_SK_THREADS, smem, st>>>(d_codes, d_tasks, d_tile_off, d_base_off, n_tasks, w, k, bf, d_ord, d_elig);
+		wm_count_launch(); wm_sketch_order_kernel<<<(unsigned)n_tiles, WM_SK_THREADS, smem, st>>>(d_codes, d_tasks, d_tile_off, d_base_off, n_tasks, w, k, bf, d_ord, d_elig);
 		WM_CUDA_CHECK(cudaGetLastError());
-		wm_sketch_winnow_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, st>>>(d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, w, d_ord, d_elig, d_flag);
+		wm_count_launch(); wm_sketch_winnow_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, st>>>(d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, w, d_ord, d_elig, d_flag);
 		WM_CUDA_CHECK(cudaGetLastError());
 	} else {
 		double *d_ring = (double*)ws->ord.need(sizeof(double) * 512 * (size_t)n_tasks);
-		wm_sketch_seq_kernel<<<(n_tasks + 63) / 64, 64, 0, st>>>(d_codes, d_tasks, d_base_off, n_tasks, w, k, bf, d_flag, d_ring);
+		wm_count_launch(); wm_sketch_seq_kernel<<<(n_tasks + 63) / 64, 64, 0, st>>>(d_codes, d_tasks, d_base_off, n_tasks, w, k, bf, d_flag, d_ring);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	int32_t *d_cnt = (int32_t*)ws->cnt.need(sizeof(int32_t) * (n_chunks + 1));
 	int64_t *d_rank = (int64_t*)ws->rank.need(sizeof(int64_t) * (n_chunks + 2));
 	int64_t *d_tmp = (int64_t*)ws->scan_tmp.need(sizeof(int64_t) * wm_scan_tmp_elems(n_chunks));
-	wm_sketch_count_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, st>>>(d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, d_flag, d_cnt);
+	wm_count_launch(); wm_sketch_count_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, st>>>(d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, d_flag, d_cnt);
 	WM_CUDA_CHECK(cudaGetLastError());
 	wm_exclusive_scan(d_cnt, n_chunks, d_rank, d_tmp, st);
 	int64_t total = 0;
@@ -347,7 +347,7 @@ void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_co
 		std::vector<int64_t> fill(n_tasks + 1, total);
 		WM_CUDA_CHECK(cudaMemcpyAsync(d_mz_off, fill.data(), sizeof(int64_t) * (n_tasks + 1), cudaMemcpyHostToDevice, st));
 	}
-	wm_sketch_emit_kernel<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, st>>>(d_codes, d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, k,
+	wm_count_launch(); wm_sketch_emit_kernel<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, st>>>(d_codes, d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, k,
 	                                                                               d_flag, d_rank, d_mz, d_mz_off);
 	WM_CUDA_CHECK(cudaGetLastError());
 	*n_mz = total;

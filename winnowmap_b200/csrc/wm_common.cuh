@@ -16,6 +16,17 @@
 
 #define WM_NEG_INF (-0x40000000)
 
+// Lightweight instrumentation used by bench.py: number of kernel launches and, when enabled, the device time and
+// algorithmic bytes of the dominant kernel (the extension-DP fill kernel), measured with CUDA events on the
+// launching stream.
+struct wm_prof_t {
+	long long n_launches;
+	int enabled;
+	double fill_ms; long long fill_launches; double fill_alg_bytes, fill_cells, fill_jobs;
+};
+extern wm_prof_t g_wm_prof;
+static inline void wm_count_launch() { ++g_wm_prof.n_launches; }
+
 // One extension-DP job; sequences live in a device byte pool (0..4 codes).
 struct wm_dp_job {
 	int64_t q_off, t_off;   // byte offsets of query / target codes in the sequence pool
