@@ -119,7 +119,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--reads", type=int, default=int(os.environ.get("WM_BENCH_READS", 1500)))
-    ap.add_argument("--cpu-reads", type=int, default=int(os.environ.get("WM_BENCH_CPU_READS", 400)))
+    ap.add_argument("--cpu-reads", type=int, default=int(os.environ.get("WM_BENCH_CPU_READS", 3000)))
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     import gen_data
@@ -217,6 +217,7 @@ def main():
     for s in range(a.warmup):
         map_resident(batches[s])
     L.wm_prof_enable(1); L.wm_prof_reset()
+    L.wm_dump_timers() if os.environ.get("WM_TIMING") else None
     sampler = ClockSampler(local); sampler.start()
     barrier()
     t_steps, bases = 0.0, 0
@@ -225,6 +226,9 @@ def main():
         t_steps += dt; bases += nb
     barrier()
     clocks = sampler.result()
+    if os.environ.get("WM_TIMING"):
+        log(f"timers over {a.steps} timed steps:")
+        L.wm_dump_timers()
     prof = (C.c_double * 6)(); L.wm_prof_get(prof)
     L.wm_prof_enable(0)
     # end to end through the host-buffer API (fresh batches)

@@ -245,6 +245,7 @@ void wm_prof_enable(int on);
 void wm_prof_reset(void);
 void wm_prof_get(double *out6); /* launches, fill_ms, fill_launches, fill_algorithmic_bytes, fill_block_cells, fill_jobs */
 int wm_device_synchronize(void);
+void wm_dump_timers(void); /* prints and resets the orchestration wall-clock accumulators (stderr) */
 
 void wm_get_stats(wm_gpu_ctx *ctx, double *out, int n);
 void wm_reset_stats(wm_gpu_ctx *ctx);

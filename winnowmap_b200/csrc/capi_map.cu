@@ -10,6 +10,7 @@
 #include "sketch.cuh"
 #include "gpu_backend.h"
 #include "host_io.h"
+#include "host_timers.h"
 
 using namespace wmh;
 
@@ -298,3 +299,5 @@ extern "C" int wm_bench_map_resident(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, in
 	for (auto &v : regs) for (auto &r : v) free(r.p);
 	return 0;
 }
+
+extern "C" void wm_dump_timers(void) { wmh::g_timers.dump(stderr); wmh::g_timers.reset(); }

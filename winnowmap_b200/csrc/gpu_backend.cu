@@ -10,6 +10,7 @@
 #include "seed.cuh"
 #include "chain.cuh"
 #include "gpu_backend.h"
+#include "host_timers.h"
 
 // from ksw_extd2.cu / ksw_ll.cu
 struct wm_extd2_ws { wm_dbuf scratch, counter; };
@@ -394,6 +395,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			++end;
 		}
 		const int m = end - done;
+		double tp0 = Timers::now();
 		std::vector<wm_gather_job> gj; std::vector<int64_t> joff(1, 0); std::vector<wm_dp_job> dj(m);
 		gj.reserve(2 * m); joff.reserve(2 * m + 1);
 		int64_t pool_off = 0, p_off = 0, c_off = 0;
@@ -405,23 +407,13 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			D.qlen = J.q.len, D.tlen = J.t.len, D.w = J.w, D.zdrop = J.zdrop, D.end_bonus = J.end_bonus, D.flag = J.flag;
 			D.p_off = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.q.len, J.t.len, J.w);
 			D.cig_off = c_off; D.cig_cap = J.q.len + J.t.len + 2; c_off += D.cig_cap; D.pad = 0;
-			if (g_wm_prof.enabled) { // qlen + tlen + C_block + (qlen + tlen) + 4 n_cigar + 48 per call
-				const int ql = J.q.len, tl = J.t.len, w = J.w < 0 ? (tl > ql ? tl : ql) : J.w;
-				double cb = 0;
-				for (int r = 0; r < ql + tl - 1; ++r) {
-					int st = 0, en = tl - 1;
-					if (st < r - ql + 1) st = r - ql + 1;
-					if (en > r) en = r;
-					if (st < ((r - w + 1) >> 1)) st = (r - w + 1) >> 1;
-					if (en > ((r + w) >> 1)) en = (r + w) >> 1;
-					if (st > en) break;
-					cb += (en + 16) / 16 * 16 - st / 16 * 16;
-				}
-				g_wm_prof.fill_cells += cb;
-				g_wm_prof.fill_alg_bytes += 2.0 * (ql + tl) + cb + 48;
+			if (g_wm_prof.enabled) { // qlen + tlen (codes in) + C_block (counted on the device) + (qlen + tlen) (traceback) + 4 n_cigar + 48
+				g_wm_prof.fill_alg_bytes += 2.0 * (J.q.len + J.t.len) + 48;
 				g_wm_prof.fill_jobs += 1;
 			}
 		}
+		g_timers.add("dp.host_prep", Timers::now() - tp0);
+		double tq0 = Timers::now();
 		wm_gather_job *d_gj = (wm_gather_job*)g.g_jobs.need(sizeof(wm_gather_job) * gj.size());
 		int64_t *d_joff = (int64_t*)g.g_joff.need(sizeof(int64_t) * joff.size());
 		uint8_t *d_pool = (uint8_t*)g.seq_pool.need(pool_off + 16);
@@ -439,6 +431,8 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		wm_extd2_launch(&g.dpws, d_dj, m, max_tlen, d_pool, d_bt, d_ez, d_cig, P, st);
 		WM_CUDA_CHECK(cudaMemcpyAsync(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
 		WM_CUDA_CHECK(cudaStreamSynchronize(st));
+		g_timers.add("dp.gpu_fill_bt", Timers::now() - tq0);
+		double tr0 = Timers::now();
 		// compact the CIGARs on the device, then one copy
 		std::vector<int64_t> o_off(m + 1, 0);
 		for (int i = 0; i < m; ++i) {
@@ -457,6 +451,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		WM_CUDA_CHECK(cudaStreamSynchronize(st));
 		g.h_cig.resize(base + o_off[m]);
 		for (int i = 0; i < m; ++i) cig_base[done + i] = (int64_t)base + o_off[i];
+		g_timers.add("dp.cigar_d2h", Timers::now() - tr0);
 		if (g_wm_prof.enabled) g_wm_prof.fill_alg_bytes += 4.0 * (double)o_off[m];
 		done = end;
 	}

@@ -14,8 +14,11 @@
 #include "host_backend.h"
 #include "host_glue.h"
 #include "host_sort.h"
+#include "host_timers.h"
 
 namespace wmh {
+
+Timers g_timers;
 
 static inline uint32_t x31_hash(const char *s)
 { // __ac_X31_hash_string (src/khash.h:383-388)
@@ -168,10 +171,11 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		// window length does not enter the chaining parameters unless max_frag_len is set (never by the CLI presets)
 		cp[0] = chain_params(stage == 1 ? &opt2 : opt, opt, 0);
 		cp[1] = chain_params(&opt3, opt, 0);
-		be->seed_chain(tasks, mask_pool.data(), pre_pool.data(), cp, opt->mid_occ, sout);
+		{ WM_TIMED("wave.seed_chain"); be->seed_chain(tasks, mask_pool.data(), pre_pool.data(), cp, opt->mid_occ, sout); }
 		double t1 = now_s();
 		if (st) st->t_seed += t1 - t0, st->n_minimaps += n;
 		wins.resize(n);
+		double tg0 = Timers::now();
 		#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
 		for (int i = 0; i < n; ++i) {
 			MiniMap &M = mm[i];
@@ -195,12 +199,14 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			if (M.aligning) M.at.init(M.opt, mi, i, M.win.wl, rd->seq.data() + M.win.wb, M.regs, M.a.data());
 			M.sink.dp.clear(), M.sink.ll.clear();
 		}
+		g_timers.add("wave.glue_pre_align", Timers::now() - tg0);
 		if (st) for (int i = 0; i < n; ++i) st->n_chained += (int64_t)mm[i].a.size();
 		// alignment rounds (align_regs, src/map.c:267-277 -> mm_align_skeleton)
 		std::vector<int> active;
 		for (int i = 0; i < n; ++i) if (mm[i].aligning) active.push_back(i);
 		dp_res.clear(), ll_res.clear();
 		while (!active.empty()) {
+			double ta0 = Timers::now();
 			#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
 			for (size_t k = 0; k < active.size(); ++k) {
 				MiniMap &M = mm[active[k]];
@@ -209,6 +215,8 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 				M.sink.dp.clear(), M.sink.ll.clear();
 				M.aligning = !M.at.advance(dpp, llp, M.sink);
 			}
+			g_timers.add("round.advance", Timers::now() - ta0);
+			double tm0 = Timers::now();
 			dp_jobs.clear(), ll_jobs.clear();
 			std::vector<int> next;
 			for (int i : active) {
@@ -220,14 +228,16 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 				next.push_back(i);
 			}
 			active.swap(next);
+			g_timers.add("round.merge_jobs", Timers::now() - tm0);
 			if (active.empty()) break;
 			double t2 = now_s();
-			be->run_dp(dp_jobs, wins, sc, dp_res);
-			be->run_ll(ll_jobs, wins, sc, ll_res);
+			{ WM_TIMED("round.run_dp"); be->run_dp(dp_jobs, wins, sc, dp_res); }
+			{ WM_TIMED("round.run_ll"); be->run_ll(ll_jobs, wins, sc, ll_res); }
 			if (st) {
 				st->t_dp += now_s() - t2, st->n_dp_jobs += (int64_t)dp_jobs.size(), st->n_ll_jobs += (int64_t)ll_jobs.size(), ++st->n_rounds;
 			}
 		}
+		double tf0 = Timers::now();
 		#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
 		for (int i = 0; i < n; ++i) {
 			MiniMap &M = mm[i];
@@ -240,11 +250,13 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			}
 			set_mapq(M.regs, M.opt->min_chain_score, M.opt->a, M.rep_len, 0);
 		}
+		g_timers.add("wave.final_mapq", Timers::now() - tf0);
 		if (st) st->t_host += now_s() - t1;
 	};
 
 	// ---------------- stage 1: minimal confidently-alignable substrings (src/map.c:314-700) ----------------
 	for (;;) {
+		double tb0 = Timers::now();
 		mm.clear(), tasks.clear(), mask_pool.clear(), pre_pool.clear();
 		std::vector<int> cur_ids;
 		for (size_t c = 0; c < cursors.size(); ++c) {
@@ -260,8 +272,10 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			tasks.push_back(t);
 			cur_ids.push_back((int)c);
 		}
+		g_timers.add("stage1.build_wave", Timers::now() - tb0);
 		if (mm.empty()) break;
 		run_wave(1);
+		double tk0 = Timers::now();
 		for (size_t k = 0; k < mm.size(); ++k) { // acceptance test and bookkeeping (src/map.c:440-515, :612-687)
 			MiniMap &M = mm[k];
 			Cursor &C = cursors[cur_ids[k]];
@@ -293,25 +307,32 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			if (found >= 0 || !n_regs0) C.done = true;
 			else if (++C.step >= C.steps.size()) C.done = true;
 		}
+		g_timers.add("stage1.bookkeeping", Timers::now() - tk0);
 	}
 
 	// ---------------- stage 2: re-map with the selected anchors (src/map.c:709-954) ----------------
 	mm.clear(), tasks.clear(), mask_pool.clear(), pre_pool.clear();
 	std::vector<int> mm_read;
+	double ts0 = Timers::now();
+	std::vector<std::vector<wm_pair_t>> stage2_a(n_reads);
+	#pragma omp parallel for schedule(dynamic, 8) num_threads(n_threads)
+	for (int i = 0; i < n_reads; ++i) { // gather, de-duplicate and sort the stage-1 anchors of every read (src/map.c:742-774)
+		ReadState &R = rs[i];
+		std::vector<wm_pair_t> &a = stage2_a[i];
+		if (!R.stage1) continue;
+		for (auto &v : R.collect_a) a.insert(a.end(), v.begin(), v.end());
+		if (!a.empty()) { // src/map.c:752-773
+			std::sort(a.begin(), a.end(), [](const wm_pair_t &p, const wm_pair_t &q) { return std::tie(p.x, p.y) < std::tie(q.x, q.y); });
+			a.erase(std::unique(a.begin(), a.end(), [](const wm_pair_t &p, const wm_pair_t &q) { return p.x == q.x && p.y == q.y; }), a.end());
+			radix_sort(a.data(), a.data() + a.size());
+			if ((int64_t)a.size() < opt3.min_cnt) a.clear();
+		}
+	}
 	for (int i = 0; i < n_reads; ++i) {
 		ReadState &R = rs[i];
 		if (R.qlen == 0) continue; // src/map.c:724
 		if (opt3.max_qlen > 0 && R.qlen > opt3.max_qlen) continue;
-		std::vector<wm_pair_t> a;
-		if (R.stage1) {
-			for (auto &v : R.collect_a) a.insert(a.end(), v.begin(), v.end());
-			if (!a.empty()) { // src/map.c:752-773
-				std::sort(a.begin(), a.end(), [](const wm_pair_t &p, const wm_pair_t &q) { return std::tie(p.x, p.y) < std::tie(q.x, q.y); });
-				a.erase(std::unique(a.begin(), a.end(), [](const wm_pair_t &p, const wm_pair_t &q) { return p.x == q.x && p.y == q.y; }), a.end());
-				radix_sort(a.data(), a.data() + a.size());
-				if ((int64_t)a.size() < opt3.min_cnt) a.clear();
-			}
-		}
+		std::vector<wm_pair_t> &a = stage2_a[i];
 		mm.emplace_back();
 		MiniMap &M = mm.back();
 		M.win.read = i, M.win.wb = 0, M.win.wl = R.qlen;
@@ -344,6 +365,7 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		tasks.push_back(t);
 		mm_read.push_back(i);
 	}
+	g_timers.add("stage2.prep", Timers::now() - ts0);
 	run_wave(2);
 	for (size_t k = 0; k < mm.size(); ++k) {
 		MiniMap &M = mm[k];
