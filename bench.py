@@ -229,7 +229,7 @@ def main():
     if os.environ.get("WM_TIMING"):
         log(f"timers over {a.steps} timed steps:")
         L.wm_dump_timers()
-    prof = (C.c_double * 6)(); L.wm_prof_get(prof)
+    prof = (C.c_double * 8)(); L.wm_prof_get(prof)
     L.wm_prof_enable(0)
     # end to end through the host-buffer API (fresh batches)
     e2e_t, e2e_b, d2h_b = 0.0, 0, 0
@@ -271,7 +271,8 @@ def main():
         "gpu_launches": int(prof[0]),
         "roofline": {"bound": "hbm", "kernel": "wm_extd2_fill_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "of": "measured" if peaks else "fallback", "launches": int(prof[2]), "kernel_ms": prof[1],
-                     "block_cells_per_s": prof[4] / (prof[1] * 1e-3) if prof[1] > 0 else 0.0},
+                     "block_cells_per_s": prof[4] / (prof[1] * 1e-3) if prof[1] > 0 else 0.0,
+                     "jobs": int(prof[5]), "block_cells": prof[4], "frac_cells_in_16x2_path": prof[6] / prof[4] if prof[4] > 0 else 0.0},
         "cpu_baseline": cpu, "clocks": clocks,
         "breakdown_s": {"seed_chain": st["t_seed"], "dp_rounds": st["t_dp"], "host_glue": st["t_host"]},
     }))

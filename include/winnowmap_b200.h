@@ -243,7 +243,7 @@ int wm_bench_map_resident(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_threads
 /* bench instrumentation: launch counter and CUDA-event timing of the dominant (DP fill) kernel */
 void wm_prof_enable(int on);
 void wm_prof_reset(void);
-void wm_prof_get(double *out6); /* launches, fill_ms, fill_launches, fill_algorithmic_bytes, fill_block_cells, fill_jobs */
+void wm_prof_get(double *out7); /* launches, fill_ms, fill_launches, fill_algorithmic_bytes, fill_block_cells, fill_jobs, cells in the 16x2 path */
 int wm_device_synchronize(void);
 void wm_dump_timers(void); /* prints and resets the orchestration wall-clock accumulators (stderr) */
 

@@ -253,7 +253,7 @@ extern "C" void wm_prof_reset(void) { int e = g_wm_prof.enabled; memset(&g_wm_pr
 extern "C" void wm_prof_get(double *o)
 {
 	o[0] = (double)g_wm_prof.n_launches; o[1] = g_wm_prof.fill_ms; o[2] = (double)g_wm_prof.fill_launches;
-	o[3] = g_wm_prof.fill_alg_bytes; o[4] = g_wm_prof.fill_cells; o[5] = g_wm_prof.fill_jobs;
+	o[3] = g_wm_prof.fill_alg_bytes; o[4] = g_wm_prof.fill_cells; o[5] = g_wm_prof.fill_jobs; o[6] = g_wm_prof.fill_cells_v2;
 }
 extern "C" int wm_device_synchronize(void) { WM_CUDA_CHECK(cudaDeviceSynchronize()); return 0; }
 

@@ -257,26 +257,33 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 	// ---------------- stage 1: minimal confidently-alignable substrings (src/map.c:314-700) ----------------
 	for (;;) {
 		double tb0 = Timers::now();
-		mm.clear(), tasks.clear(), mask_pool.clear(), pre_pool.clear();
+		tasks.clear(), mask_pool.clear(), pre_pool.clear();
 		std::vector<int> cur_ids;
-		for (size_t c = 0; c < cursors.size(); ++c) {
-			Cursor &C = cursors[c];
-			if (C.done) continue;
-			const int sub_len = C.steps[C.step].first, dir = C.steps[C.step].second;
-			mm.emplace_back();
-			MiniMap &M = mm.back();
-			M.win.read = C.read, M.win.wl = sub_len, M.win.wb = dir == 0 ? C.sub_begin : C.sub_begin - sub_len + 1;
-			M.opt = &opt2, M.chain_set = 0, M.est_err = true;
-			SeedTask t;
-			t.win = M.win, t.flags = 0, t.chain_set = 0, t.n_mask = 0, t.mask_off = 0, t.n_pre = 0, t.pre_off = 0;
-			tasks.push_back(t);
-			cur_ids.push_back((int)c);
+		for (size_t c = 0; c < cursors.size(); ++c) if (!cursors[c].done) cur_ids.push_back((int)c);
+		{ // (re)build the wave's mini-mappings in parallel: they own many small vectors
+			const int n_new = (int)cur_ids.size();
+			#pragma omp parallel for schedule(static) num_threads(n_threads)
+			for (int k = 0; k < (int)mm.size(); ++k) mm[k] = MiniMap();
+			mm.resize(n_new);
+			tasks.resize(n_new);
+			#pragma omp parallel for schedule(static) num_threads(n_threads)
+			for (int k = 0; k < n_new; ++k) {
+				const Cursor &C = cursors[cur_ids[k]];
+				const int sub_len = C.steps[C.step].first, dir = C.steps[C.step].second;
+				MiniMap &M = mm[k];
+				M.win.read = C.read, M.win.wl = sub_len, M.win.wb = dir == 0 ? C.sub_begin : C.sub_begin - sub_len + 1;
+				M.opt = &opt2, M.chain_set = 0, M.est_err = true;
+				SeedTask t;
+				t.win = M.win, t.flags = 0, t.chain_set = 0, t.n_mask = 0, t.mask_off = 0, t.n_pre = 0, t.pre_off = 0;
+				tasks[k] = t;
+			}
 		}
 		g_timers.add("stage1.build_wave", Timers::now() - tb0);
 		if (mm.empty()) break;
 		run_wave(1);
 		double tk0 = Timers::now();
-		for (size_t k = 0; k < mm.size(); ++k) { // acceptance test and bookkeeping (src/map.c:440-515, :612-687)
+		#pragma omp parallel for schedule(dynamic, 32) num_threads(n_threads)
+		for (int k = 0; k < (int)mm.size(); ++k) { // acceptance test and bookkeeping (src/map.c:440-515, :612-687)
 			MiniMap &M = mm[k];
 			Cursor &C = cursors[cur_ids[k]];
 			ReadState &R = rs[C.read];
@@ -311,6 +318,8 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 	}
 
 	// ---------------- stage 2: re-map with the selected anchors (src/map.c:709-954) ----------------
+	#pragma omp parallel for schedule(static) num_threads(n_threads)
+	for (int k = 0; k < (int)mm.size(); ++k) mm[k] = MiniMap();
 	mm.clear(), tasks.clear(), mask_pool.clear(), pre_pool.clear();
 	std::vector<int> mm_read;
 	double ts0 = Timers::now();

@@ -452,7 +452,7 @@ wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8
 		const wm_dp_job J = jobs[j];
 		const int tlen16 = (J.tlen + 15) / 16 * 16;
 		if (use_v2 && J.qlen > 0 && J.tlen > 0 && !P.early_out && tlen16 <= WM_V2_T && J.qlen <= WM_V2_Q)
-			wm_extd2_fill_job_v2(J, seq, bt, ez + j, P, (uint8_t*)my_smem, lane, cell_ctr);
+			wm_extd2_fill_job_v2(J, seq, bt, ez + j, P, (uint8_t*)my_smem, lane, cell_ctr ? cell_ctr + 1 : 0);
 		else
 			wm_extd2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane, cell_ctr);
 		__syncwarp();
@@ -551,7 +551,7 @@ size_t wm_extd2_bt_bytes(int qlen, int tlen, int w)
 }
 
 // jobs/seq/bt/ez/cigar are device pointers; max_tlen = largest tlen among the jobs.
-wm_prof_t g_wm_prof = {0, 0, 0.0, 0, 0.0, 0.0, 0.0};
+wm_prof_t g_wm_prof = {0, 0, 0.0, 0, 0.0, 0.0, 0.0, 0.0};
 
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream)
@@ -571,8 +571,8 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 	int tlen16 = (max_tlen + 15) / 16 * 16;
 	if (tlen16 > WM_SMEM_CELLS) stride = (size_t)tlen16 * 11;
 	int8_t *gs = (int8_t*)ws->scratch.need(stride * grid * WM_FILL_WARPS + 16);
-	int *counter = (int*)ws->counter.need(sizeof(int) + 16);
-	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) + 16, stream));
+	int *counter = (int*)ws->counter.need(sizeof(int) + 32);
+	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) + 32, stream));
 	unsigned long long *cell_ctr = g_wm_prof.enabled ? (unsigned long long*)((char*)counter + 8) : 0;
 	static bool attr_set = false;
 	if (!attr_set) {
@@ -594,8 +594,9 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 		WM_CUDA_CHECK(cudaEventSynchronize(ev1));
 		WM_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
 		g_wm_prof.fill_ms += ms; ++g_wm_prof.fill_launches;
-		unsigned long long cells = 0;
-		WM_CUDA_CHECK(cudaMemcpy(&cells, cell_ctr, sizeof(cells), cudaMemcpyDeviceToHost));
-		g_wm_prof.fill_cells += (double)cells; g_wm_prof.fill_alg_bytes += (double)cells; // 1 B of backtrack per block cell
+		unsigned long long cells[2] = {0, 0};
+		WM_CUDA_CHECK(cudaMemcpy(cells, cell_ctr, sizeof(cells), cudaMemcpyDeviceToHost));
+		g_wm_prof.fill_cells += (double)(cells[0] + cells[1]); g_wm_prof.fill_alg_bytes += (double)(cells[0] + cells[1]); // 1 B of backtrack per block cell
+		g_wm_prof.fill_cells_v2 += (double)cells[1];
 	}
 }

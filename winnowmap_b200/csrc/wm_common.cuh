@@ -22,7 +22,7 @@
 struct wm_prof_t {
 	long long n_launches;
 	int enabled;
-	double fill_ms; long long fill_launches; double fill_alg_bytes, fill_cells, fill_jobs;
+	double fill_ms; long long fill_launches; double fill_alg_bytes, fill_cells, fill_jobs, fill_cells_v2;
 };
 extern wm_prof_t g_wm_prof;
 static inline void wm_count_launch() { ++g_wm_prof.n_launches; }
