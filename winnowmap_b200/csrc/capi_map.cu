@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 #include "wm_common.cuh"
 #include "sketch.cuh"
@@ -23,6 +24,7 @@ struct wm_gpu_ctx_s {
 	double t_index, t_map;
 	int64_t n_keys, n_pos;
 	std::vector<wm_read> resident; // bench: reads already uploaded by wm_bench_upload
+	std::vector<Backend*> lanes;   // lanes[0] == be; further lanes share the index and own a stream + workspaces
 };
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -33,6 +35,56 @@ static void require_device(const char *who)
 	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
 		fprintf(stderr, "[ERROR] %s: no CUDA device visible; winnowmap-b200 has no CPU fallback\n", who);
 		exit(1);
+	}
+}
+
+// Orchestration lanes: the reads of a batch are dealt round-robin to L lanes that run map_batch concurrently, each on
+// its own host thread and CUDA stream, so that one lane's host glue overlaps another lane's kernels.  Results do not
+// depend on the grouping (reads never interact, src/map.c:1008-1048).
+static int n_lanes_wanted()
+{
+	const char *e = getenv("WM_LANES");
+	int n = e ? atoi(e) : 4;
+	return n < 1 ? 1 : n > 16 ? 16 : n;
+}
+
+static void ensure_lanes(wm_gpu_ctx_s *c)
+{
+	if (!c->lanes.empty()) return;
+	const int L = n_lanes_wanted();
+	c->lanes.push_back(c->be);
+	const size_t budget = gpu_backend_get_budget(c->be) / (size_t)L;
+	for (int i = 1; i < L; ++i) c->lanes.push_back(gpu_backend_clone(c->be, L));
+	for (int i = 0; i < L; ++i) gpu_backend_set_budget(c->lanes[i], budget);
+}
+
+static void map_lanes(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const std::vector<const wm_read*> &reads, std::vector<std::vector<wm_reg1_t>> &regs,
+                      std::vector<int> &rl, std::vector<int> &fg, int n_threads, bool resident)
+{
+	ensure_lanes(c);
+	const int n = (int)reads.size();
+	int L = (int)c->lanes.size();
+	if (!resident && n < 4 * L) L = 1;
+	regs.assign(n, std::vector<wm_reg1_t>()); rl.assign(n, 0); fg.assign(n, 0);
+	if (L == 1) { map_batch(c->lanes[0], &c->hidx, opt, reads, regs, rl, fg, n_threads, &c->stats, resident); return; }
+	std::vector<MapStats> st(L);
+	std::vector<std::thread> th;
+	const int thr = n_threads / L > 0 ? n_threads / L : 1;
+	for (int l = 0; l < L; ++l) {
+		memset(&st[l], 0, sizeof(MapStats));
+		th.emplace_back([&, l]() {
+			std::vector<const wm_read*> sub;
+			for (int i = l; i < n; i += L) sub.push_back(reads[i]);
+			std::vector<std::vector<wm_reg1_t>> r2; std::vector<int> rl2, fg2;
+			map_batch(c->lanes[l], &c->hidx, opt, sub, r2, rl2, fg2, thr, &st[l], resident);
+			for (size_t k = 0; k < sub.size(); ++k) { const int i = l + (int)k * L; regs[i].swap(r2[k]); rl[i] = rl2[k]; fg[i] = fg2[k]; }
+		});
+	}
+	for (auto &t : th) t.join();
+	for (int l = 0; l < L; ++l) {
+		MapStats &a = c->stats; const MapStats &b = st[l];
+		a.n_reads += b.n_reads, a.n_bases += b.n_bases, a.n_minimaps += b.n_minimaps, a.n_chained += b.n_chained, a.n_dp_jobs += b.n_dp_jobs;
+		a.n_ll_jobs += b.n_ll_jobs, a.n_rounds += b.n_rounds, a.t_seed += b.t_seed, a.t_dp += b.t_dp, a.t_host += b.t_host;
 	}
 }
 
@@ -57,6 +109,7 @@ extern "C" wm_gpu_ctx_s *wm_gpu_idx_upload(const wm_idx_view_t *v, int device)
 extern "C" void wm_gpu_destroy(wm_gpu_ctx_s *c)
 {
 	if (!c) return;
+	for (size_t i = 1; i < c->lanes.size(); ++i) gpu_backend_destroy(c->lanes[i]);
 	gpu_backend_destroy(c->be);
 	delete c;
 }
@@ -157,7 +210,7 @@ extern "C" int wm_gpu_map_batch(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, int n_s
 		reads[i] = &store[i];
 	}
 	std::vector<std::vector<wm_reg1_t>> regs; std::vector<int> rl, fg;
-	map_batch(c->be, &c->hidx, opt, reads, regs, rl, fg, n_threads, &c->stats);
+	map_lanes(c, opt, reads, regs, rl, fg, n_threads, false);
 	for (int i = 0; i < n_seq; ++i) {
 		n_reg[i] = (int32_t)regs[i].size();
 		reg[i] = 0;
@@ -212,7 +265,7 @@ extern "C" int wm_map_file(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const char *
 			while (s1 < mine.size() && (s1 == s0 || nb + (int64_t)mine[s1]->seq.size() <= max_batch_bases)) nb += (int64_t)mine[s1]->seq.size(), ++s1;
 			std::vector<const wm_read*> sub(mine.begin() + s0, mine.begin() + s1);
 			std::vector<std::vector<wm_reg1_t>> regs; std::vector<int> rl, fg;
-			map_batch(c->be, &c->hidx, opt, sub, regs, rl, fg, n_threads, &c->stats);
+			map_lanes(c, opt, sub, regs, rl, fg, n_threads, false);
 			for (size_t i = 0; i < sub.size(); ++i) {
 				const wm_read *t = sub[i];
 				auto emit = [&](const wm_reg1_t *rr) {
@@ -275,7 +328,13 @@ extern "C" int wm_bench_upload(wm_gpu_ctx_s *c, int n_seq, const char *const *na
 		c->resident[i].seq.assign(seqs[i], lens[i]);
 		reads[i] = &c->resident[i];
 	}
-	c->be->begin_batch(reads);
+	ensure_lanes(c);
+	const int L = (int)c->lanes.size();
+	for (int l = 0; l < L; ++l) {
+		std::vector<const wm_read*> sub;
+		for (int i = l; i < n_seq; i += L) sub.push_back(reads[i]);
+		c->lanes[l]->begin_batch(sub);
+	}
 	WM_CUDA_CHECK(cudaDeviceSynchronize());
 	return 0;
 }
@@ -290,7 +349,7 @@ extern "C" int wm_bench_map_resident(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, in
 	for (size_t i = 0; i < reads.size(); ++i) reads[i] = &c->resident[i];
 	std::vector<std::vector<wm_reg1_t>> regs; std::vector<int> rl, fg;
 	WM_CUDA_CHECK(cudaEventRecord(e0, 0));
-	map_batch(c->be, &c->hidx, opt, reads, regs, rl, fg, n_threads, &c->stats, true);
+	map_lanes(c, opt, reads, regs, rl, fg, n_threads, true);
 	WM_CUDA_CHECK(cudaEventRecord(e1, 0));
 	WM_CUDA_CHECK(cudaEventSynchronize(e1));
 	float f = 0.f;

@@ -3,6 +3,7 @@
 // sized for a batch; nothing is allocated per read.
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <vector>
 #include "wm_common.cuh"
 #include "scan.cuh"
@@ -380,7 +381,8 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 	g.h_cig.clear();
 	if (n == 0) return;
 	wm_dp_params P; wm_dp_params_init(&P, sc.mat, sc.q, sc.e, sc.q2, sc.e2);
-	std::vector<int64_t> cig_base(n + 1, 0); // offsets into h_cig
+	std::vector<int64_t> cig_base(n + 1, 0); // offsets into h_cig, by execution slot
+	std::vector<int> slot_of(n, 0);           // job -> execution slot (jobs of a chunk run sorted by size)
 	g.h_ez.resize(n);
 	std::vector<uint32_t> chunk_cig;
 	int done = 0;
@@ -399,18 +401,22 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		std::vector<wm_gather_job> gj; std::vector<int64_t> joff(1, 0); std::vector<wm_dp_job> dj(m);
 		gj.reserve(2 * m); joff.reserve(2 * m + 1);
 		int64_t pool_off = 0, p_off = 0, c_off = 0;
+		double prof_bytes = 0;
+		// the persistent warps pull jobs in array order: biggest first, so that the tail of the launch is made of small jobs
+		std::vector<int> perm(m);
+		for (int i = 0; i < m; ++i) perm[i] = i;
+		std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) {
+			return jobs[done + x].q.len + jobs[done + x].t.len > jobs[done + y].q.len + jobs[done + y].t.len; });
+		for (int i = 0; i < m; ++i) slot_of[done + perm[i]] = done + i;
 		for (int i = 0; i < m; ++i) {
-			const DpJob &J = jobs[done + i];
+			const DpJob &J = jobs[done + perm[i]];
 			wm_dp_job &D = dj[i];
 			D.q_off = pool_off; add_gather(gj, joff, g, J.q, wins[J.task], &pool_off);
 			D.t_off = pool_off; add_gather(gj, joff, g, J.t, wins[J.task], &pool_off);
 			D.qlen = J.q.len, D.tlen = J.t.len, D.w = J.w, D.zdrop = J.zdrop, D.end_bonus = J.end_bonus, D.flag = J.flag;
 			D.p_off = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.q.len, J.t.len, J.w);
 			D.cig_off = c_off; D.cig_cap = J.q.len + J.t.len + 2; c_off += D.cig_cap; D.pad = 0;
-			if (g_wm_prof.enabled) { // qlen + tlen (codes in) + C_block (counted on the device) + (qlen + tlen) (traceback) + 4 n_cigar + 48
-				g_wm_prof.fill_alg_bytes += 2.0 * (J.q.len + J.t.len) + 48;
-				g_wm_prof.fill_jobs += 1;
-			}
+			prof_bytes += 2.0 * (J.q.len + J.t.len) + 48; // qlen + tlen (codes in) + (qlen + tlen) (traceback) + 48; C_block is counted on the device
 		}
 		g_timers.add("dp.host_prep", Timers::now() - tp0);
 		double tq0 = Timers::now();
@@ -452,16 +458,22 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		g.h_cig.resize(base + o_off[m]);
 		for (int i = 0; i < m; ++i) cig_base[done + i] = (int64_t)base + o_off[i];
 		g_timers.add("dp.cigar_d2h", Timers::now() - tr0);
-		if (g_wm_prof.enabled) g_wm_prof.fill_alg_bytes += 4.0 * (double)o_off[m];
+		if (g_wm_prof.enabled) { // + 4 n_cigar
+			static std::mutex mu;
+			std::lock_guard<std::mutex> lk(mu);
+			g_wm_prof.fill_alg_bytes += prof_bytes + 4.0 * (double)o_off[m];
+			g_wm_prof.fill_jobs += m;
+		}
 		done = end;
 	}
 	g.h_cig.push_back(0);
 	for (int i = 0; i < n; ++i) {
-		const wm_extz_dev &e = g.h_ez[i];
+		const int s = slot_of[i]; // where job i ran
+		const wm_extz_dev &e = g.h_ez[s];
 		DpRes &r = res[i];
 		r.max = e.max, r.zdropped = e.zdropped, r.max_q = e.max_q, r.max_t = e.max_t, r.mqe = e.mqe, r.mqe_t = e.mqe_t;
 		r.mte = e.mte, r.mte_q = e.mte_q, r.score = e.score, r.reach_end = e.reach_end, r.n_cigar = e.n_cigar;
-		r.cigar = g.h_cig.data() + cig_base[i];
+		r.cigar = g.h_cig.data() + cig_base[s];
 	}
 }
 
@@ -537,6 +549,23 @@ Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64
 	if (g.bt_budget > ((size_t)32 << 30)) g.bt_budget = (size_t)32 << 30;
 	return be;
 }
+
+// A second orchestration lane on the same device: shares the resident index, owns its stream and workspaces.
+Backend *gpu_backend_clone(Backend *base_, int n_lanes)
+{
+	GpuBackend *base = static_cast<GpuBackend*>(base_);
+	WM_CUDA_CHECK(cudaSetDevice(base->g.device));
+	GpuBackend *be = new GpuBackend();
+	GpuBackendImpl &g = be->g;
+	g.device = base->g.device; g.hidx = base->g.hidx; g.n_bases = 0;
+	g.ix = base->g.ix; g.bf = base->g.bf;
+	WM_CUDA_CHECK(cudaStreamCreate(&g.st));
+	g.bt_budget = base->g.bt_budget / (size_t)(n_lanes > 0 ? n_lanes : 1);
+	return be;
+}
+
+void gpu_backend_set_budget(Backend *be, size_t bytes) { static_cast<GpuBackend*>(be)->g.bt_budget = bytes; }
+size_t gpu_backend_get_budget(Backend *be) { return static_cast<GpuBackend*>(be)->g.bt_budget; }
 
 void gpu_backend_destroy(Backend *be) { delete be; }
 

@@ -8,3 +8,9 @@ Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64
                             uint64_t bloom_bits, const uint8_t *bloom_table, int device);
 void gpu_backend_destroy(Backend *be);
 }
+
+namespace wmh {
+Backend *gpu_backend_clone(Backend *base, int n_lanes);
+void gpu_backend_set_budget(Backend *be, size_t bytes);
+size_t gpu_backend_get_budget(Backend *be);
+}

@@ -322,7 +322,9 @@ static void fix_bad_ends(const wm_reg1_t *r, const wm_pair_t *a, int bw, int min
 void AlignTask::init(const wm_mapopt_t *opt_, const wm_host_idx *mi_, int task_id_, int qlen_, const char *qstr, std::vector<wm_reg1_t> &regs_in, wm_pair_t *a_)
 {
 	opt = opt_, mi = mi_, task_id = task_id_, qlen = qlen_, a = a_;
+	regs.clear(); // the task object is reused across waves
 	regs.swap(regs_in);
+	firsts.clear(); out.clear(); from_first.clear();
 	qcodes.resize((size_t)qlen * 2);
 	for (int i = 0; i < qlen; ++i) { // src/align.c:871-877
 		uint8_t c = nt4((unsigned char)qstr[i]);
@@ -500,19 +502,25 @@ bool AlignTask::walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink
 	if (A.state == 9) return true;
 	const int rev = A.rev, rid = A.rid;
 	if (!A.captured) { // keep the pass-1 results: later rounds reuse the result buffers
-		auto grab = [&](int job, DpRes &res, std::vector<uint32_t> &cig) {
+		size_t tot = 0;
+		if (A.left_job >= 0) tot += dp[A.left_job].n_cigar > 0 ? dp[A.left_job].n_cigar : 0;
+		if (A.right_job >= 0) tot += dp[A.right_job].n_cigar > 0 ? dp[A.right_job].n_cigar : 0;
+		for (auto &g : A.gaps) tot += dp[g.job].n_cigar > 0 ? dp[g.job].n_cigar : 0;
+		A.cig_pool.clear(); A.cig_pool.reserve(tot);
+		auto grab = [&](int job, DpRes &res, size_t &off) {
 			res = dp[job];
-			cig.assign(res.cigar, res.cigar + (res.n_cigar > 0 ? res.n_cigar : 0));
+			off = A.cig_pool.size();
+			if (res.n_cigar > 0) A.cig_pool.insert(A.cig_pool.end(), res.cigar, res.cigar + res.n_cigar);
 			res.cigar = 0;
 		};
 		if (A.left_job >= 0) grab(A.left_job, A.left_res, A.left_cig);
 		if (A.right_job >= 0) grab(A.right_job, A.right_res, A.right_cig);
-		for (auto &g : A.gaps) grab(g.job, g.res, g.cig);
+		for (auto &g : A.gaps) grab(g.job, g.res, g.cig_off);
 		A.captured = true;
 	}
 	if (!A.left_done) { // :690-708
 		if (A.left_job >= 0) {
-			DpRes ez = A.left_res; ez.cigar = A.left_cig.data();
+			DpRes ez = A.left_res; ez.cigar = A.cig_pool.data() + A.left_cig;
 			if (ez.n_cigar > 0) { append_cigar(r, ez.n_cigar, ez.cigar); r->p->dp_score += ez.max; }
 			A.rs1 = A.rs_init - (ez.reach_end ? ez.mqe_t + 1 : ez.max_t + 1);
 			A.qs1 = A.qs_init - (ez.reach_end ? A.qs_init - A.qs0 : ez.max_q + 1);
@@ -530,7 +538,7 @@ bool AlignTask::walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink
 			tbuf.resize(g.re - g.rs);
 			mi->getseq(rid, g.rs, g.re, tbuf.data());
 			int pos[2][2];
-			const int max_zdrop = zdrop_scan(opt, qs_ptr, tbuf.data(), g.res.n_cigar, g.cig.data(), mat, pos);
+			const int max_zdrop = zdrop_scan(opt, qs_ptr, tbuf.data(), g.res.n_cigar, A.cig_pool.data() + g.cig_off, mat, pos);
 			const int q_len = pos[1][1] - pos[1][0], t_len = pos[0][1] - pos[0][0];
 			A.zd_max_zdrop = max_zdrop;
 			if (!(opt->flag & (WM_F_SPLICE | WM_F_SR | WM_F_FOR_ONLY | WM_F_REV_ONLY)) && max_zdrop > opt->zdrop_inv && q_len < opt->max_gap && t_len < opt->max_gap) {
@@ -568,7 +576,7 @@ bool AlignTask::walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink
 			A.zd_max_zdrop = zdrop_code;
 			A.state = 3;
 			return false;
-		} else { ez = g.res; ez.cigar = g.cig.data(); }
+		} else { ez = g.res; ez.cigar = A.cig_pool.data() + g.cig_off; }
 		// :739-765
 		if (ez.n_cigar > 0) append_cigar(r, ez.n_cigar, ez.cigar);
 		if (ez.zdropped) {
@@ -596,7 +604,7 @@ bool AlignTask::walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink
 	if (!A.dropped) {
 		A.re1 = A.re, A.qe1 = A.qe; // :715 re1/qe1 follow the last seed
 		if (A.right_job >= 0) { // :767-778
-			DpRes ez = A.right_res; ez.cigar = A.right_cig.data();
+			DpRes ez = A.right_res; ez.cigar = A.cig_pool.data() + A.right_cig;
 			if (ez.n_cigar > 0) { append_cigar(r, ez.n_cigar, ez.cigar); r->p->dp_score += ez.max; }
 			A.re1 = A.re + (ez.reach_end ? ez.mqe_t + 1 : ez.max_t + 1);
 			A.qe1 = A.qe + (ez.reach_end ? A.qe0 - A.qe : ez.max_q + 1);

@@ -49,10 +49,11 @@ struct Align1 {
 	int32_t rs, qs, re, qe, rs0, qs0, re0, qe0, rs1, qs1, re1, qe1;
 	int32_t rs_init, qs_init;
 	int left_job, right_job; // indices into the round's job list, -1 if none
-	struct Gap { int32_t i, rs, qs, re, qe, bw1; int job; DpRes res; std::vector<uint32_t> cig; };
+	struct Gap { int32_t i, rs, qs, re, qe, bw1; int job; DpRes res; size_t cig_off; };
 	bool captured;          // pass-1 results copied out of the round buffers
 	DpRes left_res, right_res;
-	std::vector<uint32_t> left_cig, right_cig;
+	size_t left_cig, right_cig;       // offsets into cig_pool
+	std::vector<uint32_t> cig_pool;    // one pool for all captured pass-1 CIGARs of this hit
 	std::vector<Gap> gaps;
 	size_t gap_cur;
 	bool left_done, dropped;

@@ -262,9 +262,7 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		for (size_t c = 0; c < cursors.size(); ++c) if (!cursors[c].done) cur_ids.push_back((int)c);
 		{ // (re)build the wave's mini-mappings in parallel: they own many small vectors
 			const int n_new = (int)cur_ids.size();
-			#pragma omp parallel for schedule(static) num_threads(n_threads)
-			for (int k = 0; k < (int)mm.size(); ++k) mm[k] = MiniMap();
-			mm.resize(n_new);
+			mm.resize(n_new); // objects are reused wave after wave: their vectors keep their capacity (no malloc/free churn)
 			tasks.resize(n_new);
 			#pragma omp parallel for schedule(static) num_threads(n_threads)
 			for (int k = 0; k < n_new; ++k) {
@@ -318,9 +316,8 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 	}
 
 	// ---------------- stage 2: re-map with the selected anchors (src/map.c:709-954) ----------------
-	#pragma omp parallel for schedule(static) num_threads(n_threads)
-	for (int k = 0; k < (int)mm.size(); ++k) mm[k] = MiniMap();
-	mm.clear(), tasks.clear(), mask_pool.clear(), pre_pool.clear();
+	tasks.clear(), mask_pool.clear(), pre_pool.clear();
+	size_t n_mm2 = 0; // stage 2 reuses the mini-mapping objects of stage 1
 	std::vector<int> mm_read;
 	double ts0 = Timers::now();
 	std::vector<std::vector<wm_pair_t>> stage2_a(n_reads);
@@ -342,8 +339,8 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		if (R.qlen == 0) continue; // src/map.c:724
 		if (opt3.max_qlen > 0 && R.qlen > opt3.max_qlen) continue;
 		std::vector<wm_pair_t> &a = stage2_a[i];
-		mm.emplace_back();
-		MiniMap &M = mm.back();
+		if (n_mm2 >= mm.size()) mm.emplace_back();
+		MiniMap &M = mm[n_mm2++];
 		M.win.read = i, M.win.wb = 0, M.win.wl = R.qlen;
 		M.est_err = false;
 		SeedTask t;
@@ -374,6 +371,7 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		tasks.push_back(t);
 		mm_read.push_back(i);
 	}
+	mm.resize(n_mm2);
 	g_timers.add("stage2.prep", Timers::now() - ts0);
 	run_wave(2);
 	for (size_t k = 0; k < mm.size(); ++k) {

@@ -3,6 +3,7 @@
 #include <chrono>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 
 namespace wmh {
 struct Timers {
@@ -10,7 +11,9 @@ struct Timers {
 	const char *name[MAXT]; double sec[MAXT]; long cnt[MAXT]; int n;
 	Timers() : n(0) {}
 	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	std::mutex mu;
 	void add(const char *nm, double dt) {
+		std::lock_guard<std::mutex> lk(mu);
 		for (int i = 0; i < n; ++i) if (name[i] == nm || strcmp(name[i], nm) == 0) { sec[i] += dt; ++cnt[i]; return; }
 		if (n < MAXT) { name[n] = nm; sec[n] = dt; cnt[n] = 1; ++n; }
 	}

@@ -14,6 +14,7 @@
 // L2-resident global scratch slice otherwise.  Direction bytes are streamed to HBM, one
 // row of the rotated matrix per diagonal; a second kernel walks them back (one thread per
 // job) and emits the CIGAR.
+#include <mutex>
 #include "wm_common.cuh"
 
 #define WM_FILL_WARPS 4
@@ -240,6 +241,14 @@ __device__ void wm_extd2_fill_job(const wm_dp_job &J, const uint8_t *__restrict_
 
 __device__ __forceinline__ uint32_t wm_pack2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 __device__ __forceinline__ uint32_t wm_rep2(int v) { return wm_pack2(v, v); }
+// prmt.b32 in its default mode: a selector nibble with bit 3 set replicates the sign bit of the selected byte
+// (the __byte_perm intrinsic only defines the low 3 bits of each nibble)
+__device__ __forceinline__ uint32_t wm_prmt(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
 
 __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
                                      wm_extz_dev *out, const wm_dp_params &P, uint8_t *S8, int lane, unsigned long long *cell_ctr)
@@ -267,6 +276,9 @@ __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restri
 	const uint32_t QE8 = wm_rep2((q + e) * 8), QE28 = wm_rep2((q2 + e2) * 8), Q8 = wm_rep2(q * 8), Q28 = wm_rep2(q2 * 8), MCH8 = wm_rep2(P.sc_mch * 8);
 	const uint32_t KEY_MCH = wm_rep2(P.sc_mch * 8 + TAG_S), KEY_MIS = wm_rep2(P.sc_mis * 8 + TAG_S), KEY_N = wm_rep2(P.sc_N * 8 + TAG_S);
 	const uint32_t TA = wm_rep2(TAG_A), TB = wm_rep2(TAG_B), TA2 = wm_rep2(TAG_A2), TB2 = wm_rep2(TAG_B2);
+	const uint32_t NQE8 = wm_rep2(-(q + e) * 8), NQE28 = wm_rep2(-(q2 + e2) * 8);
+	const uint32_t NE8P1 = wm_rep2(-e * 8 + 1), NE28P1 = wm_rep2(-e2 * 8 + 1); // "-e - z" as (~z) + (-e + 1)
+	const uint32_t QE8M8 = wm_rep2((q + e) * 8 - 8), QE28M8 = wm_rep2((q2 + e2) * 8 - 8);
 	{
 		const int16_t i1 = (int16_t)(-(q + e) * 8), i2 = (int16_t)(-(q2 + e2) * 8), s0 = (int16_t)TAG_S;
 		for (int i = lane; i < tlen16; i += 32) {
@@ -300,10 +312,12 @@ __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restri
 			uint32_t cx = (uint32_t)x1 << 16, cv = (uint32_t)v1 << 16, cx2 = (uint32_t)x21 << 16;
 			uint8_t *pr = bt + J.p_off + (size_t)r * n_col16;
 			const int qoff = qlen - 1 - r; // qr index of cell t is qoff + t
+			const uint32_t LENM1 = wm_rep2(lim - st0 - 1);
 			for (int c = st; c <= en; c += 128) {
 				const int t = c + lane * 4;
 				const bool act = t <= en;
-				uint2 u_ = make_uint2(0, 0), v_ = u_, x_ = u_, y_ = u_, x2_ = u_, y2_ = u_, s_ = u_;
+				uint2 u_, v_, x_, y_, x2_, y2_, s_; // lanes beyond the band keep garbage: nobody consumes it
+				x_.y = v_.y = x2_.y = 0;
 				if (act) {
 					u_ = *(const uint2*)(U + t); v_ = *(const uint2*)(V + t); x_ = *(const uint2*)(X + t); y_ = *(const uint2*)(Y + t);
 					x2_ = *(const uint2*)(X2 + t); y2_ = *(const uint2*)(Y2 + t); s_ = *(const uint2*)(SK + t);
@@ -312,22 +326,24 @@ __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restri
 				if (lane == 0) px = cx, pv = cv, px2 = cx2;
 				cx = __shfl_sync(FULL, x_.y, 31), cv = __shfl_sync(FULL, v_.y, 31), cx2 = __shfl_sync(FULL, x2_.y, 31);
 				if (act) {
-					// fresh scores for the cells inside [st0, lim); others keep their stale key
+					// fresh scores for the cells inside [st0, lim); others keep their stale key.  Codes are 0..4, so a byte of
+					// (target ^ query) is non-zero iff adding 0x7f sets its bit 7, and "either is N" is bit 2 of (target | query).
 					{
 						const uint32_t tw = *(const uint32_t*)(tg + t);
 						const int o = qoff + t + 16; // index into (qr - 16)
 						const uint32_t *qw = (const uint32_t*)(qr - 16) + (o >> 2);
 						const uint32_t qv = __funnelshift_r(qw[0], qw[1], (o & 3) * 8);
-						const uint32_t eq = __vcmpeq4(tw, qv), nn = __vcmpeq4(tw, 0x04040404u) | __vcmpeq4(qv, 0x04040404u);
+						const uint32_t neq = (tw ^ qv) + 0x7f7f7f7fu, nn = (tw | qv) << 5;
+						const int rel = t - st0;
+						const uint32_t idx0 = __byte_perm((uint32_t)rel, (uint32_t)(rel + 1), 0x5410), idx1 = __vadd2(idx0, 0x00020002u);
 						#pragma unroll
 						for (int h = 0; h < 2; ++h) {
-							const uint32_t e16 = __byte_perm(eq, 0, h ? 0x3322 : 0x1100), n16 = __byte_perm(nn, 0, h ? 0x3322 : 0x1100);
-							uint32_t key = KEY_MIS ^ ((KEY_MIS ^ KEY_MCH) & e16);
+							const uint32_t ne16 = wm_prmt(neq, 0, h ? 0xbbaa : 0x9988), n16 = wm_prmt(nn, 0, h ? 0xbbaa : 0x9988); // sign replicate
+							uint32_t key = KEY_MCH ^ ((KEY_MCH ^ KEY_MIS) & ne16);
 							key = key ^ ((key ^ KEY_N) & n16);
-							const int t0 = t + 2 * h;
-							const uint32_t m = ((unsigned)(t0 - st0) < (unsigned)(lim - st0) ? 0x0000ffffu : 0u) |
-							                   ((unsigned)(t0 + 1 - st0) < (unsigned)(lim - st0) ? 0xffff0000u : 0u);
-							if (h == 0) s_.x = (key & m) | (s_.x & ~m); else s_.y = (key & m) | (s_.y & ~m);
+							const uint32_t idx = h ? idx1 : idx0;
+							const uint32_t oor = wm_prmt(__vsub2(LENM1, idx) | idx, 0, 0xbb99); // 0xffff where the cell is outside [st0, lim)
+							if (h == 0) s_.x = (key & ~oor) | (s_.x & oor); else s_.y = (key & ~oor) | (s_.y & oor);
 						}
 						*(uint2*)(SK + t) = s_;
 					}
@@ -348,15 +364,24 @@ __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restri
 						if (!right) dt = 0x00070007u - dt;
 						z = __vmins2(z, MCH8);
 						const uint32_t u1 = __vsub2(z, vl), v1n = __vsub2(z, uo);
-						const uint32_t ntq = __vsub2(Q8, z), ntq2 = __vsub2(Q28, z);
-						const uint32_t ap = __vadd2(a, ntq), bp = __vadd2(b, ntq), a2p = __vadd2(a2, ntq2), b2p = __vadd2(b2, ntq2);
-						const uint32_t xa = __vmaxs2(ap, 0), yb = __vmaxs2(bp, 0), xa2 = __vmaxs2(a2p, 0), yb2 = __vmaxs2(b2p, 0);
+						// x' = max(a - (z - q), 0) - (q + e) = max(a + (-e - z), -(q + e)), likewise the other three (:253-264 / :300-311)
+						// (16x2 subtraction costs three instructions: fold the two's-complement "+1" into constants instead)
+						const uint32_t notz = ~z, nz1 = __vadd2(notz, NE8P1), nz2 = __vadd2(notz, NE28P1); // -e - z, -e2 - z
+						const uint32_t xo = __viaddmax_s16x2(a, nz1, NQE8), yo2 = __viaddmax_s16x2(b, nz1, NQE8);
+						const uint32_t x2o = __viaddmax_s16x2(a2, nz2, NQE28), y2o2 = __viaddmax_s16x2(b2, nz2, NQE28);
 						uint32_t fa, fb, fa2, fb2; // sign bit set <=> continuation flag set
-						if (!right) { fa = __vsub2(0u, xa); fb = __vsub2(0u, yb); fa2 = __vsub2(0u, xa2); fb2 = __vsub2(0u, yb2); } // value > 0 (:253-264)
-						else fa = ~ap, fb = ~bp, fa2 = ~a2p, fb2 = ~b2p;                                                      // value >= 0 (:300-311)
-						const uint32_t fl = ((fa >> 12) & 0x00080008u) | ((fb >> 11) & 0x00100010u) | ((fa2 >> 10) & 0x00200020u) | ((fb2 >> 9) & 0x00400040u);
-						dd[h] = dt | fl;
-						const uint32_t xo = __vsub2(xa, QE8), yo2 = __vsub2(yb, QE8), x2o = __vsub2(xa2, QE28), y2o2 = __vsub2(yb2, QE28);
+						if (!right) { // value > 0  <=>  x' > -(q + e)
+							// values are multiples of 8: x' > -(q+e)  <=>  x' + (q+e) - 8 >= 0  <=>  sign bit of ~(x' + (q+e)*8 - 8) is set
+							fa = ~__vadd2(xo, QE8M8); fb = ~__vadd2(yo2, QE8M8); fa2 = ~__vadd2(x2o, QE28M8); fb2 = ~__vadd2(y2o2, QE28M8);
+						} else {      // value >= 0
+							const uint32_t ntq = __vsub2(Q8, z), ntq2 = __vsub2(Q28, z);
+							fa = ~__vadd2(a, ntq); fb = ~__vadd2(b, ntq); fa2 = ~__vadd2(a2, ntq2); fb2 = ~__vadd2(b2, ntq2);
+						}
+						uint32_t fl = dt | ((fa >> 12) & 0x00080008u);
+						fl |= (fb >> 11) & 0x00100010u;
+						fl |= (fa2 >> 10) & 0x00200020u;
+						fl |= (fb2 >> 9) & 0x00400040u;
+						dd[h] = fl;
 						if (h == 0) un.x = u1, vn.x = v1n, xn.x = xo, yn.x = yo2, x2n.x = x2o, y2n.x = y2o2;
 						else un.y = u1, vn.y = v1n, xn.y = xo, yn.y = yo2, x2n.y = x2o, y2n.y = y2o2;
 					}
@@ -573,23 +598,26 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 	int8_t *gs = (int8_t*)ws->scratch.need(stride * grid * WM_FILL_WARPS + 16);
 	int *counter = (int*)ws->counter.need(sizeof(int) + 32);
 	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) + 32, stream));
-	unsigned long long *cell_ctr = g_wm_prof.enabled ? (unsigned long long*)((char*)counter + 8) : 0;
+	unsigned long long *cell_ctr = (unsigned long long*)((char*)counter + 8);
 	static bool attr_set = false;
 	if (!attr_set) {
 		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_extd2_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	static cudaEvent_t ev0 = 0, ev1 = 0;
-	if (g_wm_prof.enabled) {
+	static thread_local cudaEvent_t ev0 = 0, ev1 = 0; // one pair per orchestration thread (each drives its own stream)
+	static std::mutex prof_mutex; // bench mode: fill kernels of concurrent orchestration threads are timed one at a time
+	const bool prof = g_wm_prof.enabled != 0;
+	if (prof) {
+		prof_mutex.lock();
 		if (!ev0) { WM_CUDA_CHECK(cudaEventCreate(&ev0)); WM_CUDA_CHECK(cudaEventCreate(&ev1)); }
 		WM_CUDA_CHECK(cudaEventRecord(ev0, stream));
 	}
 	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, stream>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, counter, use_v2, cell_ctr);
 	WM_CUDA_CHECK(cudaGetLastError());
-	if (g_wm_prof.enabled) WM_CUDA_CHECK(cudaEventRecord(ev1, stream));
+	if (prof) WM_CUDA_CHECK(cudaEventRecord(ev1, stream));
 	wm_count_launch(); wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar);
 	WM_CUDA_CHECK(cudaGetLastError());
-	if (g_wm_prof.enabled) { // bench mode: serialise to read the kernel's own duration
+	if (prof) { // bench mode: serialise to read the kernel's own duration
 		float ms = 0.f;
 		WM_CUDA_CHECK(cudaEventSynchronize(ev1));
 		WM_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -598,5 +626,6 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 		WM_CUDA_CHECK(cudaMemcpy(cells, cell_ctr, sizeof(cells), cudaMemcpyDeviceToHost));
 		g_wm_prof.fill_cells += (double)(cells[0] + cells[1]); g_wm_prof.fill_alg_bytes += (double)(cells[0] + cells[1]); // 1 B of backtrack per block cell
 		g_wm_prof.fill_cells_v2 += (double)cells[1];
+		prof_mutex.unlock();
 	}
 }

@@ -25,7 +25,7 @@ struct wm_prof_t {
 	double fill_ms; long long fill_launches; double fill_alg_bytes, fill_cells, fill_jobs, fill_cells_v2;
 };
 extern wm_prof_t g_wm_prof;
-static inline void wm_count_launch() { ++g_wm_prof.n_launches; }
+static inline void wm_count_launch() { __atomic_fetch_add(&g_wm_prof.n_launches, 1LL, __ATOMIC_RELAXED); }
 
 // One extension-DP job; sequences live in a device byte pool (0..4 codes).
 struct wm_dp_job {
