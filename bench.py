@@ -176,7 +176,7 @@ def main():
         if rank != 0:
             ref, wf, contigs = workload(REF_LEN)  # cached files; every rank needs the contigs to draw reads
     t0 = time.time()
-    n_thr = max(1, min(int(os.environ.get("WM_HOST_THREADS", 128)), cores // max(1, world)))
+    n_thr = max(1, min(int(os.environ.get("WM_HOST_THREADS", 64)), (cores // 2) // max(1, world)))  # physical cores; leave room for CUDA driver threads
     mp = Mapper(ref, wf, preset="map-ont", cigar=True, device=local, n_threads=n_thr)
     log(f"rank {rank}: index built/uploaded in {time.time() - t0:.1f}s ({mp.stats()['n_keys']:.0f} keys)")
 

@@ -30,6 +30,8 @@ def lib():
         if not os.path.exists(_SO):
             raise RuntimeError(f"{_SO} is missing: build it with `python -m winnowmap_b200.build` "
                                "(winnowmap_b200 has no CPU fallback)")
+        # the orchestration threads start many short OpenMP regions; spinning idle workers starve the CUDA driver threads
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
         L = C.CDLL(_SO)
         L.wm_version.restype = C.c_char_p
         L.wm_device_count.restype = C.c_int
