@@ -174,11 +174,26 @@ def main():
     if dist is not None:
         dist.barrier()
         if rank != 0:
-            ref, wf, contigs = workload(REF_LEN)  # cached files; every rank needs the contigs to draw reads
+            ref, wf, contigs = workload(REF_LEN)  # cached files; every rank needs the contigs to draw its own reads
     t0 = time.time()
     n_thr = max(1, min(int(os.environ.get("WM_HOST_THREADS", 64)), (cores // 2) // max(1, world)))  # physical cores; leave room for CUDA driver threads
-    mp = Mapper(ref, wf, preset="map-ont", cigar=True, device=local, n_threads=n_thr)
-    log(f"rank {rank}: index built/uploaded in {time.time() - t0:.1f}s ({mp.stats()['n_keys']:.0f} keys)")
+    if world == 1:
+        mp = Mapper(ref, wf, preset="map-ont", cigar=True, device=local, n_threads=n_thr)
+    else:
+        # one-time index fan-out: rank 0 builds, one NCCL broadcast (GPU to GPU over NVLink), the others adopt the blob
+        from winnowmap_b200 import multi
+        import torch
+        if rank == 0:
+            mp = Mapper(ref, wf, preset="map-ont", cigar=True, device=local, n_threads=n_thr)
+            blob = mp.index_blob()
+        else:
+            blob = None
+        tb = time.time()
+        blob = multi.broadcast_blob(blob, 0, rank, device=torch.device("cuda", local))
+        if rank != 0:
+            mp = Mapper(None, None, preset="map-ont", cigar=True, device=local, n_threads=n_thr, blob=blob)
+        log(f"rank {rank}: index blob {blob.nbytes / 1e6:.0f} MB broadcast+adopted in {time.time() - tb:.2f}s")
+    log(f"rank {rank}: index ready in {time.time() - t0:.1f}s ({mp.stats()['n_keys']:.0f} keys)")
 
     def pack(recs):
         n = len(recs)

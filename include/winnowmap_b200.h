@@ -223,6 +223,12 @@ void wm_gpu_destroy(wm_gpu_ctx *ctx);
  * sequences are sketched by the same CUDA kernel as the reads, the -W list goes into the down-weight filter. */
 wm_gpu_ctx *wm_index_build(const char *ref_fn, const char *kmer_freq_fn, int k, int w, int device);
 
+/* One-time index fan-out: the flattened index as one relocatable blob.  Rank 0 builds it, it travels
+ * GPU-to-GPU in a single NCCL broadcast, every other rank re-creates its context with wm_idx_blob_load. */
+int64_t wm_idx_blob_size(const wm_gpu_ctx *ctx);
+int wm_idx_blob_write(const wm_gpu_ctx *ctx, uint8_t *buf);
+wm_gpu_ctx *wm_idx_blob_load(const uint8_t *buf, int64_t size, int device);
+
 /* Replaces kt_for(p->n_threads, worker_for, in, n_frag) (src/map.c:1162-1165; worker_for :1008-1048): one call per
  * mini-batch, blocking; fills n_reg[i], reg[i] (malloc()ed array whose ->p are malloc()ed, freed by the caller as
  * at src/map.c:1210-1211), rep_len[i] and frag_gap[i] (src/map.c:1025-1034).  n_threads = host threads for the glue. */

@@ -25,6 +25,10 @@ struct wm_gpu_ctx_s {
 	int64_t n_keys, n_pos;
 	std::vector<wm_read> resident; // bench: reads already uploaded by wm_bench_upload
 	std::vector<Backend*> lanes;   // lanes[0] == be; further lanes share the index and own a stream + workspaces
+	// host copy of the flattened index, kept for the one-time fan-out to the other GPUs (wm_idx_blob_*)
+	std::vector<uint64_t> keys, pos_off, pos;
+	std::vector<uint8_t> bloom;
+	uint64_t bloom_bits;
 };
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -102,6 +106,11 @@ extern "C" wm_gpu_ctx_s *wm_gpu_idx_upload(const wm_idx_view_t *v, int device)
 	}
 	c->hidx.S.assign(v->S, v->S + v->S_words);
 	c->n_keys = v->n_keys, c->n_pos = (int64_t)v->pos_off[v->n_keys];
+	c->keys.assign(v->keys, v->keys + v->n_keys);
+	c->pos_off.assign(v->pos_off, v->pos_off + v->n_keys + 1);
+	c->pos.assign(v->pos, v->pos + v->pos_off[v->n_keys]);
+	c->bloom.assign(v->bloom_table, v->bloom_table + v->bloom_bits / 8);
+	c->bloom_bits = v->bloom_bits;
 	c->be = gpu_backend_create(&c->hidx, v->keys, v->n_keys, v->pos_off, v->pos, v->bloom_bits, v->bloom_table, device);
 	return c;
 }
@@ -185,6 +194,9 @@ extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_fre
 	pos_off.push_back(mz.size());
 	c->n_keys = (int64_t)keys.size(), c->n_pos = (int64_t)pos.size();
 	c->be = gpu_backend_create(&H, keys.data(), (int64_t)keys.size(), pos_off.data(), pos.data(), wm_bloom_bits(bloom), wm_bloom_table(bloom), device);
+	c->bloom_bits = wm_bloom_bits(bloom);
+	c->bloom.assign(wm_bloom_table(bloom), wm_bloom_table(bloom) + c->bloom_bits / 8);
+	c->keys.swap(keys); c->pos_off.swap(pos_off); c->pos.swap(pos);
 	wm_bloom_destroy(bloom);
 	c->t_index = now_s() - t0;
 	return c;
@@ -360,3 +372,60 @@ extern "C" int wm_bench_map_resident(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, in
 }
 
 extern "C" void wm_dump_timers(void) { wmh::g_timers.dump(stderr); wmh::g_timers.reset(); }
+
+// ---- one-time index fan-out: the flattened index as one relocatable blob ----
+// Rank 0 builds the index, the blob travels GPU-to-GPU with one NCCL broadcast (torch.distributed in bench.py) and
+// every other rank re-creates its context from it.  Layout: 8 x uint64 header, then the arrays, each 8-byte aligned.
+static inline size_t pad8(size_t x) { return (x + 7) & ~(size_t)7; }
+
+extern "C" int64_t wm_idx_blob_size(const wm_gpu_ctx_s *c)
+{
+	const wm_host_idx &H = c->hidx;
+	size_t names = 0;
+	for (auto &s : H.name) names += s.size() + 1;
+	return (int64_t)(8 * 8 + pad8(H.len.size() * 4) + H.offset.size() * 8 + pad8(names) + pad8(H.S.size() * 4) + c->keys.size() * 8 +
+	                 c->pos_off.size() * 8 + c->pos.size() * 8 + pad8(c->bloom.size()));
+}
+
+extern "C" int wm_idx_blob_write(const wm_gpu_ctx_s *c, uint8_t *buf)
+{
+	const wm_host_idx &H = c->hidx;
+	size_t names = 0;
+	for (auto &s : H.name) names += s.size() + 1;
+	uint64_t *h = (uint64_t*)buf;
+	h[0] = 0x31584449424d57ULL; /* "WMBIDX1" */ h[1] = (uint64_t)H.k << 32 | (uint32_t)H.w; h[2] = H.len.size(); h[3] = names;
+	h[4] = H.S.size(); h[5] = c->keys.size(); h[6] = c->pos.size(); h[7] = c->bloom_bits;
+	uint8_t *p = buf + 64;
+	memcpy(p, H.len.data(), H.len.size() * 4); p += pad8(H.len.size() * 4);
+	memcpy(p, H.offset.data(), H.offset.size() * 8); p += H.offset.size() * 8;
+	{ uint8_t *q = p; for (auto &s : H.name) { memcpy(q, s.c_str(), s.size() + 1); q += s.size() + 1; } p += pad8(names); }
+	memcpy(p, H.S.data(), H.S.size() * 4); p += pad8(H.S.size() * 4);
+	memcpy(p, c->keys.data(), c->keys.size() * 8); p += c->keys.size() * 8;
+	memcpy(p, c->pos_off.data(), c->pos_off.size() * 8); p += c->pos_off.size() * 8;
+	memcpy(p, c->pos.data(), c->pos.size() * 8); p += c->pos.size() * 8;
+	memcpy(p, c->bloom.data(), c->bloom.size());
+	return 0;
+}
+
+extern "C" wm_gpu_ctx_s *wm_idx_blob_load(const uint8_t *buf, int64_t size, int device)
+{
+	require_device("wm_idx_blob_load");
+	const uint64_t *h = (const uint64_t*)buf;
+	if (size < 64 || h[0] != 0x31584449424d57ULL) { fprintf(stderr, "[ERROR] wm_idx_blob_load: bad blob\n"); return 0; }
+	const size_t n_seq = h[2], names = h[3], s_words = h[4], n_keys = h[5], n_pos = h[6];
+	const uint8_t *p = buf + 64;
+	const uint32_t *len = (const uint32_t*)p; p += pad8(n_seq * 4);
+	const uint64_t *off = (const uint64_t*)p; p += n_seq * 8;
+	const char *nm = (const char*)p; p += pad8(names);
+	const uint32_t *S = (const uint32_t*)p; p += pad8(s_words * 4);
+	const uint64_t *keys = (const uint64_t*)p; p += n_keys * 8;
+	const uint64_t *pos_off = (const uint64_t*)p; p += (n_keys + 1) * 8;
+	const uint64_t *pos = (const uint64_t*)p; p += n_pos * 8;
+	std::vector<const char*> name_ptr(n_seq);
+	for (size_t i = 0; i < n_seq; ++i) { name_ptr[i] = nm; nm += strlen(nm) + 1; }
+	wm_idx_view_t v;
+	v.k = (int32_t)(h[1] >> 32), v.w = (int32_t)(uint32_t)h[1], v.n_seq = (int32_t)n_seq;
+	v.seq_name = name_ptr.data(), v.seq_len = len, v.seq_offset = off, v.S = S, v.S_words = s_words;
+	v.n_keys = (int64_t)n_keys, v.keys = keys, v.pos_off = pos_off, v.pos = pos, v.bloom_bits = h[7], v.bloom_table = p;
+	return wm_gpu_idx_upload(&v, device);
+}

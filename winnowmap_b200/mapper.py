@@ -42,6 +42,11 @@ def _setup(L):
     L.wm_index_build.restype = C.c_void_p
     L.wm_index_build.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
     L.wm_gpu_destroy.argtypes = [C.c_void_p]
+    L.wm_idx_blob_size.restype = C.c_int64
+    L.wm_idx_blob_size.argtypes = [C.c_void_p]
+    L.wm_idx_blob_write.argtypes = [C.c_void_p, C.c_void_p]
+    L.wm_idx_blob_load.restype = C.c_void_p
+    L.wm_idx_blob_load.argtypes = [C.c_void_p, C.c_int64, C.c_int]
     L.wm_map_file.argtypes = [C.c_void_p, C.POINTER(MapOpt), C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
     L.wm_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
     L.wm_reset_stats.argtypes = [C.c_void_p]
@@ -68,13 +73,25 @@ def make_options(preset=None, cigar=True):
 class Mapper:
     """winnowmap [-W rep.txt] -x preset -c ref.fa reads.fa  on one GPU."""
 
-    def __init__(self, ref, kmer_freq=None, preset="map-ont", cigar=True, device=0, n_threads=None):
+    def __init__(self, ref, kmer_freq=None, preset="map-ont", cigar=True, device=0, n_threads=None, blob=None):
         self.L = _setup(lib())
         self.io, self.mo = make_options(preset, cigar)
-        self.n_threads = n_threads or max(1, min(64, (os.cpu_count() or 1)))
-        self.ctx = self.L.wm_index_build(ref.encode(), kmer_freq.encode() if kmer_freq else None, self.io.k, self.io.w, device)
+        self.n_threads = n_threads or max(1, min(64, (os.cpu_count() or 2) // 2))
+        if blob is not None:  # index received from another rank (numpy uint8 array)
+            self._blob_keep = blob
+            self.ctx = self.L.wm_idx_blob_load(blob.ctypes.data, blob.nbytes, device)
+        else:
+            self.ctx = self.L.wm_index_build(ref.encode(), kmer_freq.encode() if kmer_freq else None, self.io.k, self.io.w, device)
         if not self.ctx:
             raise RuntimeError("index construction failed")
+
+    def index_blob(self):
+        """The flattened index as one numpy uint8 array (for the one-time NCCL fan-out)."""
+        import numpy as np
+        n = self.L.wm_idx_blob_size(self.ctx)
+        buf = np.empty(n, dtype=np.uint8)
+        self.L.wm_idx_blob_write(self.ctx, buf.ctypes.data)
+        return buf
 
     def map_file(self, reads, out, rank=0, world=1, tag_order=False, max_batch_bases=200_000_000):
         rc = self.L.wm_map_file(self.ctx, C.byref(self.mo), reads.encode(), out.encode(), self.n_threads, rank, world, int(tag_order), max_batch_bases)
