@@ -23,6 +23,12 @@ CASES = {
                        preset="map-ont", use_W=True, k=15),
     "hifi_small": dict(ref_len=300000, contigs=1, tandem=True, ref_seed=1013, n_reads=40, n50=12000, err=0.005, read_seed=2013, min_len=1000,
                        preset="map-pb", use_W=True, k=15),
+    # reads drawn from a donor genome carrying deletions / insertions / inversions: Z-drop splits, long joins, inversion rescue
+    "ont_sv": dict(ref_len=400000, contigs=2, tandem=False, ref_seed=1021, n_reads=60, n50=14000, err=0.04, read_seed=2021, min_len=2000,
+                   preset="map-ont", use_W=False, k=15, sv=True),
+    # a 300-bp family present > 5000 times: minimizers above mid_occ are skipped and rl:i: becomes non-zero
+    "ont_highocc": dict(ref_len=2600000, contigs=1, tandem=False, ref_seed=1022, n_reads=40, n50=9000, err=0.05, read_seed=2022, min_len=1500,
+                        preset="map-ont", use_W=True, k=15, highocc=True),
     "asm20_small": dict(ref_len=300000, contigs=1, tandem=False, ref_seed=1014, n_reads=12, n50=40000, err=0.02, read_seed=2014, min_len=5000,
                         preset="asm20", use_W=True, k=19),
 }
@@ -40,9 +46,41 @@ def make_inputs(name, outdir):
     wfile = os.path.join(outdir, name + ".rep.txt")
     rng = np.random.default_rng(c["ref_seed"])
     contigs = gen_data.make_ref(rng, c["ref_len"], c["contigs"], c["tandem"])
+    if c.get("highocc"):
+        name, seq = contigs[0]
+        seq = seq.copy()
+        unit = gen_data.random_seq(rng, 300)
+        pos = 20000
+        for _ in range(6200):  # interspersed copies, 2 % divergence each, ~100 bp apart
+            cp = gen_data.mutate(rng, unit, 0.02, (1.0, 0.0, 0.0))
+            if pos + 300 >= len(seq) - 20000:
+                break
+            seq[pos:pos + 300] = cp
+            pos += 300 + int(rng.integers(60, 140))
+        contigs = [(name, seq)]
     gen_data.write_fasta(ref, contigs)
     rng = np.random.default_rng(c["read_seed"])
-    recs = gen_data.make_reads(rng, contigs, c["n_reads"], c["n50"], c["err"], min_len=c["min_len"])
+    donor = contigs
+    if c.get("sv"):
+        donor = []
+        for name, seq in contigs:
+            parts, p = [], 0
+            while p < len(seq):
+                step = int(rng.integers(6000, 16000))
+                seg = seq[p:p + step]
+                kind = int(rng.integers(0, 4))
+                if kind == 0 and len(seg) > 6000:      # deletion
+                    d = int(rng.integers(300, 3000))
+                    seg = np.concatenate([seg[:2000], seg[2000 + d:]])
+                elif kind == 1:                         # insertion of novel sequence
+                    seg = np.concatenate([seg[:2500], gen_data.random_seq(rng, int(rng.integers(300, 2500))), seg[2500:]])
+                elif kind == 2 and len(seg) > 6000:    # inversion
+                    L = int(rng.integers(800, 3000))
+                    seg = np.concatenate([seg[:2000], gen_data.COMP[seg[2000:2000 + L][::-1]], seg[2000 + L:]])
+                parts.append(seg)
+                p += step
+            donor.append((name, np.concatenate(parts)))
+    recs = gen_data.make_reads(rng, donor, c["n_reads"], c["n50"], c["err"], min_len=c["min_len"])
     gen_data.write_fasta(reads, recs)
     if c["use_W"]:
         gen_data.write_top_kmers(wfile, contigs, c["k"], 0.9998)
