@@ -28,6 +28,7 @@ def main():
     ap.add_argument("-k", type=int, default=15)
     ap.add_argument("--threads", type=int, default=os.cpu_count())
     ap.add_argument("--out", default="/tmp/wm_cmp")
+    ap.add_argument("--repeat", action="store_true", help="map a second time and report the warm timing")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     rng = np.random.default_rng(1005)
@@ -51,9 +52,20 @@ def main():
     t0 = time.time()
     mp.map_file(reads, os.path.join(a.out, "gpu.paf"))
     t_gpu = time.time() - t0
+    t_warm = None
+    if a.repeat:  # steady state: buffers allocated, CUDA context warm
+        from winnowmap_b200 import lib
+        if os.environ.get("WM_TIMING"):
+            print("--- first pass timers ---", file=sys.stderr, flush=True)
+            lib().wm_dump_timers()
+        t0 = time.time()
+        mp.map_file(reads, os.path.join(a.out, "gpu2.paf"))
+        t_warm = time.time() - t0
     st = mp.stats()
     same = open(os.path.join(a.out, "ref.paf"), "rb").read() == open(os.path.join(a.out, "gpu.paf"), "rb").read()
     print(f"reference (index+map, {a.threads} threads): {t_ref:.2f}s | gpu index {t_idx:.2f}s map {t_gpu:.2f}s ({nb / t_gpu / 1e6:.1f} Mbase/s) | identical: {same}")
+    if t_warm is not None:
+        print(f"gpu map, second pass (warm): {t_warm:.2f}s ({nb / t_warm / 1e6:.1f} Mbase/s)")
     print({k: round(v, 3) for k, v in st.items()})
     if os.environ.get("WM_TIMING"):
         from winnowmap_b200 import lib

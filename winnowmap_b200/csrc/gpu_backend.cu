@@ -210,7 +210,8 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		const int ns = (int)skt.size();
 		if (ns == 0) continue;
 		int64_t n_mz = 0;
-		wm_sketch_run(&g.sk, g.bf, pass == 0 ? d_codes : d_masked, skt.data(), ns, w, k, &n_mz, st);
+		{ WM_TIMED("seed.sketch"); wm_sketch_run(&g.sk, g.bf, pass == 0 ? d_codes : d_masked, skt.data(), ns, w, k, &n_mz, st); }
+		WM_TIMED("seed.lookup_sort");
 		std::vector<int32_t> qlen(ns);
 		for (int i = 0; i < ns; ++i) qlen[i] = skt[i].len;
 		int32_t *d_qlen = (int32_t*)g.qlen_buf.need(sizeof(int32_t) * ns);
@@ -308,11 +309,13 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		P.max_dist_x = cp[s].max_dist_x, P.min_dist_x = cp[s].min_dist_x, P.max_dist_y = cp[s].max_dist_y, P.bw = cp[s].bw;
 		P.max_skip = cp[s].max_skip, P.max_iter = cp[s].max_iter, P.min_cnt = cp[s].min_cnt, P.min_sc = cp[s].min_sc, P.gap_scale = cp[s].gap_scale;
 	}
+	double t_chain0 = Timers::now();
 	wm_chain_run(&g.ch, d_A, d_foff, f_off.data(), n, PP, d_set, st);
 	g.h_nu.assign(n, 0); g.h_nb.assign(n, 0);
 	WM_CUDA_CHECK(cudaMemcpyAsync(g.h_nu.data(), g.ch.n_u.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
 	WM_CUDA_CHECK(cudaMemcpyAsync(g.h_nb.data(), g.ch.n_b.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
 	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	g_timers.add("seed.chain", Timers::now() - t_chain0);
 	std::vector<int64_t> nb_off(n + 1, 0), nu_off(n + 1, 0);
 	for (int i = 0; i < n; ++i) nb_off[i + 1] = nb_off[i] + g.h_nb[i], nu_off[i + 1] = nu_off[i] + g.h_nu[i];
 	int64_t *d_nb = (int64_t*)g.nb_off.need(sizeof(int64_t) * (n + 1)), *d_nu = (int64_t*)g.nu_off.need(sizeof(int64_t) * (n + 1));
@@ -419,6 +422,17 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			prof_bytes += 2.0 * (J.q.len + J.t.len) + 48; // qlen + tlen (codes in) + (qlen + tlen) (traceback) + 48; C_block is counted on the device
 		}
 		g_timers.add("dp.host_prep", Timers::now() - tp0);
+		if (getenv("WM_DP_STATS")) {
+			int n_big = 0, mq = 0, mt = 0, mw = 0; double cells = 0, big_cells = 0;
+			for (int i = 0; i < m; ++i) {
+				const DpJob &J = jobs[done + i];
+				const double c = (double)J.t.len * std::min(J.q.len, 2 * (J.w < 0 ? J.q.len : J.w) + 1);
+				cells += c;
+				if (J.t.len > 512 || J.q.len > 640) ++n_big, big_cells += c;
+				mq = std::max(mq, J.q.len), mt = std::max(mt, J.t.len), mw = std::max(mw, J.w);
+			}
+			fprintf(stderr, "[dp-stats] jobs=%d big=%d max_q=%d max_t=%d max_w=%d band_cells=%.3g big_cells=%.3g bt=%.3g MB\n", m, n_big, mq, mt, mw, cells, big_cells, p_off / 1e6);
+		}
 		double tq0 = Timers::now();
 		wm_gather_job *d_gj = (wm_gather_job*)g.g_jobs.need(sizeof(wm_gather_job) * gj.size());
 		int64_t *d_joff = (int64_t*)g.g_joff.need(sizeof(int64_t) * joff.size());

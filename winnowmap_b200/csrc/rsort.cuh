@@ -58,6 +58,85 @@ __device__ void wm_rs_pass(T *a, wm_rs_frame &F, int *b)
 	}
 }
 
+// ---- warp-cooperative variant ----
+// The cycle-leader walk of one pass is a serial dependence chain and stays on lane 0, but everything
+// around it is data parallel: the byte histogram (shared-memory atomics), the bucket prefix, and the
+// <= 64-element insertion sorts that finish the leaf buckets (disjoint ranges, one per lane).  Buckets
+// that need another pass go to a work list; the ranges are disjoint, so the order in which they are
+// processed cannot change the result.  `a` may point to shared memory (the caller staged the array)
+// or to global memory.
+struct wm_rs_range { int beg, end, s; };
+struct wm_rs_warp_ws { int e[256], b[256]; };
+
+template <typename T>
+__device__ void wm_radix_sort_warp(T *a, int n, wm_rs_warp_ws *W, wm_rs_range *wl, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	if (n <= WM_RS_MIN_SIZE) { if (lane == 0) wm_rs_insertsort(a, a + n); __syncwarp(); return; }
+	int n_wl = 0;
+	int beg = 0, end = n, s = 56;
+	for (;;) {
+		// histogram of byte s>>3 (ksort.h:121-122)
+		#pragma unroll
+		for (int k = 0; k < 8; ++k) W->e[lane * 8 + k] = 0;
+		__syncwarp();
+		for (int i = beg + lane; i < end; i += 32) atomicAdd(&W->e[wm_rs_key<T>::get(a[i]) >> s & 255], 1);
+		__syncwarp();
+		int cnt[8], sum = 0; bool single = false;
+		#pragma unroll
+		for (int k = 0; k < 8; ++k) { cnt[k] = W->e[lane * 8 + k]; sum += cnt[k]; single |= cnt[k] == end - beg; }
+		int incl = sum;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+		int acc = beg + incl - sum;
+		#pragma unroll
+		for (int k = 0; k < 8; ++k) { W->b[lane * 8 + k] = acc; acc += cnt[k]; W->e[lane * 8 + k] = acc; }
+		const bool one_bucket = __any_sync(FULL, single);
+		__syncwarp();
+		if (one_bucket) { // identity permutation: straight to the next byte
+			if (s > 0) { s = s > 8 ? s - 8 : 0; continue; }
+		} else {
+			if (lane == 0) { // ksort.h:126-138
+				int *b = W->b; const int *e = W->e;
+				for (int k = 0; k < 256;) {
+					const int bk = b[k];
+					if (bk != e[k]) {
+						int l = (int)(wm_rs_key<T>::get(a[bk]) >> s & 255);
+						if (l != k) {
+							T tmp = a[bk], swap;
+							do {
+								const int bl = b[l];
+								swap = tmp; tmp = a[bl]; a[bl] = swap; b[l] = bl + 1;
+								l = (int)(wm_rs_key<T>::get(tmp) >> s & 255);
+							} while (l != k);
+							a[bk] = tmp; b[k] = bk + 1;
+						} else b[k] = bk + 1;
+					} else ++k;
+				}
+			}
+			__syncwarp();
+			if (s > 0) { // ksort.h:140-145: finish or queue the sub-buckets
+				const int ns = s > 8 ? s - 8 : 0;
+				#pragma unroll 1
+				for (int kb = 0; kb < 256; kb += 32) {
+					const int k = kb + lane;
+					const int cb = k ? W->e[k - 1] : beg, ce = W->e[k];
+					const bool big = ce - cb > WM_RS_MIN_SIZE;
+					const unsigned m = __ballot_sync(FULL, big);
+					if (big) { wm_rs_range r; r.beg = cb, r.end = ce, r.s = ns; wl[n_wl + __popc(m & ((1u << lane) - 1u))] = r; }
+					else if (ce - cb > 1) wm_rs_insertsort(a + cb, a + ce);
+					n_wl += __popc(m);
+				}
+				__syncwarp();
+			}
+		}
+		if (n_wl == 0) break;
+		const wm_rs_range r = wl[--n_wl];
+		beg = r.beg, end = r.end, s = r.s;
+	}
+	__syncwarp();
+}
+
 // radix_sort_##name (ksort.h:146-150) on a[0,n)
 template <typename T>
 __device__ void wm_radix_sort_emul(T *a, int n, wm_rs_stack *stk)

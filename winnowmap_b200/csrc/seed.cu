@@ -7,6 +7,7 @@
 // open-addressing hash table key -> key index for O(1) probes.  The bucket/khash structure of the
 // reference is an implementation detail; the contract "hash -> (sorted list, n)" is what is kept.
 #include <vector>
+#include <algorithm>
 #include "wm_common.cuh"
 #include "scan.cuh"
 #include "sketch.cuh"
@@ -131,13 +132,30 @@ __global__ void wm_anchor_sort_small_kernel(wm128_dev *__restrict__ a, const int
 	if (n <= WM_RS_MIN_SIZE) wm_rs_insertsort(a + off[t], a + off[t] + n);
 }
 
-__global__ void wm_anchor_sort_big_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__ off, const int32_t *__restrict__ big_ids, int n_big,
-                                          wm_rs_stack *__restrict__ stacks)
+// One warp per array of more than 64 anchors.  Arrays of up to smem_cap anchors are staged in shared
+// memory, where the serial cycle-leader walk of lane 0 runs at shared-memory instead of L2 latency.
+__global__ void __launch_bounds__(32)
+wm_anchor_sort_big_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__ off, const int32_t *__restrict__ big_ids, int n_big,
+                          wm_rs_range *__restrict__ wl_all, int smem_cap)
 {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_big) return;
-	const int t = big_ids[i];
-	wm_radix_sort_emul(a + off[t], (int)(off[t + 1] - off[t]), stacks + i);
+	extern __shared__ __align__(16) unsigned char wm_sort_smem[];
+	__shared__ wm_rs_warp_ws W;
+	const int lane = threadIdx.x;
+	for (int i = blockIdx.x; i < n_big; i += gridDim.x) {
+		const int t = big_ids[i];
+		const int64_t base = off[t];
+		const int n = (int)(off[t + 1] - base);
+		wm_rs_range *wl = wl_all + (base >> 6) + t;
+		wm128_dev *g = a + base;
+		if (n <= smem_cap) {
+			wm128_dev *s = (wm128_dev*)wm_sort_smem;
+			for (int j = lane; j < n; j += 32) s[j] = g[j];
+			__syncwarp();
+			wm_radix_sort_warp(s, n, &W, wl, lane);
+			for (int j = lane; j < n; j += 32) g[j] = s[j];
+			__syncwarp();
+		} else wm_radix_sort_warp(g, n, &W, wl, lane);
+	}
 }
 
 // sort n_arr arrays (device); h_off is the host copy of the offsets
@@ -146,13 +164,28 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 	if (n_arr <= 0) return;
 	std::vector<int32_t> big;
 	for (int i = 0; i < n_arr; ++i) if (h_off[i + 1] - h_off[i] > WM_RS_MIN_SIZE) big.push_back(i);
+	if (getenv("WM_DP_STATS")) {
+		int64_t mx = 0, n_2k = 0, n_10k = 0;
+		for (int i = 0; i < n_arr; ++i) { int64_t n = h_off[i + 1] - h_off[i]; mx = n > mx ? n : mx; n_2k += n > 2560; n_10k += n > 10240; }
+		fprintf(stderr, "[sort-stats] arrays=%d big=%d >2560:%ld >10240:%ld max=%ld total=%ld\n", n_arr, (int)big.size(), (long)n_2k, (long)n_10k, (long)mx, (long)h_off[n_arr]);
+	}
 	wm_count_launch(); wm_anchor_sort_small_kernel<<<(n_arr + 127) / 128, 128, 0, st>>>(d_a, d_off, n_arr);
 	WM_CUDA_CHECK(cudaGetLastError());
 	if (!big.empty()) {
+		// three launches by size class: the shared-memory stage of the array sets the occupancy
+		const int cap_s = 2048, cap_m = 13312; // 32 KB and 208 KB of anchors
+		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_m * (int)sizeof(wm128_dev)));
+		std::stable_sort(big.begin(), big.end(), [&](int x, int y) { return h_off[x + 1] - h_off[x] > h_off[y + 1] - h_off[y]; });
+		size_t n_l = 0, n_m = 0;
+		while (n_l < big.size() && h_off[big[n_l] + 1] - h_off[big[n_l]] > cap_m) ++n_l;
+		while (n_l + n_m < big.size() && h_off[big[n_l + n_m] + 1] - h_off[big[n_l + n_m]] > cap_s) ++n_m;
+		const size_t n_s = big.size() - n_l - n_m;
 		int32_t *d_big = (int32_t*)ws->big_ids.need(sizeof(int32_t) * big.size());
-		wm_rs_stack *d_stk = (wm_rs_stack*)ws->rs_stacks.need(sizeof(wm_rs_stack) * big.size());
+		wm_rs_range *d_wl = (wm_rs_range*)ws->rs_stacks.need(sizeof(wm_rs_range) * (size_t)((h_off[n_arr] >> 6) + n_arr + 2));
 		WM_CUDA_CHECK(cudaMemcpyAsync(d_big, big.data(), sizeof(int32_t) * big.size(), cudaMemcpyHostToDevice, st));
-		wm_count_launch(); wm_anchor_sort_big_kernel<<<((int)big.size() + 31) / 32, 32, 0, st>>>(d_a, d_off, d_big, (int)big.size(), d_stk);
+		if (n_l) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_l, 32, 0, st>>>(d_a, d_off, d_big, (int)n_l, d_wl, 0); }
+		if (n_m) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_m, 32, cap_m * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, cap_m); }
+		if (n_s) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_s, 32, cap_s * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l + n_m, (int)n_s, d_wl, cap_s); }
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 }
