@@ -68,16 +68,45 @@ def make_batch(contigs, n_reads, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML is polled in-process
+    every 20 ms (an nvidia-smi subprocess takes longer than a short timed region); nvidia-smi is the fallback."""
 
-    def __init__(self, index=0):
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index=0, uuid=None):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.index, self.uuid, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, uuid, [], set(), False, None
+        self.source = None
 
-    def run(self):
+    def _nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid if isinstance(self.uuid, bytes) else self.uuid.encode())
+            except Exception:
+                h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        self.source = "nvml"
+        while not self.stop_flag:
+            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            try:
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for nm, bit in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(nm)
+            time.sleep(0.02)
+
+    def _smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.source = "nvidia-smi"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
@@ -89,12 +118,20 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
+
+    def run(self):
+        try:
+            self._nvml()
+        except Exception:
+            if not self.stop_flag:
+                self._smi()
 
     def result(self):
         self.stop_flag = True
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "source": self.source}
 
 
 def run_reference(refbin, ref, wf, reads_fa, threads):
@@ -233,7 +270,14 @@ def main():
         map_resident(batches[s])
     L.wm_prof_enable(1); L.wm_prof_reset()
     L.wm_dump_timers() if os.environ.get("WM_TIMING") else None
-    sampler = ClockSampler(local); sampler.start()
+    phys, uuid = local, None  # NVML numbers the physical devices: honour CUDA_VISIBLE_DEVICES
+    vis = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+    if local < len(vis):
+        if vis[local].isdigit():
+            phys = int(vis[local])
+        elif vis[local].startswith("GPU-"):
+            uuid = vis[local]
+    sampler = ClockSampler(phys, uuid); sampler.start()
     barrier()
     t_steps, bases = 0.0, 0
     for s in range(a.warmup, a.warmup + a.steps):
@@ -256,6 +300,8 @@ def main():
         t = torch.tensor([t_steps, e2e_t], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         b = torch.tensor([float(bases), float(e2e_b)], device="cuda"); dist.all_reduce(b, op=dist.ReduceOp.SUM)
         t_steps, e2e_t = t.tolist(); bases, e2e_b = b.tolist()
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = {}
@@ -264,7 +310,9 @@ def main():
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
-    ach = prof[3] / (prof[1] * 1e-3) / 1e9 if prof[1] > 0 else 0.0
+    # lanes launch their fill kernels concurrently: the denominator is the time during which at least one of them ran
+    k_ms = prof[7] if prof[7] > 0 else prof[1]
+    ach = prof[3] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     cpu = None
     try:  # the reference beside it, bounded sample, all host cores
         recs = make_batch(contigs, a.cpu_reads, 777)
@@ -281,12 +329,13 @@ def main():
         "metric": "mapped bases/sec", "value": bases / t_steps, "unit": "bases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * t_steps / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
         "config": {"workload": f"{REF_LEN / 1e6:.0f} Mbp random ref, ONT reads N50=20kb 5% err, -x map-ont -W top-0.02% k=15 -c (BASELINE configs[1]); "
-                               f"{a.reads} fresh reads per step per GPU, working set >> L2", "reads_per_step": a.reads, "host_threads": n_thr},
+                               f"{a.reads} fresh reads per step per GPU, working set >> L2", "reads_per_step": a.reads, "host_threads": n_thr,
+                   "lanes": int(os.environ.get("WM_LANES", "4"))},
         "e2e": {"value": e2e_b / e2e_t, "unit": "bases/s", "h2d_bytes_per_step": int(e2e_b / a.steps / world), "d2h_bytes_per_step": int(d2h_b / a.steps)},
         "gpu_launches": int(prof[0]),
         "roofline": {"bound": "hbm", "kernel": "wm_extd2_fill_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": None, "of": "measured" if peaks else "fallback", "launches": int(prof[2]), "kernel_ms": prof[1],
-                     "block_cells_per_s": prof[4] / (prof[1] * 1e-3) if prof[1] > 0 else 0.0,
+                     "traffic": None, "of": "measured" if peaks else "fallback", "launches": int(prof[2]), "kernel_ms": k_ms, "kernel_ms_sum_over_launches": prof[1],
+                     "block_cells_per_s": prof[4] / (k_ms * 1e-3) if k_ms > 0 else 0.0,
                      "jobs": int(prof[5]), "block_cells": prof[4], "frac_cells_in_16x2_path": prof[6] / prof[4] if prof[4] > 0 else 0.0},
         "cpu_baseline": cpu, "clocks": clocks,
         "breakdown_s": {"seed_chain": st["t_seed"], "dp_rounds": st["t_dp"], "host_glue": st["t_host"]},

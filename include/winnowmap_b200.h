@@ -249,7 +249,8 @@ int wm_bench_map_resident(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_threads
 /* bench instrumentation: launch counter and CUDA-event timing of the dominant (DP fill) kernel */
 void wm_prof_enable(int on);
 void wm_prof_reset(void);
-void wm_prof_get(double *out7); /* launches, fill_ms, fill_launches, fill_algorithmic_bytes, fill_block_cells, fill_jobs, cells in the 16x2 path */
+void wm_prof_get(double *out8); /* launches, sum of fill-kernel ms, fill launches, fill algorithmic bytes, fill block cells, fill jobs,
+                                   block cells in the 16x2 path, ms during which at least one fill kernel ran (launches of concurrent lanes overlap) */
 int wm_device_synchronize(void);
 void wm_dump_timers(void); /* prints and resets the orchestration wall-clock accumulators (stderr) */
 

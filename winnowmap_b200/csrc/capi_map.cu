@@ -314,11 +314,13 @@ extern "C" void wm_reset_stats(wm_gpu_ctx_s *c) { memset(&c->stats, 0, sizeof(c-
 
 // ---- bench instrumentation ----
 extern "C" void wm_prof_enable(int on) { g_wm_prof.enabled = on; }
-extern "C" void wm_prof_reset(void) { int e = g_wm_prof.enabled; memset(&g_wm_prof, 0, sizeof(g_wm_prof)); g_wm_prof.enabled = e; }
+extern "C" void wm_prof_reset(void) { int e = g_wm_prof.enabled; memset(&g_wm_prof, 0, sizeof(g_wm_prof)); g_wm_prof.enabled = e; wm_prof_fill_begin(); }
 extern "C" void wm_prof_get(double *o)
-{
+{ // o[0..7]: launches, sum of fill-kernel ms, fill launches, algorithmic bytes, block cells, jobs, block cells in the 16x2 path, union of fill-kernel ms
+	wm_prof_fill_collect();
 	o[0] = (double)g_wm_prof.n_launches; o[1] = g_wm_prof.fill_ms; o[2] = (double)g_wm_prof.fill_launches;
 	o[3] = g_wm_prof.fill_alg_bytes; o[4] = g_wm_prof.fill_cells; o[5] = g_wm_prof.fill_jobs; o[6] = g_wm_prof.fill_cells_v2;
+	o[7] = g_wm_prof.fill_union_ms;
 }
 extern "C" int wm_device_synchronize(void) { WM_CUDA_CHECK(cudaDeviceSynchronize()); return 0; }
 

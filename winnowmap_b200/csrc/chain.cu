@@ -29,6 +29,99 @@ __device__ __forceinline__ int wm_warp_incl_max(int v, int lane)
 	return v;
 }
 
+// score of predecessor j for anchor i (src/chain.c:61-84); false when j is not a candidate
+__device__ __forceinline__ bool wm_chain_score(const wm128_dev aj, uint64_t ri, int32_t qi, int32_t q_span, const wm_chain_params &P, double avg_d, double scale_d, int *sc_out)
+{
+	const int64_t dr = (int64_t)(ri - aj.x);
+	const int32_t dq = qi - (int32_t)aj.y;
+	if (dr == 0 || dq <= 0) return false;
+	if (dq > P.max_dist_y || dq > P.max_dist_x) return false;
+	const int32_t dd = (int32_t)(dr > dq ? dr - dq : dq - dr);
+	if (dd > P.bw) return false;
+	const int32_t min_d = dq < dr ? dq : (int32_t)dr;
+	int sc = min_d > q_span ? q_span : min_d;
+	const int log_dd = dd ? 31 - __clz(dd) : 0;
+	const int gap_cost = (int)__dmul_rn(__dmul_rn((double)dd, .01), avg_d) + (log_dd >> 1);
+	sc -= (int)__dadd_rn(__dmul_rn((double)gap_cost, scale_d), .499);
+	*sc_out = sc;
+	return true;
+}
+
+// replay of the n_skip arithmetic (src/chain.c:85-88) over one 32-predecessor chunk: R = lanes that set a new
+// maximum, K = lanes that hit a t[j]==i mark without setting one.  Returns the lane at which the reference
+// leaves the loop (32 = it does not).
+__device__ __forceinline__ int wm_chain_replay(unsigned R, unsigned K, int *n_skip_io, int max_skip)
+{
+	int n_skip = *n_skip_io, brk = 32;
+	if (K == 0) {
+		n_skip -= __popc(R); if (n_skip < 0) n_skip = 0;
+	} else {
+		unsigned ev = R | K;
+		while (ev) {
+			const int l = __ffs(ev) - 1;
+			ev &= ev - 1;
+			if (R >> l & 1) { if (n_skip > 0) --n_skip; }
+			else if (++n_skip > max_skip) { brk = l; break; }
+		}
+	}
+	*n_skip_io = n_skip;
+	return brk;
+}
+
+// one warp, one task
+__device__ void wm_chain_fill_warp(const wm128_dev *__restrict__ a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	// avg_qspan (src/chain.c:41-42)
+	unsigned long long sum = 0;
+	for (int i = lane; i < n; i += 32) { sum += a[i].y >> 32 & 0xff; t[i] = 0; }
+	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+	const float avg_qspan = __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n));
+	const double avg_d = (double)avg_qspan, scale_d = (double)P.gap_scale;
+	__syncwarp();
+	int st = 0;
+	for (int i = 0; i < n; ++i) {
+		const uint64_t ri = a[i].x;
+		const int32_t qi = (int32_t)a[i].y, q_span = (int32_t)(a[i].y >> 32 & 0xff);
+		while (st < i && ri > a[st].x + (uint64_t)(int64_t)P.max_dist_x) ++st;
+		if (i - st > P.max_iter) // the relaxed window of Winnowmap (src/chain.c:52-55)
+			while (i - st > P.max_iter && ri > a[st].x + (uint64_t)(int64_t)P.min_dist_x) ++st;
+		int max_f = q_span, max_j = -1, n_skip = 0;
+		for (int jb = i - 1; jb >= st; jb -= 32) {
+			const int j = jb - lane;
+			bool cand = false;
+			int sc = INT_MIN, pj = -1;
+			if (j >= st && wm_chain_score(a[j], ri, qi, q_span, P, avg_d, scale_d, &sc)) {
+				sc += f[j]; pj = p[j]; cand = true;
+			}
+			if (cand && pj >= 0) t[pj] = i; // src/chain.c:87 (only indices below every j still to be visited)
+			__syncwarp();
+			const bool marked = cand && t[j] == i;
+			const int incl = wm_warp_incl_max(cand ? sc : INT_MIN, lane);
+			int excl = __shfl_up_sync(FULL, incl, 1);
+			if (lane == 0) excl = INT_MIN;
+			excl = max(excl, max_f);
+			const bool rec = cand && sc > excl;
+			const unsigned R = __ballot_sync(FULL, rec), K = __ballot_sync(FULL, marked && !rec);
+			const int brk = wm_chain_replay(R, K, &n_skip, P.max_skip);
+			const unsigned Rv = brk < 32 ? (R & ((1u << brk) - 1u)) : R;
+			if (Rv) {
+				const int top = 31 - __clz(Rv);
+				max_f = __shfl_sync(FULL, sc, top);
+				max_j = jb - top;
+			}
+			if (brk < 32) break;
+		}
+		if (lane == 0) {
+			f[i] = max_f, p[i] = max_j;
+			const int vj = max_j >= 0 ? v[max_j] : INT_MIN;
+			v[i] = (max_j >= 0 && vj > max_f) ? vj : max_f; // src/chain.c:89
+		}
+		__syncwarp();
+	}
+}
+
+// Tasks come largest first (order[]), one warp per task.
 __global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
 wm_chain_fill_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ order, int n_tasks,
                      wm_chain_params2 PP, const uint8_t *__restrict__ set_id, int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
@@ -45,82 +138,7 @@ wm_chain_fill_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restr
 		const int64_t base = off[task];
 		const int n = (int)(off[task + 1] - base);
 		if (n <= 0) continue;
-		const wm_chain_params P = PP.p[set_id ? set_id[task] : 0];
-		const wm128_dev *a = a_all + base;
-		int32_t *f = f_all + base, *p = p_all + base, *t = t_all + base, *v = v_all + base;
-		// avg_qspan (src/chain.c:41-42)
-		unsigned long long sum = 0;
-		for (int i = lane; i < n; i += 32) { sum += a[i].y >> 32 & 0xff; t[i] = 0; }
-		for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-		const float avg_qspan = __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n));
-		const double avg_d = (double)avg_qspan, scale_d = (double)P.gap_scale;
-		__syncwarp();
-		int st = 0;
-		for (int i = 0; i < n; ++i) {
-			const uint64_t ri = a[i].x;
-			const int32_t qi = (int32_t)a[i].y, q_span = (int32_t)(a[i].y >> 32 & 0xff);
-			while (st < i && ri > a[st].x + (uint64_t)(int64_t)P.max_dist_x) ++st;
-			if (i - st > P.max_iter) // the relaxed window of Winnowmap (src/chain.c:52-55)
-				while (i - st > P.max_iter && ri > a[st].x + (uint64_t)(int64_t)P.min_dist_x) ++st;
-			int max_f = q_span, max_j = -1, n_skip = 0;
-			for (int jb = i - 1; jb >= st; jb -= 32) {
-				const int j = jb - lane;
-				bool cand = false;
-				int sc = INT_MIN, pj = -1;
-				if (j >= st) {
-					const wm128_dev aj = a[j];
-					const int64_t dr = (int64_t)(ri - aj.x);
-					const int32_t dq = qi - (int32_t)aj.y;
-					if (!(dr == 0 || dq <= 0) && !(dq > P.max_dist_y || dq > P.max_dist_x)) {
-						const int32_t dd = (int32_t)(dr > dq ? dr - dq : dq - dr);
-						if (dd <= P.bw) {
-							const int32_t min_d = dq < dr ? dq : (int32_t)dr;
-							sc = min_d > q_span ? q_span : min_d;
-							const int log_dd = dd ? 31 - __clz(dd) : 0;
-							const int gap_cost = (int)__dmul_rn(__dmul_rn((double)dd, .01), avg_d) + (log_dd >> 1);
-							sc -= (int)__dadd_rn(__dmul_rn((double)gap_cost, scale_d), .499);
-							sc += f[j];
-							pj = p[j];
-							cand = true;
-						}
-					}
-				}
-				if (cand && pj >= 0) t[pj] = i; // src/chain.c:87 (only indices below every j still to be visited)
-				__syncwarp();
-				const bool marked = cand && t[j] == i;
-				const int incl = wm_warp_incl_max(cand ? sc : INT_MIN, lane);
-				int excl = __shfl_up_sync(FULL, incl, 1);
-				if (lane == 0) excl = INT_MIN;
-				excl = max(excl, max_f);
-				const bool rec = cand && sc > excl;
-				unsigned R = __ballot_sync(FULL, rec), K = __ballot_sync(FULL, marked && !rec);
-				int brk = 32; // first lane at which the reference breaks out of the j loop
-				if (K == 0) {
-					n_skip -= __popc(R); if (n_skip < 0) n_skip = 0;
-				} else {
-					unsigned ev = R | K;
-					while (ev) {
-						const int l = __ffs(ev) - 1;
-						ev &= ev - 1;
-						if (R >> l & 1) { if (n_skip > 0) --n_skip; }
-						else if (++n_skip > P.max_skip) { brk = l; break; }
-					}
-				}
-				const unsigned Rv = brk < 32 ? (R & ((1u << brk) - 1u)) : R;
-				if (Rv) {
-					const int top = 31 - __clz(Rv);
-					max_f = __shfl_sync(FULL, sc, top);
-					max_j = jb - top;
-				}
-				if (brk < 32) break;
-			}
-			if (lane == 0) {
-				f[i] = max_f, p[i] = max_j;
-				const int vj = max_j >= 0 ? v[max_j] : INT_MIN;
-				v[i] = (max_j >= 0 && vj > max_f) ? vj : max_f; // src/chain.c:89
-			}
-			__syncwarp();
-		}
+		wm_chain_fill_warp(a_all + base, n, PP.p[set_id ? set_id[task] : 0], f_all + base, p_all + base, t_all + base, v_all + base, lane);
 	}
 }
 
@@ -264,7 +282,7 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	int dev = 0, n_sm = 148;
 	WM_CUDA_CHECK(cudaGetDevice(&dev));
 	WM_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-	int grid = n_sm * 8;
+	int grid = n_sm * (32 / WM_CHAIN_WARPS);
 	const int need = (n_tasks + WM_CHAIN_WARPS - 1) / WM_CHAIN_WARPS;
 	if (grid > need) grid = need;
 	wm_rs_stack *stk = (wm_rs_stack*)ws->stacks.need(sizeof(wm_rs_stack) * (size_t)grid * WM_CHAIN_WARPS);

@@ -15,6 +15,9 @@
 // row of the rotated matrix per diagonal; a second kernel walks them back (one thread per
 // job) and emits the CIGAR.
 #include <mutex>
+#include <vector>
+#include <algorithm>
+#include <utility>
 #include "wm_common.cuh"
 
 #define WM_FILL_WARPS 4
@@ -576,7 +579,14 @@ size_t wm_extd2_bt_bytes(int qlen, int tlen, int w)
 }
 
 // jobs/seq/bt/ez/cigar are device pointers; max_tlen = largest tlen among the jobs.
-wm_prof_t g_wm_prof = {0, 0, 0.0, 0, 0.0, 0.0, 0.0, 0.0};
+wm_prof_t g_wm_prof = {0, 0, 0.0, 0, 0.0, 0.0, 0.0, 0.0, 0.0};
+
+#define WM_PROF_SLOTS 65536
+struct wm_prof_launch { cudaEvent_t e0, e1; int slot; };
+static std::vector<wm_prof_launch> g_prof_launches;
+static std::mutex g_prof_mu;
+static cudaEvent_t g_prof_base = 0;
+static unsigned long long *g_prof_cells = 0;
 
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream)
@@ -604,28 +614,72 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_extd2_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	static thread_local cudaEvent_t ev0 = 0, ev1 = 0; // one pair per orchestration thread (each drives its own stream)
-	static std::mutex prof_mutex; // bench mode: fill kernels of concurrent orchestration threads are timed one at a time
+	// bench mode: an event pair and a cell-counter slot per launch, read back by wm_prof_fill_collect(); nothing is
+	// synchronised here, so the timed region runs exactly as it does without profiling
 	const bool prof = g_wm_prof.enabled != 0;
+	wm_prof_launch pl; pl.e0 = pl.e1 = 0; pl.slot = -1;
 	if (prof) {
-		prof_mutex.lock();
-		if (!ev0) { WM_CUDA_CHECK(cudaEventCreate(&ev0)); WM_CUDA_CHECK(cudaEventCreate(&ev1)); }
-		WM_CUDA_CHECK(cudaEventRecord(ev0, stream));
+		std::lock_guard<std::mutex> lk(g_prof_mu);
+		if (!g_prof_cells) { WM_CUDA_CHECK(cudaMalloc((void**)&g_prof_cells, sizeof(unsigned long long) * 2 * WM_PROF_SLOTS)); }
+		if ((int)g_prof_launches.size() < WM_PROF_SLOTS) pl.slot = (int)g_prof_launches.size();
+		if (pl.slot >= 0) {
+			WM_CUDA_CHECK(cudaEventCreate(&pl.e0)); WM_CUDA_CHECK(cudaEventCreate(&pl.e1));
+			cell_ctr = g_prof_cells + 2 * pl.slot;
+			g_prof_launches.push_back(pl);
+		}
+	}
+	if (pl.slot >= 0) {
+		WM_CUDA_CHECK(cudaMemsetAsync(cell_ctr, 0, 2 * sizeof(unsigned long long), stream));
+		WM_CUDA_CHECK(cudaEventRecord(pl.e0, stream));
 	}
 	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, stream>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, counter, use_v2, cell_ctr);
 	WM_CUDA_CHECK(cudaGetLastError());
-	if (prof) WM_CUDA_CHECK(cudaEventRecord(ev1, stream));
+	if (pl.slot >= 0) WM_CUDA_CHECK(cudaEventRecord(pl.e1, stream));
 	wm_count_launch(); wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar);
 	WM_CUDA_CHECK(cudaGetLastError());
-	if (prof) { // bench mode: serialise to read the kernel's own duration
-		float ms = 0.f;
-		WM_CUDA_CHECK(cudaEventSynchronize(ev1));
-		WM_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
-		g_wm_prof.fill_ms += ms; ++g_wm_prof.fill_launches;
-		unsigned long long cells[2] = {0, 0};
-		WM_CUDA_CHECK(cudaMemcpy(cells, cell_ctr, sizeof(cells), cudaMemcpyDeviceToHost));
-		g_wm_prof.fill_cells += (double)(cells[0] + cells[1]); g_wm_prof.fill_alg_bytes += (double)(cells[0] + cells[1]); // 1 B of backtrack per block cell
-		g_wm_prof.fill_cells_v2 += (double)cells[1];
-		prof_mutex.unlock();
+}
+
+// start of a profiled region: a base event on the legacy stream gives all launches a common time axis
+void wm_prof_fill_begin(void)
+{
+	std::lock_guard<std::mutex> lk(g_prof_mu);
+	for (auto &l : g_prof_launches) { cudaEventDestroy(l.e0); cudaEventDestroy(l.e1); }
+	g_prof_launches.clear();
+	if (!g_prof_base) WM_CUDA_CHECK(cudaEventCreate(&g_prof_base));
+	WM_CUDA_CHECK(cudaDeviceSynchronize());
+	WM_CUDA_CHECK(cudaEventRecord(g_prof_base, 0));
+	WM_CUDA_CHECK(cudaEventSynchronize(g_prof_base));
+}
+
+// Fold the recorded launches into g_wm_prof: fill_ms is the sum of the launch durations, fill_union_ms the time during
+// which at least one fill kernel was running (launches of concurrent lanes overlap and slow each other down).
+void wm_prof_fill_collect(void)
+{
+	std::lock_guard<std::mutex> lk(g_prof_mu);
+	if (g_prof_launches.empty()) return;
+	WM_CUDA_CHECK(cudaDeviceSynchronize());
+	std::vector<std::pair<float, float>> iv;
+	std::vector<unsigned long long> cells(2 * g_prof_launches.size());
+	WM_CUDA_CHECK(cudaMemcpy(cells.data(), g_prof_cells, sizeof(unsigned long long) * cells.size(), cudaMemcpyDeviceToHost));
+	for (size_t i = 0; i < g_prof_launches.size(); ++i) {
+		wm_prof_launch &l = g_prof_launches[i];
+		float t0 = 0.f, t1 = 0.f;
+		WM_CUDA_CHECK(cudaEventElapsedTime(&t0, g_prof_base, l.e0));
+		WM_CUDA_CHECK(cudaEventElapsedTime(&t1, g_prof_base, l.e1));
+		iv.push_back(std::make_pair(t0, t1));
+		g_wm_prof.fill_ms += t1 - t0; ++g_wm_prof.fill_launches;
+		const double c = (double)(cells[2 * i] + cells[2 * i + 1]);
+		g_wm_prof.fill_cells += c; g_wm_prof.fill_alg_bytes += c; // 1 B of backtrack per block cell
+		g_wm_prof.fill_cells_v2 += (double)cells[2 * i + 1];
+		cudaEventDestroy(l.e0); cudaEventDestroy(l.e1);
 	}
+	g_prof_launches.clear();
+	std::sort(iv.begin(), iv.end());
+	float cur0 = iv[0].first, cur1 = iv[0].second; double uni = 0;
+	for (size_t i = 1; i < iv.size(); ++i) {
+		if (iv[i].first > cur1) { uni += cur1 - cur0; cur0 = iv[i].first; cur1 = iv[i].second; }
+		else if (iv[i].second > cur1) cur1 = iv[i].second;
+	}
+	uni += cur1 - cur0;
+	g_wm_prof.fill_union_ms += uni;
 }

@@ -22,9 +22,11 @@
 struct wm_prof_t {
 	long long n_launches;
 	int enabled;
-	double fill_ms; long long fill_launches; double fill_alg_bytes, fill_cells, fill_jobs, fill_cells_v2;
+	double fill_ms; long long fill_launches; double fill_alg_bytes, fill_cells, fill_jobs, fill_cells_v2, fill_union_ms;
 };
 extern wm_prof_t g_wm_prof;
+void wm_prof_fill_begin(void);   // ksw_extd2.cu
+void wm_prof_fill_collect(void);
 static inline void wm_count_launch() { __atomic_fetch_add(&g_wm_prof.n_launches, 1LL, __ATOMIC_RELAXED); }
 
 // One extension-DP job; sequences live in a device byte pool (0..4 codes).
