@@ -3,6 +3,7 @@
 // mm_map_file (src/map.c:1244-1276) for PAF output.
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -23,7 +24,8 @@ struct wm_gpu_ctx_s {
 	MapStats stats;
 	double t_index, t_map;
 	int64_t n_keys, n_pos;
-	std::vector<wm_read> resident; // bench: reads already uploaded by wm_bench_upload
+	std::vector<wm_read> resident; // bench: reads already uploaded by wm_bench_upload ...
+	char *d_resident = 0;          // ... their bases, one device pool (wm_read::dev_off)
 	std::vector<Backend*> lanes;   // lanes[0] == be; further lanes share the index and own a stream + workspaces
 	// host copy of the flattened index, kept for the one-time fan-out to the other GPUs (wm_idx_blob_*)
 	std::vector<uint64_t> keys, pos_off, pos;
@@ -65,23 +67,52 @@ static void ensure_lanes(wm_gpu_ctx_s *c)
 static void map_lanes(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const std::vector<const wm_read*> &reads, std::vector<std::vector<wm_reg1_t>> &regs,
                       std::vector<int> &rl, std::vector<int> &fg, int n_threads, bool resident)
 {
+	(void)resident;
 	ensure_lanes(c);
 	const int n = (int)reads.size();
-	int L = (int)c->lanes.size();
-	if (!resident && n < 4 * L) L = 1;
 	regs.assign(n, std::vector<wm_reg1_t>()); rl.assign(n, 0); fg.assign(n, 0);
-	if (L == 1) { map_batch(c->lanes[0], &c->hidx, opt, reads, regs, rl, fg, n_threads, &c->stats, resident); return; }
+	if (n == 0) return;
+	// The reads are cut into chunks of about chunk_bases bases (in input order) that the lanes pull from a shared counter:
+	// a lane that finishes early takes the next chunk, and lanes drift out of phase so that one lane's host glue
+	// overlaps the other lanes' kernels.
+	std::vector<int> cb(1, 0);
+	{
+		// large chunks amortise the per-wave latencies of a batch; two chunks per lane leave room for the lanes to drift apart
+		const char *e = getenv("WM_CHUNK_BASES");
+		int64_t total = 0, acc = 0;
+		for (int i = 0; i < n; ++i) total += (int64_t)reads[i]->seq.size();
+		int64_t chunk_bases = total / (2 * (int64_t)c->lanes.size()) + 1;
+		if (chunk_bases < 4000000) chunk_bases = 4000000;
+		if (chunk_bases > 32000000) chunk_bases = 32000000;
+		if (e && atoll(e) > 0) chunk_bases = atoll(e);
+		for (int i = 0; i < n; ++i) {
+			acc += (int64_t)reads[i]->seq.size();
+			if (acc >= chunk_bases || i == n - 1) { cb.push_back(i + 1); acc = 0; }
+		}
+	}
+	const int n_chunks = (int)cb.size() - 1;
+	int L = (int)c->lanes.size();
+	if (L > n_chunks) L = n_chunks;
+	if (L == 1 && n_chunks == 1) {
+		map_batch(c->lanes[0], &c->hidx, opt, reads, regs, rl, fg, n_threads, &c->stats);
+		wm_dbuf_async = false; // the caller's thread may go on to the one-shot kernel entry points, which allocate synchronously
+		return;
+	}
 	std::vector<MapStats> st(L);
 	std::vector<std::thread> th;
+	std::atomic<int> next(0);
 	const int thr = n_threads / L > 0 ? n_threads / L : 1;
 	for (int l = 0; l < L; ++l) {
 		memset(&st[l], 0, sizeof(MapStats));
 		th.emplace_back([&, l]() {
-			std::vector<const wm_read*> sub;
-			for (int i = l; i < n; i += L) sub.push_back(reads[i]);
-			std::vector<std::vector<wm_reg1_t>> r2; std::vector<int> rl2, fg2;
-			map_batch(c->lanes[l], &c->hidx, opt, sub, r2, rl2, fg2, thr, &st[l], resident);
-			for (size_t k = 0; k < sub.size(); ++k) { const int i = l + (int)k * L; regs[i].swap(r2[k]); rl[i] = rl2[k]; fg[i] = fg2[k]; }
+			for (;;) {
+				const int j = next.fetch_add(1);
+				if (j >= n_chunks) break;
+				std::vector<const wm_read*> sub(reads.begin() + cb[j], reads.begin() + cb[j + 1]);
+				std::vector<std::vector<wm_reg1_t>> r2; std::vector<int> rl2, fg2;
+				map_batch(c->lanes[l], &c->hidx, opt, sub, r2, rl2, fg2, thr, &st[l]);
+				for (size_t k = 0; k < sub.size(); ++k) { const int i = cb[j] + (int)k; regs[i].swap(r2[k]); rl[i] = rl2[k]; fg[i] = fg2[k]; }
+			}
 		});
 	}
 	for (auto &t : th) t.join();
@@ -120,6 +151,7 @@ extern "C" void wm_gpu_destroy(wm_gpu_ctx_s *c)
 	if (!c) return;
 	for (size_t i = 1; i < c->lanes.size(); ++i) gpu_backend_destroy(c->lanes[i]);
 	gpu_backend_destroy(c->be);
+	if (c->d_resident) cudaFree(c->d_resident);
 	delete c;
 }
 
@@ -216,6 +248,7 @@ extern "C" int wm_gpu_map_batch(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, int n_s
 	require_device("wm_gpu_map_batch");
 	std::vector<wm_read> store(n_seq);
 	std::vector<const wm_read*> reads(n_seq);
+	#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads > 0 ? n_threads : 1)
 	for (int i = 0; i < n_seq; ++i) {
 		store[i].name = names && names[i] ? names[i] : "";
 		store[i].seq.assign(seqs[i], lens[i]);
@@ -336,19 +369,23 @@ extern "C" void wm_free_regs(int n, const int32_t *n_reg, wm_reg1_t **reg)
 extern "C" int wm_bench_upload(wm_gpu_ctx_s *c, int n_seq, const char *const *names, const char *const *seqs, const int32_t *lens)
 {
 	c->resident.assign(n_seq, wm_read());
-	std::vector<const wm_read*> reads(n_seq);
+	int64_t tot = 0;
 	for (int i = 0; i < n_seq; ++i) {
 		c->resident[i].name = names && names[i] ? names[i] : "";
 		c->resident[i].seq.assign(seqs[i], lens[i]);
-		reads[i] = &c->resident[i];
+		c->resident[i].dev_off = tot;
+		tot += lens[i];
 	}
 	ensure_lanes(c);
-	const int L = (int)c->lanes.size();
-	for (int l = 0; l < L; ++l) {
-		std::vector<const wm_read*> sub;
-		for (int i = l; i < n_seq; i += L) sub.push_back(reads[i]);
-		c->lanes[l]->begin_batch(sub);
+	WM_CUDA_CHECK(cudaDeviceSynchronize());
+	if (c->d_resident) { WM_CUDA_CHECK(cudaFree(c->d_resident)); c->d_resident = 0; }
+	WM_CUDA_CHECK(cudaMalloc((void**)&c->d_resident, (size_t)tot + 16));
+	{
+		std::vector<char> stage((size_t)tot + 1);
+		for (int i = 0; i < n_seq; ++i) memcpy(stage.data() + c->resident[i].dev_off, seqs[i], lens[i]);
+		WM_CUDA_CHECK(cudaMemcpy(c->d_resident, stage.data(), (size_t)tot, cudaMemcpyHostToDevice));
 	}
+	for (auto *be : c->lanes) be->set_resident_pool(c->d_resident);
 	WM_CUDA_CHECK(cudaDeviceSynchronize());
 	return 0;
 }

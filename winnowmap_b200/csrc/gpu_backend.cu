@@ -101,8 +101,10 @@ struct GpuBackendImpl {
 	const wm_host_idx *hidx;
 	// batch state
 	std::vector<int64_t> read_off; // host
-	wm_dbuf ascii, codes, rcodes, d_read_off;
+	wm_dbuf ascii, codes, rcodes, d_read_off, d_src_off;
 	int64_t n_bases;
+	const char *resident_pool = 0;         // device ASCII of reads that carry a dev_off (bench: inputs resident in HBM)
+	char *h_stage = 0; size_t h_stage_cap = 0; // pinned staging buffer of begin_batch
 	// workspaces
 	wm_sketch_ws sk; wm_seed_ws sd, sd2; wm_chain_ws ch; wm_extd2_ws dpws;
 	wm_dbuf masked, mask_tasks, mask_toff, mask_pool, qlen_buf, pre_buf, cat_tasks, cat_toff, cat_a, set_id, off_buf, nb_off, nu_off, b_out, u_out;
@@ -118,29 +120,71 @@ class GpuBackend : public Backend {
 public:
 	GpuBackendImpl g;
 	GpuBackend() {}
-	~GpuBackend() {}
+	~GpuBackend() { if (g.h_stage) cudaFreeHost(g.h_stage); }
 	void begin_batch(const std::vector<const wm_read*> &reads) override;
+	void set_resident_pool(const char *device_ascii) override { g.resident_pool = device_ascii; }
 	void seed_chain(const std::vector<SeedTask> &tasks, const int32_t *mask_pool, const wm_pair_t *pre_pool, const ChainParams cp[2], int max_occ, std::vector<SeedOut> &out) override;
 	void run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<DpRes> &res) override;
 	void run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<LlRes> &res) override;
 	void end_batch() override {}
 };
 
+// bases of reads scattered over a device ASCII pool -> contiguous 0..4 codes (seq_nt4_table, src/sketch.c:19-36)
+__global__ void wm_gather_code_kernel(const char *__restrict__ pool, const int64_t *__restrict__ src_off, const int64_t *__restrict__ dst_off, int n_reads,
+                                      uint8_t *__restrict__ out, int64_t n)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int lo = 0, hi = n_reads;
+	while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (dst_off[m] <= i) lo = m; else hi = m; }
+	const unsigned char c = (unsigned char)pool[src_off[lo] + (i - dst_off[lo])];
+	uint8_t v;
+	switch (c) {
+		case 'A': case 'a': v = 0; break;
+		case 'C': case 'c': v = 1; break;
+		case 'G': case 'g': v = 2; break;
+		case 'T': case 't': case 'U': case 'u': v = 3; break;
+		default: v = c < 4 ? c : 4;
+	}
+	out[i] = v;
+}
+
 void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
 {
 	WM_CUDA_CHECK(cudaSetDevice(g.device));
+	wm_dbuf_use_stream(g.st);
 	const int n = (int)reads.size();
 	g.read_off.assign(n + 1, 0);
 	for (int i = 0; i < n; ++i) g.read_off[i + 1] = g.read_off[i] + (int64_t)reads[i]->seq.size();
 	g.n_bases = g.read_off[n];
-	char *d_ascii = (char*)g.ascii.need(g.n_bases + 16);
 	uint8_t *d_codes = (uint8_t*)g.codes.need(g.n_bases + 16), *d_rc = (uint8_t*)g.rcodes.need(g.n_bases + 16);
 	int64_t *d_off = (int64_t*)g.d_read_off.need(sizeof(int64_t) * (n + 1));
-	for (int i = 0; i < n; ++i)
-		if (!reads[i]->seq.empty())
-			WM_CUDA_CHECK(cudaMemcpyAsync(d_ascii + g.read_off[i], reads[i]->seq.data(), reads[i]->seq.size(), cudaMemcpyHostToDevice, g.st));
+	bool resident = g.resident_pool != 0;
+	for (int i = 0; i < n && resident; ++i) resident = reads[i]->dev_off >= 0;
 	WM_CUDA_CHECK(cudaMemcpyAsync(d_off, g.read_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, g.st));
-	wm_ascii_to_code(d_ascii, d_codes, g.n_bases, g.st);
+	if (resident) { // the bases are in HBM already: gather + encode on the device
+		std::vector<int64_t> src(n);
+		for (int i = 0; i < n; ++i) src[i] = reads[i]->dev_off;
+		int64_t *d_src = (int64_t*)g.d_src_off.need(sizeof(int64_t) * (n + 1));
+		WM_CUDA_CHECK(cudaMemcpyAsync(d_src, src.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, g.st));
+		if (g.n_bases > 0) {
+			wm_count_launch(); wm_gather_code_kernel<<<(unsigned)((g.n_bases + 255) / 256), 256, 0, g.st>>>(g.resident_pool, d_src, d_off, n, d_codes, g.n_bases);
+			WM_CUDA_CHECK(cudaGetLastError());
+		}
+		WM_CUDA_CHECK(cudaStreamSynchronize(g.st)); // src[] is a local
+	} else { // one host staging buffer (pinned), one copy
+		if ((size_t)g.n_bases + 16 > g.h_stage_cap) {
+			if (g.h_stage) WM_CUDA_CHECK(cudaFreeHost(g.h_stage));
+			g.h_stage_cap = (size_t)(g.n_bases + 16) * 5 / 4;
+			WM_CUDA_CHECK(cudaMallocHost((void**)&g.h_stage, g.h_stage_cap));
+		}
+		WM_CUDA_CHECK(cudaStreamSynchronize(g.st)); // the previous batch's copy out of the staging buffer
+		for (int i = 0; i < n; ++i)
+			if (!reads[i]->seq.empty()) memcpy(g.h_stage + g.read_off[i], reads[i]->seq.data(), reads[i]->seq.size());
+		char *d_ascii = (char*)g.ascii.need(g.n_bases + 16);
+		if (g.n_bases > 0) WM_CUDA_CHECK(cudaMemcpyAsync(d_ascii, g.h_stage, g.n_bases, cudaMemcpyHostToDevice, g.st));
+		wm_ascii_to_code(d_ascii, d_codes, g.n_bases, g.st);
+	}
 	if (g.n_bases > 0) {
 		wm_count_launch(); wm_revcomp_kernel<<<(unsigned)((g.n_bases + 255) / 256), 256, 0, g.st>>>(d_codes, d_rc, d_off, n, g.n_bases);
 		WM_CUDA_CHECK(cudaGetLastError());
@@ -150,6 +194,7 @@ void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
 void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *mask_pool, const wm_pair_t *pre_pool, const ChainParams cp[2], int max_occ, std::vector<SeedOut> &out)
 {
 	WM_CUDA_CHECK(cudaSetDevice(g.device));
+	wm_dbuf_use_stream(g.st);
 	cudaStream_t st = g.st;
 	const int n = (int)tasks.size();
 	out.assign(n, SeedOut());
@@ -378,6 +423,7 @@ __global__ void wm_gather2_kernel(const wm_gather_job *__restrict__ jobs, const 
 void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<DpRes> &res)
 {
 	WM_CUDA_CHECK(cudaSetDevice(g.device));
+	wm_dbuf_use_stream(g.st);
 	cudaStream_t st = g.st;
 	const int n = (int)jobs.size();
 	res.assign(n, DpRes());
@@ -432,6 +478,20 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 				mq = std::max(mq, J.q.len), mt = std::max(mt, J.t.len), mw = std::max(mw, J.w);
 			}
 			fprintf(stderr, "[dp-stats] jobs=%d big=%d max_q=%d max_t=%d max_w=%d band_cells=%.3g big_cells=%.3g bt=%.3g MB\n", m, n_big, mq, mt, mw, cells, big_cells, p_off / 1e6);
+			// histogram of the longest diagonal of a job (in cells), by job count and by band cells
+			const int edges[8] = {16, 32, 64, 128, 256, 512, 1024, 1 << 30};
+			double hc[8] = {0}, hn[8] = {0}; int n_approx = 0;
+			for (int i = 0; i < m; ++i) {
+				const DpJob &J = jobs[done + i];
+				const int ww = J.w < 0 ? std::max(J.q.len, J.t.len) : J.w;
+				const int L = std::min(std::min(J.q.len, J.t.len), ww + 1);
+				int b = 0; while (L > edges[b]) ++b;
+				hn[b] += 1, hc[b] += (double)J.t.len * std::min(J.q.len, 2 * ww + 1);
+				n_approx += (J.flag & 0x08) != 0;
+			}
+			fprintf(stderr, "[dp-hist] approx_max=%d/%d;", n_approx, m);
+			for (int b = 0; b < 8; ++b) fprintf(stderr, " <=%d: %.1f%% jobs %.1f%% cells;", edges[b] > 100000 ? 99999 : edges[b], 100.0 * hn[b] / m, 100.0 * hc[b] / (cells > 0 ? cells : 1));
+			fprintf(stderr, "\n");
 		}
 		double tq0 = Timers::now();
 		wm_gather_job *d_gj = (wm_gather_job*)g.g_jobs.need(sizeof(wm_gather_job) * gj.size());
@@ -494,6 +554,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 void GpuBackend::run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<LlRes> &res)
 {
 	WM_CUDA_CHECK(cudaSetDevice(g.device));
+	wm_dbuf_use_stream(g.st);
 	cudaStream_t st = g.st;
 	const int n = (int)jobs.size();
 	res.assign(n, LlRes());
@@ -561,6 +622,12 @@ Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64
 	WM_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
 	g.bt_budget = free_b / 4; // backtrack matrices of one DP chunk
 	if (g.bt_budget > ((size_t)32 << 30)) g.bt_budget = (size_t)32 << 30;
+	{ // workspaces grow through the stream-ordered allocator (wm_dbuf): keep freed blocks in the pool for reuse
+		cudaMemPool_t pool;
+		uint64_t thr = ~(uint64_t)0;
+		WM_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+		WM_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+	}
 	return be;
 }
 

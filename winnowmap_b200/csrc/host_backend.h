@@ -42,6 +42,7 @@ class Backend {
 public:
 	virtual ~Backend() {}
 	virtual void begin_batch(const std::vector<const wm_read*> &reads) = 0;
+	virtual void set_resident_pool(const char *device_ascii) { (void)device_ascii; } // reads with dev_off >= 0 are taken from here instead of the host
 	virtual void seed_chain(const std::vector<SeedTask> &tasks, const int32_t *mask_pool, const wm_pair_t *pre_pool,
 	                        const ChainParams cp[2], int max_occ, std::vector<SeedOut> &out) = 0;
 	// `wins[job.task]` locates the query window of each job
@@ -58,7 +59,6 @@ struct MapStats { // work counters for the roofline accounting
 // mm_map_frag for every read of a batch (src/map.c:279-974 with n_segs == 1): fills regs[i] (malloc-owned, as the
 // reference returns them), rep_len[i] and frag_gap[i] exactly as worker_for does (src/map.c:1025-1034).
 void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const std::vector<const wm_read*> &reads,
-               std::vector<std::vector<wm_reg1_t>> &regs, std::vector<int> &rep_len, std::vector<int> &frag_gap, int n_threads, MapStats *stats,
-               bool reads_resident = false);
+               std::vector<std::vector<wm_reg1_t>> &regs, std::vector<int> &rep_len, std::vector<int> &frag_gap, int n_threads, MapStats *stats);
 
 } // namespace wmh

@@ -95,8 +95,7 @@ ChainParams chain_params(const wm_mapopt_t *o, const wm_mapopt_t *base, int qlen
 } // namespace
 
 void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const std::vector<const wm_read*> &reads,
-               std::vector<std::vector<wm_reg1_t>> &regs_out, std::vector<int> &rep_len_out, std::vector<int> &frag_gap_out, int n_threads, MapStats *st,
-               bool reads_resident)
+               std::vector<std::vector<wm_reg1_t>> &regs_out, std::vector<int> &rep_len_out, std::vector<int> &frag_gap_out, int n_threads, MapStats *st)
 {
 	const int n_reads = (int)reads.size();
 	regs_out.assign(n_reads, std::vector<wm_reg1_t>());
@@ -112,7 +111,7 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		fprintf(stderr, "[ERROR] winnowmap-b200: single-affine scoring (ksw_extz2) is not built yet\n");
 		exit(1);
 	}
-	if (!reads_resident) be->begin_batch(reads);
+	be->begin_batch(reads);
 
 	// the three option sets of mm_map_frag: stage 1 (src/map.c:300-302), stage 2 (:711-717), fallback (= user options, :857)
 	wm_mapopt_t opt2 = *opt, opt3 = *opt;

@@ -79,4 +79,5 @@ struct wm_read {
 	std::string name, comment;
 	std::string seq;   // ASCII
 	std::string qual;
+	int64_t dev_off = -1; // >= 0: the bases are also resident in the device pool given to Backend::set_resident_pool, at this offset
 };

@@ -229,239 +229,7 @@ __device__ void wm_extd2_fill_job(const wm_dp_job &J, const uint8_t *__restrict_
 	if (lane == 0) { *out = ez; if (cell_ctr) atomicAdd(cell_ctr, cells_acc); }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Second-generation fill for jobs whose state fits the per-warp shared-memory slice (the common gap-fill
-// case): four cells per lane per step, two cells per 32-bit register as signed 16-bit halves, native
-// 16x2 SIMD (VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2).  All DP quantities are kept multiplied by 8: the
-// reference's int8 values (|v| <= 127 by mm_check_opt, src/options.c:169) fit 16 bits without ever wrapping,
-// and the three free low bits carry a tie-break tag so that one max() yields both the best state value and
-// WHICH state produced it, in the reference's tie order (left-aligned: first of equals, :227-234;
-// right-aligned: last of equals, :274-281).  Direction bytes are stored 4 per lane (128 B per warp store).
-// Semantics (block rounding, stale score cells, H tracking, Z-drop) are those of the first-generation code.
-#define WM_V2_T 512      // max tlen16 handled in shared memory
-#define WM_V2_Q 640      // max qlen
-#define WM_V2_SLICE (7 * 2 * (WM_V2_T + 8) + 4 * WM_V2_T + (WM_V2_T + 16) + (WM_V2_Q + 64))
-
-__device__ __forceinline__ uint32_t wm_pack2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
-__device__ __forceinline__ uint32_t wm_rep2(int v) { return wm_pack2(v, v); }
-// prmt.b32 in its default mode: a selector nibble with bit 3 set replicates the sign bit of the selected byte
-// (the __byte_perm intrinsic only defines the low 3 bits of each nibble)
-__device__ __forceinline__ uint32_t wm_prmt(uint32_t a, uint32_t b, uint32_t c)
-{
-	uint32_t d;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-	return d;
-}
-
-__device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
-                                     wm_extz_dev *out, const wm_dp_params &P, uint8_t *S8, int lane, unsigned long long *cell_ctr)
-{
-	unsigned long long cells_acc = 0;
-	const unsigned FULL = 0xffffffffu;
-	const uint8_t *query = seq + J.q_off, *target = seq + J.t_off;
-	const int qlen = J.qlen, tlen = J.tlen, flag = J.flag;
-	int w = J.w;
-	wm_extz_dev ez;
-	ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
-	ez.max = 0, ez.score = ez.mqe = ez.mte = WM_NEG_INF;
-	ez.n_cigar = 0, ez.zdropped = 0, ez.reach_end = 0, ez.reserved = 0;
-	const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2;
-	const bool approx_max = (flag & 0x08) != 0, right = (flag & 0x02) != 0;
-	if (w < 0) w = tlen > qlen ? tlen : qlen;
-	const int tlen16 = (tlen + 15) / 16 * 16;
-	const int n_col16 = wm_ncol16(qlen, tlen, w);
-	const int TS = WM_V2_T + 8; // row stride (entries)
-	int16_t *U = (int16_t*)S8, *V = U + TS, *X = V + TS, *Y = X + TS, *X2 = Y + TS, *Y2 = X2 + TS, *SK = Y2 + TS;
-	int32_t *H = (int32_t*)(SK + TS);
-	uint8_t *tg = (uint8_t*)(H + WM_V2_T);       // target codes, zero padded
-	uint8_t *qr = tg + WM_V2_T + 16 + 16;          // reversed query with 16 zero bytes in front and 32 behind
-	const int TAG_S = right ? 0 : 7, TAG_A = right ? 1 : 6, TAG_B = right ? 2 : 5, TAG_A2 = right ? 3 : 4, TAG_B2 = right ? 4 : 3;
-	const uint32_t QE8 = wm_rep2((q + e) * 8), QE28 = wm_rep2((q2 + e2) * 8), Q8 = wm_rep2(q * 8), Q28 = wm_rep2(q2 * 8), MCH8 = wm_rep2(P.sc_mch * 8);
-	const uint32_t KEY_MCH = wm_rep2(P.sc_mch * 8 + TAG_S), KEY_MIS = wm_rep2(P.sc_mis * 8 + TAG_S), KEY_N = wm_rep2(P.sc_N * 8 + TAG_S);
-	const uint32_t TA = wm_rep2(TAG_A), TB = wm_rep2(TAG_B), TA2 = wm_rep2(TAG_A2), TB2 = wm_rep2(TAG_B2);
-	const uint32_t NQE8 = wm_rep2(-(q + e) * 8), NQE28 = wm_rep2(-(q2 + e2) * 8);
-	const uint32_t NE8P1 = wm_rep2(-e * 8 + 1), NE28P1 = wm_rep2(-e2 * 8 + 1); // "-e - z" as (~z) + (-e + 1)
-	const uint32_t QE8M8 = wm_rep2((q + e) * 8 - 8), QE28M8 = wm_rep2((q2 + e2) * 8 - 8);
-	{
-		const int16_t i1 = (int16_t)(-(q + e) * 8), i2 = (int16_t)(-(q2 + e2) * 8), s0 = (int16_t)TAG_S;
-		for (int i = lane; i < tlen16; i += 32) {
-			U[i] = V[i] = X[i] = Y[i] = i1; X2[i] = Y2[i] = i2; SK[i] = s0;
-			if (!approx_max) H[i] = WM_NEG_INF;
-		}
-		for (int i = lane; i < WM_V2_T + 16; i += 32) tg[i] = i < tlen ? target[i] : 0;
-		for (int i = lane; i < WM_V2_Q + 48; i += 32) { const int j = i - 16; (qr - 16)[i] = (j >= 0 && j < qlen) ? query[qlen - 1 - j] : 0; }
-	}
-	__syncwarp();
-
-	int32_t H0 = 0, last_H0_t = 0;
-	int last_st = -1, last_en = -1;
-	const int n_diag = qlen + tlen - 1;
-	for (int r = 0; r < n_diag; ++r) {
-		const int st0 = wm_band_st(r, qlen, w), en0 = wm_band_en(r, tlen, w);
-		if (st0 > en0) { ez.zdropped = 1; break; }
-		const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
-		cells_acc += (unsigned long long)(en - st + 1);
-		const int lim = st0 + ((en0 - st0) / 16 + 1) * 16; // end of the score refresh (:158)
-		int x1, x21, v1;
-		const int bnd = (r == 0 ? -q - e : r < P.long_thres ? -e : r == P.long_thres ? P.long_diff : -e2) * 8;
-		if (st > 0) {
-			if (st - 1 >= last_st && st - 1 <= last_en) x1 = X[st - 1], x21 = X2[st - 1], v1 = V[st - 1];
-			else x1 = -(q + e) * 8, x21 = -(q2 + e2) * 8, v1 = -(q + e) * 8;
-		} else x1 = -(q + e) * 8, x21 = -(q2 + e2) * 8, v1 = bnd;
-		if (en >= r && lane == 0) { Y[r] = (int16_t)(-(q + e) * 8), Y2[r] = (int16_t)(-(q2 + e2) * 8); U[r] = (int16_t)bnd; }
-		__syncwarp();
-		{
-			// old values of the cell left of this lane's group: from lane-1, or the boundary / previous step for lane 0
-			uint32_t cx = (uint32_t)x1 << 16, cv = (uint32_t)v1 << 16, cx2 = (uint32_t)x21 << 16;
-			uint8_t *pr = bt + J.p_off + (size_t)r * n_col16;
-			const int qoff = qlen - 1 - r; // qr index of cell t is qoff + t
-			const uint32_t LENM1 = wm_rep2(lim - st0 - 1);
-			for (int c = st; c <= en; c += 128) {
-				const int t = c + lane * 4;
-				const bool act = t <= en;
-				uint2 u_, v_, x_, y_, x2_, y2_, s_; // lanes beyond the band keep garbage: nobody consumes it
-				x_.y = v_.y = x2_.y = 0;
-				if (act) {
-					u_ = *(const uint2*)(U + t); v_ = *(const uint2*)(V + t); x_ = *(const uint2*)(X + t); y_ = *(const uint2*)(Y + t);
-					x2_ = *(const uint2*)(X2 + t); y2_ = *(const uint2*)(Y2 + t); s_ = *(const uint2*)(SK + t);
-				}
-				uint32_t px = __shfl_up_sync(FULL, x_.y, 1), pv = __shfl_up_sync(FULL, v_.y, 1), px2 = __shfl_up_sync(FULL, x2_.y, 1);
-				if (lane == 0) px = cx, pv = cv, px2 = cx2;
-				cx = __shfl_sync(FULL, x_.y, 31), cv = __shfl_sync(FULL, v_.y, 31), cx2 = __shfl_sync(FULL, x2_.y, 31);
-				if (act) {
-					// fresh scores for the cells inside [st0, lim); others keep their stale key.  Codes are 0..4, so a byte of
-					// (target ^ query) is non-zero iff adding 0x7f sets its bit 7, and "either is N" is bit 2 of (target | query).
-					{
-						const uint32_t tw = *(const uint32_t*)(tg + t);
-						const int o = qoff + t + 16; // index into (qr - 16)
-						const uint32_t *qw = (const uint32_t*)(qr - 16) + (o >> 2);
-						const uint32_t qv = __funnelshift_r(qw[0], qw[1], (o & 3) * 8);
-						const uint32_t neq = (tw ^ qv) + 0x7f7f7f7fu, nn = (tw | qv) << 5;
-						const int rel = t - st0;
-						const uint32_t idx0 = __byte_perm((uint32_t)rel, (uint32_t)(rel + 1), 0x5410), idx1 = __vadd2(idx0, 0x00020002u);
-						#pragma unroll
-						for (int h = 0; h < 2; ++h) {
-							const uint32_t ne16 = wm_prmt(neq, 0, h ? 0xbbaa : 0x9988), n16 = wm_prmt(nn, 0, h ? 0xbbaa : 0x9988); // sign replicate
-							uint32_t key = KEY_MCH ^ ((KEY_MCH ^ KEY_MIS) & ne16);
-							key = key ^ ((key ^ KEY_N) & n16);
-							const uint32_t idx = h ? idx1 : idx0;
-							const uint32_t oor = wm_prmt(__vsub2(LENM1, idx) | idx, 0, 0xbb99); // 0xffff where the cell is outside [st0, lim)
-							if (h == 0) s_.x = (key & ~oor) | (s_.x & oor); else s_.y = (key & ~oor) | (s_.y & oor);
-						}
-						*(uint2*)(SK + t) = s_;
-					}
-					uint32_t dd[2];
-					uint2 un, vn, xn, yn, x2n, y2n;
-					#pragma unroll
-					for (int h = 0; h < 2; ++h) {
-						const uint32_t uo = h ? u_.y : u_.x, yo = h ? y_.y : y_.x, y2o = h ? y2_.y : y2_.x, sk = h ? s_.y : s_.x;
-						const uint32_t xl = h ? __byte_perm(x_.x, x_.y, 0x5432) : __byte_perm(px, x_.x, 0x5432);
-						const uint32_t vl = h ? __byte_perm(v_.x, v_.y, 0x5432) : __byte_perm(pv, v_.x, 0x5432);
-						const uint32_t x2l = h ? __byte_perm(x2_.x, x2_.y, 0x5432) : __byte_perm(px2, x2_.x, 0x5432);
-						const uint32_t a = __vadd2(xl, vl), b = __vadd2(yo, uo), a2 = __vadd2(x2l, vl), b2 = __vadd2(y2o, uo);
-						uint32_t m = __viaddmax_s16x2(a, TA, sk);
-						m = __viaddmax_s16x2(b, TB, m);
-						m = __viaddmax_s16x2(a2, TA2, m);
-						m = __viaddmax_s16x2(b2, TB2, m);
-						uint32_t z = m & 0xfff8fff8u, dt = m & 0x00070007u;
-						if (!right) dt = 0x00070007u - dt;
-						z = __vmins2(z, MCH8);
-						const uint32_t u1 = __vsub2(z, vl), v1n = __vsub2(z, uo);
-						// x' = max(a - (z - q), 0) - (q + e) = max(a + (-e - z), -(q + e)), likewise the other three (:253-264 / :300-311)
-						// (16x2 subtraction costs three instructions: fold the two's-complement "+1" into constants instead)
-						const uint32_t notz = ~z, nz1 = __vadd2(notz, NE8P1), nz2 = __vadd2(notz, NE28P1); // -e - z, -e2 - z
-						const uint32_t xo = __viaddmax_s16x2(a, nz1, NQE8), yo2 = __viaddmax_s16x2(b, nz1, NQE8);
-						const uint32_t x2o = __viaddmax_s16x2(a2, nz2, NQE28), y2o2 = __viaddmax_s16x2(b2, nz2, NQE28);
-						uint32_t fa, fb, fa2, fb2; // sign bit set <=> continuation flag set
-						if (!right) { // value > 0  <=>  x' > -(q + e)
-							// values are multiples of 8: x' > -(q+e)  <=>  x' + (q+e) - 8 >= 0  <=>  sign bit of ~(x' + (q+e)*8 - 8) is set
-							fa = ~__vadd2(xo, QE8M8); fb = ~__vadd2(yo2, QE8M8); fa2 = ~__vadd2(x2o, QE28M8); fb2 = ~__vadd2(y2o2, QE28M8);
-						} else {      // value >= 0
-							const uint32_t ntq = __vsub2(Q8, z), ntq2 = __vsub2(Q28, z);
-							fa = ~__vadd2(a, ntq); fb = ~__vadd2(b, ntq); fa2 = ~__vadd2(a2, ntq2); fb2 = ~__vadd2(b2, ntq2);
-						}
-						uint32_t fl = dt | ((fa >> 12) & 0x00080008u);
-						fl |= (fb >> 11) & 0x00100010u;
-						fl |= (fa2 >> 10) & 0x00200020u;
-						fl |= (fb2 >> 9) & 0x00400040u;
-						dd[h] = fl;
-						if (h == 0) un.x = u1, vn.x = v1n, xn.x = xo, yn.x = yo2, x2n.x = x2o, y2n.x = y2o2;
-						else un.y = u1, vn.y = v1n, xn.y = xo, yn.y = yo2, x2n.y = x2o, y2n.y = y2o2;
-					}
-					*(uint2*)(U + t) = un; *(uint2*)(V + t) = vn; *(uint2*)(X + t) = xn; *(uint2*)(Y + t) = yn;
-					*(uint2*)(X2 + t) = x2n; *(uint2*)(Y2 + t) = y2n;
-					*(uint32_t*)(pr + (t - st)) = __byte_perm(dd[0], dd[1], 0x6420);
-				}
-			}
-			// the unaligned score refresh may run up to 15 cells past the last computed block (:158-172): those cells
-			// are not computed on this diagonal but keep the refreshed score for later ones
-			for (int i = en + 1 + lane; i < lim && i < tlen16; i += 32) {
-				const int sq = tg[i], sr = qr[qoff + i];
-				SK[i] = (int16_t)(((sq == 4 || sr == 4) ? P.sc_N : (sq == sr ? P.sc_mch : P.sc_mis)) * 8 + TAG_S);
-			}
-		}
-		__syncwarp();
-		if (!approx_max) {
-			int32_t max_H, max_t;
-			if (r > 0) {
-				const int32_t Hm1 = en0 > 0 ? H[en0 - 1] : 0, Hen = H[en0];
-				__syncwarp();
-				const int en1 = st0 + (en0 - st0) / 4 * 4;
-				long long best = (long long)0x8000000000000000LL;
-				for (int t = st0 + lane; t < en0; t += 32) {
-					int32_t h = H[t] + (V[t] >> 3);
-					H[t] = h;
-					uint32_t prio = t < en1 ? 1u + ((uint32_t)((t - st0) & 3) << 24) + (uint32_t)((t - st0) >> 2 << 2)
-					                        : (1u << 27) + (uint32_t)(t - st0);
-					long long key = ((long long)h << 32) | (long long)(0xffffffffu - prio);
-					best = key > best ? key : best;
-				}
-				const int32_t Hn = en0 > 0 ? Hm1 + (U[en0] >> 3) : Hen + (V[en0] >> 3);
-				if (lane == 0) H[en0] = Hn;
-				{
-					long long key = ((long long)Hn << 32) | (long long)0xffffffffu;
-					best = key > best ? key : best;
-				}
-				#pragma unroll
-				for (int o = 16; o; o >>= 1) {
-					long long other = __shfl_xor_sync(FULL, best, o);
-					best = other > best ? other : best;
-				}
-				max_H = (int32_t)(best >> 32);
-				uint32_t prio = 0xffffffffu - (uint32_t)(best & 0xffffffffLL);
-				if (prio == 0) max_t = en0;
-				else if (prio < (1u << 27)) max_t = st0 + (int)((prio - 1) & 0xffffffu) + (int)((prio - 1) >> 24);
-				else max_t = st0 + (int)(prio - (1u << 27));
-				__syncwarp();
-			} else {
-				max_H = (V[0] >> 3) - P.qe_h, max_t = 0;
-				if (lane == 0) H[0] = max_H;
-				__syncwarp();
-			}
-			const int32_t Hen0 = H[en0], Hst0 = H[st0];
-			if (en0 == tlen - 1 && Hen0 > ez.mte) ez.mte = Hen0, ez.mte_q = r - en;
-			if (r - st0 == qlen - 1 && Hst0 > ez.mqe) ez.mqe = Hst0, ez.mqe_t = st0;
-			if (wm_apply_zdrop(ez, max_H, r, max_t, J.zdrop, e2)) break;
-			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
-		} else {
-			if (r > 0) {
-				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
-					int32_t d0 = V[last_H0_t] >> 3, d1 = U[last_H0_t + 1] >> 3;
-					if (d0 > d1) H0 += d0;
-					else H0 += d1, ++last_H0_t;
-				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
-					H0 += V[last_H0_t] >> 3;
-				} else {
-					++last_H0_t, H0 += U[last_H0_t] >> 3;
-				}
-			} else H0 = (V[0] >> 3) - P.qe_h, last_H0_t = 0;
-			if ((flag & 0x10) && wm_apply_zdrop(ez, H0, r, last_H0_t, J.zdrop, e2)) break;
-			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
-		}
-		last_st = st, last_en = en;
-	}
-	if (lane == 0) { *out = ez; if (cell_ctr) atomicAdd(cell_ctr, cells_acc); }
-}
+#include "ksw_extd2_v2.cuh"
 
 __global__ void __launch_bounds__(WM_FILL_WARPS * 32)
 wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
@@ -580,6 +348,8 @@ size_t wm_extd2_bt_bytes(int qlen, int tlen, int w)
 
 // jobs/seq/bt/ez/cigar are device pointers; max_tlen = largest tlen among the jobs.
 wm_prof_t g_wm_prof = {0, 0, 0.0, 0, 0.0, 0.0, 0.0, 0.0, 0.0};
+thread_local cudaStream_t wm_dbuf_stream = 0;
+thread_local bool wm_dbuf_async = false;
 
 #define WM_PROF_SLOTS 65536
 struct wm_prof_launch { cudaEvent_t e0, e1; int slot; };

@@ -60,17 +60,31 @@ static inline T *wm_dev_alloc(size_t n)
 }
 
 // Growable device buffer (never shrinks): pre-sized pools instead of a per-call allocator.
+// Grow-only device buffer.  Growth goes through the stream-ordered allocator on the stream the calling thread
+// declared with wm_dbuf_use_stream() (each orchestration lane drives one stream): unlike cudaFree/cudaMalloc it does
+// not synchronise the device, so one lane growing a workspace does not stall the kernels of the others.
+extern thread_local cudaStream_t wm_dbuf_stream;
+extern thread_local bool wm_dbuf_async;
+static inline void wm_dbuf_use_stream(cudaStream_t st) { wm_dbuf_stream = st; wm_dbuf_async = true; }
 struct wm_dbuf {
-	void *p; size_t cap;
-	wm_dbuf() : p(0), cap(0) {}
+	void *p; size_t cap; bool async; cudaStream_t st;
+	wm_dbuf() : p(0), cap(0), async(false), st(0) {}
+	void drop() {
+		if (!p) return;
+		if (async) WM_CUDA_CHECK(cudaFreeAsync(p, st)); else WM_CUDA_CHECK(cudaFree(p));
+		p = 0, cap = 0;
+	}
 	void *need(size_t bytes) {
 		if (bytes > cap) {
-			if (p) WM_CUDA_CHECK(cudaFree(p));
-			size_t nc = bytes + bytes / 4 + 256;
-			WM_CUDA_CHECK(cudaMalloc(&p, nc));
+			drop();
+			size_t nc = bytes + bytes / 2 + 256;
+			if (wm_dbuf_async) {
+				st = wm_dbuf_stream, async = true;
+				WM_CUDA_CHECK(cudaMallocAsync(&p, nc, st));
+			} else { async = false; WM_CUDA_CHECK(cudaMalloc(&p, nc)); }
 			cap = nc;
 		}
 		return p;
 	}
-	void release() { if (p) cudaFree(p); p = 0; cap = 0; }
+	void release() { if (p) { if (async) cudaFreeAsync(p, st); else cudaFree(p); } p = 0; cap = 0; }
 };
