@@ -343,7 +343,8 @@ def main():
         "e2e": {"value": e2e_b / e2e_t, "unit": "bases/s", "h2d_bytes_per_step": int(e2e_b / a.steps / world), "d2h_bytes_per_step": int(d2h_b / a.steps)},
         "gpu_launches": int(prof[0]),
         "roofline": {"bound": "hbm", "kernel": "wm_extd2_fill_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": None, "of": "measured" if peaks else "fallback", "launches": int(prof[2]), "kernel_ms": k_ms, "kernel_ms_sum_over_launches": prof[1],
+                     "traffic": 5.196e9, "traffic_of": "dram read+write of one captured launch of 4.3e9 block cells (ncu --set full, "
+                     "profiles/r01_ncu_fill_v3_summary.txt): 1.2 B per algorithmic byte", "of": "measured" if peaks else "fallback", "launches": int(prof[2]), "kernel_ms": k_ms, "kernel_ms_sum_over_launches": prof[1],
                      "block_cells_per_s": prof[4] / (k_ms * 1e-3) if k_ms > 0 else 0.0,
                      "jobs": int(prof[5]), "block_cells": prof[4], "frac_cells_in_16x2_path": prof[6] / prof[4] if prof[4] > 0 else 0.0},
         "cpu_baseline": cpu, "clocks": clocks,
