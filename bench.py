@@ -213,7 +213,10 @@ def main():
         if rank != 0:
             ref, wf, contigs = workload(REF_LEN)  # cached files; every rank needs the contigs to draw its own reads
     t0 = time.time()
-    n_thr = max(1, min(int(os.environ.get("WM_HOST_THREADS", 64)), (cores // 2) // max(1, world)))  # physical cores; leave room for CUDA driver threads
+    # one worker per physical core at N=1; with several ranks per node the ranks share the node's hardware threads
+    n_thr = max(1, min(int(os.environ.get("WM_HOST_THREADS", 64)), (cores // 2) // max(1, world)))
+    if "WM_THREADS_PER_RANK" in os.environ:
+        n_thr = max(1, int(os.environ["WM_THREADS_PER_RANK"]))
     if world == 1:
         mp = Mapper(ref, wf, preset="map-ont", cigar=True, device=local, n_threads=n_thr)
     else:

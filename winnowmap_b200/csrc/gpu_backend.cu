@@ -389,6 +389,17 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	}
 }
 
+static inline wm_gather_job make_gather(const GpuBackendImpl &g, const SeqRef &s, const MapWin &w, int64_t dst_off)
+{
+	wm_gather_job j;
+	j.len = s.len, j.reversed = s.reversed, j.pad = 0, j.dst_off = dst_off;
+	const int64_t L = g.read_off[w.read + 1] - g.read_off[w.read];
+	if (s.kind == SEQ_Q0) j.kind = 0, j.src_off = g.read_off[w.read] + w.wb + s.off;
+	else if (s.kind == SEQ_Q1) j.kind = 2, j.src_off = g.read_off[w.read] + (L - w.wb - w.wl) + s.off; // strand 1 of the window is a slice of strand 1 of the read
+	else j.kind = 1, j.src_off = (int64_t)g.hidx->offset[s.rid] + s.off;
+	return j;
+}
+
 // query / target slices of a job -> gather descriptors
 static inline void add_gather(std::vector<wm_gather_job> &gj, std::vector<int64_t> &joff, const GpuBackendImpl &g, const SeqRef &s, const MapWin &w, int64_t *pool_off)
 {
@@ -447,25 +458,43 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		}
 		const int m = end - done;
 		double tp0 = Timers::now();
-		std::vector<wm_gather_job> gj; std::vector<int64_t> joff(1, 0); std::vector<wm_dp_job> dj(m);
-		gj.reserve(2 * m); joff.reserve(2 * m + 1);
+		std::vector<wm_gather_job> gj(2 * (size_t)m); std::vector<int64_t> joff(2 * (size_t)m + 1, 0); std::vector<wm_dp_job> dj(m);
 		int64_t pool_off = 0, p_off = 0, c_off = 0;
 		double prof_bytes = 0;
 		// the persistent warps pull jobs in array order: biggest first, so that the tail of the launch is made of small jobs
+		// (stable counting sort on qlen + tlen, descending)
 		std::vector<int> perm(m);
-		for (int i = 0; i < m; ++i) perm[i] = i;
-		std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) {
-			return jobs[done + x].q.len + jobs[done + x].t.len > jobs[done + y].q.len + jobs[done + y].t.len; });
-		for (int i = 0; i < m; ++i) slot_of[done + perm[i]] = done + i;
+		{
+			int maxk = 0;
+			for (int i = 0; i < m; ++i) maxk = std::max(maxk, jobs[done + i].q.len + jobs[done + i].t.len);
+			std::vector<int> pos(maxk + 2, 0);
+			for (int i = 0; i < m; ++i) ++pos[jobs[done + i].q.len + jobs[done + i].t.len];
+			int acc = 0;
+			for (int k = maxk; k >= 0; --k) { const int c = pos[k]; pos[k] = acc; acc += c; }
+			for (int i = 0; i < m; ++i) perm[pos[jobs[done + i].q.len + jobs[done + i].t.len]++] = i;
+		}
+		// offsets: a serial prefix over the execution order; descriptors: filled in parallel
+		std::vector<int64_t> h_poff(m), h_coff(m);
+		for (int i = 0; i < m; ++i) {
+			const DpJob &J = jobs[done + perm[i]];
+			slot_of[done + perm[i]] = done + i;
+			joff[2 * i] = pool_off; pool_off += J.q.len;
+			joff[2 * i + 1] = pool_off; pool_off += J.t.len;
+			h_poff[i] = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.q.len, J.t.len, J.w);
+			h_coff[i] = c_off; c_off += J.q.len + J.t.len + 2;
+			prof_bytes += 2.0 * (J.q.len + J.t.len) + 48; // SURVEY.md 8d: qlen + tlen (codes in) + (qlen + tlen) (traceback) + 48; C_block is counted on the device
+		}
+		joff[2 * (size_t)m] = pool_off;
+		#pragma omp parallel for schedule(static) num_threads(8)
 		for (int i = 0; i < m; ++i) {
 			const DpJob &J = jobs[done + perm[i]];
 			wm_dp_job &D = dj[i];
-			D.q_off = pool_off; add_gather(gj, joff, g, J.q, wins[J.task], &pool_off);
-			D.t_off = pool_off; add_gather(gj, joff, g, J.t, wins[J.task], &pool_off);
+			D.q_off = joff[2 * i], D.t_off = joff[2 * i + 1];
+			gj[2 * i] = make_gather(g, J.q, wins[J.task], D.q_off);
+			gj[2 * i + 1] = make_gather(g, J.t, wins[J.task], D.t_off);
 			D.qlen = J.q.len, D.tlen = J.t.len, D.w = J.w, D.zdrop = J.zdrop, D.end_bonus = J.end_bonus, D.flag = J.flag;
-			D.p_off = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.q.len, J.t.len, J.w);
-			D.cig_off = c_off; D.cig_cap = J.q.len + J.t.len + 2; c_off += D.cig_cap; D.pad = 0;
-			prof_bytes += 2.0 * (J.q.len + J.t.len) + 48; // SURVEY.md 8d: qlen + tlen (codes in) + (qlen + tlen) (traceback) + 48; C_block is counted on the device
+			D.p_off = h_poff[i];
+			D.cig_off = h_coff[i]; D.cig_cap = J.q.len + J.t.len + 2; D.pad = 0;
 		}
 		g_timers.add("dp.host_prep", Timers::now() - tp0);
 		if (getenv("WM_DP_STATS")) {

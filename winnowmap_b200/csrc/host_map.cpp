@@ -216,15 +216,21 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			}
 			g_timers.add("round.advance", Timers::now() - ta0);
 			double tm0 = Timers::now();
-			dp_jobs.clear(), ll_jobs.clear();
 			std::vector<int> next;
+			size_t n_dp = 0, n_ll = 0;
 			for (int i : active) {
 				MiniMap &M = mm[i];
 				if (!M.aligning) { M.regs.swap(M.at.regs); continue; }
-				M.base_dp = dp_jobs.size(), M.base_ll = ll_jobs.size();
-				dp_jobs.insert(dp_jobs.end(), M.sink.dp.begin(), M.sink.dp.end());
-				ll_jobs.insert(ll_jobs.end(), M.sink.ll.begin(), M.sink.ll.end());
+				M.base_dp = n_dp, M.base_ll = n_ll;
+				n_dp += M.sink.dp.size(), n_ll += M.sink.ll.size();
 				next.push_back(i);
+			}
+			dp_jobs.resize(n_dp), ll_jobs.resize(n_ll);
+			#pragma omp parallel for schedule(static) num_threads(n_threads)
+			for (size_t k = 0; k < next.size(); ++k) {
+				const MiniMap &M = mm[next[k]];
+				std::copy(M.sink.dp.begin(), M.sink.dp.end(), dp_jobs.begin() + M.base_dp);
+				std::copy(M.sink.ll.begin(), M.sink.ll.end(), ll_jobs.begin() + M.base_ll);
 			}
 			active.swap(next);
 			g_timers.add("round.merge_jobs", Timers::now() - tm0);

@@ -1,6 +1,7 @@
 // Tiny named wall-clock accumulators for the orchestration thread (bench / tuning aid; dumped by wm_dump_timers()).
 #pragma once
 #include <chrono>
+#include <time.h>
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
@@ -8,23 +9,25 @@
 namespace wmh {
 struct Timers {
 	enum { MAXT = 48 };
-	const char *name[MAXT]; double sec[MAXT]; long cnt[MAXT]; int n;
+	const char *name[MAXT]; double sec[MAXT], cpu[MAXT]; long cnt[MAXT]; int n;
 	Timers() : n(0) {}
 	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 	std::mutex mu;
-	void add(const char *nm, double dt) {
+	// CPU time of the whole process (all threads): the cost of a phase when a single lane is running (WM_LANES=1)
+	static double cpu_now() { struct timespec ts; clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+	void add(const char *nm, double dt, double dcpu = 0.0) {
 		std::lock_guard<std::mutex> lk(mu);
-		for (int i = 0; i < n; ++i) if (name[i] == nm || strcmp(name[i], nm) == 0) { sec[i] += dt; ++cnt[i]; return; }
-		if (n < MAXT) { name[n] = nm; sec[n] = dt; cnt[n] = 1; ++n; }
+		for (int i = 0; i < n; ++i) if (name[i] == nm || strcmp(name[i], nm) == 0) { sec[i] += dt; cpu[i] += dcpu; ++cnt[i]; return; }
+		if (n < MAXT) { name[n] = nm; sec[n] = dt; cpu[n] = dcpu; cnt[n] = 1; ++n; }
 	}
-	void dump(FILE *fp) { for (int i = 0; i < n; ++i) fprintf(fp, "[timer] %-28s %9.3f ms  n=%ld\n", name[i], sec[i] * 1e3, cnt[i]); }
+	void dump(FILE *fp) { for (int i = 0; i < n; ++i) fprintf(fp, "[timer] %-28s %9.3f ms  cpu %9.3f ms  n=%ld\n", name[i], sec[i] * 1e3, cpu[i] * 1e3, cnt[i]); }
 	void reset() { n = 0; }
 };
 extern Timers g_timers;
 struct ScopedTimer {
-	const char *nm; double t0;
-	ScopedTimer(const char *n_) : nm(n_), t0(Timers::now()) {}
-	~ScopedTimer() { g_timers.add(nm, Timers::now() - t0); }
+	const char *nm; double t0, c0;
+	ScopedTimer(const char *n_) : nm(n_), t0(Timers::now()), c0(Timers::cpu_now()) {}
+	~ScopedTimer() { g_timers.add(nm, Timers::now() - t0, Timers::cpu_now() - c0); }
 };
 }
 #define WM_TIMED(name) wmh::ScopedTimer wm_scoped_timer_##__LINE__(name)
