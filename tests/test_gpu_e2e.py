@@ -40,3 +40,21 @@ def test_paf_matches_reference(name, tmp_path):
     mp.close()
     assert st["n_dp_jobs"] > 0
     assert got == exp, _first_diff(exp, got)
+
+
+@pytest.mark.parametrize("name,chunk,lanes", [("ont_small", 150000, 4), ("ont_sv", 60000, 3)])
+def test_paf_independent_of_lane_chunking(name, chunk, lanes, tmp_path, monkeypatch):
+    """The orchestration lanes pull chunks of reads from a shared queue (csrc/capi_map.cu map_lanes): small chunks force
+    every read set through several concurrent lanes; the output must not depend on the grouping."""
+    from winnowmap_b200.mapper import Mapper
+    monkeypatch.setenv("WM_CHUNK_BASES", str(chunk))
+    monkeypatch.setenv("WM_LANES", str(lanes))
+    m = MANIFEST[name]
+    ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
+    exp = gzip.open(os.path.join(ROOT, "tests", "golden", name + ".paf.gz")).read()
+    mp = Mapper(ref, wfile, preset=m["params"]["preset"], cigar=True)
+    out = str(tmp_path / "out.paf")
+    mp.map_file(reads, out)
+    got = open(out, "rb").read()
+    mp.close()
+    assert got == exp, _first_diff(exp, got)

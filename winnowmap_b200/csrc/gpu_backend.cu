@@ -17,7 +17,7 @@
 struct wm_extd2_ws { wm_dbuf scratch, counter; };
 void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2);
 size_t wm_extd2_bt_bytes(int qlen, int tlen, int w);
-void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, const uint8_t *d_seq, uint8_t *d_bt,
+void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, int max_qlen, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream);
 struct wm_ll_job { int64_t q_off, t_off; int64_t s_off; int32_t qlen, tlen; };
 void wm_ksw_ll_launch(const wm_ll_job *d_jobs, int n, const uint8_t *d_seq, const int8_t *d_mat, int gapo, int gape, int32_t *d_scratch, int32_t *d_out, cudaStream_t st);
@@ -448,12 +448,12 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 	int done = 0;
 	while (done < n) {
 		// a chunk of jobs whose backtrack matrices fit the budget
-		size_t bt_bytes = 0; int end = done; int64_t cig_cap = 0, pool = 0; int max_tlen = 0;
+		size_t bt_bytes = 0; int end = done; int64_t cig_cap = 0, pool = 0; int max_tlen = 0, max_qlen = 0;
 		while (end < n) {
 			const DpJob &J = jobs[end];
 			size_t b = wm_extd2_bt_bytes(J.q.len, J.t.len, J.w);
 			if (end > done && bt_bytes + b > g.bt_budget) break;
-			bt_bytes += b; cig_cap += J.q.len + J.t.len + 2; pool += J.q.len + J.t.len; max_tlen = std::max(max_tlen, J.t.len);
+			bt_bytes += b; cig_cap += J.q.len + J.t.len + 2; pool += J.q.len + J.t.len; max_tlen = std::max(max_tlen, J.t.len); max_qlen = std::max(max_qlen, J.q.len);
 			++end;
 		}
 		const int m = end - done;
@@ -537,7 +537,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
 			WM_CUDA_CHECK(cudaGetLastError());
 		}
-		wm_extd2_launch(&g.dpws, d_dj, m, max_tlen, d_pool, d_bt, d_ez, d_cig, P, st);
+		wm_extd2_launch(&g.dpws, d_dj, m, max_tlen, max_qlen, d_pool, d_bt, d_ez, d_cig, P, st);
 		WM_CUDA_CHECK(cudaMemcpyAsync(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
 		WM_CUDA_CHECK(cudaStreamSynchronize(st));
 		g_timers.add("dp.gpu_fill_bt", Timers::now() - tq0);

@@ -231,9 +231,9 @@ __device__ void wm_extd2_fill_job(const wm_dp_job &J, const uint8_t *__restrict_
 
 #include "ksw_extd2_v2.cuh"
 
-__global__ void __launch_bounds__(WM_FILL_WARPS * 32)
+__global__ void __launch_bounds__(WM_FILL_WARPS * 32, 4)
 wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
-                     wm_extz_dev *__restrict__ ez, wm_dp_params P, int8_t *gscratch, size_t gscratch_stride, int *counter, int use_v2,
+                     wm_extz_dev *__restrict__ ez, wm_dp_params P, int8_t *gscratch, size_t gscratch_stride, int g_tcap, int g_qcap, int *counter, int use_v2,
                      unsigned long long *cell_ctr)
 {
 	extern __shared__ __align__(16) int8_t smem[];
@@ -247,9 +247,10 @@ wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8
 		if (j >= n_jobs) break;
 		const wm_dp_job J = jobs[j];
 		const int tlen16 = (J.tlen + 15) / 16 * 16;
-		if (use_v2 && J.qlen > 0 && J.tlen > 0 && !P.early_out && tlen16 <= WM_V2_T && J.qlen <= WM_V2_Q)
-			wm_extd2_fill_job_v2(J, seq, bt, ez + j, P, (uint8_t*)my_smem, lane, cell_ctr ? cell_ctr + 1 : 0);
-		else
+		if (use_v2 && J.qlen > 0 && J.tlen > 0 && !P.early_out) {
+			if (tlen16 <= WM_V2_T && J.qlen <= WM_V2_Q) wm_extd2_fill_job_v2<true>(J, seq, bt, ez + j, P, (uint8_t*)my_smem, 0, 0, lane, cell_ctr ? cell_ctr + 1 : 0);
+			else wm_extd2_fill_job_v2<false>(J, seq, bt, ez + j, P, (uint8_t*)my_g, g_tcap, g_qcap, lane, cell_ctr ? cell_ctr + 1 : 0);
+		} else
 			wm_extd2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane, cell_ctr);
 		__syncwarp();
 	}
@@ -358,7 +359,7 @@ static std::mutex g_prof_mu;
 static cudaEvent_t g_prof_base = 0;
 static unsigned long long *g_prof_cells = 0;
 
-void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, const uint8_t *d_seq, uint8_t *d_bt,
+void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, int max_qlen, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream)
 {
 	if (n_jobs <= 0) return;
@@ -372,9 +373,11 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 	int grid = n_sm * per_sm;
 	int need = (n_jobs + WM_FILL_WARPS - 1) / WM_FILL_WARPS;
 	if (grid > need) grid = need;
+	// per-warp global state slice for the jobs that do not fit the shared-memory slice
 	size_t stride = 0;
-	int tlen16 = (max_tlen + 15) / 16 * 16;
-	if (tlen16 > WM_SMEM_CELLS) stride = (size_t)tlen16 * 11;
+	const int tlen16 = (max_tlen + 15) / 16 * 16;
+	if (use_v2) { if (tlen16 > WM_V2_T || max_qlen > WM_V2_Q) stride = wm_v2_slice_bytes(tlen16, max_qlen); }
+	else if (tlen16 > WM_SMEM_CELLS) stride = (size_t)tlen16 * 11;
 	int8_t *gs = (int8_t*)ws->scratch.need(stride * grid * WM_FILL_WARPS + 16);
 	int *counter = (int*)ws->counter.need(sizeof(int) + 32);
 	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) + 32, stream));
@@ -402,7 +405,7 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 		WM_CUDA_CHECK(cudaMemsetAsync(cell_ctr, 0, 2 * sizeof(unsigned long long), stream));
 		WM_CUDA_CHECK(cudaEventRecord(pl.e0, stream));
 	}
-	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, stream>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, counter, use_v2, cell_ctr);
+	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, stream>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, tlen16, max_qlen, counter, use_v2, cell_ctr);
 	WM_CUDA_CHECK(cudaGetLastError());
 	if (pl.slot >= 0) WM_CUDA_CHECK(cudaEventRecord(pl.e1, stream));
 	wm_count_launch(); wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar);

@@ -138,9 +138,19 @@ __device__ __forceinline__ void wm_v2_step(const wm_v2_k &K, int c, int lane, in
 	}
 }
 
-__device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
-                                     wm_extz_dev *out, const wm_dp_params &P, uint8_t *S8, int lane, unsigned long long *cell_ctr)
+// bytes of one state slice for jobs of up to tcap (multiple of 16) target and qcap query bases
+__host__ __device__ __forceinline__ size_t wm_v2_slice_bytes(int tcap, int qcap)
 {
+	return ((size_t)7 * 2 * (tcap + 8) + (size_t)4 * tcap + (size_t)(tcap + 16) + (size_t)(qcap + 64) + 15) / 16 * 16;
+}
+
+// SM: the slice S8 is the warp's shared-memory slice (capacity WM_V2_T / WM_V2_Q); otherwise it is an L2-resident global
+// slice sized for (tcap, qcap) -- the same code, for the few jobs that do not fit shared memory.
+template <bool SM>
+__device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
+                                     wm_extz_dev *out, const wm_dp_params &P, uint8_t *S8, int tcap_rt, int qcap_rt, int lane, unsigned long long *cell_ctr)
+{
+	const int tcap = SM ? WM_V2_T : tcap_rt, qcap = SM ? WM_V2_Q : qcap_rt, ts = tcap + 8;
 	const unsigned FULL = 0xffffffffu;
 	const uint8_t *query = seq + J.q_off, *target = seq + J.t_off;
 	const int qlen = J.qlen, tlen = J.tlen, flag = J.flag;
@@ -155,11 +165,11 @@ __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restri
 	const int tlen16 = (tlen + 15) / 16 * 16;
 	const int n_col16 = wm_ncol16(qlen, tlen, w);
 	wm_v2_k K;
-	K.U = (int16_t*)S8, K.V = K.U + WM_V2_TS, K.X = K.V + WM_V2_TS, K.Y = K.X + WM_V2_TS, K.X2 = K.Y + WM_V2_TS, K.Y2 = K.X2 + WM_V2_TS, K.SK = K.Y2 + WM_V2_TS;
+	K.U = (int16_t*)S8, K.V = K.U + ts, K.X = K.V + ts, K.Y = K.X + ts, K.X2 = K.Y + ts, K.Y2 = K.X2 + ts, K.SK = K.Y2 + ts;
 	int16_t *const U = K.U, *const V = K.V, *const X = K.X, *const Y = K.Y, *const X2 = K.X2, *const Y2 = K.Y2, *const SK = K.SK;
-	int32_t *H = (int32_t*)(SK + WM_V2_TS);
-	uint8_t *tg = (uint8_t*)(H + WM_V2_T);       // target codes, zero padded
-	uint8_t *qr = tg + WM_V2_T + 16 + 16;          // reversed query with 16 zero bytes in front and 32 behind
+	int32_t *H = (int32_t*)(SK + ts);
+	uint8_t *tg = (uint8_t*)(H + tcap);          // target codes, zero padded
+	uint8_t *qr = tg + tcap + 16 + 16;             // reversed query with 16 zero bytes in front and 32 behind
 	K.tg = tg, K.qr16 = qr - 16;
 	{
 		const int TAG_S = right ? 0 : 7, TAG_A = right ? 1 : 6, TAG_B = right ? 2 : 5, TAG_A2 = right ? 3 : 4, TAG_B2 = right ? 4 : 3;
@@ -177,8 +187,8 @@ __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restri
 			U[i] = V[i] = X[i] = Y[i] = i1; X2[i] = Y2[i] = i2; SK[i] = s0;
 			if (!approx_max) H[i] = WM_NEG_INF;
 		}
-		for (int i = lane; i < WM_V2_T + 16; i += 32) tg[i] = i < tlen ? target[i] : 0;
-		for (int i = lane; i < WM_V2_Q + 48; i += 32) { const int j = i - 16; (qr - 16)[i] = (j >= 0 && j < qlen) ? query[qlen - 1 - j] : 0; }
+		for (int i = lane; i < tcap + 16; i += 32) tg[i] = i < tlen ? target[i] : 0;
+		for (int i = lane; i < qcap + 48; i += 32) { const int j = i - 16; (qr - 16)[i] = (j >= 0 && j < qlen) ? query[qlen - 1 - j] : 0; }
 	}
 	__syncwarp();
 
