@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -281,56 +283,96 @@ extern "C" int wm_map_file(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const char *
 	FILE *out = out_fn && strcmp(out_fn, "-") ? fopen(out_fn, "wb") : stdout;
 	if (!out) return -1;
 	const double t0 = now_s();
-	std::string line;
-	wm_read pending; bool has_pending = false;
-	int64_t batch_no = 0;
 	const int64_t chunk = opt->mini_batch_size;
-	for (;;) {
-		std::vector<wm_read> batch;
-		int64_t size = 0;
-		wm_read r;
-		while (rd.next(r)) {
-			size += (int64_t)r.seq.size();
-			batch.push_back(r);
-			if (size >= chunk) break;
+	// The three steps of the reference's pipeline (src/map.c:1107-1224: read, map, write) run on three threads with
+	// one mini-batch of slack between them: the next batch is parsed and the previous one formatted while the GPU maps.
+	struct FileBatch {
+		int64_t no;
+		std::vector<wm_read> reads;
+		std::vector<const wm_read*> mine; std::vector<int> mine_pos;          // this rank's reads, in output order
+		std::vector<std::vector<wm_reg1_t>> regs; std::vector<int> rl;        // aligned with `mine`
+	};
+	struct Slot { // a one-element hand-over queue
+		std::mutex mu; std::condition_variable cv; FileBatch *item = 0; bool closed = false;
+		void put(FileBatch *b) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return item == 0; }); item = b; cv.notify_all(); }
+		void close() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return item == 0; }); closed = true; cv.notify_all(); }
+		FileBatch *get() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return item != 0 || closed; }); FileBatch *b = item; item = 0; cv.notify_all(); return b; }
+	} q_in, q_out;
+	std::thread reader([&]() {
+		int64_t batch_no = 0;
+		for (;;) {
+			FileBatch *b = new FileBatch();
+			int64_t size = 0;
+			wm_read r;
+			while (rd.next(r)) {
+				size += (int64_t)r.seq.size();
+				b->reads.push_back(r);
+				if (size >= chunk) break;
+			}
+			if (b->reads.empty()) { delete b; break; }
+			b->no = batch_no++;
+			q_in.put(b);
 		}
-		if (batch.empty()) break;
-		(void)has_pending; (void)pending;
+		q_in.close();
+	});
+	std::thread writer([&]() {
+		std::vector<std::string> lines;
+		for (;;) {
+			FileBatch *b = q_out.get();
+			if (!b) break;
+			const int n = (int)b->mine.size();
+			lines.assign(n, std::string());
+			#pragma omp parallel num_threads(n_threads > 8 ? 8 : (n_threads > 0 ? n_threads : 1))
+			{
+				std::string line; char tag[64];
+				#pragma omp for schedule(dynamic, 16)
+				for (int i = 0; i < n; ++i) {
+					const wm_read *t = b->mine[i];
+					std::string &dst = lines[i];
+					auto emit = [&](const wm_reg1_t *rr) {
+						write_paf(line, &c->hidx, t, rr, opt->flag, b->rl[i]);
+						if (tag_order) { snprintf(tag, sizeof(tag), "%lld\t%d\t", (long long)b->no, b->mine_pos[i]); dst += tag; }
+						dst += line; dst += '\n';
+					};
+					if (!b->regs[i].empty()) {
+						for (size_t j = 0; j < b->regs[i].size(); ++j) {
+							const wm_reg1_t *rr = &b->regs[i][j];
+							if ((opt->flag & WM_F_NO_PRINT_2ND) && rr->id != rr->parent) continue;
+							emit(rr);
+						}
+					} else if (opt->flag & WM_F_PAF_NO_HIT) emit(0);
+					for (auto &rr : b->regs[i]) free(rr.p);
+				}
+			}
+			for (int i = 0; i < n; ++i) fwrite(lines[i].data(), 1, lines[i].size(), out);
+			delete b;
+		}
+	});
+	for (;;) {
+		FileBatch *b = q_in.get();
+		if (!b) break;
 		// longer reads first; ties by larger input index first (std::greater on (len, index), src/map.c:1129)
 		std::vector<std::pair<int, int>> ord;
-		for (size_t i = 0; i < batch.size(); ++i) ord.emplace_back((int)batch[i].seq.size(), (int)i);
+		for (size_t i = 0; i < b->reads.size(); ++i) ord.emplace_back((int)b->reads[i].seq.size(), (int)i);
 		std::sort(ord.begin(), ord.end(), std::greater<std::pair<int, int>>());
-		std::vector<const wm_read*> mine; std::vector<int> mine_pos;
 		for (size_t p = 0; p < ord.size(); ++p)
-			if ((int)(p % (size_t)world) == rank) { mine.push_back(&batch[ord[p].second]); mine_pos.push_back((int)p); }
+			if ((int)(p % (size_t)world) == rank) { b->mine.push_back(&b->reads[ord[p].second]); b->mine_pos.push_back((int)p); }
+		b->regs.resize(b->mine.size()); b->rl.assign(b->mine.size(), 0);
 		// internal sub-batches bound device memory; results do not depend on how reads are grouped
 		size_t s0 = 0;
-		while (s0 < mine.size()) {
+		while (s0 < b->mine.size()) {
 			size_t s1 = s0; int64_t nb = 0;
-			while (s1 < mine.size() && (s1 == s0 || nb + (int64_t)mine[s1]->seq.size() <= max_batch_bases)) nb += (int64_t)mine[s1]->seq.size(), ++s1;
-			std::vector<const wm_read*> sub(mine.begin() + s0, mine.begin() + s1);
+			while (s1 < b->mine.size() && (s1 == s0 || nb + (int64_t)b->mine[s1]->seq.size() <= max_batch_bases)) nb += (int64_t)b->mine[s1]->seq.size(), ++s1;
+			std::vector<const wm_read*> sub(b->mine.begin() + s0, b->mine.begin() + s1);
 			std::vector<std::vector<wm_reg1_t>> regs; std::vector<int> rl, fg;
 			map_lanes(c, opt, sub, regs, rl, fg, n_threads, false);
-			for (size_t i = 0; i < sub.size(); ++i) {
-				const wm_read *t = sub[i];
-				auto emit = [&](const wm_reg1_t *rr) {
-					write_paf(line, &c->hidx, t, rr, opt->flag, rl[i]);
-					if (tag_order) fprintf(out, "%lld\t%d\t", (long long)batch_no, mine_pos[s0 + i]);
-					fwrite(line.data(), 1, line.size(), out); fputc('\n', out);
-				};
-				if (!regs[i].empty()) {
-					for (size_t j = 0; j < regs[i].size(); ++j) {
-						const wm_reg1_t *rr = &regs[i][j];
-						if ((opt->flag & WM_F_NO_PRINT_2ND) && rr->id != rr->parent) continue;
-						emit(rr);
-					}
-				} else if (opt->flag & WM_F_PAF_NO_HIT) emit(0);
-				for (auto &rr : regs[i]) free(rr.p);
-			}
+			for (size_t i = 0; i < sub.size(); ++i) { b->regs[s0 + i].swap(regs[i]); b->rl[s0 + i] = rl[i]; }
 			s0 = s1;
 		}
-		++batch_no;
+		q_out.put(b);
 	}
+	q_out.close();
+	reader.join(); writer.join();
 	if (out != stdout) fclose(out); else fflush(out);
 	c->t_map += now_s() - t0;
 	return 0;
