@@ -6,11 +6,7 @@
 #include "wm_common.cuh"
 #include "../../include/winnowmap_b200.h"
 
-struct wm_extd2_ws { wm_dbuf scratch, counter; };
-void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2);
-size_t wm_extd2_bt_bytes(int qlen, int tlen, int w);
-void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, int max_qlen, const uint8_t *d_seq, uint8_t *d_bt,
-                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream);
+// wm_extd2_ws / wm_extd2_plan / wm_extd2_launch: wm_common.cuh
 
 extern "C" const char *wm_version(void) { return "winnowmap-b200 0.1 (Winnowmap 2.03 semantics)"; }
 
@@ -42,17 +38,15 @@ extern "C" int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qof
 	const int64_t qtot = qoff[n], ttot = toff[n];
 	std::vector<wm_dp_job> jobs(n);
 	int64_t p_off = 0;
-	int max_tlen = 0, max_qlen = 0;
 	for (int i = 0; i < n; ++i) {
 		wm_dp_job &J = jobs[i];
 		J.q_off = qoff[i]; J.t_off = qtot + toff[i];
 		J.qlen = (int32_t)(qoff[i + 1] - qoff[i]); J.tlen = (int32_t)(toff[i + 1] - toff[i]);
 		J.w = w[i]; J.zdrop = zdrop[i]; J.end_bonus = end_bonus[i]; J.flag = flag[i];
 		J.p_off = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.qlen, J.tlen, J.w);
-		J.cig_off = cigar_off[i]; J.cig_cap = (int32_t)(cigar_off[i + 1] - cigar_off[i]); J.pad = 0;
-		if (J.tlen > max_tlen) max_tlen = J.tlen;
-		if (J.qlen > max_qlen) max_qlen = J.qlen;
+		J.cig_off = cigar_off[i]; J.cig_cap = (int32_t)(cigar_off[i + 1] - cigar_off[i]); J.pad = -1;
 	}
+	const wm_extd2_plan_t plan = wm_extd2_plan(jobs.data(), n);
 	uint8_t *d_seq = wm_dev_alloc<uint8_t>(qtot + ttot + 16);
 	uint8_t *d_bt = wm_dev_alloc<uint8_t>(p_off + 16);
 	wm_dp_job *d_jobs = wm_dev_alloc<wm_dp_job>(n);
@@ -63,11 +57,12 @@ extern "C" int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qof
 	WM_CUDA_CHECK(cudaMemcpy(d_jobs, jobs.data(), sizeof(wm_dp_job) * n, cudaMemcpyHostToDevice));
 	wm_dp_params P; wm_dp_params_init(&P, mat, q, e, q2, e2);
 	wm_extd2_ws ws;
-	wm_extd2_launch(&ws, d_jobs, n, max_tlen, max_qlen, d_seq, d_bt, d_ez, d_cig, P, 0);
+	wm_extd2_launch(&ws, d_jobs, n, plan, d_seq, d_bt, d_ez, d_cig, P, 0);
 	WM_CUDA_CHECK(cudaDeviceSynchronize());
 	WM_CUDA_CHECK(cudaMemcpy(ez, d_ez, sizeof(wm_extz_dev) * n, cudaMemcpyDeviceToHost));
 	if (cigar_off[n] > 0) WM_CUDA_CHECK(cudaMemcpy(cigar, d_cig, sizeof(uint32_t) * cigar_off[n], cudaMemcpyDeviceToHost));
-	ws.scratch.release(); ws.counter.release();
+	ws.scratch.release();
+	if (ws.fill_st) { cudaStreamDestroy(ws.fill_st); cudaEventDestroy(ws.ev_ready); cudaEventDestroy(ws.ev_done); }
 	cudaFree(d_seq); cudaFree(d_bt); cudaFree(d_jobs); cudaFree(d_ez); cudaFree(d_cig);
 	return 0;
 }

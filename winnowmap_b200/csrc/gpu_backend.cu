@@ -14,11 +14,7 @@
 #include "host_timers.h"
 
 // from ksw_extd2.cu / ksw_ll.cu
-struct wm_extd2_ws { wm_dbuf scratch, counter; };
-void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2);
-size_t wm_extd2_bt_bytes(int qlen, int tlen, int w);
-void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, int max_qlen, const uint8_t *d_seq, uint8_t *d_bt,
-                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream);
+// (wm_extd2_ws / wm_extd2_plan / wm_extd2_launch are declared in wm_common.cuh)
 struct wm_ll_job { int64_t q_off, t_off; int64_t s_off; int32_t qlen, tlen; };
 void wm_ksw_ll_launch(const wm_ll_job *d_jobs, int n, const uint8_t *d_seq, const int8_t *d_mat, int gapo, int gape, int32_t *d_scratch, int32_t *d_out, cudaStream_t st);
 
@@ -494,8 +490,9 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			gj[2 * i + 1] = make_gather(g, J.t, wins[J.task], D.t_off);
 			D.qlen = J.q.len, D.tlen = J.t.len, D.w = J.w, D.zdrop = J.zdrop, D.end_bonus = J.end_bonus, D.flag = J.flag;
 			D.p_off = h_poff[i];
-			D.cig_off = h_coff[i]; D.cig_cap = J.q.len + J.t.len + 2; D.pad = 0;
+			D.cig_off = h_coff[i]; D.cig_cap = J.q.len + J.t.len + 2; D.pad = -1;
 		}
+		const wm_extd2_plan_t plan = wm_extd2_plan(dj.data(), m);
 		g_timers.add("dp.host_prep", Timers::now() - tp0);
 		if (getenv("WM_DP_STATS")) {
 			int n_big = 0, mq = 0, mt = 0, mw = 0; double cells = 0, big_cells = 0;
@@ -537,7 +534,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
 			WM_CUDA_CHECK(cudaGetLastError());
 		}
-		wm_extd2_launch(&g.dpws, d_dj, m, max_tlen, max_qlen, d_pool, d_bt, d_ez, d_cig, P, st);
+		wm_extd2_launch(&g.dpws, d_dj, m, plan, d_pool, d_bt, d_ez, d_cig, P, st);
 		WM_CUDA_CHECK(cudaMemcpyAsync(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
 		WM_CUDA_CHECK(cudaStreamSynchronize(st));
 		g_timers.add("dp.gpu_fill_bt", Timers::now() - tq0);
@@ -631,7 +628,7 @@ Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64
 	GpuBackend *be = new GpuBackend();
 	GpuBackendImpl &g = be->g;
 	g.device = device; g.hidx = hidx; g.n_bases = 0;
-	WM_CUDA_CHECK(cudaStreamCreate(&g.st));
+	g.st = wm_stream_create_high_priority(); // the DP fill kernels go to a lowest-priority side stream (wm_extd2_launch)
 	const uint64_t n_pos = pos_off[n_keys];
 	uint64_t *d_keys = wm_dev_alloc<uint64_t>(n_keys + 1), *d_poff = wm_dev_alloc<uint64_t>(n_keys + 2), *d_pos = wm_dev_alloc<uint64_t>(n_pos + 1);
 	uint32_t *d_S = wm_dev_alloc<uint32_t>(hidx->S.size() + 4);
@@ -669,7 +666,7 @@ Backend *gpu_backend_clone(Backend *base_, int n_lanes)
 	GpuBackendImpl &g = be->g;
 	g.device = base->g.device; g.hidx = base->g.hidx; g.n_bases = 0;
 	g.ix = base->g.ix; g.bf = base->g.bf;
-	WM_CUDA_CHECK(cudaStreamCreate(&g.st));
+	g.st = wm_stream_create_high_priority(); // the DP fill kernels go to a lowest-priority side stream (wm_extd2_launch)
 	g.bt_budget = base->g.bt_budget / (size_t)(n_lanes > 0 ? n_lanes : 1);
 	return be;
 }

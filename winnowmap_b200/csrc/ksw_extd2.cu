@@ -233,27 +233,25 @@ __device__ void wm_extd2_fill_job(const wm_dp_job &J, const uint8_t *__restrict_
 
 __global__ void __launch_bounds__(WM_FILL_WARPS * 32, 4)
 wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
-                     wm_extz_dev *__restrict__ ez, wm_dp_params P, int8_t *gscratch, size_t gscratch_stride, int g_tcap, int g_qcap, int *counter, int use_v2,
+                     wm_extz_dev *__restrict__ ez, wm_dp_params P, int8_t *gscratch, size_t gscratch_stride, int g_tcap, int g_qcap, int use_v2,
                      unsigned long long *cell_ctr)
 {
+	// One job per warp, four consecutive jobs per CTA: jobs come largest first, so the four are of similar size and the
+	// CTA leaves its SM as soon as they are done (a persistent grid would hold every SM for the whole launch and keep
+	// the short kernels of the other orchestration lanes waiting).
 	extern __shared__ __align__(16) int8_t smem[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	int8_t *my_smem = smem + (size_t)wid * WM_FILL_SLICE;
-	int8_t *my_g = gscratch + (size_t)(blockIdx.x * WM_FILL_WARPS + wid) * gscratch_stride;
-	for (;;) {
-		int j = 0;
-		if (lane == 0) j = atomicAdd(counter, 1);
-		j = __shfl_sync(0xffffffffu, j, 0);
-		if (j >= n_jobs) break;
-		const wm_dp_job J = jobs[j];
-		const int tlen16 = (J.tlen + 15) / 16 * 16;
-		if (use_v2 && J.qlen > 0 && J.tlen > 0 && !P.early_out) {
-			if (tlen16 <= WM_V2_T && J.qlen <= WM_V2_Q) wm_extd2_fill_job_v2<true>(J, seq, bt, ez + j, P, (uint8_t*)my_smem, 0, 0, lane, cell_ctr ? cell_ctr + 1 : 0);
-			else wm_extd2_fill_job_v2<false>(J, seq, bt, ez + j, P, (uint8_t*)my_g, g_tcap, g_qcap, lane, cell_ctr ? cell_ctr + 1 : 0);
-		} else
-			wm_extd2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane, cell_ctr);
-		__syncwarp();
-	}
+	const int j = blockIdx.x * WM_FILL_WARPS + wid;
+	if (j >= n_jobs) return;
+	const wm_dp_job J = jobs[j];
+	int8_t *my_g = J.pad >= 0 ? gscratch + (size_t)J.pad * gscratch_stride : (int8_t*)0;
+	const int tlen16 = (J.tlen + 15) / 16 * 16;
+	if (use_v2 && J.qlen > 0 && J.tlen > 0 && !P.early_out) {
+		if (J.pad < 0) wm_extd2_fill_job_v2<true>(J, seq, bt, ez + j, P, (uint8_t*)my_smem, 0, 0, lane, cell_ctr ? cell_ctr + 1 : 0);
+		else wm_extd2_fill_job_v2<false>(J, seq, bt, ez + j, P, (uint8_t*)my_g, g_tcap, g_qcap, lane, cell_ctr ? cell_ctr + 1 : 0);
+	} else
+		wm_extd2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane, cell_ctr);
 }
 
 // ksw_backtrack (src/ksw2.h:119-151, is_rot = 1, min_intron_len = 0) + the start-cell choice of
@@ -320,7 +318,6 @@ __global__ void wm_extd2_backtrack_kernel(const wm_dp_job *__restrict__ jobs, in
 }
 
 // ---- host-side launcher on device-resident jobs ----
-struct wm_extd2_ws { wm_dbuf scratch, counter; };
 
 void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2)
 { // src/ksw2_extd2_sse.c:61-97
@@ -359,29 +356,54 @@ static std::mutex g_prof_mu;
 static cudaEvent_t g_prof_base = 0;
 static unsigned long long *g_prof_cells = 0;
 
-void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int max_tlen, int max_qlen, const uint8_t *d_seq, uint8_t *d_bt,
+static int wm_use_v2(void)
+{
+	static int use_v2 = -1;
+	if (use_v2 < 0) { const char *e = getenv("WM_DP_V1"); use_v2 = (e && *e == '1') ? 0 : 1; }
+	return use_v2;
+}
+
+wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n)
+{
+	wm_extd2_plan_t pl; pl.n_slots = 0, pl.max_tlen = 0, pl.max_qlen = 0;
+	const int use_v2 = wm_use_v2();
+	for (int i = 0; i < n; ++i) {
+		wm_dp_job &J = h_jobs[i];
+		const int tlen16 = (J.tlen + 15) / 16 * 16;
+		const bool fits = use_v2 ? (tlen16 <= WM_V2_T && J.qlen <= WM_V2_Q) : tlen16 <= WM_SMEM_CELLS;
+		J.pad = fits ? -1 : pl.n_slots++;
+		if (!fits) { if (J.tlen > pl.max_tlen) pl.max_tlen = J.tlen; if (J.qlen > pl.max_qlen) pl.max_qlen = J.qlen; }
+	}
+	return pl;
+}
+
+cudaStream_t wm_stream_create_high_priority(void)
+{
+	int lo = 0, hi = 0;
+	cudaStream_t st;
+	WM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); // numerically: hi <= lo
+	WM_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamDefault, hi));
+	return st;
+}
+
+void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream)
 {
 	if (n_jobs <= 0) return;
-	int dev = 0, n_sm = 148;
-	WM_CUDA_CHECK(cudaGetDevice(&dev));
-	WM_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
 	const size_t smem = (size_t)WM_FILL_WARPS * WM_FILL_SLICE;
-	static int use_v2 = -1;
-	if (use_v2 < 0) { const char *e = getenv("WM_DP_V1"); use_v2 = (e && *e == '1') ? 0 : 1; }
-	int per_sm = 4; // 45 KB of shared memory per block
-	int grid = n_sm * per_sm;
-	int need = (n_jobs + WM_FILL_WARPS - 1) / WM_FILL_WARPS;
-	if (grid > need) grid = need;
-	// per-warp global state slice for the jobs that do not fit the shared-memory slice
-	size_t stride = 0;
-	const int tlen16 = (max_tlen + 15) / 16 * 16;
-	if (use_v2) { if (tlen16 > WM_V2_T || max_qlen > WM_V2_Q) stride = wm_v2_slice_bytes(tlen16, max_qlen); }
-	else if (tlen16 > WM_SMEM_CELLS) stride = (size_t)tlen16 * 11;
-	int8_t *gs = (int8_t*)ws->scratch.need(stride * grid * WM_FILL_WARPS + 16);
-	int *counter = (int*)ws->counter.need(sizeof(int) + 32);
-	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) + 32, stream));
-	unsigned long long *cell_ctr = (unsigned long long*)((char*)counter + 8);
+	const int use_v2 = wm_use_v2();
+	const int grid = (n_jobs + WM_FILL_WARPS - 1) / WM_FILL_WARPS;
+	// global state slices of the jobs that do not fit the shared-memory slice (wm_extd2_plan gave them slots)
+	const int tcap = (plan.max_tlen + 15) / 16 * 16;
+	const size_t stride = plan.n_slots == 0 ? 0 : use_v2 ? wm_v2_slice_bytes(tcap, plan.max_qlen) : (size_t)tcap * 11;
+	int8_t *gs = (int8_t*)ws->scratch.need(stride * (size_t)plan.n_slots + 16);
+	if (!ws->fill_st) {
+		int lo = 0, hi = 0;
+		WM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->fill_st, cudaStreamNonBlocking, lo));
+		WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_ready, cudaEventDisableTiming));
+		WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_done, cudaEventDisableTiming));
+	}
 	static bool attr_set = false;
 	if (!attr_set) {
 		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_extd2_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -390,6 +412,7 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 	// bench mode: an event pair and a cell-counter slot per launch, read back by wm_prof_fill_collect(); nothing is
 	// synchronised here, so the timed region runs exactly as it does without profiling
 	const bool prof = g_wm_prof.enabled != 0;
+	unsigned long long *cell_ctr = 0;
 	wm_prof_launch pl; pl.e0 = pl.e1 = 0; pl.slot = -1;
 	if (prof) {
 		std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -401,13 +424,15 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, int m
 			g_prof_launches.push_back(pl);
 		}
 	}
-	if (pl.slot >= 0) {
-		WM_CUDA_CHECK(cudaMemsetAsync(cell_ctr, 0, 2 * sizeof(unsigned long long), stream));
-		WM_CUDA_CHECK(cudaEventRecord(pl.e0, stream));
-	}
-	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, stream>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, tlen16, max_qlen, counter, use_v2, cell_ctr);
+	if (pl.slot >= 0) WM_CUDA_CHECK(cudaMemsetAsync(cell_ctr, 0, 2 * sizeof(unsigned long long), stream));
+	WM_CUDA_CHECK(cudaEventRecord(ws->ev_ready, stream));
+	WM_CUDA_CHECK(cudaStreamWaitEvent(ws->fill_st, ws->ev_ready, 0));
+	if (pl.slot >= 0) WM_CUDA_CHECK(cudaEventRecord(pl.e0, ws->fill_st));
+	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, ws->fill_st>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, tcap, plan.max_qlen, use_v2, cell_ctr);
 	WM_CUDA_CHECK(cudaGetLastError());
-	if (pl.slot >= 0) WM_CUDA_CHECK(cudaEventRecord(pl.e1, stream));
+	if (pl.slot >= 0) WM_CUDA_CHECK(cudaEventRecord(pl.e1, ws->fill_st));
+	WM_CUDA_CHECK(cudaEventRecord(ws->ev_done, ws->fill_st));
+	WM_CUDA_CHECK(cudaStreamWaitEvent(stream, ws->ev_done, 0));
 	wm_count_launch(); wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar);
 	WM_CUDA_CHECK(cudaGetLastError());
 }

@@ -35,7 +35,7 @@ struct wm_dp_job {
 	int64_t p_off;          // byte offset of this job's backtrack matrix
 	int64_t cig_off;        // uint32 offset of this job's CIGAR buffer
 	int32_t qlen, tlen, w, zdrop, end_bonus, flag;
-	int32_t cig_cap, pad;
+	int32_t cig_cap, pad;   // pad: slot of the job's state rows in the global scratch, -1 = they fit shared memory (wm_extd2_plan)
 };
 
 // Scoring parameters shared by a batch (src/ksw2_extd2_sse.c:61-97)
@@ -88,3 +88,21 @@ struct wm_dbuf {
 	}
 	void release() { if (p) { if (async) cudaFreeAsync(p, st); else cudaFree(p); } p = 0; cap = 0; }
 };
+
+// ---- batched ksw_extd2 on device-resident jobs (ksw_extd2.cu) ----
+// The fill kernel runs on its own lowest-priority stream, ordered against the caller's stream by two events: its
+// CTAs leave the SMs job group by job group, and the short kernels of the other orchestration lanes (created with
+// the highest priority) take the freed slots first instead of queueing behind a whole DP launch.
+struct wm_extd2_ws {
+	wm_dbuf scratch;
+	cudaStream_t fill_st; cudaEvent_t ev_ready, ev_done;
+	wm_extd2_ws() : fill_st(0), ev_ready(0), ev_done(0) {}
+};
+struct wm_extd2_plan_t { int n_slots, max_tlen, max_qlen; };
+void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2);
+size_t wm_extd2_bt_bytes(int qlen, int tlen, int w);
+// sets h_jobs[i].pad (global-scratch slot or -1) for the n jobs of one launch, in launch order
+wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n);
+void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
+                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream);
+cudaStream_t wm_stream_create_high_priority(void);
