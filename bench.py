@@ -342,7 +342,7 @@ def main():
         "ms_per_step": 1e3 * t_steps / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
         "config": {"workload": f"{REF_LEN / 1e6:.0f} Mbp random ref, ONT reads N50=20kb 5% err, -x map-ont -W top-0.02% k=15 -c (BASELINE configs[1]); "
                                f"{a.reads} fresh reads per step per GPU, working set >> L2", "reads_per_step": a.reads, "host_threads": n_thr,
-                   "lanes": int(os.environ.get("WM_LANES", "4"))},
+                   "lanes": int(os.environ.get("WM_LANES", max(2, min(8, n_thr // 8))))},
         "e2e": {"value": e2e_b / e2e_t, "unit": "bases/s", "h2d_bytes_per_step": int(e2e_b / a.steps / world), "d2h_bytes_per_step": int(d2h_b / a.steps)},
         "gpu_launches": int(prof[0]),
         "roofline": {"bound": "hbm", "kernel": "wm_extd2_fill_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

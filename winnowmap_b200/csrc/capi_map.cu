@@ -49,28 +49,29 @@ static void require_device(const char *who)
 // Orchestration lanes: the reads of a batch are dealt round-robin to L lanes that run map_batch concurrently, each on
 // its own host thread and CUDA stream, so that one lane's host glue overlaps another lane's kernels.  Results do not
 // depend on the grouping (reads never interact, src/map.c:1008-1048).
-static int n_lanes_wanted()
-{
+static int n_lanes_wanted(int n_threads)
+{ // one lane per 8 host threads (2..8) unless WM_LANES says otherwise
 	const char *e = getenv("WM_LANES");
-	int n = e ? atoi(e) : 4;
+	int n = e ? atoi(e) : n_threads / 8;
+	if (!e) n = n < 2 ? 2 : n > 8 ? 8 : n;
 	return n < 1 ? 1 : n > 16 ? 16 : n;
 }
 
-static void ensure_lanes(wm_gpu_ctx_s *c)
+static void ensure_lanes(wm_gpu_ctx_s *c, int n_threads)
 {
 	if (!c->lanes.empty()) return;
-	const int L = n_lanes_wanted();
+	const int L = n_lanes_wanted(n_threads);
 	c->lanes.push_back(c->be);
 	const size_t budget = gpu_backend_get_budget(c->be) / (size_t)L;
 	for (int i = 1; i < L; ++i) c->lanes.push_back(gpu_backend_clone(c->be, L));
-	for (int i = 0; i < L; ++i) gpu_backend_set_budget(c->lanes[i], budget);
+	for (int i = 0; i < L; ++i) { gpu_backend_set_budget(c->lanes[i], budget); c->lanes[i]->set_resident_pool(c->d_resident); }
 }
 
 static void map_lanes(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const std::vector<const wm_read*> &reads, std::vector<std::vector<wm_reg1_t>> &regs,
                       std::vector<int> &rl, std::vector<int> &fg, int n_threads, bool resident)
 {
 	(void)resident;
-	ensure_lanes(c);
+	ensure_lanes(c, n_threads);
 	const int n = (int)reads.size();
 	regs.assign(n, std::vector<wm_reg1_t>()); rl.assign(n, 0); fg.assign(n, 0);
 	if (n == 0) return;
@@ -418,7 +419,6 @@ extern "C" int wm_bench_upload(wm_gpu_ctx_s *c, int n_seq, const char *const *na
 		c->resident[i].dev_off = tot;
 		tot += lens[i];
 	}
-	ensure_lanes(c);
 	WM_CUDA_CHECK(cudaDeviceSynchronize());
 	if (c->d_resident) { WM_CUDA_CHECK(cudaFree(c->d_resident)); c->d_resident = 0; }
 	WM_CUDA_CHECK(cudaMalloc((void**)&c->d_resident, (size_t)tot + 16));
