@@ -167,14 +167,14 @@ void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
 			wm_count_launch(); wm_gather_code_kernel<<<(unsigned)((g.n_bases + 255) / 256), 256, 0, g.st>>>(g.resident_pool, d_src, d_off, n, d_codes, g.n_bases);
 			WM_CUDA_CHECK(cudaGetLastError());
 		}
-		WM_CUDA_CHECK(cudaStreamSynchronize(g.st)); // src[] is a local
+		wm_stream_sync(g.st); // src[] is a local
 	} else { // one host staging buffer (pinned), one copy
 		if ((size_t)g.n_bases + 16 > g.h_stage_cap) {
 			if (g.h_stage) WM_CUDA_CHECK(cudaFreeHost(g.h_stage));
 			g.h_stage_cap = (size_t)(g.n_bases + 16) * 5 / 4;
 			WM_CUDA_CHECK(cudaMallocHost((void**)&g.h_stage, g.h_stage_cap));
 		}
-		WM_CUDA_CHECK(cudaStreamSynchronize(g.st)); // the previous batch's copy out of the staging buffer
+		wm_stream_sync(g.st); // the previous batch's copy out of the staging buffer
 		for (int i = 0; i < n; ++i)
 			if (!reads[i]->seq.empty()) memcpy(g.h_stage + g.read_off[i], reads[i]->seq.data(), reads[i]->seq.size());
 		char *d_ascii = (char*)g.ascii.need(g.n_bases + 16);
@@ -266,7 +266,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		WM_CUDA_CHECK(cudaMemcpyAsync(rep.data(), sdp[pass]->rep_len.p, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
 		WM_CUDA_CHECK(cudaMemcpyAsync(pass_mzoff[pass].data(), g.sk.mz_off.p, sizeof(int64_t) * (ns + 1), cudaMemcpyDeviceToHost, st));
 		if (n_mz > 0) WM_CUDA_CHECK(cudaMemcpyAsync(pass_mzpos[pass].data(), sdp[pass]->mini_pos.p, sizeof(uint32_t) * n_mz, cudaMemcpyDeviceToHost, st));
-		WM_CUDA_CHECK(cudaStreamSynchronize(st));
+		wm_stream_sync(st);
 		for (int i = 0; i < ns; ++i) {
 			const int t = ids[i];
 			g.h_rep[t] = rep[i];
@@ -316,7 +316,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 			const wm128_dev *src = d_seed_a[pass] ? d_seed_a[pass] : d_A;
 			wm_count_launch(); wm_concat_kernel<<<(unsigned)((toff.back() + 255) / 256), 256, 0, st>>>(d_ct, d_toff, (int)c2.size(), d_pre, src, d_A, toff.back());
 			WM_CUDA_CHECK(cudaGetLastError());
-			WM_CUDA_CHECK(cudaStreamSynchronize(st)); // c2/toff are reused by the next pass
+			wm_stream_sync(st); // c2/toff are reused by the next pass
 		}
 		// sort #3 (src/map.c:831): only arrays that really merged two sorted runs can change
 		std::vector<int64_t> s_off(n + 1);
@@ -335,7 +335,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 					while (a1 + 1 < which.size() && which[a1 + 1] == which[a1] + 1) ++a1;
 					const int first = which[a0], cnt = (int)(a1 - a0 + 1);
 					wm_anchor_sort_run(&g.sd, d_A, d_foff + first, f_off.data() + first, cnt, st);
-					WM_CUDA_CHECK(cudaStreamSynchronize(st));
+					wm_stream_sync(st);
 					a0 = a1 + 1;
 				}
 			}
@@ -355,7 +355,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	g.h_nu.assign(n, 0); g.h_nb.assign(n, 0);
 	WM_CUDA_CHECK(cudaMemcpyAsync(g.h_nu.data(), g.ch.n_u.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
 	WM_CUDA_CHECK(cudaMemcpyAsync(g.h_nb.data(), g.ch.n_b.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
-	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	wm_stream_sync(st);
 	g_timers.add("seed.chain", Timers::now() - t_chain0);
 	std::vector<int64_t> nb_off(n + 1, 0), nu_off(n + 1, 0);
 	for (int i = 0; i < n; ++i) nb_off[i + 1] = nb_off[i] + g.h_nb[i], nu_off[i + 1] = nu_off[i] + g.h_nu[i];
@@ -369,7 +369,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	g.h_b.resize(nb_off[n] + 1); g.h_u.resize(nu_off[n] + 1);
 	if (nb_off[n] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_b.data(), d_bo, sizeof(wm128_dev) * nb_off[n], cudaMemcpyDeviceToHost, st));
 	if (nu_off[n] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_u.data(), d_uo, sizeof(uint64_t) * nu_off[n], cudaMemcpyDeviceToHost, st));
-	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	wm_stream_sync(st);
 	// 5. per task views
 	g.h_mz_off.assign(n + 1, 0);
 	for (int i = 0; i < n; ++i) g.h_mz_off[i + 1] = g.h_mz_off[i] + mz_cnt[i];
@@ -536,7 +536,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		}
 		wm_extd2_launch(&g.dpws, d_dj, m, plan, d_pool, d_bt, d_ez, d_cig, P, st);
 		WM_CUDA_CHECK(cudaMemcpyAsync(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
-		WM_CUDA_CHECK(cudaStreamSynchronize(st));
+		wm_stream_sync(st);
 		g_timers.add("dp.gpu_fill_bt", Timers::now() - tq0);
 		double tr0 = Timers::now();
 		// compact the CIGARs on the device, then one copy
@@ -554,7 +554,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		const size_t base = g.h_cig.size();
 		g.h_cig.resize(base + o_off[m] + 1);
 		if (o_off[m] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_cig.data() + base, d_cout, sizeof(uint32_t) * o_off[m], cudaMemcpyDeviceToHost, st));
-		WM_CUDA_CHECK(cudaStreamSynchronize(st));
+		wm_stream_sync(st);
 		g.h_cig.resize(base + o_off[m]);
 		for (int i = 0; i < m; ++i) cig_base[done + i] = (int64_t)base + o_off[i];
 		g_timers.add("dp.cigar_d2h", Timers::now() - tr0);
@@ -611,7 +611,7 @@ void GpuBackend::run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin
 	wm_ksw_ll_launch(d_lj, n, d_pool, d_mat, sc.q, sc.e, d_scr, d_out, st);
 	std::vector<int32_t> out(3 * (size_t)n);
 	WM_CUDA_CHECK(cudaMemcpyAsync(out.data(), d_out, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, st));
-	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	wm_stream_sync(st);
 	for (int i = 0; i < n; ++i) res[i].score = out[3 * i], res[i].qe = out[3 * i + 1], res[i].te = out[3 * i + 2];
 }
 
@@ -643,7 +643,7 @@ Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64
 	g.ix.n_keys = n_keys, g.ix.keys = d_keys, g.ix.pos_off = d_poff, g.ix.pos = d_pos, g.ix.S = d_S;
 	wm_idx_dev_build_ht(&g.ix, g.st);
 	wm_bloom_dev_from_table(&g.bf, d_bt, bloom_bits);
-	WM_CUDA_CHECK(cudaStreamSynchronize(g.st));
+	wm_stream_sync(g.st);
 	size_t free_b = 0, total_b = 0;
 	WM_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
 	g.bt_budget = free_b / 4; // backtrack matrices of one DP chunk

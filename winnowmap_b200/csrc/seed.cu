@@ -220,7 +220,7 @@ void wm_seed_run(wm_seed_ws *ws, const wm_idx_dev &ix, const wm128_dev *d_mz, co
 	wm_exclusive_scan(d_cnt, n_mz, d_aoff, d_tmp, st);
 	int64_t n_a = 0;
 	WM_CUDA_CHECK(cudaMemcpyAsync(&n_a, d_aoff + n_mz, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	wm_stream_sync(st);
 	ws->n_a = n_a;
 	wm128_dev *d_a = (wm128_dev*)ws->a.need(sizeof(wm128_dev) * (n_a + 1));
 	if (n_a > 0) {
@@ -230,7 +230,7 @@ void wm_seed_run(wm_seed_ws *ws, const wm_idx_dev &ix, const wm128_dev *d_mz, co
 	wm_count_launch(); wm_seed_task_kernel<<<(n_tasks + 1 + 127) / 128, 128, 0, st>>>(d_mz, d_mz_off, d_aoff, d_nocc, max_occ, n_tasks, d_rep, d_nmp, d_task_a_off, d_mpos);
 	WM_CUDA_CHECK(cudaGetLastError());
 	WM_CUDA_CHECK(cudaMemcpyAsync(h_task_a_off, d_task_a_off, sizeof(int64_t) * (n_tasks + 1), cudaMemcpyDeviceToHost, st));
-	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	wm_stream_sync(st);
 	wm_anchor_sort_run(ws, d_a, d_task_a_off, h_task_a_off, n_tasks, st);
 }
 

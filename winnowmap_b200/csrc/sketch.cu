@@ -315,7 +315,7 @@ void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_co
 	WM_CUDA_CHECK(cudaMemcpyAsync(d_tasks, h_tasks, sizeof(wm_sk_task) * n_tasks, cudaMemcpyHostToDevice, st));
 	WM_CUDA_CHECK(cudaMemcpyAsync(d_off, h_off.data(), sizeof(int64_t) * h_off.size(), cudaMemcpyHostToDevice, st));
 	WM_CUDA_CHECK(cudaMemsetAsync(d_mz_off, 0, sizeof(int64_t) * (n_tasks + 1), st));
-	if (n_bases == 0 || n_tasks == 0) { WM_CUDA_CHECK(cudaStreamSynchronize(st)); return; }
+	if (n_bases == 0 || n_tasks == 0) { wm_stream_sync(st); return; }
 	const int64_t *d_tile_off = d_off, *d_chunk_off = d_off + n_tasks + 1, *d_base_off = d_chunk_off + n_tasks + 1;
 	uint8_t *d_flag = (uint8_t*)ws->flag.need(n_bases);
 	WM_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, n_bases, st));
@@ -340,7 +340,7 @@ void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_co
 	wm_exclusive_scan(d_cnt, n_chunks, d_rank, d_tmp, st);
 	int64_t total = 0;
 	WM_CUDA_CHECK(cudaMemcpyAsync(&total, d_rank + n_chunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-	WM_CUDA_CHECK(cudaStreamSynchronize(st));
+	wm_stream_sync(st);
 	wm128_dev *d_mz = (wm128_dev*)ws->mz.need(sizeof(wm128_dev) * (total + 1));
 	// trailing empty sequences: their offset is the total
 	{

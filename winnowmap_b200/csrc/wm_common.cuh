@@ -106,3 +106,17 @@ wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n);
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream);
 cudaStream_t wm_stream_create_high_priority(void);
+
+// Wait for a stream without burning a core: an orchestration lane spends most of its time waiting for the GPU, and
+// with several lanes per process and several processes per node the spinning waits of cudaStreamSynchronize compete
+// with the OpenMP workers.  (WM_SPIN_SYNC=1 restores the spinning wait.)
+static inline void wm_stream_sync(cudaStream_t st)
+{
+	static thread_local cudaEvent_t ev = 0;
+	static int spin = -1;
+	if (spin < 0) { const char *e = getenv("WM_SPIN_SYNC"); spin = (e && *e == '1') ? 1 : 0; }
+	if (spin) { WM_CUDA_CHECK(cudaStreamSynchronize(st)); return; }
+	if (!ev) WM_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming));
+	WM_CUDA_CHECK(cudaEventRecord(ev, st));
+	WM_CUDA_CHECK(cudaEventSynchronize(ev));
+}
