@@ -200,3 +200,7 @@ extern "C" int wmt_map_file(const char *ref_fn, const char *kmer_fn, const char 
 	wmo_idx_free(be.idx); wmo_bloom_free(bloom);
 	return 0;
 }
+
+#include "../../winnowmap_b200/csrc/host_timers.h"
+// tuning aid: the orchestration's phase timers (WM_SUBTIMING=1 adds the per-task breakdown)
+extern "C" void wmt_dump_timers(void) { wmh::g_timers.dump(stderr); wmh::g_timers.reset(); }

@@ -108,7 +108,7 @@ struct GpuBackendImpl {
 	// host result pools
 	std::vector<uint32_t> h_mzpos; std::vector<int64_t> h_mz_off; std::vector<int32_t> h_rep;
 	std::vector<uint64_t> h_u; std::vector<wm_pair_t> h_b; std::vector<int32_t> h_nu; std::vector<int64_t> h_nb;
-	std::vector<uint32_t> h_cig; std::vector<wm_extz_dev> h_ez;
+	std::vector<uint32_t> h_cig; std::vector<wm_extz_dev> h_ez; std::vector<int32_t> h_zd; wm_dbuf zd;
 	size_t bt_budget;
 };
 
@@ -439,7 +439,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 	wm_dp_params P; wm_dp_params_init(&P, sc.mat, sc.q, sc.e, sc.q2, sc.e2);
 	std::vector<int64_t> cig_base(n + 1, 0); // offsets into h_cig, by execution slot
 	std::vector<int> slot_of(n, 0);           // job -> execution slot (jobs of a chunk run sorted by size)
-	g.h_ez.resize(n);
+	g.h_ez.resize(n); g.h_zd.resize(5 * (size_t)n);
 	std::vector<uint32_t> chunk_cig;
 	int done = 0;
 	while (done < n) {
@@ -534,8 +534,12 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
 			WM_CUDA_CHECK(cudaGetLastError());
 		}
-		wm_extd2_launch(&g.dpws, d_dj, m, plan, d_pool, d_bt, d_ez, d_cig, P, st);
+		int32_t *d_zd = (int32_t*)g.zd.need(sizeof(int32_t) * 5 * (size_t)m);
+		wm_zd_params zp; memset(&zp, 0, sizeof(zp));
+		zp.q = sc.q, zp.e = sc.e; memcpy(zp.mat, sc.mat, 25);
+		wm_extd2_launch(&g.dpws, d_dj, m, plan, d_pool, d_bt, d_ez, d_cig, P, st, &zp, d_zd);
 		WM_CUDA_CHECK(cudaMemcpyAsync(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(cudaMemcpyAsync(g.h_zd.data() + 5 * (size_t)done, d_zd, sizeof(int32_t) * 5 * m, cudaMemcpyDeviceToHost, st));
 		wm_stream_sync(st);
 		g_timers.add("dp.gpu_fill_bt", Timers::now() - tq0);
 		double tr0 = Timers::now();
@@ -574,6 +578,9 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		r.max = e.max, r.zdropped = e.zdropped, r.max_q = e.max_q, r.max_t = e.max_t, r.mqe = e.mqe, r.mqe_t = e.mqe_t;
 		r.mte = e.mte, r.mte_q = e.mte_q, r.score = e.score, r.reach_end = e.reach_end, r.n_cigar = e.n_cigar;
 		r.cigar = g.h_cig.data() + cig_base[s];
+		const int32_t *z = g.h_zd.data() + 5 * (size_t)s;
+		r.has_zd = (jobs[i].flag & WM_DP_SCAN_ZDROP) && z[0] >= 0;
+		if (r.has_zd) r.zd_max = z[0], r.zd_pos[0] = z[1], r.zd_pos[1] = z[2], r.zd_pos[2] = z[3], r.zd_pos[3] = z[4];
 	}
 }
 

@@ -5,25 +5,27 @@
 #include <string.h>
 #include <algorithm>
 #include "host_align.h"
+#include "host_timers.h"
 #include "host_glue.h"
 
 namespace wmh {
 
 #define EZ_RIGHT      0x02
 #define EZ_APPROX_MAX 0x08
+#define EZ_SCAN_ZDROP 0x10000 // not a ksw2 flag: asks the backend for the mm_test_zdrop score walk over the result (DpRes::has_zd)
 #define EZ_EXTZ_ONLY  0x40
 #define EZ_REV_CIGAR  0x80
 
-static inline uint8_t nt4(unsigned char c)
-{ // seq_nt4_table (src/sketch.c:19-36): bytes 0..3 and ACGT/acgt (U/u as T) are bases, everything else 4
-	switch (c) {
-		case 0: case 'A': case 'a': return 0;
-		case 1: case 'C': case 'c': return 1;
-		case 2: case 'G': case 'g': return 2;
-		case 3: case 'T': case 't': case 'U': case 'u': return 3;
-		default: return 4;
+// seq_nt4_table (src/sketch.c:19-36): bytes 0..3 and ACGT/acgt (U/u as T) are bases, everything else 4
+struct Nt4Table {
+	uint8_t t[256];
+	Nt4Table() {
+		for (int i = 0; i < 256; ++i) t[i] = 4;
+		t[0] = t['A'] = t['a'] = 0; t[1] = t['C'] = t['c'] = 1; t[2] = t['G'] = t['g'] = 2; t[3] = t['T'] = t['t'] = t['U'] = t['u'] = 3;
 	}
-}
+};
+static const Nt4Table g_nt4;
+static inline uint8_t nt4(unsigned char c) { return g_nt4.t[c]; }
 
 void gen_simple_mat(int8_t *mat, int8_t a, int8_t b, int8_t sc_ambi)
 { // ksw_gen_simple_mat, src/align.c:9-22 with m = 5
@@ -345,6 +347,8 @@ static inline void adjust_minier(int k, const wm_pair_t *p, int32_t *r, int32_t 
 // everything mm_align1 decides before its first DP (:565-688), plus the speculative job list
 void AlignTask::plan1(Align1 &A, JobSink &sink)
 {
+	static const bool sub_t = getenv("WM_SUBTIMING") != 0;
+	struct PlanTimer { bool on; double t0; PlanTimer(bool o) : on(o), t0(o ? Timers::now() : 0) {} ~PlanTimer() { if (on) g_timers.add("adv.plan1", Timers::now() - t0); } } plan_timer(sub_t);
 	wm_reg1_t *r = &A.r;
 	A.left_job = A.right_job = -1; A.gaps.clear(); A.gap_cur = 0; A.left_done = false; A.dropped = false; A.pending_job = -1; A.captured = false;
 	A.r2.cnt = 0;
@@ -444,7 +448,7 @@ void AlignTask::plan1(Align1 &A, JobSink &sink)
 			j.task = task_id;
 			j.q = SeqRef{ rev ? SEQ_Q1 : SEQ_Q0, 0, qs, qe - qs, 0 };
 			j.t = SeqRef{ SEQ_REF, rid, rs, re - rs, 0 };
-			j.w = g.bw1, j.end_bonus = -1, j.zdrop = opt->zdrop, j.flag = EZ_APPROX_MAX; // first pass (:733)
+			j.w = g.bw1, j.end_bonus = -1, j.zdrop = opt->zdrop, j.flag = EZ_APPROX_MAX | EZ_SCAN_ZDROP; // first pass (:733)
 			g.job = (int)sink.dp.size();
 			sink.dp.push_back(j);
 			A.gaps.push_back(g);
@@ -501,6 +505,8 @@ bool AlignTask::walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink
 	wm_reg1_t *r = &A.r;
 	if (A.state == 9) return true;
 	const int rev = A.rev, rid = A.rid;
+	static const bool sub_w = getenv("WM_SUBTIMING") != 0;
+	const double w0 = sub_w ? Timers::now() : 0;
 	if (!A.captured) { // keep the pass-1 results: later rounds reuse the result buffers
 		size_t tot = 0;
 		if (A.left_job >= 0) tot += dp[A.left_job].n_cigar > 0 ? dp[A.left_job].n_cigar : 0;
@@ -518,6 +524,7 @@ bool AlignTask::walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink
 		for (auto &g : A.gaps) grab(g.job, g.res, g.cig_off);
 		A.captured = true;
 	}
+	if (sub_w) g_timers.add("walk.capture", Timers::now() - w0);
 	if (!A.left_done) { // :690-708
 		if (A.left_job >= 0) {
 			DpRes ez = A.left_res; ez.cigar = A.cig_pool.data() + A.left_cig;
@@ -535,10 +542,18 @@ bool AlignTask::walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink
 		DpRes ez;
 		int zdrop_code = 0;
 		if (A.state == 1) { // first-pass result just arrived: test Z-drop (:736)
-			tbuf.resize(g.re - g.rs);
-			mi->getseq(rid, g.rs, g.re, tbuf.data());
-			int pos[2][2];
-			const int max_zdrop = zdrop_scan(opt, qs_ptr, tbuf.data(), g.res.n_cigar, A.cig_pool.data() + g.cig_off, mat, pos);
+			static const bool sub_t = getenv("WM_SUBTIMING") != 0;
+			const double q0 = sub_t ? Timers::now() : 0;
+			int pos[2][2], max_zdrop;
+			if (g.res.has_zd) { // the device walked the CIGAR right after the traceback
+				max_zdrop = g.res.zd_max;
+				pos[0][0] = g.res.zd_pos[0], pos[0][1] = g.res.zd_pos[1], pos[1][0] = g.res.zd_pos[2], pos[1][1] = g.res.zd_pos[3];
+			} else {
+				tbuf.resize(g.re - g.rs);
+				mi->getseq(rid, g.rs, g.re, tbuf.data());
+				max_zdrop = zdrop_scan(opt, qs_ptr, tbuf.data(), g.res.n_cigar, A.cig_pool.data() + g.cig_off, mat, pos);
+			}
+			if (sub_t) g_timers.add("adv.zdrop_scan", Timers::now() - q0);
 			const int q_len = pos[1][1] - pos[1][0], t_len = pos[0][1] - pos[0][0];
 			A.zd_max_zdrop = max_zdrop;
 			if (!(opt->flag & (WM_F_SPLICE | WM_F_SR | WM_F_FOR_ONLY | WM_F_REV_ONLY)) && max_zdrop > opt->zdrop_inv && q_len < opt->max_gap && t_len < opt->max_gap) {
@@ -578,7 +593,9 @@ bool AlignTask::walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink
 			return false;
 		} else { ez = g.res; ez.cigar = A.cig_pool.data() + g.cig_off; }
 		// :739-765
+		const double w1 = sub_w ? Timers::now() : 0;
 		if (ez.n_cigar > 0) append_cigar(r, ez.n_cigar, ez.cigar);
+		if (sub_w) g_timers.add("walk.append", Timers::now() - w1);
 		if (ez.zdropped) {
 			if (!r->p) {
 				uint32_t capacity = round_up_pow2((uint32_t)(sizeof(wm_extra_t) / 4));
@@ -615,9 +632,12 @@ bool AlignTask::walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink
 	if (rev) r->qs = qlen - A.qe1, r->qe = qlen - A.qs1;
 	else r->qs = A.qs1, r->qe = A.qe1;
 	if (r->p) {
+		static const bool sub_t2 = getenv("WM_SUBTIMING") != 0;
+		const double q0 = sub_t2 ? Timers::now() : 0;
 		tbuf.resize(A.re1 > A.rs1 ? A.re1 - A.rs1 : 0);
 		if (A.re1 > A.rs1) mi->getseq(rid, A.rs1, A.re1, tbuf.data());
 		update_extra(r, qseq(r->rev) + A.qs1, tbuf.data(), mat, (int8_t)opt->q, (int8_t)opt->e, (int)(opt->flag & WM_F_EQX));
+		if (sub_t2) g_timers.add("adv.update_extra", Timers::now() - q0);
 	}
 	A.state = 9;
 	return true;
@@ -726,17 +746,22 @@ bool AlignTask::step_phase2(const DpRes *dp, const LlRes *ll, JobSink &sink)
 
 bool AlignTask::advance(const DpRes *dp, const LlRes *ll, JobSink &sink)
 {
+	static const bool sub_t = getenv("WM_SUBTIMING") != 0;
 	if (phase == 0) {
+		const double q0 = sub_t ? Timers::now() : 0;
 		firsts.resize(regs.size());
 		for (size_t i = 0; i < regs.size(); ++i) { firsts[i] = Align1(); firsts[i].r = regs[i]; firsts[i].state = 0; plan1(firsts[i], sink); }
 		phase = 1;
 		bool all = true;
 		for (auto &A : firsts) if (A.state != 9) all = false;
+		if (sub_t) g_timers.add("adv.phase0", Timers::now() - q0);
 		if (!all) return false;
 	}
 	if (phase == 1) {
+		const double q0 = sub_t ? Timers::now() : 0;
 		bool all = true;
 		for (auto &A : firsts) if (!walk1(A, dp, ll, sink)) all = false;
+		if (sub_t) g_timers.add("adv.walk1", Timers::now() - q0);
 		if (!all) return false;
 		out.clear(); from_first.clear();
 		for (auto &A : firsts) {
@@ -747,7 +772,10 @@ bool AlignTask::advance(const DpRes *dp, const LlRes *ll, JobSink &sink)
 		phase = 2; cur = 0; sub = 0;
 	}
 	if (phase == 2) {
-		if (!step_phase2(dp, ll, sink)) return false;
+		const double q0 = sub_t ? Timers::now() : 0;
+		const bool fin = step_phase2(dp, ll, sink);
+		if (sub_t) g_timers.add("adv.phase2", Timers::now() - q0);
+		if (!fin) return false;
 		regs.swap(out);
 		filter_regs(opt, qlen, regs); // :916-917
 		hit_sort(regs, opt->alt_drop);

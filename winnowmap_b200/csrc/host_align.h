@@ -28,6 +28,8 @@ struct DpJob { // one ksw_extd2 call (mm_align_pair, src/align.c:313-339)
 struct DpRes { // ksw_extz_t (src/ksw2.h:23-32)
 	int32_t max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar;
 	const uint32_t *cigar;
+	// optional: the backend already did the score walk of mm_test_zdrop over the CIGAR (jobs flagged EZ_SCAN_ZDROP)
+	int32_t has_zd, zd_max, zd_pos[4]; // pos = {t0, t1, q0, q1}
 };
 
 struct LlJob { // one ksw_ll_qinit + ksw_ll_i16 (src/ksw2_ll_sse.c:32,80)

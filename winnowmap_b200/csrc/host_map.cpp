@@ -182,6 +182,8 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			const wm_read *rd = reads[M.win.read];
 			wins[i] = M.win;
 			M.rep_len = o.rep_len;
+			static const bool sub_t = getenv("WM_SUBTIMING") != 0;
+			double q0 = sub_t ? Timers::now() : 0;
 			M.a.assign(o.b, o.b + o.n_b);
 			M.u.assign(o.u, o.u + o.n_u);
 			M.mini_pos.clear();
@@ -191,12 +193,17 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			M.hash = rd->name.empty() ? 0 : x31_hash(rd->name.c_str()); // src/map.c:358-360
 			M.hash ^= wang_hash((uint32_t)M.win.wl) + wang_hash((uint32_t)M.opt->seed);
 			M.hash = wang_hash(M.hash);
+			if (sub_t) { double q1 = Timers::now(); g_timers.add("glue.copy", q1 - q0); q0 = q1; }
 			gen_regs(M.hash, M.win.wl, (int)M.u.size(), M.u.data(), M.a.data(), M.regs);
+			if (sub_t) { double q1 = Timers::now(); g_timers.add("glue.gen_regs", q1 - q0); q0 = q1; }
 			chain_post(M.opt, mi->k, M.win.wl, M.regs, M.a.data());
+			if (sub_t) { double q1 = Timers::now(); g_timers.add("glue.chain_post", q1 - q0); q0 = q1; }
 			if (M.est_err) est_err(mi, M.win.wl, M.regs, M.a.data(), (int32_t)M.mini_pos.size(), M.mini_pos.data());
+			if (sub_t) { double q1 = Timers::now(); g_timers.add("glue.est_err", q1 - q0); q0 = q1; }
 			M.aligning = (M.opt->flag & WM_F_CIGAR) != 0;
 			if (M.aligning) M.at.init(M.opt, mi, i, M.win.wl, rd->seq.data() + M.win.wb, M.regs, M.a.data());
 			M.sink.dp.clear(), M.sink.ll.clear();
+			if (sub_t) { double q1 = Timers::now(); g_timers.add("glue.at_init", q1 - q0); q0 = q1; }
 		}
 		g_timers.add("wave.glue_pre_align", Timers::now() - tg0);
 		if (st) for (int i = 0; i < n; ++i) st->n_chained += (int64_t)mm[i].a.size();

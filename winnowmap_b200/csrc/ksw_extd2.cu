@@ -269,8 +269,38 @@ struct wm_cigar_acc {
 	}
 };
 
+// The score walk of mm_test_zdrop (src/align.c:32-70) over a finished CIGAR, for the jobs that ask for it (flag
+// WM_DP_SCAN_ZDROP: the gap fills, whose result the aligner tests before deciding on a second pass, :736).
+// out[0] = max_zdrop, out[1..4] = the most-dropped region {t0, t1, q0, q1}.
+__device__ void wm_zdrop_scan(const wm_zd_params &Z, const uint8_t *__restrict__ qseq, const uint8_t *__restrict__ tseq, int n_cigar,
+                              const uint32_t *__restrict__ cigar, int32_t *out)
+{
+	int32_t score = 0, mx = INT_MIN, max_i = -1, max_j = -1, i = 0, j = 0, max_zdrop = 0;
+	int32_t p00 = -1, p01 = -1, p10 = -1, p11 = -1;
+	for (int k = 0; k < n_cigar; ++k) {
+		const uint32_t op = cigar[k] & 0xf; const int len = (int)(cigar[k] >> 4);
+		int steps = 1;
+		if (op == 0) steps = len;
+		else if (op == 1 || op == 2 || op == 3) { score -= Z.q + Z.e * len; if (op == 1) j += len; else i += len; }
+		else continue;
+		for (int l = 0; l < steps; ++l) {
+			int ii = i, jj = j;
+			if (op == 0) { score += Z.mat[tseq[i + l] * 5 + qseq[j + l]]; ii = i + l, jj = j + l; }
+			if (score < mx) { // update_max_zdrop :32-45
+				const int li = ii - max_i, lj = jj - max_j;
+				const int diff = li > lj ? li - lj : lj - li;
+				const int z = mx - score - diff * Z.e;
+				if (z > max_zdrop) max_zdrop = z, p00 = max_i, p01 = ii, p10 = max_j, p11 = jj;
+			} else mx = score, max_i = ii, max_j = jj;
+		}
+		if (op == 0) i += len, j += len;
+	}
+	out[0] = max_zdrop, out[1] = p00, out[2] = p01, out[3] = p10, out[4] = p11;
+}
+
 __global__ void wm_extd2_backtrack_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ bt,
-                                          wm_extz_dev *__restrict__ ezs, uint32_t *__restrict__ cigar_pool)
+                                          wm_extz_dev *__restrict__ ezs, uint32_t *__restrict__ cigar_pool,
+                                          const uint8_t *__restrict__ seq, wm_zd_params Z, int32_t *__restrict__ zd)
 {
 	int jid = blockIdx.x * blockDim.x + threadIdx.x;
 	if (jid >= n_jobs) return;
@@ -278,6 +308,8 @@ __global__ void wm_extd2_backtrack_kernel(const wm_dp_job *__restrict__ jobs, in
 	wm_extz_dev ez = ezs[jid];
 	const int qlen = J.qlen, tlen = J.tlen;
 	int w = J.w;
+	const bool scan = zd != 0 && (J.flag & WM_DP_SCAN_ZDROP) != 0;
+	if (scan) zd[5 * (size_t)jid] = -1; // "no result": the host falls back to its own walk
 	if (qlen <= 0 || tlen <= 0) return;
 	if (w < 0) w = tlen > qlen ? tlen : qlen;
 	int i0 = -1, j0 = -1;
@@ -315,6 +347,7 @@ __global__ void wm_extd2_backtrack_kernel(const wm_dp_job *__restrict__ jobs, in
 	}
 	ez.n_cigar = n;
 	ezs[jid] = ez;
+	if (scan && n <= J.cig_cap) wm_zdrop_scan(Z, seq + J.q_off, seq + J.t_off, n, cigar_pool + J.cig_off, zd + 5 * (size_t)jid);
 }
 
 // ---- host-side launcher on device-resident jobs ----
@@ -387,7 +420,7 @@ cudaStream_t wm_stream_create_high_priority(void)
 }
 
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
-                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream)
+                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream, const wm_zd_params *zp, int32_t *d_zd)
 {
 	if (n_jobs <= 0) return;
 	const size_t smem = (size_t)WM_FILL_WARPS * WM_FILL_SLICE;
@@ -433,7 +466,9 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const
 	if (pl.slot >= 0) WM_CUDA_CHECK(cudaEventRecord(pl.e1, ws->fill_st));
 	WM_CUDA_CHECK(cudaEventRecord(ws->ev_done, ws->fill_st));
 	WM_CUDA_CHECK(cudaStreamWaitEvent(stream, ws->ev_done, 0));
-	wm_count_launch(); wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar);
+	wm_zd_params Z; memset(&Z, 0, sizeof(Z));
+	if (zp && d_zd) Z = *zp;
+	wm_count_launch(); wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar, d_seq, Z, zp ? d_zd : 0);
 	WM_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -103,8 +103,13 @@ void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2,
 size_t wm_extd2_bt_bytes(int qlen, int tlen, int w);
 // sets h_jobs[i].pad (global-scratch slot or -1) for the n jobs of one launch, in launch order
 wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n);
+// Jobs flagged WM_DP_SCAN_ZDROP also get the score walk of mm_test_zdrop (src/align.c:32-70) over their CIGAR: five
+// int32 per job in d_zd (max_zdrop, t0, t1, q0, q1; max_zdrop = -1: no result).  zp / d_zd may be null.
+#define WM_DP_SCAN_ZDROP 0x10000
+struct wm_zd_params { int32_t q, e; int8_t mat[25]; int8_t pad[3]; };
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
-                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream);
+                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream,
+                     const wm_zd_params *zp = 0, int32_t *d_zd = 0);
 cudaStream_t wm_stream_create_high_priority(void);
 
 // Wait for a stream without burning a core: an orchestration lane spends most of its time waiting for the GPU, and
