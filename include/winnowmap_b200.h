@@ -235,10 +235,14 @@ wm_gpu_ctx *wm_idx_blob_load(const uint8_t *buf, int64_t size, int device);
 int wm_gpu_map_batch(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_seq, const char *const *names, const char *const *seqs,
                      const int32_t *lens, int32_t *n_reg, wm_reg1_t **reg, int32_t *rep_len, int32_t *frag_gap, int n_threads);
 
-/* mm_map_file (src/map.c:1273) for PAF output into out_fn ("-" = stdout).  rank/world shard the reads of every
- * mini-batch round-robin over processes (one process per GPU); tag_order prefixes "<batch>\t<pos>\t" for merging. */
+/* mm_map_file (src/map.c:1273) into out_fn ("-" = stdout): PAF (mm_write_paf3, src/format.c:308), or SAM when
+ * opt->flag has MM_F_OUT_SAM (mm_write_sam3, src/format.c:391, single-segment reads; header as mm_write_sam_hdr,
+ * src/format.c:118, written by rank 0 when tag_order == 0).  rank/world shard the reads of every mini-batch
+ * round-robin over processes (one process per GPU); tag_order prefixes "<batch>\t<pos>\t" for merging. */
 int wm_map_file(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, const char *reads_fn, const char *out_fn, int n_threads, int rank, int world,
                 int tag_order, int64_t max_batch_bases);
+/* the command line recorded in the @PG header line of SAM output (the reference prints its own argv, src/format.c:130-135) */
+void wm_set_sam_cl(wm_gpu_ctx *ctx, const char *cl);
 
 /* frees what wm_gpu_map_batch returned (the reference's output step does this itself, src/map.c:1210-1211) */
 void wm_free_regs(int n, const int32_t *n_reg, wm_reg1_t **reg);

@@ -149,13 +149,13 @@ public:
 	}
 };
 
-// winnowmap [-W kmers] -x preset -c ref.fa reads.fa > out.paf, host orchestration on the oracle backend
-extern "C" int wmt_map_file(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads)
+static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads, int sam)
 {
 	wm_idxopt_t io; wm_mapopt_t mo;
 	set_opt(0, &io, &mo);
 	if (preset && set_opt(preset, &io, &mo) < 0) return -1;
-	mo.flag |= WM_F_OUT_CG | WM_F_CIGAR;
+	if (sam) mo.flag |= WM_F_OUT_SAM | WM_F_CIGAR; // -a (src/main.c)
+	else mo.flag |= WM_F_OUT_CG | WM_F_CIGAR;      // -c
 	if (check_opt(&io, &mo) < 0) return -2;
 	wm_host_idx H; H.k = io.k, H.w = io.w;
 	std::vector<uint64_t> kmers;
@@ -194,11 +194,30 @@ extern "C" int wmt_map_file(const char *ref_fn, const char *kmer_fn, const char 
 	map_batch(&be, &H, &mo, reads, regs, rl, fg, n_threads, 0);
 	FILE *out = fopen(out_fn, "wb");
 	std::string line;
-	for (size_t i = 0; i < reads.size(); ++i)
-		for (auto &rr : regs[i]) { write_paf(line, &H, reads[i], &rr, mo.flag, rl[i]); fwrite(line.data(), 1, line.size(), out); fputc('\n', out); free(rr.p); }
+	if (sam) { write_sam_hdr(line, &H, "2.03", 0); fwrite(line.data(), 1, line.size(), out); }
+	for (size_t i = 0; i < reads.size(); ++i) { // the output step of the reference (src/map.c:1189-1206)
+		for (size_t j = 0; j < regs[i].size(); ++j) {
+			if (sam) write_sam(line, &H, reads[i], (int)j, (int)regs[i].size(), regs[i].data(), mo.flag, rl[i], "");
+			else write_paf(line, &H, reads[i], &regs[i][j], mo.flag, rl[i]);
+			fwrite(line.data(), 1, line.size(), out); fputc('\n', out);
+		}
+		if (regs[i].empty() && sam) { write_sam(line, &H, reads[i], -1, 0, 0, mo.flag, rl[i], ""); fwrite(line.data(), 1, line.size(), out); fputc('\n', out); }
+		for (auto &rr : regs[i]) free(rr.p);
+	}
 	fclose(out);
 	wmo_idx_free(be.idx); wmo_bloom_free(bloom);
 	return 0;
+}
+
+// winnowmap [-W kmers] -x preset -c ref.fa reads.fa > out.paf, host orchestration on the oracle backend
+extern "C" int wmt_map_file(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads)
+{
+	return map_file_impl(ref_fn, kmer_fn, preset, reads_fn, out_fn, n_threads, 0);
+}
+// the same with -a: SAM
+extern "C" int wmt_map_file_sam(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads)
+{
+	return map_file_impl(ref_fn, kmer_fn, preset, reads_fn, out_fn, n_threads, 1);
 }
 
 #include "../../winnowmap_b200/csrc/host_timers.h"

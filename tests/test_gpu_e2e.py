@@ -76,3 +76,21 @@ def test_map_file_pipeline_many_mini_batches(tmp_path):
     mp.close()
     assert sorted(got.split(b"\n")) == sorted(exp.split(b"\n"))
     assert got != exp or len(exp.split(b"\n")) < 4  # the order really is per mini-batch
+
+
+@pytest.mark.parametrize("name", ["ont_small", "ont_sv"])
+def test_sam_matches_reference(name, tmp_path):
+    """-a: SAM records (flag, POS, soft/hard clips, SEQ/QUAL orientation, SA:Z of split alignments) and the @SQ header
+    against the reference's own SAM (md5 of the full text in the manifest; the @PG line carries the command line)."""
+    import hashlib
+    from winnowmap_b200.mapper import Mapper
+    m = MANIFEST[name]
+    ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
+    mp = Mapper(ref, wfile, preset=m["params"]["preset"], sam=True)
+    out = str(tmp_path / "out.sam")
+    mp.map_file(reads, out)
+    mp.close()
+    got = make_golden.sam_without_pg(open(out, "rb").read())
+    if hashlib.md5(got).hexdigest() != m["sam_md5"]:
+        exp = gzip.open(os.path.join(ROOT, "tests", "golden", name + ".sam.stripped.gz")).read()
+        raise AssertionError(_first_diff(exp, make_golden.sam_strip_seq(got)))

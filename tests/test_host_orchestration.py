@@ -45,3 +45,25 @@ def test_host_pipeline_matches_reference_golden(hostsim, name, tmp_path):
                 cols = [j for j, (p, q) in enumerate(zip(fx, fy)) if p != q]
                 raise AssertionError(f"line {i} cols {cols}: {[fx[j][:50] for j in cols[:5]]} vs {[fy[j][:50] for j in cols[:5]]}")
         raise AssertionError(f"line count {len(le)} vs {len(lg)}")
+
+
+@pytest.mark.parametrize("name", ["ont_small", "ont_sv"])
+def test_host_sam_writer_matches_reference_golden(hostsim, name, tmp_path):
+    """SAM output (-a) of the host writer, oracle-backed: byte-identical to the reference's SAM but for the @PG line."""
+    import hashlib
+    m = MANIFEST[name]
+    ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
+    out = str(tmp_path / "o.sam")
+    hostsim.wmt_map_file_sam.argtypes = hostsim.wmt_map_file.argtypes
+    rc = hostsim.wmt_map_file_sam(ref.encode(), wfile.encode() if wfile else None, m["params"]["preset"].encode(), reads.encode(), out.encode(), 8)
+    assert rc == 0
+    got = make_golden.sam_without_pg(open(out, "rb").read())
+    if hashlib.md5(got).hexdigest() != m["sam_md5"]:
+        exp = gzip.open(os.path.join(ROOT, "tests", "golden", name + ".sam.stripped.gz")).read().split(b"\n")
+        gl = make_golden.sam_strip_seq(got).split(b"\n")
+        for i, (x, y) in enumerate(zip(exp, gl)):
+            if x != y:
+                fx, fy = x.split(b"\t"), y.split(b"\t")
+                cols = [j for j, (p, q) in enumerate(zip(fx, fy)) if p != q]
+                raise AssertionError(f"line {i} cols {cols}: {[fx[j][:60] for j in cols[:5]]} vs {[fy[j][:60] for j in cols[:5]]}")
+        raise AssertionError(f"line count {len(exp)} vs {len(gl)} (or SEQ/QUAL text differs)")

@@ -89,6 +89,29 @@ def make_inputs(name, outdir):
     return ref, reads, wfile
 
 
+SAM_CASES = ["ont_small", "ont_sv"]
+
+
+def sam_without_pg(sam):
+    """The @PG line records the command line (temporary paths): everything else must match byte for byte."""
+    return b"".join(ln for ln in sam.splitlines(keepends=True) if not ln.startswith(b"@PG"))
+
+
+def sam_strip_seq(sam):
+    """SEQ and QUAL replaced by their lengths: a small committed fixture to locate a difference; the full text is
+    pinned by its md5 in the manifest."""
+    out = []
+    for ln in sam.splitlines(keepends=True):
+        if ln.startswith(b"@"):
+            out.append(ln)
+            continue
+        f = ln.rstrip(b"\n").split(b"\t")
+        f[9] = b"len=%d" % len(f[9]) if f[9] != b"*" else b"*"
+        f[10] = b"len=%d" % len(f[10]) if f[10] != b"*" else b"*"
+        out.append(b"\t".join(f) + b"\n")
+    return b"".join(out)
+
+
 def main():
     refbin = os.path.join(ROOT, "oracle", "_ref", "winnowmap")
     if not os.path.exists(refbin):
@@ -109,6 +132,20 @@ def main():
         manifest[name] = dict(params=c, ref_md5=md5(ref), reads_md5=md5(reads), w_md5=md5(wfile) if wfile else None,
                               cmd=" ".join(["winnowmap"] + cmd[1:]), n_lines=out.count(b"\n"), paf_md5=hashlib.md5(out).hexdigest())
         print(name, manifest[name]["n_lines"], "lines", len(out), "bytes")
+    for name in SAM_CASES:  # the same inputs with -a: SAM records (flags, clipping, SEQ/QUAL, SA:Z) and @SQ header
+        c = CASES[name]
+        ref, reads, wfile = make_inputs(name, tmp)
+        cmd = [refbin, "-t", "4", "-a", "-x", c["preset"]]
+        if wfile:
+            cmd += ["-W", wfile]
+        cmd += [ref, reads]
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        body = sam_without_pg(out)
+        with gzip.GzipFile(os.path.join(gdir, name + ".sam.stripped.gz"), "wb", mtime=0) as f:
+            f.write(sam_strip_seq(body))
+        manifest[name]["sam_md5"] = hashlib.md5(body).hexdigest()
+        manifest[name]["sam_lines"] = body.count(b"\n")
+        print(name, "SAM", manifest[name]["sam_lines"], "lines", len(body), "bytes")
     json.dump(manifest, open(os.path.join(gdir, "manifest.json"), "w"), indent=1, sort_keys=True)
 
 

@@ -28,6 +28,7 @@ struct wm_gpu_ctx_s {
 	int64_t n_keys, n_pos;
 	std::vector<wm_read> resident; // bench: reads already uploaded by wm_bench_upload ...
 	char *d_resident = 0;          // ... their bases, one device pool (wm_read::dev_off)
+	std::string sam_cl;            // command line recorded in the @PG line of SAM output (wm_set_sam_cl)
 	std::vector<Backend*> lanes;   // lanes[0] == be; further lanes share the index and own a stream + workspaces
 	// host copy of the flattened index, kept for the one-time fan-out to the other GPUs (wm_idx_blob_*)
 	std::vector<uint64_t> keys, pos_off, pos;
@@ -285,6 +286,11 @@ extern "C" int wm_map_file(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const char *
 	if (!out) return -1;
 	const double t0 = now_s();
 	const int64_t chunk = opt->mini_batch_size;
+	if ((opt->flag & WM_F_OUT_SAM) && rank == 0 && !tag_order) { // mm_write_sam_hdr (src/main.c:391-393)
+		std::string hdr;
+		write_sam_hdr(hdr, &c->hidx, "2.03", c->sam_cl.c_str());
+		fwrite(hdr.data(), 1, hdr.size(), out);
+	}
 	// The three steps of the reference's pipeline (src/map.c:1107-1224: read, map, write) run on three threads with
 	// one mini-batch of slack between them: the next batch is parsed and the previous one formatted while the GPU maps.
 	struct FileBatch {
@@ -330,8 +336,10 @@ extern "C" int wm_map_file(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const char *
 				for (int i = 0; i < n; ++i) {
 					const wm_read *t = b->mine[i];
 					std::string &dst = lines[i];
-					auto emit = [&](const wm_reg1_t *rr) {
-						write_paf(line, &c->hidx, t, rr, opt->flag, b->rl[i]);
+					const bool sam = (opt->flag & WM_F_OUT_SAM) != 0;
+					auto emit = [&](int j) { // hit j of the read, or the empty record (j < 0), src/map.c:1189-1206
+						if (sam) write_sam(line, &c->hidx, t, j, (int)b->regs[i].size(), b->regs[i].data(), opt->flag, b->rl[i], "");
+						else write_paf(line, &c->hidx, t, j >= 0 ? &b->regs[i][j] : 0, opt->flag, b->rl[i]);
 						if (tag_order) { snprintf(tag, sizeof(tag), "%lld\t%d\t", (long long)b->no, b->mine_pos[i]); dst += tag; }
 						dst += line; dst += '\n';
 					};
@@ -339,9 +347,9 @@ extern "C" int wm_map_file(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const char *
 						for (size_t j = 0; j < b->regs[i].size(); ++j) {
 							const wm_reg1_t *rr = &b->regs[i][j];
 							if ((opt->flag & WM_F_NO_PRINT_2ND) && rr->id != rr->parent) continue;
-							emit(rr);
+							emit((int)j);
 						}
-					} else if (opt->flag & WM_F_PAF_NO_HIT) emit(0);
+					} else if ((opt->flag & WM_F_PAF_NO_HIT) || (sam && !(opt->flag & WM_F_SAM_HIT_ONLY))) emit(-1);
 					for (auto &rr : b->regs[i]) free(rr.p);
 				}
 			}
@@ -378,6 +386,8 @@ extern "C" int wm_map_file(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const char *
 	c->t_map += now_s() - t0;
 	return 0;
 }
+
+extern "C" void wm_set_sam_cl(wm_gpu_ctx_s *c, const char *cl) { c->sam_cl = cl ? cl : ""; }
 
 extern "C" void wm_get_stats(wm_gpu_ctx_s *c, double *o, int n)
 {

@@ -1,4 +1,4 @@
-// PAF output, byte-identical to the reference writer (src/format.c:266-334; tags :280-306).
+// PAF and SAM output, byte-identical to the reference writers (src/format.c:266-334 and :341-548; tags :280-306).
 #include <stdio.h>
 #include <string.h>
 #include "host_io.h"
@@ -78,6 +78,145 @@ void write_paf(std::string &s, const wm_host_idx *mi, const wm_read *t, const wm
 		for (uint32_t k = 0; k < r->p->n_cigar; ++k) { put_int(s, (int)(r->p->cigar[k] >> 4)); s.push_back("MIDNSHP=XB"[r->p->cigar[k] & 0xf]); }
 	}
 	if ((opt_flag & WM_F_COPY_COMMENT) && !t->comment.empty()) { s.push_back('\t'); s += t->comment; }
+}
+
+// seq_comp_table (src/bseq.c): IUPAC complement, case preserved; bytes without a complement map to themselves
+static const struct CompTable {
+	unsigned char t[256];
+	CompTable() {
+		for (int i = 0; i < 256; ++i) t[i] = (unsigned char)i;
+		const char *a = "ACGTUMRWSYKVHDBN", *b = "TGCAAKYWSRMBDHVN";
+		for (int i = 0; a[i]; ++i) { t[(unsigned char)a[i]] = (unsigned char)b[i]; t[(unsigned char)(a[i] + 32)] = (unsigned char)(b[i] + 32); }
+	}
+} g_comp;
+
+static void sam_write_sq(std::string &s, const char *seq, int l, int rev, int comp)
+{ // src/format.c:341-353
+	if (rev) {
+		for (int i = 0; i < l; ++i) {
+			const int c = (unsigned char)seq[l - 1 - i];
+			s.push_back((char)(c < 128 && comp ? g_comp.t[c] : c));
+		}
+	} else s.append(seq, seq + l);
+}
+
+static void write_sam_cigar(std::string &s, int sam_flag, int in_tag, int qlen, const wm_reg1_t *r, int64_t opt_flag)
+{ // src/format.c:365-389
+	if (r->p == 0) { s.push_back('*'); return; }
+	uint32_t clip_len[2];
+	clip_len[0] = r->rev ? qlen - r->qe : r->qs;
+	clip_len[1] = r->rev ? r->qs : qlen - r->qe;
+	if (in_tag) {
+		const int clip_char = (sam_flag & 0x800) && !(opt_flag & WM_F_SOFTCLIP) ? 5 : 4;
+		s += "\tCG:B:I";
+		if (clip_len[0]) { s.push_back(','); put_int(s, (int)(clip_len[0] << 4 | clip_char)); }
+		for (uint32_t k = 0; k < r->p->n_cigar; ++k) { s.push_back(','); put_int(s, (int)r->p->cigar[k]); }
+		if (clip_len[1]) { s.push_back(','); put_int(s, (int)(clip_len[1] << 4 | clip_char)); }
+	} else {
+		const char clip_char = (sam_flag & 0x800) && !(opt_flag & WM_F_SOFTCLIP) ? 'H' : 'S';
+		if (clip_len[0]) { put_int(s, (int)clip_len[0]); s.push_back(clip_char); }
+		for (uint32_t k = 0; k < r->p->n_cigar; ++k) { put_int(s, (int)(r->p->cigar[k] >> 4)); s.push_back("MIDNSHP=XB"[r->p->cigar[k] & 0xf]); }
+		if (clip_len[1]) { put_int(s, (int)clip_len[1]); s.push_back(clip_char); }
+	}
+}
+
+// mm_write_sam3 (src/format.c:391-548) for a single-segment read (n_seg == 1); reg_idx < 0 writes the unmapped record.
+// --cs / --MD are not part of this build; rg_id is the @RG ID ("" = none).
+void write_sam(std::string &s, const wm_host_idx *mi, const wm_read *t, int reg_idx, int n_regs, const wm_reg1_t *regs, int64_t opt_flag, int rep_len,
+               const char *rg_id)
+{
+	const int max_bam_cigar_op = 65535;
+	const int l_seq = (int)t->seq.size();
+	const wm_reg1_t *r = n_regs > 0 && reg_idx < n_regs && reg_idx >= 0 ? &regs[reg_idx] : 0;
+	int flag = 0, cigar_in_tag = 0;
+	s.clear();
+	s += t->name;
+	if (r == 0) flag |= 0x4;
+	else {
+		if (r->rev) flag |= 0x10;
+		if (r->parent != r->id) flag |= 0x100;
+		else if (!r->sam_pri) flag |= 0x800;
+	}
+	s.push_back('\t'); put_int(s, flag);
+	if (r == 0) s += "\t*\t0\t0\t*";
+	else {
+		s.push_back('\t'); s += mi->name[r->rid]; s.push_back('\t'); put_int(s, r->rs + 1); s.push_back('\t'); put_int(s, (int)r->mapq); s.push_back('\t');
+		if ((opt_flag & WM_F_LONG_CIGAR) && r->p && (int)r->p->n_cigar > max_bam_cigar_op - 2) {
+			int n_cigar = (int)r->p->n_cigar;
+			if (r->qs != 0) ++n_cigar;
+			if (r->qe != l_seq) ++n_cigar;
+			if (n_cigar > max_bam_cigar_op) cigar_in_tag = 1;
+		}
+		if (cigar_in_tag) {
+			int slen;
+			if ((flag & 0x900) == 0 || (opt_flag & WM_F_SOFTCLIP)) slen = l_seq;
+			else if (flag & 0x100) slen = 0;
+			else slen = r->qe - r->qs;
+			put_int(s, slen); s.push_back('S'); put_int(s, r->re - r->rs); s.push_back('N');
+		} else write_sam_cigar(s, flag, 0, l_seq, r, opt_flag);
+	}
+	s += "\t*\t0\t0\t";
+	const char *seq = t->seq.data(), *qual = t->qual.empty() ? 0 : t->qual.data();
+	if (r == 0) {
+		sam_write_sq(s, seq, l_seq, 0, 0);
+		s.push_back('\t');
+		if (qual) sam_write_sq(s, qual, l_seq, 0, 0); else s.push_back('*');
+	} else if ((flag & 0x900) == 0 || (opt_flag & WM_F_SOFTCLIP)) {
+		sam_write_sq(s, seq, l_seq, r->rev, r->rev);
+		s.push_back('\t');
+		if (qual) sam_write_sq(s, qual, l_seq, r->rev, 0); else s.push_back('*');
+	} else if (flag & 0x100) {
+		s += "*\t*";
+	} else {
+		sam_write_sq(s, seq + r->qs, r->qe - r->qs, r->rev, r->rev);
+		s.push_back('\t');
+		if (qual) sam_write_sq(s, qual + r->qs, r->qe - r->qs, r->rev, 0); else s.push_back('*');
+	}
+	if (rg_id && rg_id[0]) { s += "\tRG:Z:"; s += rg_id; }
+	if (r) {
+		write_tags(s, r);
+		if (r->parent == r->id && r->p && n_regs > 1) { // supplementary alignments may exist
+			int n_sa = 0;
+			for (int i = 0; i < n_regs; ++i)
+				if (i != reg_idx && regs[i].parent == regs[i].id && regs[i].p) ++n_sa;
+			if (n_sa > 0) {
+				s += "\tSA:Z:";
+				for (int i = 0; i < n_regs; ++i) {
+					const wm_reg1_t *q = &regs[i];
+					int l_M, l_I = 0, l_D = 0, clip5, clip3;
+					if (r == q || q->parent != q->id || q->p == 0) continue;
+					if (q->qe - q->qs < q->re - q->rs) l_M = q->qe - q->qs, l_D = (q->re - q->rs) - l_M;
+					else l_M = q->re - q->rs, l_I = (q->qe - q->qs) - l_M;
+					clip5 = q->rev ? l_seq - q->qe : q->qs;
+					clip3 = q->rev ? q->qs : l_seq - q->qe;
+					s += mi->name[q->rid]; s.push_back(','); put_int(s, q->rs + 1); s.push_back(','); s.push_back("+-"[q->rev]); s.push_back(',');
+					if (clip5) { put_int(s, clip5); s.push_back('S'); }
+					if (l_M) { put_int(s, l_M); s.push_back('M'); }
+					if (l_I) { put_int(s, l_I); s.push_back('I'); }
+					if (l_D) { put_int(s, l_D); s.push_back('D'); }
+					if (clip3) { put_int(s, clip3); s.push_back('S'); }
+					s.push_back(','); put_int(s, (int)q->mapq); s.push_back(','); put_int(s, q->blen - q->mlen + q->p->n_ambi); s.push_back(';');
+				}
+			}
+		}
+		if (cigar_in_tag) write_sam_cigar(s, flag, 1, l_seq, r, opt_flag);
+	}
+	if (rep_len >= 0) { s += "\trl:i:"; put_int(s, rep_len); }
+	if ((opt_flag & WM_F_COPY_COMMENT) && !t->comment.empty()) { s.push_back('\t'); s += t->comment; }
+}
+
+// mm_write_sam_hdr (src/format.c:118-139) without a read group: @SQ lines and the @PG line; `cl` is the command
+// line the caller wants recorded (the reference prints its own argv), may be null
+void write_sam_hdr(std::string &s, const wm_host_idx *mi, const char *version, const char *cl)
+{
+	s.clear();
+	for (size_t i = 0; i < mi->name.size(); ++i) {
+		s += "@SQ\tSN:"; s += mi->name[i]; s += "\tLN:"; put_int(s, (int)mi->len[i]); s.push_back('\n');
+	}
+	s += "@PG\tID:Winnowmap\tPN:Winnowmap";
+	if (version) { s += "\tVN:"; s += version; }
+	if (cl && cl[0]) { s += "\tCL:"; s += cl; }
+	s.push_back('\n');
 }
 
 } // namespace wmh

@@ -26,5 +26,10 @@ int read_kmer_list(const char *fn, int k, std::vector<uint64_t> &canon_kmers);
 
 // PAF line of one hit / of an unmapped read (mm_write_paf3, src/format.c:308-334)
 void write_paf(std::string &s, const wm_host_idx *mi, const wm_read *t, const wm_reg1_t *r, int64_t opt_flag, int rep_len);
+// SAM record of hit reg_idx of a single-segment read (reg_idx < 0: the unmapped record), mm_write_sam3 (src/format.c:391-548)
+void write_sam(std::string &s, const wm_host_idx *mi, const wm_read *t, int reg_idx, int n_regs, const wm_reg1_t *regs, int64_t opt_flag, int rep_len,
+               const char *rg_id);
+// @SQ and @PG header lines (mm_write_sam_hdr, src/format.c:118-139)
+void write_sam_hdr(std::string &s, const wm_host_idx *mi, const char *version, const char *cl);
 
 } // namespace wmh

@@ -55,14 +55,20 @@ def _setup(L):
     return L
 
 
-def make_options(preset=None, cigar=True):
-    """mm_set_opt(0) then mm_set_opt(preset) (reference main.c:144-159); -c sets MM_F_OUT_CG|MM_F_CIGAR (main.c:179)."""
+F_OUT_SAM = 0x008
+
+
+def make_options(preset=None, cigar=True, sam=False):
+    """mm_set_opt(0) then mm_set_opt(preset) (reference main.c:144-159); -c sets MM_F_OUT_CG|MM_F_CIGAR, -a sets
+    MM_F_OUT_SAM|MM_F_CIGAR (main.c)."""
     L = _setup(lib())
     io, mo = IdxOpt(), MapOpt()
     L.wm_set_opt(None, C.byref(io), C.byref(mo))
     if preset is not None and L.wm_set_opt(preset.encode(), C.byref(io), C.byref(mo)) != 0:
         raise ValueError(f"unknown preset {preset}")
-    if cigar:
+    if sam:
+        mo.flag |= F_OUT_SAM | F_CIGAR
+    elif cigar:
         mo.flag |= F_OUT_CG | F_CIGAR
     rc = L.wm_check_opt(C.byref(io), C.byref(mo))
     if rc < 0:
@@ -73,9 +79,9 @@ def make_options(preset=None, cigar=True):
 class Mapper:
     """winnowmap [-W rep.txt] -x preset -c ref.fa reads.fa  on one GPU."""
 
-    def __init__(self, ref, kmer_freq=None, preset="map-ont", cigar=True, device=0, n_threads=None, blob=None):
+    def __init__(self, ref, kmer_freq=None, preset="map-ont", cigar=True, device=0, n_threads=None, blob=None, sam=False):
         self.L = _setup(lib())
-        self.io, self.mo = make_options(preset, cigar)
+        self.io, self.mo = make_options(preset, cigar, sam)
         self.n_threads = n_threads or max(1, min(64, (os.cpu_count() or 2) // 2))
         if blob is not None:  # index received from another rank (numpy uint8 array)
             self._blob_keep = blob
