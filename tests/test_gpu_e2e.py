@@ -94,3 +94,23 @@ def test_sam_matches_reference(name, tmp_path):
     if hashlib.md5(got).hexdigest() != m["sam_md5"]:
         exp = gzip.open(os.path.join(ROOT, "tests", "golden", name + ".sam.stripped.gz")).read()
         raise AssertionError(_first_diff(exp, make_golden.sam_strip_seq(got)))
+
+
+def test_rank_sharded_outputs_merge_to_the_reference(tmp_path):
+    """One process per GPU maps the reads whose position in the length-sorted mini-batch is rank mod world
+    (wm_map_file(rank, world)); the tagged shards merge back into the reference's output, byte for byte."""
+    from winnowmap_b200 import multi
+    from winnowmap_b200.mapper import Mapper
+    name = "ont_sv"
+    m = MANIFEST[name]
+    ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
+    exp = gzip.open(os.path.join(ROOT, "tests", "golden", name + ".paf.gz")).read()
+    mp = Mapper(ref, wfile, preset=m["params"]["preset"], cigar=True)
+    shards = []
+    for rank in range(3):
+        out = str(tmp_path / f"out{rank}.paf")
+        mp.map_file(reads, out, rank=rank, world=3, tag_order=True)
+        shards.append(open(out, "rb").read())
+    mp.close()
+    assert all(shards), "every rank maps a share of the reads"
+    assert multi.merge_tagged(shards) == exp
