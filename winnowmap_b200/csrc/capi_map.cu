@@ -47,9 +47,9 @@ static void require_device(const char *who)
 	}
 }
 
-// Orchestration lanes: the reads of a batch are dealt round-robin to L lanes that run map_batch concurrently, each on
-// its own host thread and CUDA stream, so that one lane's host glue overlaps another lane's kernels.  Results do not
-// depend on the grouping (reads never interact, src/map.c:1008-1048).
+// Orchestration lanes: the reads of a call are cut into chunks that L lanes pull from a shared counter and run through
+// map_batch concurrently, each lane on its own host thread and CUDA stream, so that one lane's host glue overlaps the
+// other lanes' kernels.  Results do not depend on the grouping (reads never interact, src/map.c:1008-1048).
 static int n_lanes_wanted(int n_threads)
 { // one lane per 8 host threads (2..8) unless WM_LANES says otherwise
 	const char *e = getenv("WM_LANES");
