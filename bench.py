@@ -8,10 +8,16 @@ N50 = 20 kb at 5 % error, -x map-ont -W <top-0.02 % k-mers> k=15 -c.  The 100 k 
 batches of --reads reads (fresh reads each step, so nothing is cached between steps; each batch's working set --
 read pool, backtrack matrices, 2.6 GB index -- is far larger than L2).
 
-  value : bases/s with the batch's reads already resident in HBM (device code arrays built before the timed region)
-  e2e   : bases/s through wm_gpu_map_batch with host buffers (H2D of the reads and D2H of every result inside)
-  roofline : the DP fill kernel, algorithmic bytes / CUDA-event duration vs the measured HBM peak
-  cpu_baseline : the real reference (oracle/_ref/winnowmap, SSE4.1, all host cores) on a bounded sample
+The K timed steps are submitted together (K batches): the library's orchestration lanes pull chunks of reads from
+the whole submission, so the steps pipeline instead of draining the GPU at every step boundary.  The timed region is
+bracketed by a barrier + device synchronisation on both sides; the warm-up has the same shape (W steps together).
+
+  value : bases/s with the raw reads of all K steps already resident in one HBM pool (wm_bench_upload); CUDA events
+          bracket the whole pass (ASCII -> 2-bit codes is inside: it is part of the path)
+  e2e   : bases/s through wm_gpu_map_batch with host buffers (staging + H2D of the reads, D2H of every result inside)
+  roofline : the DP fill kernel, algorithmic bytes over the time during which a fill kernel was running
+          (CUDA events around every launch), vs the measured HBM peak
+  cpu_baseline : the real reference (oracle/_ref/winnowmap, SSE4.1, all host cores) on a bounded sample (N = 1 only)
 
 --impl reference times the reference binary itself on the same workload (CPU, all host threads).
 Under torchrun (N > 1) every rank maps its own batches (reads shard with no data-path collective): weak scaling.
@@ -25,6 +31,8 @@ import sys
 import tempfile
 import threading
 import time
+
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")  # before anything loads libgomp: idle workers must not spin (see _lib.py)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -326,7 +334,9 @@ def main():
     k_ms = prof[7] if prof[7] > 0 else prof[1]
     ach = prof[3] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     cpu = None
-    try:  # the reference beside it, bounded sample, all host cores
+    try:  # the reference beside it (N = 1 only), bounded sample, all host cores
+        if world > 1:
+            raise RuntimeError("reported by the N=1 run only")
         recs = make_batch(contigs, a.cpu_reads, 777)
         with tempfile.TemporaryDirectory() as td:
             fa = os.path.join(td, "cpu.fa"); gen_data.write_fasta(fa, recs)
