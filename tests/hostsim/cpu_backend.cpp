@@ -149,13 +149,14 @@ public:
 	}
 };
 
-static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads, int sam)
+static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads, int sam, int64_t extra_flags = 0)
 {
 	wm_idxopt_t io; wm_mapopt_t mo;
 	set_opt(0, &io, &mo);
 	if (preset && set_opt(preset, &io, &mo) < 0) return -1;
 	if (sam) mo.flag |= WM_F_OUT_SAM | WM_F_CIGAR; // -a (src/main.c)
 	else mo.flag |= WM_F_OUT_CG | WM_F_CIGAR;      // -c
+	mo.flag |= extra_flags;                        // --cs / --cs=long / --MD (src/main.c:227,249-266)
 	if (check_opt(&io, &mo) < 0) return -2;
 	wm_host_idx H; H.k = io.k, H.w = io.w;
 	std::vector<uint64_t> kmers;
@@ -213,6 +214,12 @@ static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *pr
 extern "C" int wmt_map_file(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads)
 {
 	return map_file_impl(ref_fn, kmer_fn, preset, reads_fn, out_fn, n_threads, 0);
+}
+// -c or -a plus extra MM_F_* output flags
+extern "C" int wmt_map_file_flags(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads,
+                                  int sam, int64_t extra_flags)
+{
+	return map_file_impl(ref_fn, kmer_fn, preset, reads_fn, out_fn, n_threads, sam, extra_flags);
 }
 // the same with -a: SAM
 extern "C" int wmt_map_file_sam(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads)

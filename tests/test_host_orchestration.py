@@ -67,3 +67,26 @@ def test_host_sam_writer_matches_reference_golden(hostsim, name, tmp_path):
                 cols = [j for j, (p, q) in enumerate(zip(fx, fy)) if p != q]
                 raise AssertionError(f"line {i} cols {cols}: {[fx[j][:60] for j in cols[:5]]} vs {[fy[j][:60] for j in cols[:5]]}")
         raise AssertionError(f"line count {len(exp)} vs {len(gl)} (or SEQ/QUAL text differs)")
+
+
+@pytest.mark.parametrize("key,sam,flags", [("paf_cs", 0, 0x40), ("paf_cs_long", 0, 0x40 | 0x800), ("sam_md", 1, 0x1000000)])
+def test_host_cs_md_tags_match_reference(hostsim, key, sam, flags, tmp_path):
+    """--cs / --cs=long / --MD difference strings (src/format.c:141-243) in PAF and SAM records."""
+    import hashlib
+    name = make_golden.TAG_CASES[key][0]
+    m = MANIFEST[name]
+    ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
+    out = str(tmp_path / "o.txt")
+    hostsim.wmt_map_file_flags.argtypes = [C.c_char_p] * 5 + [C.c_int, C.c_int, C.c_int64]
+    rc = hostsim.wmt_map_file_flags(ref.encode(), wfile.encode() if wfile else None, m["params"]["preset"].encode(), reads.encode(), out.encode(), 8, sam, flags)
+    assert rc == 0
+    got = make_golden.sam_without_pg(open(out, "rb").read())
+    if hashlib.md5(got).hexdigest() != m["tag_md5"][key]:
+        if key == "paf_cs":
+            exp = gzip.open(os.path.join(ROOT, "tests", "golden", name + ".cs.paf.gz")).read().split(b"\n")
+            for i, (x, y) in enumerate(zip(exp, got.split(b"\n"))):
+                if x != y:
+                    fx, fy = x.split(b"\t"), y.split(b"\t")
+                    cols = [j for j, (p, q) in enumerate(zip(fx, fy)) if p != q]
+                    raise AssertionError(f"line {i} cols {cols}: {[fx[j][:80] for j in cols[:3]]} vs {[fy[j][:80] for j in cols[:3]]}")
+        raise AssertionError(f"{key}: output differs from the reference (md5)")

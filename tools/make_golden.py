@@ -90,6 +90,12 @@ def make_inputs(name, outdir):
 
 
 SAM_CASES = ["ont_small", "ont_sv"]
+# key -> (case, reference options); flags for the library: MM_F_OUT_CS 0x40, MM_F_OUT_CS_LONG 0x800, MM_F_OUT_MD 0x1000000
+TAG_CASES = {
+    "paf_cs": ("ont_small", ["-c", "--cs"]),
+    "paf_cs_long": ("ont_small", ["-c", "--cs=long"]),
+    "sam_md": ("ont_sv", ["-a", "--MD"]),
+}
 
 
 def sam_without_pg(sam):
@@ -146,6 +152,20 @@ def main():
         manifest[name]["sam_md5"] = hashlib.md5(body).hexdigest()
         manifest[name]["sam_lines"] = body.count(b"\n")
         print(name, "SAM", manifest[name]["sam_lines"], "lines", len(body), "bytes")
+    for key, (name, args) in TAG_CASES.items():  # difference strings: --cs, --cs=long, --MD
+        c = CASES[name]
+        ref, reads, wfile = make_inputs(name, tmp)
+        cmd = [refbin, "-t", "4", "-x", c["preset"]] + args
+        if wfile:
+            cmd += ["-W", wfile]
+        cmd += [ref, reads]
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+        body = sam_without_pg(out)
+        manifest[name].setdefault("tag_md5", {})[key] = hashlib.md5(body).hexdigest()
+        if key == "paf_cs":
+            with gzip.GzipFile(os.path.join(gdir, name + ".cs.paf.gz"), "wb", mtime=0) as f:
+                f.write(body)
+        print(name, key, body.count(b"\n"), "lines", len(body), "bytes")
     json.dump(manifest, open(os.path.join(gdir, "manifest.json"), "w"), indent=1, sort_keys=True)
 
 

@@ -1,6 +1,7 @@
 // PAF and SAM output, byte-identical to the reference writers (src/format.c:266-334 and :341-548; tags :280-306).
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 #include "host_io.h"
 
 namespace wmh {
@@ -56,6 +57,81 @@ static void write_tags(std::string &s, const wm_reg1_t *r)
 	if (r->split) { s += "\tzd:i:"; put_int(s, r->split); }
 }
 
+// cs:Z: / MD:Z: difference strings (src/format.c:141-243); qseq/tseq are 0..4 codes in alignment orientation
+static void write_cs_core(std::string &s, const uint8_t *tseq, const uint8_t *qseq, const wm_reg1_t *r, int no_iden)
+{
+	s += "\tcs:Z:";
+	int q_off = 0, t_off = 0;
+	std::string tmp;
+	for (uint32_t i = 0; i < r->p->n_cigar; ++i) {
+		const int op = r->p->cigar[i] & 0xf, len = r->p->cigar[i] >> 4;
+		if (op == 0 || op == 7 || op == 8) {
+			tmp.clear();
+			auto flush = [&]() {
+				if (tmp.empty()) return;
+				if (!no_iden) { s.push_back('='); s += tmp; } else { s.push_back(':'); put_int(s, (int)tmp.size()); }
+				tmp.clear();
+			};
+			for (int j = 0; j < len; ++j) {
+				if (qseq[q_off + j] != tseq[t_off + j]) {
+					flush();
+					s.push_back('*'); s.push_back("acgtn"[tseq[t_off + j]]); s.push_back("acgtn"[qseq[q_off + j]]);
+				} else tmp.push_back("ACGTN"[qseq[q_off + j]]);
+			}
+			flush();
+			q_off += len, t_off += len;
+		} else if (op == 1) {
+			s.push_back('+');
+			for (int j = 0; j < len; ++j) s.push_back("acgtn"[qseq[q_off + j]]);
+			q_off += len;
+		} else if (op == 2) {
+			s.push_back('-');
+			for (int j = 0; j < len; ++j) s.push_back("acgtn"[tseq[t_off + j]]);
+			t_off += len;
+		} else { // intron
+			s.push_back('~'); s.push_back("acgtn"[tseq[t_off]]); s.push_back("acgtn"[tseq[t_off + 1]]); put_int(s, len);
+			s.push_back("acgtn"[tseq[t_off + len - 2]]); s.push_back("acgtn"[tseq[t_off + len - 1]]);
+			t_off += len;
+		}
+	}
+}
+
+static void write_MD_core(std::string &s, const uint8_t *tseq, const uint8_t *qseq, const wm_reg1_t *r)
+{
+	s += "\tMD:Z:";
+	int q_off = 0, t_off = 0, l_MD = 0;
+	for (uint32_t i = 0; i < r->p->n_cigar; ++i) {
+		const int op = r->p->cigar[i] & 0xf, len = r->p->cigar[i] >> 4;
+		if (op == 0 || op == 7 || op == 8) {
+			for (int j = 0; j < len; ++j) {
+				if (qseq[q_off + j] != tseq[t_off + j]) { put_int(s, l_MD); s.push_back("ACGTN"[tseq[t_off + j]]); l_MD = 0; }
+				else ++l_MD;
+			}
+			q_off += len, t_off += len;
+		} else if (op == 1) q_off += len;
+		else if (op == 2) {
+			put_int(s, l_MD); s.push_back('^');
+			for (int j = 0; j < len; ++j) s.push_back("ACGTN"[tseq[t_off + j]]);
+			l_MD = 0;
+			t_off += len;
+		} else if (op == 3) t_off += len;
+	}
+	if (l_MD > 0) put_int(s, l_MD);
+}
+
+static void write_cs_or_MD(std::string &s, const wm_host_idx *mi, const wm_read *t, const wm_reg1_t *r, int no_iden, int is_MD)
+{ // src/format.c:220-243
+	if (r->p == 0) return;
+	static const struct Nt4 { uint8_t t[256]; Nt4() { for (int i = 0; i < 256; ++i) t[i] = 4; t[0] = t['A'] = t['a'] = 0; t[1] = t['C'] = t['c'] = 1;
+		t[2] = t['G'] = t['g'] = 2; t[3] = t['T'] = t['t'] = t['U'] = t['u'] = 3; } } nt4;
+	std::vector<uint8_t> qseq(r->qe - r->qs), tseq(r->re - r->rs);
+	mi->getseq(r->rid, r->rs, r->re, tseq.data());
+	if (!r->rev) for (int i = r->qs; i < r->qe; ++i) qseq[i - r->qs] = nt4.t[(uint8_t)t->seq[i]];
+	else for (int i = r->qs; i < r->qe; ++i) { const uint8_t c = nt4.t[(uint8_t)t->seq[i]]; qseq[r->qe - i - 1] = c >= 4 ? 4 : 3 - c; }
+	if (is_MD) write_MD_core(s, tseq.data(), qseq.data(), r);
+	else write_cs_core(s, tseq.data(), qseq.data(), r, no_iden);
+}
+
 void write_paf(std::string &s, const wm_host_idx *mi, const wm_read *t, const wm_reg1_t *r, int64_t opt_flag, int rep_len)
 {
 	s.clear();
@@ -77,6 +153,7 @@ void write_paf(std::string &s, const wm_host_idx *mi, const wm_read *t, const wm
 		s += "\tcg:Z:";
 		for (uint32_t k = 0; k < r->p->n_cigar; ++k) { put_int(s, (int)(r->p->cigar[k] >> 4)); s.push_back("MIDNSHP=XB"[r->p->cigar[k] & 0xf]); }
 	}
+	if (r->p && (opt_flag & (WM_F_OUT_CS | WM_F_OUT_MD))) write_cs_or_MD(s, mi, t, r, !(opt_flag & WM_F_OUT_CS_LONG), (opt_flag & WM_F_OUT_MD) != 0);
 	if ((opt_flag & WM_F_COPY_COMMENT) && !t->comment.empty()) { s.push_back('\t'); s += t->comment; }
 }
 
@@ -121,7 +198,7 @@ static void write_sam_cigar(std::string &s, int sam_flag, int in_tag, int qlen, 
 }
 
 // mm_write_sam3 (src/format.c:391-548) for a single-segment read (n_seg == 1); reg_idx < 0 writes the unmapped record.
-// --cs / --MD are not part of this build; rg_id is the @RG ID ("" = none).
+// rg_id is the @RG ID ("" = none).
 void write_sam(std::string &s, const wm_host_idx *mi, const wm_read *t, int reg_idx, int n_regs, const wm_reg1_t *regs, int64_t opt_flag, int rep_len,
                const char *rg_id)
 {
@@ -199,6 +276,7 @@ void write_sam(std::string &s, const wm_host_idx *mi, const wm_read *t, int reg_
 				}
 			}
 		}
+		if (r->p && (opt_flag & (WM_F_OUT_CS | WM_F_OUT_MD))) write_cs_or_MD(s, mi, t, r, !(opt_flag & WM_F_OUT_CS_LONG), (opt_flag & WM_F_OUT_MD) != 0);
 		if (cigar_in_tag) write_sam_cigar(s, flag, 1, l_seq, r, opt_flag);
 	}
 	if (rep_len >= 0) { s += "\trl:i:"; put_int(s, rep_len); }
