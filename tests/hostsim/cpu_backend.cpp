@@ -198,11 +198,16 @@ static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *pr
 	if (sam) { write_sam_hdr(line, &H, "2.03", 0); fwrite(line.data(), 1, line.size(), out); }
 	for (size_t i = 0; i < reads.size(); ++i) { // the output step of the reference (src/map.c:1189-1206)
 		for (size_t j = 0; j < regs[i].size(); ++j) {
+			if ((mo.flag & WM_F_NO_PRINT_2ND) && regs[i][j].id != regs[i][j].parent) continue;
 			if (sam) write_sam(line, &H, reads[i], (int)j, (int)regs[i].size(), regs[i].data(), mo.flag, rl[i], "");
 			else write_paf(line, &H, reads[i], &regs[i][j], mo.flag, rl[i]);
 			fwrite(line.data(), 1, line.size(), out); fputc('\n', out);
 		}
-		if (regs[i].empty() && sam) { write_sam(line, &H, reads[i], -1, 0, 0, mo.flag, rl[i], ""); fwrite(line.data(), 1, line.size(), out); fputc('\n', out); }
+		if (regs[i].empty() && ((mo.flag & WM_F_PAF_NO_HIT) || (sam && !(mo.flag & WM_F_SAM_HIT_ONLY)))) {
+			if (sam) write_sam(line, &H, reads[i], -1, 0, 0, mo.flag, rl[i], "");
+			else write_paf(line, &H, reads[i], 0, mo.flag, rl[i]);
+			fwrite(line.data(), 1, line.size(), out); fputc('\n', out);
+		}
 		for (auto &rr : regs[i]) free(rr.p);
 	}
 	fclose(out);

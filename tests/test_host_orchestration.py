@@ -69,9 +69,12 @@ def test_host_sam_writer_matches_reference_golden(hostsim, name, tmp_path):
         raise AssertionError(f"line count {len(exp)} vs {len(gl)} (or SEQ/QUAL text differs)")
 
 
-@pytest.mark.parametrize("key,sam,flags", [("paf_cs", 0, 0x40), ("paf_cs_long", 0, 0x40 | 0x800), ("sam_md", 1, 0x1000000)])
-def test_host_cs_md_tags_match_reference(hostsim, key, sam, flags, tmp_path):
-    """--cs / --cs=long / --MD difference strings (src/format.c:141-243) in PAF and SAM records."""
+@pytest.mark.parametrize("key,sam,flags", [("paf_cs", 0, 0x40), ("paf_cs_long", 0, 0x40 | 0x800), ("sam_md", 1, 0x1000000),
+                                            ("paf_eqx", 0, 0x4000000), ("sam_softclip", 1, 0x80000),
+                                            ("sam_no2nd_hitonly", 1, 0x4000 | 0x40000000), ("paf_no_hit", 0, 0x8000000)])
+def test_host_output_options_match_reference(hostsim, key, sam, flags, tmp_path):
+    """Output options against the reference run with the same switches: --cs / --cs=long / --MD difference strings
+    (src/format.c:141-243), --eqx (=/X CIGAR, src/align.c:169-238), -Y, --secondary=no --sam-hit-only, --paf-no-hit."""
     import hashlib
     name = make_golden.TAG_CASES[key][0]
     m = MANIFEST[name]

@@ -95,6 +95,10 @@ TAG_CASES = {
     "paf_cs": ("ont_small", ["-c", "--cs"]),
     "paf_cs_long": ("ont_small", ["-c", "--cs=long"]),
     "sam_md": ("ont_sv", ["-a", "--MD"]),
+    "paf_eqx": ("ont_sv", ["-c", "--eqx"]),                      # MM_F_EQX 0x4000000
+    "sam_softclip": ("ont_sv", ["-a", "-Y"]),                    # MM_F_SOFTCLIP 0x80000
+    "sam_no2nd_hitonly": ("ont_highocc", ["-a", "--secondary=no", "--sam-hit-only"]),  # 0x4000 | 0x40000000
+    "paf_no_hit": ("ont_highocc", ["-c", "--paf-no-hit"]),       # MM_F_PAF_NO_HIT 0x8000000
 }
 
 
