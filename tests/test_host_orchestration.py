@@ -71,14 +71,19 @@ def test_host_sam_writer_matches_reference_golden(hostsim, name, tmp_path):
 
 @pytest.mark.parametrize("key,sam,flags", [("paf_cs", 0, 0x40), ("paf_cs_long", 0, 0x40 | 0x800), ("sam_md", 1, 0x1000000),
                                             ("paf_eqx", 0, 0x4000000), ("sam_softclip", 1, 0x80000),
-                                            ("sam_no2nd_hitonly", 1, 0x4000 | 0x40000000), ("paf_no_hit", 0, 0x8000000)])
+                                            ("sam_no2nd_hitonly", 1, 0x4000 | 0x40000000), ("paf_no_hit", 0, 0x8000000),
+                                            ("sam_fastq_comment", 1, 0x2000000)])
 def test_host_output_options_match_reference(hostsim, key, sam, flags, tmp_path):
     """Output options against the reference run with the same switches: --cs / --cs=long / --MD difference strings
-    (src/format.c:141-243), --eqx (=/X CIGAR, src/align.c:169-238), -Y, --secondary=no --sam-hit-only, --paf-no-hit."""
+    (src/format.c:141-243), --eqx (=/X CIGAR, src/align.c:169-238), -Y, --secondary=no --sam-hit-only, --paf-no-hit, and
+    gzipped FASTQ input with comments under -y (QUAL column, comment copied to the record)."""
     import hashlib
-    name = make_golden.TAG_CASES[key][0]
+    case = make_golden.TAG_CASES[key]
+    name = case[0]
     m = MANIFEST[name]
     ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
+    if len(case) > 2 and case[2] == "fastq":
+        reads = make_golden.fastq_gz_of(reads, reads + ".fq.gz")
     out = str(tmp_path / "o.txt")
     hostsim.wmt_map_file_flags.argtypes = [C.c_char_p] * 5 + [C.c_int, C.c_int, C.c_int64]
     rc = hostsim.wmt_map_file_flags(ref.encode(), wfile.encode() if wfile else None, m["params"]["preset"].encode(), reads.encode(), out.encode(), 8, sam, flags)

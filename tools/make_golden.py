@@ -99,7 +99,29 @@ TAG_CASES = {
     "sam_softclip": ("ont_sv", ["-a", "-Y"]),                    # MM_F_SOFTCLIP 0x80000
     "sam_no2nd_hitonly": ("ont_highocc", ["-a", "--secondary=no", "--sam-hit-only"]),  # 0x4000 | 0x40000000
     "paf_no_hit": ("ont_highocc", ["-c", "--paf-no-hit"]),       # MM_F_PAF_NO_HIT 0x8000000
+    "sam_fastq_comment": ("ont_small", ["-a", "-y"], "fastq"),   # gzipped FASTQ with comments: QUAL column, MM_F_COPY_COMMENT 0x2000000
 }
+
+
+def fastq_gz_of(reads_fa, out):
+    """The reads as gzipped FASTQ with a comment and a deterministic quality string (input for the QUAL / -y tests)."""
+    recs, name, seq = [], None, []
+    for ln in open(reads_fa):
+        ln = ln.rstrip("\n")
+        if ln.startswith(">"):
+            if name is not None:
+                recs.append((name, "".join(seq)))
+            name, seq = ln[1:], []
+        else:
+            seq.append(ln)
+    if name is not None:
+        recs.append((name, "".join(seq)))
+    with gzip.GzipFile(out, "wb", mtime=0) as f:
+        for i, (nm, sq) in enumerate(recs):
+            q = "".join(chr(33 + (7 * j + 3 * i) % 41) for j in range(len(sq)))
+            f.write(f"@{nm} RG:Z:grp{i % 3}\tXX:i:{i}\n{sq}\n+\n{q}\n".encode())
+    return out
+
 
 
 def sam_without_pg(sam):
@@ -156,9 +178,12 @@ def main():
         manifest[name]["sam_md5"] = hashlib.md5(body).hexdigest()
         manifest[name]["sam_lines"] = body.count(b"\n")
         print(name, "SAM", manifest[name]["sam_lines"], "lines", len(body), "bytes")
-    for key, (name, args) in TAG_CASES.items():  # difference strings: --cs, --cs=long, --MD
+    for key, case in TAG_CASES.items():  # output options: --cs, --cs=long, --MD, --eqx, -Y, ...
+        name, args = case[0], case[1]
         c = CASES[name]
         ref, reads, wfile = make_inputs(name, tmp)
+        if len(case) > 2 and case[2] == "fastq":
+            reads = fastq_gz_of(reads, reads + ".fq.gz")
         cmd = [refbin, "-t", "4", "-x", c["preset"]] + args
         if wfile:
             cmd += ["-W", wfile]
