@@ -114,3 +114,22 @@ def test_rank_sharded_outputs_merge_to_the_reference(tmp_path):
     mp.close()
     assert all(shards), "every rank maps a share of the reads"
     assert multi.merge_tagged(shards) == exp
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: verified through the host path "
+                                        "(tests/test_host_orchestration.py, oracle backend), not yet on hardware")
+@pytest.mark.parametrize("key,sam", [("paf_edge", False), ("sam_edge", True)])
+def test_edge_case_reads_match_reference(key, sam, tmp_path):
+    """Empty, shorter-than-k, N-rich, IUPAC, lower-case, chimeric and unmappable reads (tools/make_golden.py edge_reads_of)."""
+    import hashlib
+    from winnowmap_b200.mapper import Mapper
+    name = make_golden.TAG_CASES[key][0]
+    m = MANIFEST[name]
+    ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
+    reads = make_golden.edge_reads_of(reads, reads + ".edge.fa")
+    mp = Mapper(ref, wfile, preset=m["params"]["preset"], cigar=True, sam=sam)
+    out = str(tmp_path / "out.txt")
+    mp.map_file(reads, out)
+    mp.close()
+    got = make_golden.sam_without_pg(open(out, "rb").read())
+    assert hashlib.md5(got).hexdigest() == m["tag_md5"][key]

@@ -72,7 +72,7 @@ def test_host_sam_writer_matches_reference_golden(hostsim, name, tmp_path):
 @pytest.mark.parametrize("key,sam,flags", [("paf_cs", 0, 0x40), ("paf_cs_long", 0, 0x40 | 0x800), ("sam_md", 1, 0x1000000),
                                             ("paf_eqx", 0, 0x4000000), ("sam_softclip", 1, 0x80000),
                                             ("sam_no2nd_hitonly", 1, 0x4000 | 0x40000000), ("paf_no_hit", 0, 0x8000000),
-                                            ("sam_fastq_comment", 1, 0x2000000)])
+                                            ("sam_fastq_comment", 1, 0x2000000), ("paf_edge", 0, 0), ("sam_edge", 1, 0)])
 def test_host_output_options_match_reference(hostsim, key, sam, flags, tmp_path):
     """Output options against the reference run with the same switches: --cs / --cs=long / --MD difference strings
     (src/format.c:141-243), --eqx (=/X CIGAR, src/align.c:169-238), -Y, --secondary=no --sam-hit-only, --paf-no-hit, and
@@ -84,6 +84,8 @@ def test_host_output_options_match_reference(hostsim, key, sam, flags, tmp_path)
     ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
     if len(case) > 2 and case[2] == "fastq":
         reads = make_golden.fastq_gz_of(reads, reads + ".fq.gz")
+    if len(case) > 2 and case[2] == "edge":  # empty, tiny, N-rich, lower-case, chimeric, unmappable reads
+        reads = make_golden.edge_reads_of(reads, reads + ".edge.fa")
     out = str(tmp_path / "o.txt")
     hostsim.wmt_map_file_flags.argtypes = [C.c_char_p] * 5 + [C.c_int, C.c_int, C.c_int64]
     rc = hostsim.wmt_map_file_flags(ref.encode(), wfile.encode() if wfile else None, m["params"]["preset"].encode(), reads.encode(), out.encode(), 8, sam, flags)

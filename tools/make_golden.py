@@ -100,7 +100,50 @@ TAG_CASES = {
     "sam_no2nd_hitonly": ("ont_highocc", ["-a", "--secondary=no", "--sam-hit-only"]),  # 0x4000 | 0x40000000
     "paf_no_hit": ("ont_highocc", ["-c", "--paf-no-hit"]),       # MM_F_PAF_NO_HIT 0x8000000
     "sam_fastq_comment": ("ont_small", ["-a", "-y"], "fastq"),   # gzipped FASTQ with comments: QUAL column, MM_F_COPY_COMMENT 0x2000000
+    "paf_edge": ("ont_small", ["-c"], "edge"),                   # empty / tiny / N-rich / lower-case / chimeric / unmappable reads
+    "sam_edge": ("ont_small", ["-a"], "edge"),
 }
+
+
+def read_fasta(path):
+    recs, name, seq = [], None, []
+    for ln in open(path):
+        ln = ln.rstrip("\n")
+        if ln.startswith(">"):
+            if name is not None:
+                recs.append((name, "".join(seq)))
+            name, seq = ln[1:], []
+        else:
+            seq.append(ln)
+    if name is not None:
+        recs.append((name, "".join(seq)))
+    return recs
+
+
+def edge_reads_of(reads_fa, out):
+    """Awkward inputs derived from the case's reads: empty, shorter than k, around k, short, lower case, N runs and IUPAC
+    codes, an unmappable random read, a chimera of two reads (second half reverse-complemented), a long read with a big
+    N block, and two untouched reads for reference."""
+    recs = read_fasta(reads_fa)
+    rng = np.random.default_rng(77)
+    comp = str.maketrans("ACGTacgt", "TGCAtgca")
+    a, b, c = recs[0][1], recs[1][1], max(recs, key=lambda r: len(r[1]))[1]
+    out_recs = [
+        ("e_empty", ""), ("e_len10", a[100:110]), ("e_len14", a[200:214]), ("e_len15", a[300:315]), ("e_len30", a[400:430]),
+        ("e_len200", a[500:700]), ("e_len999", b[100:1099]), ("e_lower", b.lower()),
+        ("e_nrun", a[:1500] + "N" * 300 + a[1800:]), ("e_iupac", b[:800] + "RYKMSWN" * 20 + b[940:]),
+        ("e_random", "".join("ACGT"[i] for i in rng.integers(0, 4, 5000))),
+        ("e_chimera", a[:len(a) // 2] + b[:len(b) // 2].translate(comp)[::-1]),
+        ("e_bigN", c[:4000] + "N" * 3000 + c[7000:]),
+        ("e_plain0", a), ("e_plain1", b),
+    ]
+    with open(out, "w") as f:
+        for nm, sq in out_recs:
+            f.write(f">{nm}\n")
+            for i in range(0, len(sq), 80):
+                f.write(sq[i:i + 80] + "\n")
+    return out
+
 
 
 def fastq_gz_of(reads_fa, out):
@@ -184,6 +227,8 @@ def main():
         ref, reads, wfile = make_inputs(name, tmp)
         if len(case) > 2 and case[2] == "fastq":
             reads = fastq_gz_of(reads, reads + ".fq.gz")
+        if len(case) > 2 and case[2] == "edge":
+            reads = edge_reads_of(reads, reads + ".edge.fa")
         cmd = [refbin, "-t", "4", "-x", c["preset"]] + args
         if wfile:
             cmd += ["-W", wfile]
