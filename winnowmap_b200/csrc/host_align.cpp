@@ -321,17 +321,27 @@ static void fix_bad_ends(const wm_reg1_t *r, const wm_pair_t *a, int bw, int min
 }
 
 // ---- AlignTask ----
-void AlignTask::init(const wm_mapopt_t *opt_, const wm_host_idx *mi_, int task_id_, int qlen_, const char *qstr, std::vector<wm_reg1_t> &regs_in, wm_pair_t *a_)
+void encode_strands(const char *seq, int len, uint8_t *fwd, uint8_t *rev)
+{ // src/align.c:871-877
+	for (int i = 0; i < len; ++i) {
+		const uint8_t c = nt4((unsigned char)seq[i]);
+		fwd[i] = c;
+		rev[len - 1 - i] = c < 4 ? 3 - c : 4;
+	}
+}
+
+void AlignTask::init(const wm_mapopt_t *opt_, const wm_host_idx *mi_, int task_id_, int qlen_, const char *qstr, std::vector<wm_reg1_t> &regs_in, wm_pair_t *a_,
+                     const uint8_t *q0, const uint8_t *q1)
 {
 	opt = opt_, mi = mi_, task_id = task_id_, qlen = qlen_, a = a_;
 	regs.clear(); // the task object is reused across waves
 	regs.swap(regs_in);
 	firsts.clear(); out.clear(); from_first.clear();
-	qcodes.resize((size_t)qlen * 2);
-	for (int i = 0; i < qlen; ++i) { // src/align.c:871-877
-		uint8_t c = nt4((unsigned char)qstr[i]);
-		qcodes[i] = c;
-		qcodes[(size_t)qlen + (qlen - 1 - i)] = c < 4 ? 3 - c : 4;
+	if (q0 && q1) q_strand[0] = q0, q_strand[1] = q1;
+	else {
+		qcodes.resize((size_t)qlen * 2);
+		encode_strands(qstr, qlen, qcodes.data(), qcodes.data() + qlen);
+		q_strand[0] = qcodes.data(), q_strand[1] = qcodes.data() + qlen;
 	}
 	gen_simple_mat(mat, (int8_t)opt->a, (int8_t)opt->b, (int8_t)opt->sc_ambi);
 	n_a = squeeze_a(regs, a); // :880

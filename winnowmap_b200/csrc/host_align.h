@@ -67,7 +67,8 @@ struct AlignTask {
 	const wm_mapopt_t *opt;
 	const wm_host_idx *mi;
 	int task_id, qlen;
-	std::vector<uint8_t> qcodes; // 2*qlen: strand 0 then strand 1 of the window (src/align.c:871-877)
+	std::vector<uint8_t> qcodes; // 2*qlen: strand 0 then strand 1 of the window (src/align.c:871-877), when the caller has no codes
+	const uint8_t *q_strand[2];  // 0..4 codes of the window, strand 0 / strand 1
 	wm_pair_t *a;
 	int n_a;
 	std::vector<wm_reg1_t> regs; // in/out
@@ -84,13 +85,15 @@ struct AlignTask {
 	std::vector<char> from_first; // out[i] was aligned in phase 1
 	int inv_job; int32_t inv_ql, inv_tl, inv_qoff, inv_toff;
 
-	void init(const wm_mapopt_t *opt_, const wm_host_idx *mi_, int task_id_, int qlen_, const char *qstr, std::vector<wm_reg1_t> &regs_in, wm_pair_t *a_);
+	// q0 / q1: codes of the window's two strands if the caller already has them (slices of the read's code arrays), else null
+	void init(const wm_mapopt_t *opt_, const wm_host_idx *mi_, int task_id_, int qlen_, const char *qstr, std::vector<wm_reg1_t> &regs_in, wm_pair_t *a_,
+	          const uint8_t *q0 = 0, const uint8_t *q1 = 0);
 	// Advance as far as possible. `dp`/`ll` are the results of the jobs this task pushed in the previous call
 	// (indexed by the job numbers it was given: base_dp/base_ll + local index).  New jobs are appended to `sink`.
 	// Returns true when the task is complete (regs holds the result of mm_align_skeleton).
 	bool advance(const DpRes *dp, const LlRes *ll, JobSink &sink);
 
-	const uint8_t *qseq(int strand) const { return qcodes.data() + (size_t)strand * qlen; }
+	const uint8_t *qseq(int strand) const { return q_strand[strand]; }
 private:
 	void plan1(Align1 &A, JobSink &sink);
 	bool walk1(Align1 &A, const DpRes *dp, const LlRes *ll, JobSink &sink);
@@ -98,6 +101,8 @@ private:
 };
 
 void gen_simple_mat(int8_t *mat, int8_t a, int8_t b, int8_t sc_ambi);
+// 0..4 codes of a sequence and of its reverse complement (src/align.c:871-877)
+void encode_strands(const char *seq, int len, uint8_t *fwd, uint8_t *rev);
 void update_extra(wm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq, const int8_t *mat, int8_t q, int8_t e, int is_eqx);
 void append_cigar(wm_reg1_t *r, uint32_t n_cigar, const uint32_t *cigar);
 

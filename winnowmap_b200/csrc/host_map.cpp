@@ -112,6 +112,13 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		exit(1);
 	}
 	be->begin_batch(reads);
+	// 0..4 codes of every read, both strands, once per batch: the alignment tasks of all windows of a read slice them
+	std::vector<int64_t> code_off(n_reads + 1, 0);
+	for (int i = 0; i < n_reads; ++i) code_off[i + 1] = code_off[i] + (int64_t)reads[i]->seq.size();
+	std::vector<uint8_t> codes_fwd((size_t)code_off[n_reads] + 1), codes_rev((size_t)code_off[n_reads] + 1);
+	#pragma omp parallel for schedule(dynamic, 8) num_threads(n_threads)
+	for (int i = 0; i < n_reads; ++i)
+		encode_strands(reads[i]->seq.data(), (int)reads[i]->seq.size(), codes_fwd.data() + code_off[i], codes_rev.data() + code_off[i]);
 
 	// the three option sets of mm_map_frag: stage 1 (src/map.c:300-302), stage 2 (:711-717), fallback (= user options, :857)
 	wm_mapopt_t opt2 = *opt, opt3 = *opt;
@@ -201,7 +208,12 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			if (M.est_err) est_err(mi, M.win.wl, M.regs, M.a.data(), (int32_t)M.mini_pos.size(), M.mini_pos.data());
 			if (sub_t) { double q1 = Timers::now(); g_timers.add("glue.est_err", q1 - q0); q0 = q1; }
 			M.aligning = (M.opt->flag & WM_F_CIGAR) != 0;
-			if (M.aligning) M.at.init(M.opt, mi, i, M.win.wl, rd->seq.data() + M.win.wb, M.regs, M.a.data());
+			if (M.aligning) {
+				const int64_t L = (int64_t)rd->seq.size(), o = code_off[M.win.read];
+				// strand 1 of the window [wb, wb+wl) is a slice of strand 1 of the read
+				M.at.init(M.opt, mi, i, M.win.wl, rd->seq.data() + M.win.wb, M.regs, M.a.data(),
+				          codes_fwd.data() + o + M.win.wb, codes_rev.data() + o + (L - M.win.wb - M.win.wl));
+			}
 			M.sink.dp.clear(), M.sink.ll.clear();
 			if (sub_t) { double q1 = Timers::now(); g_timers.add("glue.at_init", q1 - q0); q0 = q1; }
 		}
