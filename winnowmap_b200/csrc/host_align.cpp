@@ -183,16 +183,41 @@ void update_extra(wm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq, const 
 	fix_cigar(r, qseq, tseq, &qshift, &tshift);
 	qseq += qshift, tseq += tshift;
 	r->blen = r->mlen = 0;
+	// the four match scores are equal and positive for every matrix ksw_gen_simple_mat builds (src/align.c:9-22)
+	const int32_t match_sc = mat[0];
+	const bool uniform_match = match_sc > 0 && mat[6] == match_sc && mat[12] == match_sc && mat[18] == match_sc;
 	for (uint32_t k = 0; k < p->n_cigar; ++k) {
 		const uint32_t op = p->cigar[k] & 0xf, len = p->cigar[k] >> 4;
 		if (op == 0) {
 			int n_ambi = 0, n_diff = 0;
-			for (uint32_t l = 0; l < len; ++l) {
-				const int cq = qseq[qoff + l], ct = tseq[toff + l];
+			const uint8_t *qp = qseq + qoff, *tp = tseq + toff;
+			uint32_t l = 0;
+			while (l < len) {
+				if (uniform_match) { // a run of identical unambiguous bases adds a match score per base: s only grows, max follows
+					uint32_t run = 0;
+					while (l + run + 8 <= len) {
+						uint64_t wq, wt;
+						memcpy(&wq, qp + l + run, 8); memcpy(&wt, tp + l + run, 8);
+						const uint64_t x = (wq ^ wt) | (wq & 0xfcfcfcfcfcfcfcfcULL); // a non-zero byte: mismatch or ambiguous base
+						if (x == 0) { run += 8; continue; }
+						run += (uint32_t)(__builtin_ctzll(x) >> 3);
+						goto run_done;
+					}
+					while (l + run < len && qp[l + run] == tp[l + run] && qp[l + run] <= 3) ++run;
+				run_done:
+					if (run > 0) {
+						s += match_sc * (int32_t)run; // s >= 0 on entry (every other step clamps it), so no clamp can trigger inside the run
+						max = max > s ? max : s;
+						l += run;
+						continue;
+					}
+				}
+				const int cq = qp[l], ct = tp[l];
 				if (ct > 3 || cq > 3) ++n_ambi;
 				else if (ct != cq) ++n_diff;
 				s += mat[ct * 5 + cq];
 				if (s < 0) s = 0; else max = max > s ? max : s;
+				++l;
 			}
 			r->blen += len - n_ambi, r->mlen += len - (n_ambi + n_diff), p->n_ambi += n_ambi;
 			toff += len, qoff += len;
