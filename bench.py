@@ -314,7 +314,16 @@ def main():
     L.wm_prof_enable(0)
     # end to end through the host-buffer API (fresh batches)
     e2e_recs = [r for s in range(a.steps) for r in make_batch(contigs, a.reads, seed0 + 500 + s)]
+    L.wm_prof_reset()  # zeroes the library's host<->device byte counters
     e2e_t, e2e_b, d2h_b = map_host(e2e_recs)  # K steps in one call: host buffers in, alignment records out
+    h2d_step, d2h_step = int(e2e_b / a.steps), int(d2h_b / a.steps)
+    try:  # what the library actually copied: reads and job tables in; chains, DP results and CIGARs out
+        cp = (C.c_double * 2)()
+        L.wm_prof_get_copies(cp)
+        if cp[0] > 0:
+            h2d_step, d2h_step = int(cp[0] / a.steps), int(cp[1] / a.steps)
+    except AttributeError:
+        pass
     if dist is not None:
         import torch
         t = torch.tensor([t_steps, e2e_t], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -353,7 +362,7 @@ def main():
         "config": {"workload": f"{REF_LEN / 1e6:.0f} Mbp random ref, ONT reads N50=20kb 5% err, -x map-ont -W top-0.02% k=15 -c (BASELINE configs[1]); "
                                f"{a.reads} fresh reads per step per GPU, working set >> L2", "reads_per_step": a.reads, "host_threads": n_thr,
                    "lanes": int(os.environ.get("WM_LANES", max(2, min(8, n_thr // 8))))},
-        "e2e": {"value": e2e_b / e2e_t, "unit": "bases/s", "h2d_bytes_per_step": int(e2e_b / a.steps / world), "d2h_bytes_per_step": int(d2h_b / a.steps)},
+        "e2e": {"value": e2e_b / e2e_t, "unit": "bases/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step},
         "gpu_launches": int(prof[0]),
         "roofline": {"bound": "hbm", "kernel": "wm_extd2_fill_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": 5.196e9, "traffic_of": "dram read+write of one captured launch of 4.3e9 block cells (ncu --set full, "

@@ -255,6 +255,7 @@ void wm_prof_enable(int on);
 void wm_prof_reset(void);
 void wm_prof_get(double *out8); /* launches, sum of fill-kernel ms, fill launches, fill algorithmic bytes, fill block cells, fill jobs,
                                    block cells in the 16x2 path, ms during which at least one fill kernel ran (launches of concurrent lanes overlap) */
+void wm_prof_get_copies(double *out2); /* bytes copied host-to-device / device-to-host by the mapping path since wm_prof_reset */
 int wm_device_synchronize(void);
 void wm_dump_timers(void); /* prints and resets the orchestration wall-clock accumulators (stderr) */
 

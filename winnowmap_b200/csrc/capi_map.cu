@@ -408,6 +408,8 @@ extern "C" void wm_prof_get(double *o)
 	o[3] = g_wm_prof.fill_alg_bytes; o[4] = g_wm_prof.fill_cells; o[5] = g_wm_prof.fill_jobs; o[6] = g_wm_prof.fill_cells_v2;
 	o[7] = g_wm_prof.fill_union_ms;
 }
+// host<->device traffic of the mapping path since wm_prof_reset: o[0] = host-to-device bytes, o[1] = device-to-host bytes
+extern "C" void wm_prof_get_copies(double *o) { o[0] = (double)g_wm_prof.h2d_bytes; o[1] = (double)g_wm_prof.d2h_bytes; }
 extern "C" int wm_device_synchronize(void) { WM_CUDA_CHECK(cudaDeviceSynchronize()); return 0; }
 
 extern "C" void wm_free_regs(int n, const int32_t *n_reg, wm_reg1_t **reg)

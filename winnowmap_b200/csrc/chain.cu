@@ -278,7 +278,7 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	for (int i = 0; i < n_tasks; ++i) order[i] = i;
 	std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return h_off[x + 1] - h_off[x] > h_off[y + 1] - h_off[y]; });
 	int32_t *d_order = (int32_t*)ws->order.need(sizeof(int32_t) * n_tasks);
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_order, order.data(), sizeof(int32_t) * n_tasks, cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_order, order.data(), sizeof(int32_t) * n_tasks, cudaMemcpyHostToDevice, st));
 	int dev = 0, n_sm = 148;
 	WM_CUDA_CHECK(cudaGetDevice(&dev));
 	WM_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));

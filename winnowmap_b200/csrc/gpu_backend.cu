@@ -157,12 +157,12 @@ void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
 	int64_t *d_off = (int64_t*)g.d_read_off.need(sizeof(int64_t) * (n + 1));
 	bool resident = g.resident_pool != 0;
 	for (int i = 0; i < n && resident; ++i) resident = reads[i]->dev_off >= 0;
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_off, g.read_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, g.st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_off, g.read_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, g.st));
 	if (resident) { // the bases are in HBM already: gather + encode on the device
 		std::vector<int64_t> src(n);
 		for (int i = 0; i < n; ++i) src[i] = reads[i]->dev_off;
 		int64_t *d_src = (int64_t*)g.d_src_off.need(sizeof(int64_t) * (n + 1));
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_src, src.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, g.st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_src, src.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, g.st));
 		if (g.n_bases > 0) {
 			wm_count_launch(); wm_gather_code_kernel<<<(unsigned)((g.n_bases + 255) / 256), 256, 0, g.st>>>(g.resident_pool, d_src, d_off, n, d_codes, g.n_bases);
 			WM_CUDA_CHECK(cudaGetLastError());
@@ -178,7 +178,7 @@ void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
 		for (int i = 0; i < n; ++i)
 			if (!reads[i]->seq.empty()) memcpy(g.h_stage + g.read_off[i], reads[i]->seq.data(), reads[i]->seq.size());
 		char *d_ascii = (char*)g.ascii.need(g.n_bases + 16);
-		if (g.n_bases > 0) WM_CUDA_CHECK(cudaMemcpyAsync(d_ascii, g.h_stage, g.n_bases, cudaMemcpyHostToDevice, g.st));
+		if (g.n_bases > 0) WM_CUDA_CHECK(wm_memcpy_async(d_ascii, g.h_stage, g.n_bases, cudaMemcpyHostToDevice, g.st));
 		wm_ascii_to_code(d_ascii, d_codes, g.n_bases, g.st);
 	}
 	if (g.n_bases > 0) {
@@ -214,9 +214,9 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		wm_mask_task *d_mt = (wm_mask_task*)g.mask_tasks.need(sizeof(wm_mask_task) * mt.size());
 		int64_t *d_mtoff = (int64_t*)g.mask_toff.need(sizeof(int64_t) * mtoff.size());
 		int32_t *d_mp = (int32_t*)g.mask_pool.need(sizeof(int32_t) * 2 * (n_mask_iv + 1));
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_mt, mt.data(), sizeof(wm_mask_task) * mt.size(), cudaMemcpyHostToDevice, st));
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_mtoff, mtoff.data(), sizeof(int64_t) * mtoff.size(), cudaMemcpyHostToDevice, st));
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_mp, mask_pool, sizeof(int32_t) * 2 * n_mask_iv, cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_mt, mt.data(), sizeof(wm_mask_task) * mt.size(), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_mtoff, mtoff.data(), sizeof(int64_t) * mtoff.size(), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_mp, mask_pool, sizeof(int32_t) * 2 * n_mask_iv, cudaMemcpyHostToDevice, st));
 		wm_count_launch(); wm_mask_copy_kernel<<<(unsigned)((mtoff.back() + 255) / 256), 256, 0, st>>>(d_codes, d_masked, d_mt, d_mtoff, (int)mt.size(), d_mp, mtoff.back());
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
@@ -256,16 +256,16 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		std::vector<int32_t> qlen(ns);
 		for (int i = 0; i < ns; ++i) qlen[i] = skt[i].len;
 		int32_t *d_qlen = (int32_t*)g.qlen_buf.need(sizeof(int32_t) * ns);
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_qlen, qlen.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_qlen, qlen.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, st));
 		std::vector<int64_t> a_off(ns + 1);
 		wm_seed_run(sdp[pass], g.ix, (const wm128_dev*)g.sk.mz.p, (const int64_t*)g.sk.mz_off.p, n_mz, ns, d_qlen, max_occ, a_off.data(), st);
 		d_seed_a[pass] = (wm128_dev*)sdp[pass]->a.p;
 		// small per-task results
 		std::vector<int32_t> rep(ns);
 		pass_mzoff[pass].assign(ns + 1, 0); pass_mzpos[pass].resize(n_mz);
-		WM_CUDA_CHECK(cudaMemcpyAsync(rep.data(), sdp[pass]->rep_len.p, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
-		WM_CUDA_CHECK(cudaMemcpyAsync(pass_mzoff[pass].data(), g.sk.mz_off.p, sizeof(int64_t) * (ns + 1), cudaMemcpyDeviceToHost, st));
-		if (n_mz > 0) WM_CUDA_CHECK(cudaMemcpyAsync(pass_mzpos[pass].data(), sdp[pass]->mini_pos.p, sizeof(uint32_t) * n_mz, cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(wm_memcpy_async(rep.data(), sdp[pass]->rep_len.p, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(wm_memcpy_async(pass_mzoff[pass].data(), g.sk.mz_off.p, sizeof(int64_t) * (ns + 1), cudaMemcpyDeviceToHost, st));
+		if (n_mz > 0) WM_CUDA_CHECK(wm_memcpy_async(pass_mzpos[pass].data(), sdp[pass]->mini_pos.p, sizeof(uint32_t) * n_mz, cudaMemcpyDeviceToHost, st));
 		wm_stream_sync(st);
 		for (int i = 0; i < ns; ++i) {
 			const int t = ids[i];
@@ -288,14 +288,14 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	const int64_t n_f = f_off[n];
 	wm128_dev *d_A;
 	int64_t *d_foff = (int64_t*)g.off_buf.need(sizeof(int64_t) * (n + 1));
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_foff, f_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_foff, f_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
 	if (!any_pre && !any_mask_pass) {
 		d_A = d_seed_a[0]; // the plain pass' array already has exactly this layout (tasks in order, no gaps)
 		if (d_A == 0) d_A = (wm128_dev*)g.cat_a.need(16);
 	} else {
 		d_A = (wm128_dev*)g.cat_a.need(sizeof(wm128_dev) * (n_f + 1));
 		wm128_dev *d_pre = (wm128_dev*)g.pre_buf.need(sizeof(wm128_dev) * (n_pre + 1));
-		if (n_pre > 0) WM_CUDA_CHECK(cudaMemcpyAsync(d_pre, pre_pool, sizeof(wm128_dev) * n_pre, cudaMemcpyHostToDevice, st));
+		if (n_pre > 0) WM_CUDA_CHECK(wm_memcpy_async(d_pre, pre_pool, sizeof(wm128_dev) * n_pre, cudaMemcpyHostToDevice, st));
 		// tasks fed from the plain pass and from the masked pass need different source arrays: two launches
 		for (int pass = 0; pass < 2; ++pass) {
 			std::vector<wm_cat_task> c2; std::vector<int64_t> toff(1, 0);
@@ -311,8 +311,8 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 			if (c2.empty()) continue;
 			wm_cat_task *d_ct = (wm_cat_task*)g.cat_tasks.need(sizeof(wm_cat_task) * c2.size());
 			int64_t *d_toff = (int64_t*)g.cat_toff.need(sizeof(int64_t) * toff.size());
-			WM_CUDA_CHECK(cudaMemcpyAsync(d_ct, c2.data(), sizeof(wm_cat_task) * c2.size(), cudaMemcpyHostToDevice, st));
-			WM_CUDA_CHECK(cudaMemcpyAsync(d_toff, toff.data(), sizeof(int64_t) * toff.size(), cudaMemcpyHostToDevice, st));
+			WM_CUDA_CHECK(wm_memcpy_async(d_ct, c2.data(), sizeof(wm_cat_task) * c2.size(), cudaMemcpyHostToDevice, st));
+			WM_CUDA_CHECK(wm_memcpy_async(d_toff, toff.data(), sizeof(int64_t) * toff.size(), cudaMemcpyHostToDevice, st));
 			const wm128_dev *src = d_seed_a[pass] ? d_seed_a[pass] : d_A;
 			wm_count_launch(); wm_concat_kernel<<<(unsigned)((toff.back() + 255) / 256), 256, 0, st>>>(d_ct, d_toff, (int)c2.size(), d_pre, src, d_A, toff.back());
 			WM_CUDA_CHECK(cudaGetLastError());
@@ -343,7 +343,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	}
 	// 4. chaining
 	uint8_t *d_set = (uint8_t*)g.set_id.need(n);
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_set, set_id.data(), n, cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_set, set_id.data(), n, cudaMemcpyHostToDevice, st));
 	wm_chain_params2 PP;
 	for (int s = 0; s < 2; ++s) {
 		wm_chain_params &P = PP.p[s];
@@ -353,22 +353,22 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	double t_chain0 = Timers::now();
 	wm_chain_run(&g.ch, d_A, d_foff, f_off.data(), n, PP, d_set, st);
 	g.h_nu.assign(n, 0); g.h_nb.assign(n, 0);
-	WM_CUDA_CHECK(cudaMemcpyAsync(g.h_nu.data(), g.ch.n_u.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-	WM_CUDA_CHECK(cudaMemcpyAsync(g.h_nb.data(), g.ch.n_b.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(wm_memcpy_async(g.h_nu.data(), g.ch.n_u.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(wm_memcpy_async(g.h_nb.data(), g.ch.n_b.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
 	wm_stream_sync(st);
 	g_timers.add("seed.chain", Timers::now() - t_chain0);
 	std::vector<int64_t> nb_off(n + 1, 0), nu_off(n + 1, 0);
 	for (int i = 0; i < n; ++i) nb_off[i + 1] = nb_off[i] + g.h_nb[i], nu_off[i + 1] = nu_off[i] + g.h_nu[i];
 	int64_t *d_nb = (int64_t*)g.nb_off.need(sizeof(int64_t) * (n + 1)), *d_nu = (int64_t*)g.nu_off.need(sizeof(int64_t) * (n + 1));
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_nb, nb_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_nu, nu_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_nb, nb_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_nu, nu_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
 	wm128_dev *d_bo = (wm128_dev*)g.b_out.need(sizeof(wm128_dev) * (nb_off[n] + 1));
 	uint64_t *d_uo = (uint64_t*)g.u_out.need(sizeof(uint64_t) * (nu_off[n] + 1));
 	wm_count_launch(); wm_compact_chain_kernel<<<(unsigned)(((int64_t)n * 32 + 127) / 128), 128, 0, st>>>(d_foff, d_nb, d_nu, n, d_A, (const uint64_t*)g.ch.u2.p, d_bo, d_uo);
 	WM_CUDA_CHECK(cudaGetLastError());
 	g.h_b.resize(nb_off[n] + 1); g.h_u.resize(nu_off[n] + 1);
-	if (nb_off[n] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_b.data(), d_bo, sizeof(wm128_dev) * nb_off[n], cudaMemcpyDeviceToHost, st));
-	if (nu_off[n] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_u.data(), d_uo, sizeof(uint64_t) * nu_off[n], cudaMemcpyDeviceToHost, st));
+	if (nb_off[n] > 0) WM_CUDA_CHECK(wm_memcpy_async(g.h_b.data(), d_bo, sizeof(wm128_dev) * nb_off[n], cudaMemcpyDeviceToHost, st));
+	if (nu_off[n] > 0) WM_CUDA_CHECK(wm_memcpy_async(g.h_u.data(), d_uo, sizeof(uint64_t) * nu_off[n], cudaMemcpyDeviceToHost, st));
 	wm_stream_sync(st);
 	// 5. per task views
 	g.h_mz_off.assign(n + 1, 0);
@@ -527,9 +527,9 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		uint8_t *d_bt = (uint8_t*)g.bt.need(p_off + 16);
 		wm_extz_dev *d_ez = (wm_extz_dev*)g.ez.need(sizeof(wm_extz_dev) * m);
 		uint32_t *d_cig = (uint32_t*)g.cig.need(sizeof(uint32_t) * (c_off + 1));
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_gj, gj.data(), sizeof(wm_gather_job) * gj.size(), cudaMemcpyHostToDevice, st));
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_joff, joff.data(), sizeof(int64_t) * joff.size(), cudaMemcpyHostToDevice, st));
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_dj, dj.data(), sizeof(wm_dp_job) * m, cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_gj, gj.data(), sizeof(wm_gather_job) * gj.size(), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_joff, joff.data(), sizeof(int64_t) * joff.size(), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_dj, dj.data(), sizeof(wm_dp_job) * m, cudaMemcpyHostToDevice, st));
 		if (pool_off > 0) {
 			wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
 			WM_CUDA_CHECK(cudaGetLastError());
@@ -538,8 +538,8 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		wm_zd_params zp; memset(&zp, 0, sizeof(zp));
 		zp.q = sc.q, zp.e = sc.e; memcpy(zp.mat, sc.mat, 25);
 		wm_extd2_launch(&g.dpws, d_dj, m, plan, d_pool, d_bt, d_ez, d_cig, P, st, &zp, d_zd);
-		WM_CUDA_CHECK(cudaMemcpyAsync(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
-		WM_CUDA_CHECK(cudaMemcpyAsync(g.h_zd.data() + 5 * (size_t)done, d_zd, sizeof(int32_t) * 5 * m, cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(wm_memcpy_async(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(wm_memcpy_async(g.h_zd.data() + 5 * (size_t)done, d_zd, sizeof(int32_t) * 5 * m, cudaMemcpyDeviceToHost, st));
 		wm_stream_sync(st);
 		g_timers.add("dp.gpu_fill_bt", Timers::now() - tq0);
 		double tr0 = Timers::now();
@@ -552,12 +552,12 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		}
 		int64_t *d_ooff = (int64_t*)g.cig_off.need(sizeof(int64_t) * (m + 1));
 		uint32_t *d_cout = (uint32_t*)g.cig_out.need(sizeof(uint32_t) * (o_off[m] + 1));
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_ooff, o_off.data(), sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_ooff, o_off.data(), sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
 		wm_count_launch(); wm_compact_cigar_kernel<<<(unsigned)(((int64_t)m * 32 + 127) / 128), 128, 0, st>>>(d_dj, d_ez, d_ooff, m, d_cig, d_cout);
 		WM_CUDA_CHECK(cudaGetLastError());
 		const size_t base = g.h_cig.size();
 		g.h_cig.resize(base + o_off[m] + 1);
-		if (o_off[m] > 0) WM_CUDA_CHECK(cudaMemcpyAsync(g.h_cig.data() + base, d_cout, sizeof(uint32_t) * o_off[m], cudaMemcpyDeviceToHost, st));
+		if (o_off[m] > 0) WM_CUDA_CHECK(wm_memcpy_async(g.h_cig.data() + base, d_cout, sizeof(uint32_t) * o_off[m], cudaMemcpyDeviceToHost, st));
 		wm_stream_sync(st);
 		g.h_cig.resize(base + o_off[m]);
 		for (int i = 0; i < m; ++i) cig_base[done + i] = (int64_t)base + o_off[i];
@@ -607,17 +607,17 @@ void GpuBackend::run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin
 	wm_ll_job *d_lj = (wm_ll_job*)g.ll_jobs.need(sizeof(wm_ll_job) * n);
 	int32_t *d_scr = (int32_t*)g.ll_scr.need(sizeof(int32_t) * (s_off + 4)), *d_out = (int32_t*)g.ll_out.need(sizeof(int32_t) * 3 * (size_t)n);
 	int8_t *d_mat = (int8_t*)g.mat.need(32);
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_gj, gj.data(), sizeof(wm_gather_job) * gj.size(), cudaMemcpyHostToDevice, st));
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_joff, joff.data(), sizeof(int64_t) * joff.size(), cudaMemcpyHostToDevice, st));
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_lj, lj.data(), sizeof(wm_ll_job) * n, cudaMemcpyHostToDevice, st));
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_mat, sc.mat, 25, cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_gj, gj.data(), sizeof(wm_gather_job) * gj.size(), cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_joff, joff.data(), sizeof(int64_t) * joff.size(), cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_lj, lj.data(), sizeof(wm_ll_job) * n, cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_mat, sc.mat, 25, cudaMemcpyHostToDevice, st));
 	if (pool_off > 0) {
 		wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	wm_ksw_ll_launch(d_lj, n, d_pool, d_mat, sc.q, sc.e, d_scr, d_out, st);
 	std::vector<int32_t> out(3 * (size_t)n);
-	WM_CUDA_CHECK(cudaMemcpyAsync(out.data(), d_out, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(wm_memcpy_async(out.data(), d_out, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, st));
 	wm_stream_sync(st);
 	for (int i = 0; i < n; ++i) res[i].score = out[3 * i], res[i].qe = out[3 * i + 1], res[i].te = out[3 * i + 2];
 }

@@ -312,8 +312,8 @@ void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_co
 	wm_sk_task *d_tasks = (wm_sk_task*)ws->tasks.need(sizeof(wm_sk_task) * (n_tasks + 1));
 	int64_t *d_off = (int64_t*)ws->offs.need(sizeof(int64_t) * h_off.size());
 	int64_t *d_mz_off = (int64_t*)ws->mz_off.need(sizeof(int64_t) * (n_tasks + 1));
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_tasks, h_tasks, sizeof(wm_sk_task) * n_tasks, cudaMemcpyHostToDevice, st));
-	WM_CUDA_CHECK(cudaMemcpyAsync(d_off, h_off.data(), sizeof(int64_t) * h_off.size(), cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_tasks, h_tasks, sizeof(wm_sk_task) * n_tasks, cudaMemcpyHostToDevice, st));
+	WM_CUDA_CHECK(wm_memcpy_async(d_off, h_off.data(), sizeof(int64_t) * h_off.size(), cudaMemcpyHostToDevice, st));
 	WM_CUDA_CHECK(cudaMemsetAsync(d_mz_off, 0, sizeof(int64_t) * (n_tasks + 1), st));
 	if (n_bases == 0 || n_tasks == 0) { wm_stream_sync(st); return; }
 	const int64_t *d_tile_off = d_off, *d_chunk_off = d_off + n_tasks + 1, *d_base_off = d_chunk_off + n_tasks + 1;
@@ -339,13 +339,13 @@ void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_co
 	WM_CUDA_CHECK(cudaGetLastError());
 	wm_exclusive_scan(d_cnt, n_chunks, d_rank, d_tmp, st);
 	int64_t total = 0;
-	WM_CUDA_CHECK(cudaMemcpyAsync(&total, d_rank + n_chunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+	WM_CUDA_CHECK(wm_memcpy_async(&total, d_rank + n_chunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
 	wm_stream_sync(st);
 	wm128_dev *d_mz = (wm128_dev*)ws->mz.need(sizeof(wm128_dev) * (total + 1));
 	// trailing empty sequences: their offset is the total
 	{
 		std::vector<int64_t> fill(n_tasks + 1, total);
-		WM_CUDA_CHECK(cudaMemcpyAsync(d_mz_off, fill.data(), sizeof(int64_t) * (n_tasks + 1), cudaMemcpyHostToDevice, st));
+		WM_CUDA_CHECK(wm_memcpy_async(d_mz_off, fill.data(), sizeof(int64_t) * (n_tasks + 1), cudaMemcpyHostToDevice, st));
 	}
 	wm_count_launch(); wm_sketch_emit_kernel<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, st>>>(d_codes, d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, k,
 	                                                                               d_flag, d_rank, d_mz, d_mz_off);

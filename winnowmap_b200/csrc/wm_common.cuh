@@ -23,8 +23,16 @@ struct wm_prof_t {
 	long long n_launches;
 	int enabled;
 	double fill_ms; long long fill_launches; double fill_alg_bytes, fill_cells, fill_jobs, fill_cells_v2, fill_union_ms;
+	long long h2d_bytes, d2h_bytes; // every host<->device copy of the mapping path (wm_memcpy_async)
 };
 extern wm_prof_t g_wm_prof;
+// cudaMemcpyAsync that also counts the bytes per direction (bench: e2e.h2d_bytes_per_step / d2h_bytes_per_step)
+static inline cudaError_t wm_memcpy_async(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st)
+{
+	if (kind == cudaMemcpyHostToDevice) __atomic_fetch_add(&g_wm_prof.h2d_bytes, (long long)bytes, __ATOMIC_RELAXED);
+	else if (kind == cudaMemcpyDeviceToHost) __atomic_fetch_add(&g_wm_prof.d2h_bytes, (long long)bytes, __ATOMIC_RELAXED);
+	return cudaMemcpyAsync(dst, src, bytes, kind, st);
+}
 void wm_prof_fill_begin(void);   // ksw_extd2.cu
 void wm_prof_fill_collect(void);
 static inline void wm_count_launch() { __atomic_fetch_add(&g_wm_prof.n_launches, 1LL, __ATOMIC_RELAXED); }
