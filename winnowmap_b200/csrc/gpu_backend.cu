@@ -457,7 +457,8 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		std::vector<wm_gather_job> gj(2 * (size_t)m); std::vector<int64_t> joff(2 * (size_t)m + 1, 0); std::vector<wm_dp_job> dj(m);
 		int64_t pool_off = 0, p_off = 0, c_off = 0;
 		double prof_bytes = 0;
-		// the persistent warps pull jobs in array order: biggest first, so that the tail of the launch is made of small jobs
+		// CTAs are dispatched in array order, four consecutive jobs each: biggest first, so that a CTA's jobs are of similar
+		// size and the tail of the launch is made of small jobs
 		// (stable counting sort on qlen + tlen, descending)
 		std::vector<int> perm(m);
 		{

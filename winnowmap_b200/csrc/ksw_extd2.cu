@@ -7,13 +7,14 @@
 // wrap-around arithmetic, and the backtrack uses block bounds (src/ksw2.h:119-151).
 //
 // Mapping to the GPU: one warp owns one DP job and sweeps anti-diagonals r = i + j; lanes
-// own consecutive target positions t of the diagonal (32 cells per step), the t-1 operand
-// of the recurrence comes from the neighbouring lane by shuffle (the SSE code shifts a
-// vector by one byte instead).  The seven int8 state rows (u,v,x,y,x2,y2,s) and the int32
-// H row live in shared memory for jobs up to WM_SMEM_CELLS target bases and in an
-// L2-resident global scratch slice otherwise.  Direction bytes are streamed to HBM, one
-// row of the rotated matrix per diagonal; a second kernel walks them back (one thread per
-// job) and emits the CIGAR.
+// own consecutive target positions t of the diagonal, the t-1 operand of the recurrence
+// comes from the neighbouring lane by shuffle (the SSE code shifts a vector by one byte
+// instead).  The production sweep is ksw_extd2_v2.cuh (128 cells per step, 16x2 SIMD with
+// tagged maxima); the function in this file is the first-generation sweep (32 cells per
+// step, int32 math with int8 wrap casts), kept selectable with WM_DP_V1=1.  State rows live
+// in shared memory or, for long targets, in an L2-resident global slice.  Direction bytes
+// are streamed to HBM, one row of the rotated matrix per diagonal; a second kernel walks
+// them back (one thread per job), emits the CIGAR and, for gap fills, the Z-drop score walk.
 #include <mutex>
 #include <vector>
 #include <algorithm>
