@@ -235,3 +235,13 @@ extern "C" int wmt_map_file_sam(const char *ref_fn, const char *kmer_fn, const c
 #include "../../winnowmap_b200/csrc/host_timers.h"
 // tuning aid: the orchestration's phase timers (WM_SUBTIMING=1 adds the per-task breakdown)
 extern "C" void wmt_dump_timers(void) { wmh::g_timers.dump(stderr); wmh::g_timers.reset(); }
+
+// unit hook: the index builder's parallel (hash, position) sort on an interleaved x,y array
+#include "../../winnowmap_b200/csrc/host_index.h"
+extern "C" void wmt_sort_index_pairs(uint64_t *xy, int64_t n, int n_threads)
+{
+	std::vector<wm_pair_t> a((size_t)n);
+	for (int64_t i = 0; i < n; ++i) a[i].x = xy[2 * i], a[i].y = xy[2 * i + 1];
+	wmh::sort_index_pairs(a, n_threads);
+	for (int64_t i = 0; i < n; ++i) xy[2 * i] = a[i].x, xy[2 * i + 1] = a[i].y;
+}

@@ -100,3 +100,18 @@ def test_host_output_options_match_reference(hostsim, key, sam, flags, tmp_path)
                     cols = [j for j, (p, q) in enumerate(zip(fx, fy)) if p != q]
                     raise AssertionError(f"line {i} cols {cols}: {[fx[j][:80] for j in cols[:3]]} vs {[fy[j][:80] for j in cols[:3]]}")
         raise AssertionError(f"{key}: output differs from the reference (md5)")
+
+
+def test_index_pair_sort_is_the_sorted_order(hostsim):
+    """wm_index_build orders the (minimizer, position) pairs of the reference by hash, then position (src/index.c:239)
+    with a partitioned parallel sort (csrc/host_index.h): same result as a plain sort, for any thread count."""
+    import numpy as np
+    hostsim.wmt_sort_index_pairs.argtypes = [C.c_void_p, C.c_int64, C.c_int]
+    rng = np.random.default_rng(5)
+    for n, key_bits, threads in [(0, 30, 4), (1, 30, 4), (1000, 30, 8), (70000, 12, 3), (300000, 30, 8), (500000, 38, 16)]:
+        x = (rng.integers(0, 1 << key_bits, size=n, dtype=np.uint64) << np.uint64(8)) | rng.integers(0, 256, size=n, dtype=np.uint64)
+        y = rng.permutation(n).astype(np.uint64)
+        a = np.stack([x, y], axis=1).copy()
+        hostsim.wmt_sort_index_pairs(a.ctypes.data, n, threads)
+        order = np.lexsort((y, x >> np.uint64(8)))
+        assert np.array_equal(a, np.stack([x[order], y[order]], axis=1)), (n, key_bits, threads)

@@ -14,6 +14,7 @@
 #include "sketch.cuh"
 #include "gpu_backend.h"
 #include "host_io.h"
+#include "host_index.h"
 #include "host_timers.h"
 
 using namespace wmh;
@@ -221,7 +222,7 @@ extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_fre
 	flush();
 	ws.release(); d_ascii.release(); d_codes.release(); cudaFree(d_table);
 	// (hash, position) pairs sorted by hash then position: the occurrence lists mm_idx_get returns (src/index.c:239)
-	std::sort(mz.begin(), mz.end(), [](const wm128_dev &a, const wm128_dev &b) { return (a.x >> 8) != (b.x >> 8) ? (a.x >> 8) < (b.x >> 8) : a.y < b.y; });
+	sort_index_pairs(mz, std::min(32, omp_get_max_threads()));
 	std::vector<uint64_t> keys, pos_off, pos(mz.size());
 	for (size_t i = 0; i < mz.size(); ++i) {
 		if (i == 0 || (mz[i].x >> 8) != (mz[i - 1].x >> 8)) { keys.push_back(mz[i].x >> 8); pos_off.push_back(i); }
