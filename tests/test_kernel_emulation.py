@@ -1,0 +1,103 @@
+"""CPU check of the DP kernels' arithmetic: the product's fill sweep (csrc/ksw_extd2_v2.cuh: 16x2 SIMD, tagged maxima, block
+rounding, stale score cells) and traceback / Z-drop walk (csrc/ksw_extd2_common.cuh) are compiled for the host on a
+software warp (tests/hostsim/cuda_emul.h, kernel_emul.cpp) and compared with the oracle, bit for bit.  The same code
+runs on the device in tests/test_gpu_extd2.py; this tier catches arithmetic regressions where there is no GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from test_oracle_vs_ref import FLAGS, rand_pair
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul():
+    d = os.path.join(ROOT, "tests", "hostsim")
+    subprocess.check_call([os.path.join(d, "build.sh")], stderr=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(d, "libwm_hostsim.so"))
+    L.wmt_emul_extd2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    return L
+
+
+def _run(L, q, t, mat, prm, w, zdrop, eb, flag, global_state):
+    q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8)
+    mat = np.ascontiguousarray(mat, dtype=np.int8)
+    cap = len(q) + len(t) + 2
+    ez = np.zeros(12, np.int32); cig = np.zeros(cap, np.uint32); zd = np.zeros(5, np.int32)
+    rc = L.wmt_emul_extd2(q.ctypes.data, len(q), t.ctypes.data, len(t), mat.ctypes.data, *prm, w, zdrop, eb, flag, int(global_state),
+                          ez.ctypes.data, cig.ctypes.data, cap, zd.ctypes.data)
+    assert rc == 0
+    return ez, cig[:max(0, ez[10])], zd
+
+
+def _check(L, q, t, mat, prm, w, zdrop, eb, flag, global_state):
+    ez, cig, _ = _run(L, q, t, mat, prm, w, zdrop, eb, flag, global_state)
+    e0, c0 = ol.oracle_extd2(q, t, mat, *prm, w, zdrop, eb, flag)
+    assert np.array_equal(e0[:11], ez[:11]), (len(q), len(t), w, hex(flag), global_state, e0, ez)
+    assert np.array_equal(c0, cig), (len(q), len(t), w, hex(flag), global_state)
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_fill_and_traceback_match_oracle(emul, seed):
+    rng = np.random.default_rng(4100 + seed)
+    mat = ol.simple_mat()
+    for it in range(36):
+        tlen = int(rng.choice([1, 5, 16, 17, 33, 64, 100, 130, 250, 300, 480]))
+        q, t = rand_pair(rng, tlen, err=float(rng.choice([0.02, 0.1, 0.3])), drift=int(rng.choice([0, 0, 30, 120])), n_runs=int(rng.integers(0, 3)))
+        if len(q) > 640:
+            q = q[:640]
+        w = int(rng.choice([5, 20, 50, 100, 751])); zdrop = int(rng.choice([400, 200, 50, -1])); eb = int(rng.choice([-1, 0, 10]))
+        flag = FLAGS[int(rng.integers(0, len(FLAGS)))]
+        _check(emul, q, t, mat, (4, 2, 24, 1), w, zdrop, eb, flag, global_state=bool(it & 1))
+
+
+def test_other_scorings_and_a_long_target(emul):
+    rng = np.random.default_rng(4200)
+    for a, b, q_, e_, q2, e2 in [(1, 4, 6, 2, 26, 1), (2, 4, 24, 1, 4, 2)]:  # asm-like scoring; gap pair given in swapped order
+        mat = ol.simple_mat(a, b, 1)
+        for i in range(6):
+            q, t = rand_pair(rng, int(rng.integers(20, 400)), err=0.05, drift=int(rng.choice([0, 50])))
+            _check(emul, q[:640], t, mat, (q_, e_, q2, e2), 200, 200, -1, FLAGS[i % 4], global_state=False)
+    q, t = rand_pair(rng, 1300, err=0.08, drift=100)  # beyond the shared-memory slice: global state rows only
+    _check(emul, q, t, ol.simple_mat(), (4, 2, 24, 1), 751, 400, -1, 0x40, global_state=True)
+
+
+def test_zdrop_walk_matches_the_host_walk(emul):
+    """The device-side mm_test_zdrop walk (flag 0x10000) against a direct restatement of src/align.c:32-70."""
+    rng = np.random.default_rng(4300)
+    mat = ol.simple_mat()
+    for _ in range(10):
+        q, t = rand_pair(rng, int(rng.integers(100, 400)), err=0.12, drift=int(rng.choice([0, 80])), n_runs=2)
+        q = q[:640]
+        ez, cig, zd = _run(emul, q, t, mat, (4, 2, 24, 1), 751, 400, -1, 0x08 | 0x10000, False)
+        score, mx, max_i, max_j, i, j, best, pos = 0, -(1 << 31), -1, -1, 0, 0, 0, [-1, -1, -1, -1]
+
+        def upd(sc, ii, jj):
+            nonlocal mx, max_i, max_j, best, pos
+            if sc < mx:
+                li, lj = ii - max_i, jj - max_j
+                z = mx - sc - abs(li - lj) * 2
+                if z > best:
+                    best, pos = z, [max_i, ii, max_j, jj]
+            else:
+                mx, max_i, max_j = sc, ii, jj
+        for c in cig:
+            op, ln = int(c) & 0xf, int(c) >> 4
+            if op == 0:
+                for k in range(ln):
+                    score += int(mat[int(t[i + k]) * 5 + int(q[j + k])])
+                    upd(score, i + k, j + k)
+                i += ln; j += ln
+            else:
+                score -= 4 + 2 * ln
+                if op == 1:
+                    j += ln
+                else:
+                    i += ln
+                upd(score, i, j)
+        assert list(zd) == [best] + pos

@@ -25,9 +25,13 @@ __device__ __forceinline__ uint32_t wm_rep2(int v) { return wm_pack2(v, v); }
 // (the __byte_perm intrinsic only defines the low 3 bits of each nibble)
 __device__ __forceinline__ uint32_t wm_prmt(uint32_t a, uint32_t b, uint32_t c)
 {
+#ifdef WM_HOST_EMUL // tests/hostsim/cuda_emul.h: the sweep compiled for the host
+	return wm_emul_prmt(a, b, c);
+#else
 	uint32_t d;
 	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
 	return d;
+#endif
 }
 // (a & m) | (b & ~m)
 __device__ __forceinline__ uint32_t wm_bitsel(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
