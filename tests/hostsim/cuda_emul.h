@@ -6,6 +6,7 @@
 #include <ucontext.h>
 #include <stdint.h>
 #include <string.h>
+#include <algorithm>
 #include <cuda_runtime.h> // types only (uint2, cudaStream_t); __device__ / __forceinline__ expand to host-neutral forms
 
 #define WM_HOST_EMUL 1
@@ -89,3 +90,26 @@ inline uint32_t wm_emul_prmt(uint32_t a, uint32_t b, uint32_t sel)
 	return r;
 }
 inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) { return wm_emul_prmt(a, b, sel & 0x7777u); }
+
+// ---- warp votes, bit utilities and the rounding-mode intrinsics of the chaining kernels ----
+inline unsigned __ballot_sync(unsigned, bool pred)
+{ // two rounds: everybody publishes, everybody collects
+	wm_emul::warp->xchg[wm_emul::lane] = pred ? 1 : 0;
+	wm_emul::sync();
+	unsigned m = 0;
+	for (int l = 0; l < 32; ++l) m |= (unsigned)(wm_emul::warp->xchg[l] & 1) << l;
+	wm_emul::sync();
+	return m;
+}
+inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0; }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+// compiled with -ffp-contract=off: plain C operations round to nearest even, once, like the _rn intrinsics
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __ull2float_rn(unsigned long long x) { return (float)x; }
+inline float __ll2float_rn(long long x) { return (float)x; }
+using std::max;
+using std::min;

@@ -8,9 +8,11 @@
 #include "../../winnowmap_b200/csrc/wm_common.cuh"
 #include "../../winnowmap_b200/csrc/ksw_extd2_common.cuh"
 #include "../../winnowmap_b200/csrc/ksw_extd2_v2.cuh"
+#include "../../winnowmap_b200/csrc/chain_dev.cuh"
 
 namespace wm_emul {
 thread_local Warp *warp = 0; thread_local int lane = 0;
+static long long g_total_syncs = 0; // warp-wide synchronisation points executed so far (a proxy for dependent steps)
 static void fiber_entry()
 {
 	Warp *w = warp;
@@ -41,6 +43,7 @@ void run_warp(void (*body)(int lane, void *arg), void *arg)
 	warp = &W;
 	swapcontext(&W.main_ctx, &W.ctx[0]);
 	warp = saved;
+	g_total_syncs += W.gen;
 	for (int l = 0; l < 32; ++l) free(W.stack[l]);
 }
 }
@@ -105,3 +108,69 @@ extern "C" int wmt_emul_extd2(const uint8_t *query, int qlen, const uint8_t *tar
 	memcpy(ez_out, &ez, sizeof(ez));
 	return 0;
 }
+
+// The chaining forward pass (csrc/chain_dev.cuh) on the software warp: dense = 0 the production formulation (32
+// predecessors per step), dense = 1 the dense-candidate formulation.  Outputs the f / p / v arrays the backtracking
+// kernel consumes (a is `n` anchors, x then y).
+extern "C" int wmt_emul_chain_fill(const uint64_t *a_xy, int n, int max_dist_x, int min_dist_x, int max_dist_y, int bw, int max_skip, int max_iter,
+                                   float gap_scale, int dense, int32_t *f, int32_t *p, int32_t *v)
+{
+	std::vector<wm128_dev> a((size_t)n + 1);
+	for (int i = 0; i < n; ++i) a[i].x = a_xy[2 * i], a[i].y = a_xy[2 * i + 1];
+	wm_chain_params P; memset(&P, 0, sizeof(P));
+	P.max_dist_x = max_dist_x, P.min_dist_x = min_dist_x, P.max_dist_y = max_dist_y, P.bw = bw, P.max_skip = max_skip, P.max_iter = max_iter;
+	P.gap_scale = gap_scale;
+	std::vector<int32_t> t((size_t)n + 1, 0), D(WM_CHAIN_DENSE_CAP, 0);
+	struct Args { const wm128_dev *a; int n; const wm_chain_params *P; int32_t *f, *p, *t, *v, *D; int dense; } A = { a.data(), n, &P, f, p, t.data(), v, D.data(), dense };
+	if (n <= 0) return 0;
+	wm_emul::run_warp([](int l, void *q) {
+		Args &x = *(Args*)q;
+		if (x.dense) wm_chain_fill_warp_dense(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, x.D, l);
+		else wm_chain_fill_warp(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, l);
+	}, &A);
+	return 0;
+}
+
+// Scalar restatement of the forward pass of mm_chain_dp (src/chain.c:41-90, n_segs == 1, is_cdna == 0): the yardstick
+// for the two warp formulations above.
+extern "C" int wmt_chain_fill_scalar(const uint64_t *a_xy, int n, int max_dist_x, int min_dist_x, int max_dist_y, int bw, int max_skip, int max_iter,
+                                     float gap_scale, int32_t *f, int32_t *p, int32_t *v)
+{
+	if (n <= 0) return 0;
+	std::vector<int32_t> t((size_t)n, 0);
+	uint64_t sum_qspan = 0;
+	for (int i = 0; i < n; ++i) sum_qspan += a_xy[2 * i + 1] >> 32 & 0xff;
+	const float avg_qspan = (float)sum_qspan / n;
+	int st = 0;
+	for (int i = 0; i < n; ++i) {
+		const uint64_t ri = a_xy[2 * i];
+		const int32_t qi = (int32_t)a_xy[2 * i + 1], q_span = (int32_t)(a_xy[2 * i + 1] >> 32 & 0xff);
+		int32_t max_f = q_span, max_j = -1, n_skip = 0;
+		while (st < i && ri > a_xy[2 * st] + (uint64_t)(int64_t)max_dist_x) ++st;
+		if (i - st > max_iter)
+			while (i - st > max_iter && ri > a_xy[2 * st] + (uint64_t)(int64_t)min_dist_x) ++st;
+		for (int j = i - 1; j >= st; --j) {
+			const int64_t dr = (int64_t)(ri - a_xy[2 * j]);
+			const int32_t dq = qi - (int32_t)a_xy[2 * j + 1];
+			if (dr == 0 || dq <= 0) continue;
+			if (dq > max_dist_y || dq > max_dist_x) continue;
+			const int32_t dd = (int32_t)(dr > dq ? dr - dq : dq - dr);
+			if (dd > bw) continue;
+			const int32_t min_d = dq < dr ? dq : (int32_t)dr;
+			int32_t sc = min_d > q_span ? q_span : min_d;
+			int log_dd = 0;
+			if (dd) { log_dd = 31 - __builtin_clz((unsigned)dd); }
+			const int gap_cost = (int)(dd * .01 * avg_qspan) + (log_dd >> 1);
+			sc -= (int)((double)gap_cost * gap_scale + .499);
+			sc += f[j];
+			if (sc > max_f) { max_f = sc, max_j = j; if (n_skip > 0) --n_skip; }
+			else if (t[j] == i) { if (++n_skip > max_skip) break; }
+			if (p[j] >= 0) t[p[j]] = i;
+		}
+		f[i] = max_f, p[i] = max_j;
+		v[i] = max_j >= 0 && v[max_j] > max_f ? v[max_j] : max_f;
+	}
+	return 0;
+}
+
+extern "C" long long wmt_emul_sync_count(void) { return wm_emul::g_total_syncs; }

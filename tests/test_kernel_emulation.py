@@ -101,3 +101,37 @@ def test_zdrop_walk_matches_the_host_walk(emul):
                     i += ln
                 upd(score, i, j)
         assert list(zd) == [best] + pos
+
+
+def _tandem_anchors(rng, n_q, n_copies, unit, span=15):
+    """Anchors of a read crossing a tandem array: every query minimizer hits every copy of the unit."""
+    q0 = np.sort(rng.choice(np.arange(50, 50 + n_q * 11), size=n_q, replace=False)).astype(np.int64)
+    x, y = [], []
+    for c in range(n_copies):
+        x.append(1000 + c * unit + (q0 % unit))
+        y.append(q0)
+    x = np.concatenate(x).astype(np.uint64); y = np.concatenate(y).astype(np.uint64)
+    xy = np.stack([x, np.uint64(span) << np.uint64(32) | y], axis=1)
+    return ol.ref_sort128(xy)
+
+
+@pytest.mark.parametrize("dense", [0, 1])
+def test_chain_forward_pass_formulations(emul, dense):
+    """The two warp formulations of the chaining forward pass (csrc/chain_dev.cuh: 32 predecessors per step; dense
+    candidates) against a scalar restatement of src/chain.c:45-90: identical f / p / v for every anchor."""
+    from test_oracle_vs_ref import make_anchors
+    sig = [C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_float]
+    emul.wmt_emul_chain_fill.argtypes = sig + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    emul.wmt_chain_fill_scalar.argtypes = sig + [C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(4400)
+    arrays = [make_anchors(rng, n, repeats=bool(i & 1)) for i, n in enumerate([1, 2, 33, 100, 700, 2500])]
+    arrays += [_tandem_anchors(rng, 40, 30, 171), _tandem_anchors(rng, 90, 25, 64)]
+    for a in arrays:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        n = len(a)
+        for prm in [(5000, 1000, 5000, 500, 25, 5000), (16000, 1000, 16000, 2000, 25, 5000), (5000, 50, 5000, 500, 3, 20), (5000, 500, 5000, 500, 25, 300)]:
+            out = [np.full(n, -7, np.int32) for _ in range(6)]
+            emul.wmt_chain_fill_scalar(a.ctypes.data, n, *prm, 1.0, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data)
+            emul.wmt_emul_chain_fill(a.ctypes.data, n, *prm, 1.0, dense, out[3].ctypes.data, out[4].ctypes.data, out[5].ctypes.data)
+            for k, nm in enumerate("fpv"):
+                assert np.array_equal(out[k], out[3 + k]), (n, prm, nm, int(np.argmax(out[k] != out[3 + k])))

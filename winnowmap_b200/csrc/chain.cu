@@ -12,114 +12,16 @@
 #include <vector>
 #include <algorithm>
 #include <limits.h>
+#include <stdlib.h>
 #include "wm_common.cuh"
 #include "sketch.cuh"
 #include "rsort.cuh"
 #include "chain.cuh"
 
 #define WM_CHAIN_WARPS 4
+#define WM_CHAIN_DENSE_MIN 1024 // tasks with more anchors use the dense-candidate scan when WM_CHAIN_DENSE=1
 
-__device__ __forceinline__ int wm_warp_incl_max(int v, int lane)
-{
-	#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		int t = __shfl_up_sync(0xffffffffu, v, o);
-		if (lane >= o) v = max(v, t);
-	}
-	return v;
-}
-
-// score of predecessor j for anchor i (src/chain.c:61-84); false when j is not a candidate
-__device__ __forceinline__ bool wm_chain_score(const wm128_dev aj, uint64_t ri, int32_t qi, int32_t q_span, const wm_chain_params &P, double avg_d, double scale_d, int *sc_out)
-{
-	const int64_t dr = (int64_t)(ri - aj.x);
-	const int32_t dq = qi - (int32_t)aj.y;
-	if (dr == 0 || dq <= 0) return false;
-	if (dq > P.max_dist_y || dq > P.max_dist_x) return false;
-	const int32_t dd = (int32_t)(dr > dq ? dr - dq : dq - dr);
-	if (dd > P.bw) return false;
-	const int32_t min_d = dq < dr ? dq : (int32_t)dr;
-	int sc = min_d > q_span ? q_span : min_d;
-	const int log_dd = dd ? 31 - __clz(dd) : 0;
-	const int gap_cost = (int)__dmul_rn(__dmul_rn((double)dd, .01), avg_d) + (log_dd >> 1);
-	sc -= (int)__dadd_rn(__dmul_rn((double)gap_cost, scale_d), .499);
-	*sc_out = sc;
-	return true;
-}
-
-// replay of the n_skip arithmetic (src/chain.c:85-88) over one 32-predecessor chunk: R = lanes that set a new
-// maximum, K = lanes that hit a t[j]==i mark without setting one.  Returns the lane at which the reference
-// leaves the loop (32 = it does not).
-__device__ __forceinline__ int wm_chain_replay(unsigned R, unsigned K, int *n_skip_io, int max_skip)
-{
-	int n_skip = *n_skip_io, brk = 32;
-	if (K == 0) {
-		n_skip -= __popc(R); if (n_skip < 0) n_skip = 0;
-	} else {
-		unsigned ev = R | K;
-		while (ev) {
-			const int l = __ffs(ev) - 1;
-			ev &= ev - 1;
-			if (R >> l & 1) { if (n_skip > 0) --n_skip; }
-			else if (++n_skip > max_skip) { brk = l; break; }
-		}
-	}
-	*n_skip_io = n_skip;
-	return brk;
-}
-
-// one warp, one task
-__device__ void wm_chain_fill_warp(const wm128_dev *__restrict__ a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int lane)
-{
-	const unsigned FULL = 0xffffffffu;
-	// avg_qspan (src/chain.c:41-42)
-	unsigned long long sum = 0;
-	for (int i = lane; i < n; i += 32) { sum += a[i].y >> 32 & 0xff; t[i] = 0; }
-	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-	const float avg_qspan = __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n));
-	const double avg_d = (double)avg_qspan, scale_d = (double)P.gap_scale;
-	__syncwarp();
-	int st = 0;
-	for (int i = 0; i < n; ++i) {
-		const uint64_t ri = a[i].x;
-		const int32_t qi = (int32_t)a[i].y, q_span = (int32_t)(a[i].y >> 32 & 0xff);
-		while (st < i && ri > a[st].x + (uint64_t)(int64_t)P.max_dist_x) ++st;
-		if (i - st > P.max_iter) // the relaxed window of Winnowmap (src/chain.c:52-55)
-			while (i - st > P.max_iter && ri > a[st].x + (uint64_t)(int64_t)P.min_dist_x) ++st;
-		int max_f = q_span, max_j = -1, n_skip = 0;
-		for (int jb = i - 1; jb >= st; jb -= 32) {
-			const int j = jb - lane;
-			bool cand = false;
-			int sc = INT_MIN, pj = -1;
-			if (j >= st && wm_chain_score(a[j], ri, qi, q_span, P, avg_d, scale_d, &sc)) {
-				sc += f[j]; pj = p[j]; cand = true;
-			}
-			if (cand && pj >= 0) t[pj] = i; // src/chain.c:87 (only indices below every j still to be visited)
-			__syncwarp();
-			const bool marked = cand && t[j] == i;
-			const int incl = wm_warp_incl_max(cand ? sc : INT_MIN, lane);
-			int excl = __shfl_up_sync(FULL, incl, 1);
-			if (lane == 0) excl = INT_MIN;
-			excl = max(excl, max_f);
-			const bool rec = cand && sc > excl;
-			const unsigned R = __ballot_sync(FULL, rec), K = __ballot_sync(FULL, marked && !rec);
-			const int brk = wm_chain_replay(R, K, &n_skip, P.max_skip);
-			const unsigned Rv = brk < 32 ? (R & ((1u << brk) - 1u)) : R;
-			if (Rv) {
-				const int top = 31 - __clz(Rv);
-				max_f = __shfl_sync(FULL, sc, top);
-				max_j = jb - top;
-			}
-			if (brk < 32) break;
-		}
-		if (lane == 0) {
-			f[i] = max_f, p[i] = max_j;
-			const int vj = max_j >= 0 ? v[max_j] : INT_MIN;
-			v[i] = (max_j >= 0 && vj > max_f) ? vj : max_f; // src/chain.c:89
-		}
-		__syncwarp();
-	}
-}
+#include "chain_dev.cuh"
 
 // Tasks come largest first (order[]), one warp per task.
 __global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
@@ -139,6 +41,30 @@ wm_chain_fill_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restr
 		const int n = (int)(off[task + 1] - base);
 		if (n <= 0) continue;
 		wm_chain_fill_warp(a_all + base, n, PP.p[set_id ? set_id[task] : 0], f_all + base, p_all + base, t_all + base, v_all + base, lane);
+	}
+}
+
+// The same forward pass with the dense-candidate scan of chain_dev.cuh (selected with WM_CHAIN_DENSE=1).
+__global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
+wm_chain_fill_dense_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ order, int n_tasks,
+                           wm_chain_params2 PP, const uint8_t *__restrict__ set_id, int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all,
+                           int32_t *__restrict__ v_all, int *counter)
+{
+	const unsigned FULL = 0xffffffffu;
+	__shared__ int32_t D[WM_CHAIN_WARPS][WM_CHAIN_DENSE_CAP];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (;;) {
+		int ti = 0;
+		if (lane == 0) ti = atomicAdd(counter, 1);
+		ti = __shfl_sync(FULL, ti, 0);
+		if (ti >= n_tasks) break;
+		const int task = order ? order[ti] : ti;
+		const int64_t base = off[task];
+		const int n = (int)(off[task + 1] - base);
+		if (n <= 0) continue;
+		// the dense scan pays off where windows are long (big tasks: repeats); ordinary tasks keep the plain chunk loop
+		if (n > WM_CHAIN_DENSE_MIN) wm_chain_fill_warp_dense(a_all + base, n, PP.p[set_id ? set_id[task] : 0], f_all + base, p_all + base, t_all + base, v_all + base, D[wid], lane);
+		else wm_chain_fill_warp(a_all + base, n, PP.p[set_id ? set_id[task] : 0], f_all + base, p_all + base, t_all + base, v_all + base, lane);
 	}
 }
 
@@ -286,7 +212,11 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	const int need = (n_tasks + WM_CHAIN_WARPS - 1) / WM_CHAIN_WARPS;
 	if (grid > need) grid = need;
 	wm_rs_stack *stk = (wm_rs_stack*)ws->stacks.need(sizeof(wm_rs_stack) * (size_t)grid * WM_CHAIN_WARPS);
-	wm_count_launch(); wm_chain_fill_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
+	static int dense = -1; // experimental formulation, off unless WM_CHAIN_DENSE=1 (same results, see chain_dev.cuh)
+	if (dense < 0) { const char *e = getenv("WM_CHAIN_DENSE"); dense = (e && *e == '1') ? 1 : 0; }
+	wm_count_launch();
+	if (dense) wm_chain_fill_dense_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
+	else wm_chain_fill_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
 	WM_CUDA_CHECK(cudaGetLastError());
 	wm_count_launch(); wm_chain_backtrack_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, n_tasks, PP, d_set_id, f, p, t, v, u, u2, w, b, n_u, n_b, stk, counter + 1);
 	WM_CUDA_CHECK(cudaGetLastError());

@@ -1,0 +1,208 @@
+// Device functions of the chaining forward pass (mm_chain_dp, reference src/chain.c:45-90), shared by the kernels in
+// chain.cu and by the CPU emulation harness of the tests (tests/hostsim/kernel_emul.cpp compiles this header for the host).
+#pragma once
+#include <limits.h>
+#include "wm_common.cuh"
+#include "sketch.cuh"
+#include "chain.cuh"
+
+__device__ __forceinline__ int wm_warp_incl_max(int v, int lane)
+{
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, v, o);
+		if (lane >= o) v = max(v, t);
+	}
+	return v;
+}
+
+// score of predecessor j for anchor i (src/chain.c:61-84); false when j is not a candidate
+__device__ __forceinline__ bool wm_chain_score(const wm128_dev aj, uint64_t ri, int32_t qi, int32_t q_span, const wm_chain_params &P, double avg_d, double scale_d, int *sc_out)
+{
+	const int64_t dr = (int64_t)(ri - aj.x);
+	const int32_t dq = qi - (int32_t)aj.y;
+	if (dr == 0 || dq <= 0) return false;
+	if (dq > P.max_dist_y || dq > P.max_dist_x) return false;
+	const int32_t dd = (int32_t)(dr > dq ? dr - dq : dq - dr);
+	if (dd > P.bw) return false;
+	const int32_t min_d = dq < dr ? dq : (int32_t)dr;
+	int sc = min_d > q_span ? q_span : min_d;
+	const int log_dd = dd ? 31 - __clz(dd) : 0;
+	const int gap_cost = (int)__dmul_rn(__dmul_rn((double)dd, .01), avg_d) + (log_dd >> 1);
+	sc -= (int)__dadd_rn(__dmul_rn((double)gap_cost, scale_d), .499);
+	*sc_out = sc;
+	return true;
+}
+
+// replay of the n_skip arithmetic (src/chain.c:85-88) over one 32-predecessor chunk: R = lanes that set a new
+// maximum, K = lanes that hit a t[j]==i mark without setting one.  Returns the lane at which the reference
+// leaves the loop (32 = it does not).
+__device__ __forceinline__ int wm_chain_replay(unsigned R, unsigned K, int *n_skip_io, int max_skip)
+{
+	int n_skip = *n_skip_io, brk = 32;
+	if (K == 0) {
+		n_skip -= __popc(R); if (n_skip < 0) n_skip = 0;
+	} else {
+		unsigned ev = R | K;
+		while (ev) {
+			const int l = __ffs(ev) - 1;
+			ev &= ev - 1;
+			if (R >> l & 1) { if (n_skip > 0) --n_skip; }
+			else if (++n_skip > max_skip) { brk = l; break; }
+		}
+	}
+	*n_skip_io = n_skip;
+	return brk;
+}
+
+// one warp, one task
+__device__ void wm_chain_fill_warp(const wm128_dev *__restrict__ a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	// avg_qspan (src/chain.c:41-42)
+	unsigned long long sum = 0;
+	for (int i = lane; i < n; i += 32) { sum += a[i].y >> 32 & 0xff; t[i] = 0; }
+	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+	const float avg_qspan = __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n));
+	const double avg_d = (double)avg_qspan, scale_d = (double)P.gap_scale;
+	__syncwarp();
+	int st = 0;
+	for (int i = 0; i < n; ++i) {
+		const uint64_t ri = a[i].x;
+		const int32_t qi = (int32_t)a[i].y, q_span = (int32_t)(a[i].y >> 32 & 0xff);
+		while (st < i && ri > a[st].x + (uint64_t)(int64_t)P.max_dist_x) ++st;
+		if (i - st > P.max_iter) // the relaxed window of Winnowmap (src/chain.c:52-55)
+			while (i - st > P.max_iter && ri > a[st].x + (uint64_t)(int64_t)P.min_dist_x) ++st;
+		int max_f = q_span, max_j = -1, n_skip = 0;
+		for (int jb = i - 1; jb >= st; jb -= 32) {
+			const int j = jb - lane;
+			bool cand = false;
+			int sc = INT_MIN, pj = -1;
+			if (j >= st && wm_chain_score(a[j], ri, qi, q_span, P, avg_d, scale_d, &sc)) {
+				sc += f[j]; pj = p[j]; cand = true;
+			}
+			if (cand && pj >= 0) t[pj] = i; // src/chain.c:87 (only indices below every j still to be visited)
+			__syncwarp();
+			const bool marked = cand && t[j] == i;
+			const int incl = wm_warp_incl_max(cand ? sc : INT_MIN, lane);
+			int excl = __shfl_up_sync(FULL, incl, 1);
+			if (lane == 0) excl = INT_MIN;
+			excl = max(excl, max_f);
+			const bool rec = cand && sc > excl;
+			const unsigned R = __ballot_sync(FULL, rec), K = __ballot_sync(FULL, marked && !rec);
+			const int brk = wm_chain_replay(R, K, &n_skip, P.max_skip);
+			const unsigned Rv = brk < 32 ? (R & ((1u << brk) - 1u)) : R;
+			if (Rv) {
+				const int top = 31 - __clz(Rv);
+				max_f = __shfl_sync(FULL, sc, top);
+				max_j = jb - top;
+			}
+			if (brk < 32) break;
+		}
+		if (lane == 0) {
+			f[i] = max_f, p[i] = max_j;
+			const int vj = max_j >= 0 ? v[max_j] : INT_MIN;
+			v[i] = (max_j >= 0 && vj > max_f) ? vj : max_f; // src/chain.c:89
+		}
+		__syncwarp();
+	}
+}
+
+
+// ---- second formulation: dense candidates -------------------------------------------------------------------
+// Only candidates (predecessors that pass the three `continue`s of src/chain.c:61-73) touch the state of the
+// reference's inner loop: a non-candidate changes neither max_f nor n_skip nor t[].  So the scan is split: a cheap
+// pass tests 32 predecessors per step (one load, a handful of integer operations, one ballot) and appends the
+// candidates, in scan order, to a small per-warp list; whenever 32 of them are waiting, they are resolved with the
+// exact chunk logic above.  In tandem arrays a window of `max_iter` = 5000 predecessors holds about 10 % candidates,
+// so the expensive resolve runs ten times less often.  Early termination (n_skip > max_skip) discards the rest of
+// the list; candidates scanned past the break point cost only the cheap test.
+#define WM_CHAIN_DENSE_CAP 64
+
+__device__ __forceinline__ bool wm_chain_is_cand(const wm128_dev aj, uint64_t ri, int32_t qi, const wm_chain_params &P)
+{ // the predicate of wm_chain_score without the score
+	const int64_t dr = (int64_t)(ri - aj.x);
+	const int32_t dq = qi - (int32_t)aj.y;
+	if (dr == 0 || dq <= 0) return false;
+	if (dq > P.max_dist_y || dq > P.max_dist_x) return false;
+	const int32_t dd = (int32_t)(dr > dq ? dr - dq : dq - dr);
+	return dd <= P.bw;
+}
+
+// D: the warp's candidate list (WM_CHAIN_DENSE_CAP entries, shared memory)
+__device__ void wm_chain_fill_warp_dense(const wm128_dev *__restrict__ a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v,
+                                         int32_t *D, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	unsigned long long sum = 0;
+	for (int i = lane; i < n; i += 32) { sum += a[i].y >> 32 & 0xff; t[i] = 0; }
+	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+	const float avg_qspan = __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n));
+	const double avg_d = (double)avg_qspan, scale_d = (double)P.gap_scale;
+	__syncwarp();
+	int st = 0;
+	for (int i = 0; i < n; ++i) {
+		const uint64_t ri = a[i].x;
+		const int32_t qi = (int32_t)a[i].y, q_span = (int32_t)(a[i].y >> 32 & 0xff);
+		while (st < i && ri > a[st].x + (uint64_t)(int64_t)P.max_dist_x) ++st;
+		if (i - st > P.max_iter)
+			while (i - st > P.max_iter && ri > a[st].x + (uint64_t)(int64_t)P.min_dist_x) ++st;
+		int max_f = q_span, max_j = -1, n_skip = 0;
+		int cnt = 0;      // candidates waiting in D, in scan order
+		int jb = i - 1;   // next predecessor to scan
+		bool stop = false;
+		while (!stop) {
+			// cheap scan until 32 candidates wait or the window is exhausted
+			while (cnt < 32 && jb >= st) {
+				const int j = jb - lane;
+				const bool c = j >= st && wm_chain_is_cand(a[j], ri, qi, P);
+				const unsigned m = __ballot_sync(FULL, c);
+				if (c) D[cnt + __popc(m & ((1u << lane) - 1u))] = j;
+				cnt += __popc(m);
+				jb -= 32;
+			}
+			if (cnt == 0) break;
+			__syncwarp();
+			// exact resolve of the first min(cnt, 32) candidates: the chunk logic of wm_chain_fill_warp on a dense chunk
+			const int m_act = cnt < 32 ? cnt : 32;
+			const bool cand = lane < m_act;
+			int j = -1, sc = INT_MIN, pj = -1;
+			if (cand) {
+				j = D[lane];
+				wm_chain_score(a[j], ri, qi, q_span, P, avg_d, scale_d, &sc);
+				sc += f[j]; pj = p[j];
+			}
+			if (cand && pj >= 0) t[pj] = i;
+			__syncwarp();
+			const bool marked = cand && t[j] == i;
+			const int incl = wm_warp_incl_max(cand ? sc : INT_MIN, lane);
+			int excl = __shfl_up_sync(FULL, incl, 1);
+			if (lane == 0) excl = INT_MIN;
+			excl = max(excl, max_f);
+			const bool rec = cand && sc > excl;
+			const unsigned R = __ballot_sync(FULL, rec), K = __ballot_sync(FULL, marked && !rec);
+			const int brk = wm_chain_replay(R, K, &n_skip, P.max_skip);
+			const unsigned Rv = brk < 32 ? (R & ((1u << brk) - 1u)) : R;
+			if (Rv) {
+				const int top = 31 - __clz(Rv);
+				max_f = __shfl_sync(FULL, sc, top);
+				max_j = __shfl_sync(FULL, j, top);
+			}
+			if (brk < 32) break;
+			// drop the resolved candidates
+			const int rest = cnt - m_act;
+			int keep = 0;
+			if (lane < rest) keep = D[lane + 32];
+			__syncwarp();
+			if (lane < rest) D[lane] = keep;
+			cnt = rest;
+			if (cnt == 0 && jb < st) stop = true;
+		}
+		if (lane == 0) {
+			f[i] = max_f, p[i] = max_j;
+			const int vj = max_j >= 0 ? v[max_j] : INT_MIN;
+			v[i] = (max_j >= 0 && vj > max_f) ? vj : max_f; // src/chain.c:89
+		}
+		__syncwarp();
+	}
+}
