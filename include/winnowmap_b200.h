@@ -243,6 +243,10 @@ int wm_map_file(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, const char *reads_fn, c
                 int tag_order, int64_t max_batch_bases);
 /* the command line recorded in the @PG header line of SAM output (the reference prints its own argv, src/format.c:130-135) */
 void wm_set_sam_cl(wm_gpu_ctx *ctx, const char *cl);
+/* mm_gen_cs / mm_gen_MD (src/minimap.h:389-390): the cs / MD string of one hit of read `seq` (ASCII) into *buf, which is
+ * realloc()ed when *max_len is too small; returns the length.  The reference sequence comes from the context's index. */
+int wm_gen_cs(const wm_gpu_ctx *ctx, char **buf, int *max_len, const wm_reg1_t *r, const char *seq, int no_iden);
+int wm_gen_MD(const wm_gpu_ctx *ctx, char **buf, int *max_len, const wm_reg1_t *r, const char *seq);
 
 /* frees what wm_gpu_map_batch returned (the reference's output step does this itself, src/map.c:1210-1211) */
 void wm_free_regs(int n, const int32_t *n_reg, wm_reg1_t **reg);

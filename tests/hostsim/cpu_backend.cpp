@@ -195,6 +195,7 @@ static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *pr
 	map_batch(&be, &H, &mo, reads, regs, rl, fg, n_threads, 0);
 	FILE *out = fopen(out_fn, "wb");
 	std::string line;
+	int n_gen_mismatch = 0;
 	if (sam) { write_sam_hdr(line, &H, "2.03", 0); fwrite(line.data(), 1, line.size(), out); }
 	for (size_t i = 0; i < reads.size(); ++i) { // the output step of the reference (src/map.c:1189-1206)
 		for (size_t j = 0; j < regs[i].size(); ++j) {
@@ -202,6 +203,13 @@ static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *pr
 			if (sam) write_sam(line, &H, reads[i], (int)j, (int)regs[i].size(), regs[i].data(), mo.flag, rl[i], "");
 			else write_paf(line, &H, reads[i], &regs[i][j], mo.flag, rl[i]);
 			fwrite(line.data(), 1, line.size(), out); fputc('\n', out);
+			if (regs[i][j].p && (mo.flag & (WM_F_OUT_CS | WM_F_OUT_MD))) { // mm_gen_cs / mm_gen_MD must give the tag's text
+				const bool md = (mo.flag & WM_F_OUT_MD) != 0;
+				std::string g;
+				gen_cs_or_MD(g, &H, &regs[i][j], reads[i]->seq.data(), md, !(mo.flag & WM_F_OUT_CS_LONG));
+				const size_t at = line.find(md ? "\tMD:Z:" : "\tcs:Z:");
+				if (at == std::string::npos || line.compare(at + 6, g.size(), g) != 0 || (at + 6 + g.size() < line.size() && line[at + 6 + g.size()] != '\t')) ++n_gen_mismatch;
+			}
 		}
 		if (regs[i].empty() && ((mo.flag & WM_F_PAF_NO_HIT) || (sam && !(mo.flag & WM_F_SAM_HIT_ONLY)))) {
 			if (sam) write_sam(line, &H, reads[i], -1, 0, 0, mo.flag, rl[i], "");
@@ -212,7 +220,7 @@ static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *pr
 	}
 	fclose(out);
 	wmo_idx_free(be.idx); wmo_bloom_free(bloom);
-	return 0;
+	return n_gen_mismatch ? -100 - n_gen_mismatch : 0;
 }
 
 // winnowmap [-W kmers] -x preset -c ref.fa reads.fa > out.paf, host orchestration on the oracle backend

@@ -390,6 +390,27 @@ extern "C" int wm_map_file(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const char *
 
 extern "C" void wm_set_sam_cl(wm_gpu_ctx_s *c, const char *cl) { c->sam_cl = cl ? cl : ""; }
 
+// mm_gen_cs / mm_gen_MD (src/minimap.h:389-390, src/format.c:245-266): *buf is (re)allocated with realloc() when it is too
+// small, *max_len is its capacity; the string is NUL terminated; returns its length
+static int gen_cs_or_md_c(const wm_gpu_ctx_s *c, char **buf, int *max_len, const wm_reg1_t *r, const char *seq, int is_MD, int no_iden)
+{
+	std::string s;
+	gen_cs_or_MD(s, &c->hidx, r, seq, is_MD, no_iden);
+	if ((int)s.size() + 1 > *max_len) {
+		int m = (int)s.size() + 1;
+		m += m >> 1; // kroundup-like slack
+		*buf = (char*)realloc(*buf, (size_t)m);
+		*max_len = m;
+	}
+	memcpy(*buf, s.data(), s.size());
+	(*buf)[s.size()] = 0;
+	return (int)s.size();
+}
+extern "C" int wm_gen_cs(const wm_gpu_ctx_s *c, char **buf, int *max_len, const wm_reg1_t *r, const char *seq, int no_iden)
+{ return gen_cs_or_md_c(c, buf, max_len, r, seq, 0, no_iden); }
+extern "C" int wm_gen_MD(const wm_gpu_ctx_s *c, char **buf, int *max_len, const wm_reg1_t *r, const char *seq)
+{ return gen_cs_or_md_c(c, buf, max_len, r, seq, 1, 0); }
+
 extern "C" void wm_get_stats(wm_gpu_ctx_s *c, double *o, int n)
 {
 	const MapStats &s = c->stats;

@@ -58,9 +58,9 @@ static void write_tags(std::string &s, const wm_reg1_t *r)
 }
 
 // cs:Z: / MD:Z: difference strings (src/format.c:141-243); qseq/tseq are 0..4 codes in alignment orientation
-static void write_cs_core(std::string &s, const uint8_t *tseq, const uint8_t *qseq, const wm_reg1_t *r, int no_iden)
+static void write_cs_core(std::string &s, const uint8_t *tseq, const uint8_t *qseq, const wm_reg1_t *r, int no_iden, int write_tag)
 {
-	s += "\tcs:Z:";
+	if (write_tag) s += "\tcs:Z:";
 	int q_off = 0, t_off = 0;
 	std::string tmp;
 	for (uint32_t i = 0; i < r->p->n_cigar; ++i) {
@@ -96,9 +96,9 @@ static void write_cs_core(std::string &s, const uint8_t *tseq, const uint8_t *qs
 	}
 }
 
-static void write_MD_core(std::string &s, const uint8_t *tseq, const uint8_t *qseq, const wm_reg1_t *r)
+static void write_MD_core(std::string &s, const uint8_t *tseq, const uint8_t *qseq, const wm_reg1_t *r, int write_tag)
 {
-	s += "\tMD:Z:";
+	if (write_tag) s += "\tMD:Z:";
 	int q_off = 0, t_off = 0, l_MD = 0;
 	for (uint32_t i = 0; i < r->p->n_cigar; ++i) {
 		const int op = r->p->cigar[i] & 0xf, len = r->p->cigar[i] >> 4;
@@ -119,17 +119,17 @@ static void write_MD_core(std::string &s, const uint8_t *tseq, const uint8_t *qs
 	if (l_MD > 0) put_int(s, l_MD);
 }
 
-static void write_cs_or_MD(std::string &s, const wm_host_idx *mi, const wm_read *t, const wm_reg1_t *r, int no_iden, int is_MD)
+static void write_cs_or_MD(std::string &s, const wm_host_idx *mi, const char *seq, const wm_reg1_t *r, int no_iden, int is_MD, int write_tag)
 { // src/format.c:220-243
 	if (r->p == 0) return;
 	static const struct Nt4 { uint8_t t[256]; Nt4() { for (int i = 0; i < 256; ++i) t[i] = 4; t[0] = t['A'] = t['a'] = 0; t[1] = t['C'] = t['c'] = 1;
 		t[2] = t['G'] = t['g'] = 2; t[3] = t['T'] = t['t'] = t['U'] = t['u'] = 3; } } nt4;
 	std::vector<uint8_t> qseq(r->qe - r->qs), tseq(r->re - r->rs);
 	mi->getseq(r->rid, r->rs, r->re, tseq.data());
-	if (!r->rev) for (int i = r->qs; i < r->qe; ++i) qseq[i - r->qs] = nt4.t[(uint8_t)t->seq[i]];
-	else for (int i = r->qs; i < r->qe; ++i) { const uint8_t c = nt4.t[(uint8_t)t->seq[i]]; qseq[r->qe - i - 1] = c >= 4 ? 4 : 3 - c; }
-	if (is_MD) write_MD_core(s, tseq.data(), qseq.data(), r);
-	else write_cs_core(s, tseq.data(), qseq.data(), r, no_iden);
+	if (!r->rev) for (int i = r->qs; i < r->qe; ++i) qseq[i - r->qs] = nt4.t[(uint8_t)seq[i]];
+	else for (int i = r->qs; i < r->qe; ++i) { const uint8_t c = nt4.t[(uint8_t)seq[i]]; qseq[r->qe - i - 1] = c >= 4 ? 4 : 3 - c; }
+	if (is_MD) write_MD_core(s, tseq.data(), qseq.data(), r, write_tag);
+	else write_cs_core(s, tseq.data(), qseq.data(), r, no_iden, write_tag);
 }
 
 void write_paf(std::string &s, const wm_host_idx *mi, const wm_read *t, const wm_reg1_t *r, int64_t opt_flag, int rep_len)
@@ -153,7 +153,7 @@ void write_paf(std::string &s, const wm_host_idx *mi, const wm_read *t, const wm
 		s += "\tcg:Z:";
 		for (uint32_t k = 0; k < r->p->n_cigar; ++k) { put_int(s, (int)(r->p->cigar[k] >> 4)); s.push_back("MIDNSHP=XB"[r->p->cigar[k] & 0xf]); }
 	}
-	if (r->p && (opt_flag & (WM_F_OUT_CS | WM_F_OUT_MD))) write_cs_or_MD(s, mi, t, r, !(opt_flag & WM_F_OUT_CS_LONG), (opt_flag & WM_F_OUT_MD) != 0);
+	if (r->p && (opt_flag & (WM_F_OUT_CS | WM_F_OUT_MD))) write_cs_or_MD(s, mi, t->seq.data(), r, !(opt_flag & WM_F_OUT_CS_LONG), (opt_flag & WM_F_OUT_MD) != 0, 1);
 	if ((opt_flag & WM_F_COPY_COMMENT) && !t->comment.empty()) { s.push_back('\t'); s += t->comment; }
 }
 
@@ -276,7 +276,7 @@ void write_sam(std::string &s, const wm_host_idx *mi, const wm_read *t, int reg_
 				}
 			}
 		}
-		if (r->p && (opt_flag & (WM_F_OUT_CS | WM_F_OUT_MD))) write_cs_or_MD(s, mi, t, r, !(opt_flag & WM_F_OUT_CS_LONG), (opt_flag & WM_F_OUT_MD) != 0);
+		if (r->p && (opt_flag & (WM_F_OUT_CS | WM_F_OUT_MD))) write_cs_or_MD(s, mi, t->seq.data(), r, !(opt_flag & WM_F_OUT_CS_LONG), (opt_flag & WM_F_OUT_MD) != 0, 1);
 		if (cigar_in_tag) write_sam_cigar(s, flag, 1, l_seq, r, opt_flag);
 	}
 	if (rep_len >= 0) { s += "\trl:i:"; put_int(s, rep_len); }
@@ -295,6 +295,13 @@ void write_sam_hdr(std::string &s, const wm_host_idx *mi, const char *version, c
 	if (version) { s += "\tVN:"; s += version; }
 	if (cl && cl[0]) { s += "\tCL:"; s += cl; }
 	s.push_back('\n');
+}
+
+// mm_gen_cs / mm_gen_MD (src/format.c:245-266): the difference string of one hit, without the tag prefix
+void gen_cs_or_MD(std::string &s, const wm_host_idx *mi, const wm_reg1_t *r, const char *seq, int is_MD, int no_iden)
+{
+	s.clear();
+	write_cs_or_MD(s, mi, seq, r, no_iden, is_MD, 0);
 }
 
 } // namespace wmh

@@ -29,6 +29,8 @@ void write_paf(std::string &s, const wm_host_idx *mi, const wm_read *t, const wm
 // SAM record of hit reg_idx of a single-segment read (reg_idx < 0: the unmapped record), mm_write_sam3 (src/format.c:391-548)
 void write_sam(std::string &s, const wm_host_idx *mi, const wm_read *t, int reg_idx, int n_regs, const wm_reg1_t *regs, int64_t opt_flag, int rep_len,
                const char *rg_id);
+// cs / MD difference string of one hit without the tag prefix (mm_gen_cs / mm_gen_MD, src/format.c:245-266); seq = the read, ASCII
+void gen_cs_or_MD(std::string &s, const wm_host_idx *mi, const wm_reg1_t *r, const char *seq, int is_MD, int no_iden);
 // @SQ and @PG header lines (mm_write_sam_hdr, src/format.c:118-139)
 void write_sam_hdr(std::string &s, const wm_host_idx *mi, const char *version, const char *cl);
 
