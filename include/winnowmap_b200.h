@@ -247,6 +247,13 @@ void wm_set_sam_cl(wm_gpu_ctx *ctx, const char *cl);
  * realloc()ed when *max_len is too small; returns the length.  The reference sequence comes from the context's index. */
 int wm_gen_cs(const wm_gpu_ctx *ctx, char **buf, int *max_len, const wm_reg1_t *r, const char *seq, int no_iden);
 int wm_gen_MD(const wm_gpu_ctx *ctx, char **buf, int *max_len, const wm_reg1_t *r, const char *seq);
+/* mm_idx_getseq (0..4 codes of [st,en) of sequence rid; src/index.c:161-171), mm_idx_name2id (:131-140, -1 if absent) and
+ * the sequence table (mm_idx_t::n_seq / seq[].name / seq[].len, src/minimap.h:59-77) of the index held by the context */
+int wm_idx_getseq(const wm_gpu_ctx *ctx, uint32_t rid, uint32_t st, uint32_t en, uint8_t *seq);
+int wm_idx_name2id(const wm_gpu_ctx *ctx, const char *name);
+int wm_idx_n_seq(const wm_gpu_ctx *ctx);
+const char *wm_idx_seq_name(const wm_gpu_ctx *ctx, int rid);
+uint32_t wm_idx_seq_len(const wm_gpu_ctx *ctx, int rid);
 
 /* frees what wm_gpu_map_batch returned (the reference's output step does this itself, src/map.c:1210-1211) */
 void wm_free_regs(int n, const int32_t *n_reg, wm_reg1_t **reg);
