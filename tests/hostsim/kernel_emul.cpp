@@ -9,6 +9,7 @@
 #include "../../winnowmap_b200/csrc/ksw_extd2_common.cuh"
 #include "../../winnowmap_b200/csrc/ksw_extd2_v2.cuh"
 #include "../../winnowmap_b200/csrc/chain_dev.cuh"
+#include "../../winnowmap_b200/csrc/rsort.cuh"
 
 namespace wm_emul {
 thread_local Warp *warp = 0; thread_local int lane = 0;
@@ -174,3 +175,16 @@ extern "C" int wmt_chain_fill_scalar(const uint64_t *a_xy, int n, int max_dist_x
 }
 
 extern "C" long long wmt_emul_sync_count(void) { return wm_emul::g_total_syncs; }
+
+// The warp-cooperative tie-exact radix sort of the anchor arrays (csrc/rsort.cuh) on the software warp; a = n (x, y) pairs.
+extern "C" int wmt_emul_sort128(uint64_t *a_xy, int n)
+{
+	std::vector<wm128_dev> a((size_t)n + 1);
+	for (int i = 0; i < n; ++i) a[i].x = a_xy[2 * i], a[i].y = a_xy[2 * i + 1];
+	wm_rs_warp_ws W; memset(&W, 0, sizeof(W));
+	std::vector<wm_rs_range> wl((size_t)n / 64 + 4);
+	struct Args { wm128_dev *a; int n; wm_rs_warp_ws *W; wm_rs_range *wl; } A = { a.data(), n, &W, wl.data() };
+	wm_emul::run_warp([](int l, void *q) { Args &x = *(Args*)q; wm_radix_sort_warp(x.a, x.n, x.W, x.wl, l); }, &A);
+	for (int i = 0; i < n; ++i) a_xy[2 * i] = a[i].x, a_xy[2 * i + 1] = a[i].y;
+	return 0;
+}

@@ -135,3 +135,20 @@ def test_chain_forward_pass_formulations(emul, dense):
             emul.wmt_emul_chain_fill(a.ctypes.data, n, *prm, 1.0, dense, out[3].ctypes.data, out[4].ctypes.data, out[5].ctypes.data)
             for k, nm in enumerate("fpv"):
                 assert np.array_equal(out[k], out[3 + k]), (n, prm, nm, int(np.argmax(out[k] != out[3 + k])))
+
+
+def test_warp_radix_sort_reproduces_the_unstable_tie_order(emul):
+    """csrc/rsort.cuh on the software warp against the reference's in-place MSD radix sort (src/ksort.h:98-151): equal keys
+    must end up in the reference's order (the payload column shows it)."""
+    emul.wmt_emul_sort128.argtypes = [C.c_void_p, C.c_int]
+    rng = np.random.default_rng(4500)
+    for n in [0, 1, 2, 63, 64, 65, 200, 1000, 5000, 20000]:
+        for key_bits in [3, 12, 28, 64]:
+            hi = (1 << key_bits) - 1
+            x = rng.integers(0, hi, size=n, dtype=np.uint64, endpoint=True)
+            if key_bits == 64 and n:
+                x[::3] = x[0]
+            a = np.stack([x, np.arange(n, dtype=np.uint64)], axis=1)
+            got = np.ascontiguousarray(a).copy()
+            emul.wmt_emul_sort128(got.ctypes.data, n)
+            assert np.array_equal(ol.oracle_sort128(a), got), (n, key_bits)
