@@ -188,3 +188,32 @@ extern "C" int wmt_emul_sort128(uint64_t *a_xy, int n)
 	for (int i = 0; i < n; ++i) a_xy[2 * i] = a[i].x, a_xy[2 * i + 1] = a[i].y;
 	return 0;
 }
+
+// mm_chain_dp end to end on the software warp: forward pass (either formulation) + backtracking (csrc/chain_dev.cuh).
+// a_xy is overwritten with the chained anchors (n_b of them), u receives the (score << 32 | count) words (n_u).
+extern "C" int wmt_emul_chain(uint64_t *a_xy, int n, int max_dist_x, int min_dist_x, int max_dist_y, int bw, int max_skip, int max_iter,
+                              int min_cnt, int min_sc, float gap_scale, int dense, uint64_t *u_out, int32_t *n_u_out, int64_t *n_b_out)
+{
+	*n_u_out = 0, *n_b_out = 0;
+	if (n <= 0) return 0;
+	std::vector<wm128_dev> a((size_t)n + 1), w((size_t)n + 1), b((size_t)n + 1);
+	for (int i = 0; i < n; ++i) a[i].x = a_xy[2 * i], a[i].y = a_xy[2 * i + 1];
+	wm_chain_params P; memset(&P, 0, sizeof(P));
+	P.max_dist_x = max_dist_x, P.min_dist_x = min_dist_x, P.max_dist_y = max_dist_y, P.bw = bw, P.max_skip = max_skip, P.max_iter = max_iter;
+	P.min_cnt = min_cnt, P.min_sc = min_sc, P.gap_scale = gap_scale;
+	std::vector<int32_t> f((size_t)n + 1), p((size_t)n + 1), t((size_t)n + 1, 0), v((size_t)n + 1), D(WM_CHAIN_DENSE_CAP, 0);
+	std::vector<uint64_t> u(2 * (size_t)n + 2), u2((size_t)n + 1);
+	wm_rs_stack stack;
+	struct Args { wm128_dev *a, *w, *b; int n; const wm_chain_params *P; int32_t *f, *p, *t, *v, *D; uint64_t *u, *u2; wm_rs_stack *stk; int dense; int32_t *n_u; int64_t *n_b; }
+		A = { a.data(), w.data(), b.data(), n, &P, f.data(), p.data(), t.data(), v.data(), D.data(), u.data(), u2.data(), &stack, dense, n_u_out, n_b_out };
+	wm_emul::run_warp([](int l, void *q) {
+		Args &x = *(Args*)q;
+		if (x.dense) wm_chain_fill_warp_dense(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, x.D, l);
+		else wm_chain_fill_warp(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, l);
+		__syncwarp();
+		wm_chain_backtrack_warp(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, x.u, x.u2, x.w, x.b, x.stk, x.n_u, x.n_b, l);
+	}, &A);
+	for (int i = 0; i < *n_u_out; ++i) u_out[i] = u2[i];
+	for (int64_t i = 0; i < *n_b_out; ++i) a_xy[2 * i] = a[i].x, a_xy[2 * i + 1] = a[i].y;
+	return 0;
+}

@@ -152,3 +152,23 @@ def test_warp_radix_sort_reproduces_the_unstable_tie_order(emul):
             got = np.ascontiguousarray(a).copy()
             emul.wmt_emul_sort128(got.ctypes.data, n)
             assert np.array_equal(ol.oracle_sort128(a), got), (n, key_bits)
+
+
+@pytest.mark.parametrize("dense", [0, 1])
+def test_chaining_end_to_end_matches_oracle(emul, dense):
+    """Forward pass + backtracking of csrc/chain_dev.cuh on the software warp against the oracle's mm_chain_dp: chains
+    (score, count) and chained anchors, including the unstable re-sort of the chains."""
+    from test_oracle_vs_ref import make_anchors
+    emul.wmt_emul_chain.argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 8 + [C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(4600)
+    arrays = [make_anchors(rng, n, repeats=bool(i & 1)) for i, n in enumerate([1, 3, 10, 40, 100, 700, 3000])]
+    arrays.append(_tandem_anchors(rng, 50, 30, 171))
+    for a in arrays:
+        for prm in [(5000, 1000, 5000, 500, 25, 5000), (16000, 1000, 16000, 2000, 25, 5000), (5000, 50, 5000, 500, 3, 20)]:
+            ue, be = ol.oracle_chain(a, prm[0], prm[1], prm[2], prm[3], max_skip=prm[4], max_iter=prm[5])
+            buf = np.ascontiguousarray(a, dtype=np.uint64).copy()
+            n = len(buf)
+            u = np.zeros(n + 1, np.uint64); n_u = C.c_int32(); n_b = C.c_int64()
+            emul.wmt_emul_chain(buf.ctypes.data, n, *prm, 3, 40, 1.0, dense, u.ctypes.data, C.addressof(n_u), C.addressof(n_b))
+            assert np.array_equal(ue, u[:n_u.value]), (n, prm, len(ue), n_u.value)
+            assert np.array_equal(be, buf[:n_b.value]), (n, prm)

@@ -68,23 +68,6 @@ wm_chain_fill_dense_kernel(const wm128_dev *__restrict__ a_all, const int64_t *_
 	}
 }
 
-// descending bitonic sort of m (power of two) uint64 keys by one warp
-__device__ void wm_warp_bitonic_desc(uint64_t *x, int m, int lane)
-{
-	for (int k = 2; k <= m; k <<= 1)
-		for (int j = k >> 1; j > 0; j >>= 1) {
-			for (int i = lane; i < m; i += 32) {
-				const int l = i ^ j;
-				if (l > i) {
-					const uint64_t a = x[i], b = x[l];
-					const bool up = (i & k) == 0; // first half of each k-block sorted descending
-					if (up ? a < b : a > b) x[i] = b, x[l] = a;
-				}
-			}
-			__syncwarp();
-		}
-}
-
 __global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
 wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, int n_tasks, wm_chain_params2 PP, const uint8_t *__restrict__ set_id,
                           int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
@@ -103,84 +86,9 @@ wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restri
 		const int n = (int)(off[task + 1] - base);
 		if (lane == 0) n_u_out[task] = 0, n_b_out[task] = 0;
 		if (n <= 0) continue;
-		const wm_chain_params P = PP.p[set_id ? set_id[task] : 0];
-		wm128_dev *a = a_all + base, *b = b_all + base, *w = w_all + base;
-		int32_t *f = f_all + base, *p = p_all + base, *t = t_all + base, *v = v_all + base;
-		uint64_t *u = u_all + 2 * base, *u2 = u2_all + base; // u has room for the power-of-two padding of the bitonic sort
-		// chain ends (src/chain.c:93-98): anchors that are nobody's predecessor and whose peak score passes
-		for (int i = lane; i < n; i += 32) t[i] = 0;
 		__syncwarp();
-		for (int i = lane; i < n; i += 32) if (p[i] >= 0) t[p[i]] = 1;
-		__syncwarp();
-		int n_u = 0;
-		for (int ib = 0; ib < n; ib += 32) {
-			const int i = ib + lane;
-			const bool is_end = i < n && t[i] == 0 && v[i] >= P.min_sc;
-			const unsigned m = __ballot_sync(FULL, is_end);
-			if (is_end) { // :104-110: walk back to the peak that maximises f[]
-				int j = i;
-				while (j >= 0 && f[j] < v[j]) j = p[j];
-				if (j < 0) j = i;
-				u[n_u + __popc(m & ((1u << lane) - 1u))] = (uint64_t)(uint32_t)f[j] << 32 | (uint32_t)j;
-			}
-			n_u += __popc(m);
-		}
-		__syncwarp();
-		if (n_u == 0) continue; // :99-102
-		{ // :112-116 sort by (score, index) descending; keys are distinct so any correct sort gives the reference order
-			int m = 1; while (m < n_u) m <<= 1;
-			for (int i = n_u + lane; i < m; i += 32) u[i] = 0;
-			__syncwarp();
-			wm_warp_bitonic_desc(u, m, lane);
-		}
-		for (int i = lane; i < n; i += 32) t[i] = 0;
-		__syncwarp();
-		int n_v = 0, k = 0;
-		if (lane == 0) { // :118-135 greedy claim walk, serial by construction
-			for (int i = 0; i < n_u; ++i) {
-				const int n_v0 = n_v, k0 = k;
-				int j = (int32_t)u[i];
-				do { v[n_v++] = j; t[j] = 1; j = p[j]; } while (j >= 0 && t[j] == 0);
-				if (j < 0) {
-					if (n_v - n_v0 >= P.min_cnt) u[k++] = u[i] >> 32 << 32 | (uint32_t)(n_v - n_v0);
-				} else if ((int32_t)(u[i] >> 32) - f[j] >= P.min_sc) {
-					if (n_v - n_v0 >= P.min_cnt) u[k++] = ((u[i] >> 32) - (uint64_t)f[j]) << 32 | (uint32_t)(n_v - n_v0);
-				}
-				if (k0 == k) n_v = n_v0;
-			}
-		}
-		n_v = __shfl_sync(FULL, n_v, 0); k = __shfl_sync(FULL, k, 0);
-		n_u = k;
-		__syncwarp();
-		// :141-147 write chains to b[] in ascending anchor order; :150-154 build the re-sort keys
-		{
-			int kk = 0;
-			for (int i = 0; i < n_u; ++i) {
-				const int ni = (int32_t)u[i];
-				for (int j = lane; j < ni; j += 32) b[kk + j] = a[v[kk + (ni - j - 1)]];
-				kk += ni;
-			}
-			__syncwarp();
-			if (lane == 0) {
-				int k2 = 0;
-				for (int i = 0; i < n_u; ++i) { w[i].x = b[k2].x, w[i].y = (uint64_t)k2 << 32 | (uint32_t)i; k2 += (int32_t)u[i]; }
-				wm_radix_sort_emul(w, n_u, stacks + wslot); // :155, tie order matters
-			}
-			__syncwarp();
-		}
-		{ // :156-164 chains re-ordered by the position of their first anchor
-			int kk = 0;
-			for (int i = 0; i < n_u; ++i) {
-				const int j = (int32_t)w[i].y, nn = (int32_t)u[j];
-				const wm128_dev *src = b + (w[i].y >> 32);
-				if (lane == 0) u2[i] = u[j];
-				for (int l = lane; l < nn; l += 32) a[kk + l] = src[l];
-				kk += nn;
-			}
-			__syncwarp();
-			if (lane == 0) n_u_out[task] = n_u, n_b_out[task] = kk;
-		}
-		__syncwarp();
+		wm_chain_backtrack_warp(a_all + base, n, PP.p[set_id ? set_id[task] : 0], f_all + base, p_all + base, t_all + base, v_all + base,
+		                        u_all + 2 * base, u2_all + base, w_all + base, b_all + base, stacks + wslot, n_u_out + task, n_b_out + task, lane);
 	}
 }
 

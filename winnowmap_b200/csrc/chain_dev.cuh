@@ -5,6 +5,7 @@
 #include "wm_common.cuh"
 #include "sketch.cuh"
 #include "chain.cuh"
+#include "rsort.cuh"
 
 __device__ __forceinline__ int wm_warp_incl_max(int v, int lane)
 {
@@ -206,3 +207,105 @@ __device__ void wm_chain_fill_warp_dense(const wm128_dev *__restrict__ a, int n,
 		__syncwarp();
 	}
 }
+
+// descending bitonic sort of m (power of two) uint64 keys by one warp
+__device__ void wm_warp_bitonic_desc(uint64_t *x, int m, int lane)
+{
+	for (int k = 2; k <= m; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int i = lane; i < m; i += 32) {
+				const int l = i ^ j;
+				if (l > i) {
+					const uint64_t a = x[i], b = x[l];
+					const bool up = (i & k) == 0; // first half of each k-block sorted descending
+					if (up ? a < b : a > b) x[i] = b, x[l] = a;
+				}
+			}
+			__syncwarp();
+		}
+}
+
+// Backtracking of one task by one warp (src/chain.c:92-165): chain ends, greedy claim walk (serial, lane 0), chains
+// written out in ascending anchor order and re-ordered by the position of their first anchor.  On return a[] holds the
+// chained anchors (*n_b_out of them), u2[] the (score << 32 | count) words (*n_u_out); both counts are 0 if there is no chain
+// (the caller zeroes them first).  u has room for the power-of-two padding of the bitonic sort (2n entries).
+__device__ inline void wm_chain_backtrack_warp(wm128_dev *a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v,
+                                               uint64_t *u, uint64_t *u2, wm128_dev *w, wm128_dev *b, wm_rs_stack *stack, int32_t *n_u_out, int64_t *n_b_out, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	// chain ends (src/chain.c:93-98): anchors that are nobody's predecessor and whose peak score passes
+	for (int i = lane; i < n; i += 32) t[i] = 0;
+	__syncwarp();
+	for (int i = lane; i < n; i += 32) if (p[i] >= 0) t[p[i]] = 1;
+	__syncwarp();
+	int n_u = 0;
+	for (int ib = 0; ib < n; ib += 32) {
+		const int i = ib + lane;
+		const bool is_end = i < n && t[i] == 0 && v[i] >= P.min_sc;
+		const unsigned m = __ballot_sync(FULL, is_end);
+		if (is_end) { // :104-110: walk back to the peak that maximises f[]
+			int j = i;
+			while (j >= 0 && f[j] < v[j]) j = p[j];
+			if (j < 0) j = i;
+			u[n_u + __popc(m & ((1u << lane) - 1u))] = (uint64_t)(uint32_t)f[j] << 32 | (uint32_t)j;
+		}
+		n_u += __popc(m);
+	}
+	__syncwarp();
+	if (n_u == 0) { __syncwarp(); return; } // :99-102
+	{ // :112-116 sort by (score, index) descending; keys are distinct so any correct sort gives the reference order
+		int m = 1; while (m < n_u) m <<= 1;
+		for (int i = n_u + lane; i < m; i += 32) u[i] = 0;
+		__syncwarp();
+		wm_warp_bitonic_desc(u, m, lane);
+	}
+	for (int i = lane; i < n; i += 32) t[i] = 0;
+	__syncwarp();
+	int n_v = 0, k = 0;
+	if (lane == 0) { // :118-135 greedy claim walk, serial by construction
+		for (int i = 0; i < n_u; ++i) {
+			const int n_v0 = n_v, k0 = k;
+			int j = (int32_t)u[i];
+			do { v[n_v++] = j; t[j] = 1; j = p[j]; } while (j >= 0 && t[j] == 0);
+			if (j < 0) {
+				if (n_v - n_v0 >= P.min_cnt) u[k++] = u[i] >> 32 << 32 | (uint32_t)(n_v - n_v0);
+			} else if ((int32_t)(u[i] >> 32) - f[j] >= P.min_sc) {
+				if (n_v - n_v0 >= P.min_cnt) u[k++] = ((u[i] >> 32) - (uint64_t)f[j]) << 32 | (uint32_t)(n_v - n_v0);
+			}
+			if (k0 == k) n_v = n_v0;
+		}
+	}
+	n_v = __shfl_sync(FULL, n_v, 0); k = __shfl_sync(FULL, k, 0);
+	n_u = k;
+	__syncwarp();
+	// :141-147 write chains to b[] in ascending anchor order; :150-154 build the re-sort keys
+	{
+		int kk = 0;
+		for (int i = 0; i < n_u; ++i) {
+			const int ni = (int32_t)u[i];
+			for (int j = lane; j < ni; j += 32) b[kk + j] = a[v[kk + (ni - j - 1)]];
+			kk += ni;
+		}
+		__syncwarp();
+		if (lane == 0) {
+			int k2 = 0;
+			for (int i = 0; i < n_u; ++i) { w[i].x = b[k2].x, w[i].y = (uint64_t)k2 << 32 | (uint32_t)i; k2 += (int32_t)u[i]; }
+			wm_radix_sort_emul(w, n_u, stack); // :155, tie order matters
+		}
+		__syncwarp();
+	}
+	{ // :156-164 chains re-ordered by the position of their first anchor
+		int kk = 0;
+		for (int i = 0; i < n_u; ++i) {
+			const int j = (int32_t)w[i].y, nn = (int32_t)u[j];
+			const wm128_dev *src = b + (w[i].y >> 32);
+			if (lane == 0) u2[i] = u[j];
+			for (int l = lane; l < nn; l += 32) a[kk + l] = src[l];
+			kk += nn;
+		}
+		__syncwarp();
+		if (lane == 0) *n_u_out = n_u, *n_b_out = kk;
+	}
+	__syncwarp();
+}
+
