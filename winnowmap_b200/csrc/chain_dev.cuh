@@ -229,7 +229,7 @@ __device__ void wm_warp_bitonic_desc(uint64_t *x, int m, int lane)
 // written out in ascending anchor order and re-ordered by the position of their first anchor.  On return a[] holds the
 // chained anchors (*n_b_out of them), u2[] the (score << 32 | count) words (*n_u_out); both counts are 0 if there is no chain
 // (the caller zeroes them first).  u has room for the power-of-two padding of the bitonic sort (2n entries).
-__device__ inline void wm_chain_backtrack_warp(wm128_dev *a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v,
+__device__ __forceinline__ void wm_chain_backtrack_warp(wm128_dev *a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v,
                                                uint64_t *u, uint64_t *u2, wm128_dev *w, wm128_dev *b, wm_rs_stack *stack, int32_t *n_u_out, int64_t *n_b_out, int lane)
 {
 	const unsigned FULL = 0xffffffffu;

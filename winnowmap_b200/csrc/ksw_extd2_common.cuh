@@ -84,7 +84,7 @@ __device__ void wm_zdrop_scan(const wm_zd_params &Z, const uint8_t *__restrict__
 }
 
 // One job of the traceback kernel: *ez_io is the job's fill result (updated: reach_end, n_cigar), zd its five Z-drop words or null.
-__device__ inline void wm_extd2_backtrack_job(const wm_dp_job &J, wm_extz_dev *ez_io, const uint8_t *__restrict__ bt, uint32_t *__restrict__ cigar_pool,
+__device__ __forceinline__ void wm_extd2_backtrack_job(const wm_dp_job &J, wm_extz_dev *ez_io, const uint8_t *__restrict__ bt, uint32_t *__restrict__ cigar_pool,
                                               const uint8_t *__restrict__ seq, const wm_zd_params &Z, int32_t *zd)
 {
 	wm_extz_dev ez = *ez_io;
