@@ -285,7 +285,8 @@ def main():
     seed0 = 9000 + 1000 * rank
     batches = [make_batch(contigs, a.reads, seed0 + s) for s in range(a.warmup + a.steps)]
     # warm-up in the shape of the timed passes: W steps submitted together, device-resident and through the host API
-    warm = [r for s in range(a.warmup) for r in batches[s]]
+    # at least as many steps as the timed pass, so that every lane has sized its workspaces for the same chunk size
+    warm = [r for s in range(max(a.warmup, a.steps)) for r in batches[s]]
     if warm:
         map_resident(warm)
         map_host(warm)
