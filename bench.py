@@ -286,7 +286,8 @@ def main():
     batches = [make_batch(contigs, a.reads, seed0 + s) for s in range(a.warmup + a.steps)]
     # warm-up in the shape of the timed passes: W steps submitted together, device-resident and through the host API
     # at least as many steps as the timed pass, so that every lane has sized its workspaces for the same chunk size
-    warm = [r for s in range(max(a.warmup, a.steps)) for r in batches[s]]
+    n_warm = max(a.warmup, a.steps)
+    warm = [r for s in range(n_warm) for r in (batches[s] if s < a.warmup else make_batch(contigs, a.reads, seed0 + 300 + s))]
     if warm:
         map_resident(warm)
         map_host(warm)
