@@ -1,26 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- mapped bases/sec of the seed-chain-align path on B200 (BASELINE.json metric).
 
-One "step" = one pass of the hot path (stage-1 MCAS waves + stage-2 remap: sketch, seed lookup, anchor sort,
-chaining, extension DP with traceback, host glue) over one batch of synthetic reads drawn from the workload's
-distribution.  Workload at N=1: BASELINE.json configs[1] -- 250 Mbp uniform-random reference, ONT-like reads
-N50 = 20 kb at 5 % error, -x map-ont -W <top-0.02 % k-mers> k=15 -c.  The 100 k reads of the config are sampled in
-batches of --reads reads (fresh reads each step, so nothing is cached between steps; each batch's working set --
-read pool, backtrack matrices, 2.6 GB index -- is far larger than L2).
+Workload: BASELINE.json configs[4] (the configuration the metric and north_star's target are quoted on), scaled in
+reference LENGTH only so that a default run ends within minutes on a fresh box: a tandem-repeat-enriched synthetic
+reference (every 1 Mbp an array of copies of a unit from a fixed family of 4 base units, 171 / 340 /
+2000 / 5000 bp, ~15 % of the genome; seed 1005), WM_BENCH_REF_LEN bases (default 500 Mbp instead of 3 Gbp: the
+3 Gbp reference takes the REFERENCE implementation ~10 minutes to index, and every driver run of either arm pays
+that once; the read distribution, the repeat structure and every option are those of the config), ONT-like reads
+N50 = 30 kb at 5 % error, `-x map-ont -W <top-0.02 % 15-mers> -c`.  WM_BENCH_REF_LEN=3000000000 runs the full size.
 
-The K timed steps are submitted together (K batches): the library's orchestration lanes pull chunks of reads from
-the whole submission, so the steps pipeline instead of draining the GPU at every step boundary.  The timed region is
-bracketed by a barrier + device synchronisation on both sides; the warm-up has the same shape (W steps together).
+One "step" = one pass of the hot path (stage-1 MCAS waves + stage-2 remap: sketch, seed lookup, anchor sort,
+chaining, extension DP with traceback, host glue) over --reads fresh reads (~26.5 Mbase; working set -- read pool,
+anchors, backtrack matrices, multi-GB index -- far larger than L2).  Steps are submitted to the library in groups of
+at most WM_BENCH_GROUP steps (default 8) and the library cuts each submission into chunks of WM_CHUNK_BASES bases
+(pinned here to 16 Mbase), so device and host footprints do not grow with --steps.
 
   value : bases/s with the raw reads of all K steps already resident in one HBM pool (wm_bench_upload); CUDA events
           bracket the whole pass (ASCII -> 2-bit codes is inside: it is part of the path)
-  e2e   : bases/s through wm_gpu_map_batch with host buffers (staging + H2D of the reads, D2H of every result inside)
-  roofline : the DP fill kernel, algorithmic bytes over the time during which a fill kernel was running
-          (CUDA events around every launch), vs the measured HBM peak
-  cpu_baseline : the real reference (oracle/_ref/winnowmap, SSE4.1, all host cores) on a bounded sample (N = 1 only)
+  e2e   : bases/s through wm_gpu_map_batch -- the call INTEGRATION.md binds at src/map.c:1164 -- with host buffers
+          (staging + H2D of the reads, D2H of every chain, DP result and CIGAR inside the timed region)
+  roofline : the dominant kernel of the run (the DP fill kernel or the chaining forward pass, whichever ran longer;
+          the other one is reported under roofline_other): algorithmic bytes over the time during which a
+          kernel of that class was running (CUDA events around every launch, union of the intervals), vs the measured HBM peak
+  cpu_baseline : the real reference (oracle/_ref/winnowmap, SSE4.1, all host threads) on a bounded sample (N = 1 only)
+  parity_checked : the records produced by the two timed passes (resident and host-buffer) for the reads of the CPU
+          sample, formatted as PAF, are byte-identical to the reference's output on the same reads
 
---impl reference times the reference binary itself on the same workload (CPU, all host threads).
-Under torchrun (N > 1) every rank maps its own batches (reads shard with no data-path collective): weak scaling.
+--impl reference times the reference binary itself on the same workload in ONE invocation (one index build): the
+reads of all W + K steps go into one file, the mini-batch size (-K) is a group of steps, and the timed interval is
+taken from the reference's own per-mini-batch stderr stamps.
+Under torchrun (N > 1) every rank maps its own K steps (reads shard with no data-path collective): weak scaling.
 """
 import argparse
 import ctypes as C
@@ -33,6 +42,7 @@ import threading
 import time
 
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")  # before anything loads libgomp: idle workers must not spin (see _lib.py)
+os.environ.setdefault("WM_CHUNK_BASES", "16000000")  # fixed chunk size: footprint independent of --steps
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -41,38 +51,85 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np  # noqa: E402
 
 CACHE = os.environ.get("WM_BENCH_CACHE", "/tmp/wm_bench_cache")
-REF_LEN = int(os.environ.get("WM_BENCH_REF_LEN", 250_000_000))
-N50, ERR, K = 20000, 0.05, 15
+REF_LEN = int(os.environ.get("WM_BENCH_REF_LEN", 500_000_000))
+GROUP = max(1, int(os.environ.get("WM_BENCH_GROUP", 8)))
+N50, ERR, K = 30000, 0.05, 15
+CONTIGS = None  # set by load_workload(); read by the forked read generators
 
 
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
-def workload(ref_len):
-    """Reference FASTA + -W list (cached on disk), returns (ref_path, w_path, contigs)."""
+def workload_name():
+    full = REF_LEN >= 3_000_000_000
+    return (f"BASELINE configs[4]{'' if full else ' at reduced reference length'}: {REF_LEN / 1e6:.0f} Mbp tandem-repeat-enriched synthetic ref "
+            f"(4 unit families, ~15 % of the genome), ONT reads N50=30kb 5% err, -x map-ont -W top-0.02% k=15 -c")
+
+
+def make_workload():
+    """Reference FASTA + -W list on disk (cached); only one process per node does this."""
     import gen_data
     os.makedirs(CACHE, exist_ok=True)
-    ref = os.path.join(CACHE, f"ref_{ref_len}.fa")
-    wf = os.path.join(CACHE, f"rep_{ref_len}_k{K}.txt")
+    ref = os.path.join(CACHE, f"tr_ref_{REF_LEN}.fa")
+    wf = os.path.join(CACHE, f"tr_rep_{REF_LEN}_k{K}.txt")
+    if os.path.exists(ref) and os.path.exists(wf):
+        return ref, wf
     t0 = time.time()
-    rng = np.random.default_rng(1002)
-    contigs = gen_data.make_ref(rng, ref_len, 1, False)  # one contig per 250 Mbp (SURVEY.md 8d), seed 1000 + cfg
-    if not os.path.exists(ref):
-        gen_data.write_fasta(ref + ".tmp", contigs)
-        os.replace(ref + ".tmp", ref)
-    if not os.path.exists(wf):
-        n, thr = gen_data.write_top_kmers(wf + ".tmp", contigs, K, 0.9998)
-        os.replace(wf + ".tmp", wf)
-        log(f"-W list: {n} k-mers above count {thr}")
-    log(f"workload ready in {time.time() - t0:.1f}s")
-    return ref, wf, contigs
+    rng = np.random.default_rng(1005)  # seed 1000 + cfg
+    contigs = gen_data.make_ref(rng, REF_LEN, max(1, round(REF_LEN / 250_000_000)), True)  # one contig per 250 Mbp (SURVEY.md 8d)
+    gen_data.write_fasta(ref + ".tmp", contigs)
+    n, thr = gen_data.write_top_kmers(wf + ".tmp", contigs, K, 0.9998)
+    os.replace(wf + ".tmp", wf)
+    os.replace(ref + ".tmp", ref)  # last: its presence says both files are complete
+    log(f"workload generated in {time.time() - t0:.1f}s; -W list: {n} k-mers above count {thr}")
+    return ref, wf
 
 
-def make_batch(contigs, n_reads, seed):
+def load_workload(rank):
+    """(ref_path, w_path); the contigs end up in CONTIGS.  Rank 0 generates, the others wait for the files."""
+    global CONTIGS
+    ref = os.path.join(CACHE, f"tr_ref_{REF_LEN}.fa")
+    wf = os.path.join(CACHE, f"tr_rep_{REF_LEN}_k{K}.txt")
+    if rank == 0:
+        make_workload()
+    else:
+        t0 = time.time()
+        while not (os.path.exists(ref) and os.path.exists(wf)):
+            if time.time() - t0 > 3600:
+                raise RuntimeError("timed out waiting for rank 0 to generate the workload")
+            time.sleep(1.0)
+    raw = np.fromfile(ref, dtype=np.uint8)  # one line per contig (gen_data.write_fasta)
+    nl = np.flatnonzero(raw == 10)
+    CONTIGS = []
+    for i in range(0, len(nl), 2):
+        h0 = 0 if i == 0 else nl[i - 1] + 1
+        CONTIGS.append((raw[h0 + 1:nl[i]].tobytes().decode(), raw[nl[i] + 1:nl[i + 1]]))
+    return ref, wf
+
+
+def _gen_step(args):
     import gen_data
-    rng = np.random.default_rng(seed)
-    return gen_data.make_reads(rng, contigs, n_reads, N50, ERR, min_len=1000)
+    n_reads, seed = args
+    recs = gen_data.make_reads(np.random.default_rng(seed), CONTIGS, n_reads, N50, ERR, min_len=1000)
+    return [(f"s{seed}_{nm}", s.tobytes()) for nm, s in recs]
+
+
+def gen_steps(n_steps, n_reads, seed0):
+    """n_steps batches of n_reads reads (name, bytes), deterministic per (seed0, step); forked workers share CONTIGS."""
+    import multiprocessing as mp
+    jobs = [(n_reads, seed0 + s) for s in range(n_steps)]
+    nproc = max(1, min(len(jobs), (os.cpu_count() or 2) // 2, 32))
+    if nproc == 1:
+        return [_gen_step(j) for j in jobs]
+    with mp.get_context("fork").Pool(nproc) as pool:
+        return pool.map(_gen_step, jobs)
+
+
+def write_reads(path, recs):
+    with open(path, "wb") as f:
+        for nm, s in recs:
+            f.write(b">" + nm.encode() + b"\n" + s + b"\n")
 
 
 class ClockSampler(threading.Thread):
@@ -142,61 +199,107 @@ class ClockSampler(threading.Thread):
                 "source": self.source}
 
 
-def run_reference(refbin, ref, wf, reads_fa, threads):
-    """Mapping-phase wall time of the reference from its own stderr stamps (main.c:401 -> last map.c:1220 line)."""
-    cmd = [refbin, "-t", str(threads), "-c", "-x", "map-ont", "-W", wf, ref, reads_fa]
-    p = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
-    t_idx, t_last = None, None
+def run_reference(refbin, ref, wf, reads_fa, threads, out_path=None, mini_batch=None):
+    """One invocation of the reference.  Returns (t_index, [(stamp, n_seq) per mini-batch]) from its own stderr stamps
+    (main.c:401 "loaded/built the index", map.c:1220 "mapped N sequences"); stdout goes to out_path (or is discarded)."""
+    cmd = [refbin, "-t", str(threads), "-c", "-x", "map-ont", "-W", wf]
+    if mini_batch:
+        cmd += ["-K", str(int(mini_batch))]
+    cmd += [ref, reads_fa]
+    out = open(out_path, "wb") if out_path else subprocess.DEVNULL
+    try:
+        p = subprocess.run(cmd, stdout=out, stderr=subprocess.PIPE, text=True)
+    finally:
+        if out_path:
+            out.close()
+    t_idx, stamps = None, []
     for ln in p.stderr.splitlines():
         if ln.startswith("[M::main::") and "loaded/built the index" in ln:
             t_idx = float(ln.split("::")[2].split("*")[0])
         if ln.startswith("[M::worker_pipeline::") and "mapped" in ln:
-            t_last = float(ln.split("::")[2].split("*")[0])
-    if p.returncode != 0 or t_idx is None or t_last is None:
+            stamps.append((float(ln.split("::")[2].split("*")[0]), int(ln.rsplit("mapped", 1)[1].split()[0])))
+    if p.returncode != 0 or t_idx is None or not stamps:
         raise RuntimeError("reference run failed: " + p.stderr[-400:])
-    return t_last - t_idx, t_idx
+    return t_idx, stamps
+
+
+def paf_by_read(path):
+    """read name -> list of its lines, in file order (the reference prints a mini-batch sorted by length, we print in input order)."""
+    d = {}
+    with open(path, "rb") as f:
+        for ln in f:
+            d.setdefault(ln.split(b"\t", 1)[0], []).append(ln)
+    return d
+
+
+def reference_arm(a, cores, refbin):
+    """--impl reference: the reference's own CPU implementation, one invocation, timed from its mini-batch stamps."""
+    ref, wf = load_workload(0)
+    per_step = a.cpu_reads_per_step
+    steps = gen_steps(a.warmup + a.steps, per_step, 7_000_000)
+    recs = [r for s in steps for r in s]
+    lens = [len(s) for _, s in recs]
+    # mini-batch = a group of steps (the reference cuts a batch when its bases reach -K): large enough to keep all threads busy
+    g = max(1, min(GROUP, a.warmup if a.warmup > 0 else a.steps))
+    mb = max(1, int(np.mean(lens) * per_step * g))
+    with tempfile.TemporaryDirectory(prefix="wm_bench_") as td:
+        fa = os.path.join(td, "reads.fa")
+        write_reads(fa, recs)
+        t_idx, stamps = run_reference(refbin, ref, wf, fa, cores, None, mb)
+    # the timed interval starts at the stamp of the mini-batch that holds the last warm-up read
+    n_warm = a.warmup * per_step
+    done, t_start, bases, n_timed = 0, t_idx, 0, 0
+    for t, n in stamps:
+        if done + n <= n_warm or done < n_warm:
+            t_start = t  # this batch still holds warm-up reads: excluded
+        else:
+            bases += sum(lens[done:done + n]); n_timed += n
+        done += n
+    t_end = stamps[-1][0]
+    if n_timed == 0 or t_end <= t_start:
+        raise RuntimeError("reference run: no timed mini-batch")
+    dt = t_end - t_start
+    val = bases / dt
+    eq_steps = n_timed / per_step
+    print(json.dumps({"impl": "reference", "metric": "mapped bases/sec", "value": val, "unit": "bases/s", "n_gpus": a.gpus, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": 1e3 * dt / eq_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "int8", "data": "synthetic",
+                      "config": {"workload": workload_name(), "reads_per_step": per_step, "host_threads": cores,
+                                 "note": f"one invocation, index build ({t_idx:.0f}s) excluded; mini-batches of {g} steps (-K {mb}); timed: "
+                                         f"{n_timed} reads ({bases / 1e6:.0f} Mbase) after {done - n_timed} warm-up reads"},
+                      "cpu_baseline": {"value": val, "unit": "bases/s", "cores": cores, "kind": "reference",
+                                       "sample": f"{n_timed} reads ({bases / 1e6:.0f} Mbase) in {dt:.1f}s, winnowmap -t {cores}, mapping phase only"},
+                      "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--reads", type=int, default=int(os.environ.get("WM_BENCH_READS", 1500)))
-    ap.add_argument("--cpu-reads", type=int, default=int(os.environ.get("WM_BENCH_CPU_READS", 3000)))
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("WM_BENCH_READS", 1000)))
+    ap.add_argument("--cpu-reads", type=int, default=int(os.environ.get("WM_BENCH_CPU_READS", 8000)), help="reads of the cpu_baseline / parity sample")
+    ap.add_argument("--cpu-reads-per-step", type=int, default=int(os.environ.get("WM_BENCH_CPU_READS_PER_STEP", 500)),
+                    help="--impl reference: reads per step (a bounded sample of the step)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
-    import gen_data
     cores = os.cpu_count() or 1
     refbin = os.path.join(ROOT, "oracle", "_ref", "winnowmap")
 
     if a.impl == "reference":
-        if rank != 0:
-            return
-        ref, wf, contigs = workload(REF_LEN)
-        vals = []
-        tmp = tempfile.mkdtemp(prefix="wm_bench_")
-        nb = 0
-        for s in range(a.warmup + a.steps):
-            recs = make_batch(contigs, a.cpu_reads, 7000 + s)
-            fa = os.path.join(tmp, f"r{s}.fa")
-            gen_data.write_fasta(fa, recs)
-            nb = sum(len(x) for _, x in recs)
-            dt, _ = run_reference(refbin, ref, wf, fa, cores)
-            if s >= a.warmup:
-                vals.append((nb, dt))
-        tb, tt = sum(v[0] for v in vals), sum(v[1] for v in vals)
-        val = tb / tt
-        print(json.dumps({"impl": "reference", "metric": "mapped bases/sec", "value": val, "unit": "bases/s", "n_gpus": a.gpus, "steps": a.steps,
-                          "warmup": a.warmup, "ms_per_step": 1e3 * tt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "int8", "data": "synthetic",
-                          "config": {"workload": f"{REF_LEN / 1e6:.0f} Mbp random ref, ONT reads N50=20kb 5% err, -x map-ont -W top-0.02% k=15 -c; "
-                                                 f"{a.cpu_reads} reads per step (index build excluded)"},
-                          "cpu_baseline": {"value": val, "unit": "bases/s", "cores": cores, "kind": "reference",
-                                           "sample": f"{a.cpu_reads} reads ({nb / 1e6:.1f} Mbase) per step, winnowmap -t {cores}"},
-                          "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        if rank == 0:
+            reference_arm(a, cores, refbin)
         return
+
+    # ---- inputs first (forked generators must not inherit a CUDA context) ----
+    t0 = time.time()
+    ref, wf = load_workload(rank)
+    seed0 = 2_005_000 + 100_000 * rank  # seeds 2000 + cfg, per rank and step
+    steps = gen_steps(a.warmup + a.steps, a.reads, seed0)
+    warm = [r for s in steps[:a.warmup] for r in s]
+    timed = [r for s in steps[a.warmup:] for r in s]
+    log(f"rank {rank}: workload + {len(warm) + len(timed)} reads ready in {time.time() - t0:.1f}s")
 
     dist = None
     if world > 1:
@@ -206,20 +309,19 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from winnowmap_b200 import lib
-    from winnowmap_b200.mapper import MapOpt, Mapper, _setup  # noqa: F401
+    from winnowmap_b200.mapper import MapOpt, Mapper
     L = lib()
     L.wm_prof_get.argtypes = [C.POINTER(C.c_double)]
+    L.wm_prof_get_copies.argtypes = [C.POINTER(C.c_double)]
     L.wm_gpu_map_batch.argtypes = [C.c_void_p, C.POINTER(MapOpt), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int32),
                                    C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
+    L.wm_format_batch.argtypes = [C.c_void_p, C.POINTER(MapOpt), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_char_p]
     L.wm_bench_upload.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
-    L.wm_bench_map_resident.argtypes = [C.c_void_p, C.POINTER(MapOpt), C.c_int, C.POINTER(C.c_double)]
+    L.wm_bench_map_resident.argtypes = [C.c_void_p, C.POINTER(MapOpt), C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.wm_bench_write.argtypes = [C.c_void_p, C.POINTER(MapOpt), C.c_int, C.c_char_p]
     L.wm_free_regs.argtypes = [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
 
-    ref, wf, contigs = workload(REF_LEN) if rank == 0 or world == 1 else (None, None, None)
-    if dist is not None:
-        dist.barrier()
-        if rank != 0:
-            ref, wf, contigs = workload(REF_LEN)  # cached files; every rank needs the contigs to draw its own reads
     t0 = time.time()
     # one worker per physical core at N=1; with several ranks per node the ranks share the node's hardware threads
     n_thr = max(1, min(int(os.environ.get("WM_HOST_THREADS", 64)), (cores // 2) // max(1, world)))
@@ -241,58 +343,60 @@ def main():
         if rank != 0:
             mp = Mapper(None, None, preset="map-ont", cigar=True, device=local, n_threads=n_thr, blob=blob)
         log(f"rank {rank}: index blob {blob.nbytes / 1e6:.0f} MB broadcast+adopted in {time.time() - tb:.2f}s")
-    log(f"rank {rank}: index ready in {time.time() - t0:.1f}s ({mp.stats()['n_keys']:.0f} keys)")
+        del blob
+    t_index = time.time() - t0
+    log(f"rank {rank}: index ready in {t_index:.1f}s ({mp.stats()['n_keys']:.0f} keys, {mp.stats()['n_pos']:.0f} positions)")
 
     def pack(recs):
         n = len(recs)
         names = (C.c_char_p * n)(*[nm.encode() for nm, _ in recs])
-        seqs_b = [s.tobytes() for _, s in recs]
-        seqs = (C.c_char_p * n)(*seqs_b)
-        lens = (C.c_int32 * n)(*[len(s) for s in seqs_b])
-        return n, names, seqs, lens, seqs_b
+        seqs = (C.c_char_p * n)(*[s for _, s in recs])
+        lens = (C.c_int32 * n)(*[len(s) for _, s in recs])
+        return n, names, seqs, lens
 
-    def map_host(recs):
-        n, names, seqs, lens, keep = pack(recs)
-        n_reg = (C.c_int32 * n)(); regs = (C.c_void_p * n)(); rl = (C.c_int32 * n)(); fg = (C.c_int32 * n)()
-        t = time.perf_counter()
-        L.wm_gpu_map_batch(mp.ctx, C.byref(mp.mo), n, names, seqs, lens, n_reg, regs, rl, fg, n_thr)
-        L.wm_device_synchronize()
-        dt = time.perf_counter() - t
-        d2h = sum(n_reg) * 80
-        L.wm_free_regs(n, n_reg, regs)
-        return dt, sum(lens), d2h
+    group_reads = GROUP * a.reads
+
+    def map_host(recs, keep_first=0, out_path=None):
+        """recs through wm_gpu_map_batch in groups of GROUP steps; wall time of the calls; optionally formats the first keep_first reads."""
+        dt, d2h = 0.0, 0
+        for g0 in range(0, len(recs), group_reads):
+            sub = recs[g0:g0 + group_reads]
+            n, names, seqs, lens = pack(sub)
+            n_reg = (C.c_int32 * n)(); regs = (C.c_void_p * n)(); rl = (C.c_int32 * n)(); fg = (C.c_int32 * n)()
+            t = time.perf_counter()
+            L.wm_gpu_map_batch(mp.ctx, C.byref(mp.mo), n, names, seqs, lens, n_reg, regs, rl, fg, n_thr)
+            L.wm_device_synchronize()
+            dt += time.perf_counter() - t
+            if g0 == 0 and keep_first > 0 and out_path:
+                m = min(keep_first, n)
+                L.wm_format_batch(mp.ctx, C.byref(mp.mo), m, names, seqs, lens, n_reg, regs, rl, out_path.encode())
+            d2h += sum(n_reg) * 80
+            L.wm_free_regs(n, n_reg, regs)
+        return dt, d2h
 
     def upload(recs):
-        n, names, seqs, lens, keep = pack(recs)
+        n, names, seqs, lens = pack(recs)
         L.wm_bench_upload(mp.ctx, n, names, seqs, lens)  # raw reads -> one HBM pool (not timed)
         L.wm_device_synchronize()
-        return sum(lens)
 
     def map_uploaded():
         ms = C.c_double()
-        L.wm_bench_map_resident(mp.ctx, C.byref(mp.mo), n_thr, C.byref(ms))  # CUDA events bracketing the whole pass
+        L.wm_bench_map_resident(mp.ctx, C.byref(mp.mo), n_thr, group_reads, C.byref(ms))  # CUDA events bracketing the whole pass
         return ms.value / 1e3
-
-    def map_resident(recs):
-        nb = upload(recs)
-        return map_uploaded(), nb
 
     def barrier():
         L.wm_device_synchronize()
         if dist is not None:
             dist.barrier()
 
-    seed0 = 9000 + 1000 * rank
-    batches = [make_batch(contigs, a.reads, seed0 + s) for s in range(a.warmup + a.steps)]
-    # warm-up in the shape of the timed passes: W steps submitted together, device-resident and through the host API
-    # at least as many steps as the timed pass, so that every lane has sized its workspaces for the same chunk size
-    n_warm = max(a.warmup, a.steps)
-    warm = [r for s in range(n_warm) for r in (batches[s] if s < a.warmup else make_batch(contigs, a.reads, seed0 + 300 + s))]
+    # warm-up in the shape of the timed passes: W steps, device-resident and through the host API
     if warm:
-        map_resident(warm)
+        upload(warm)
+        map_uploaded()
         map_host(warm)
     L.wm_prof_enable(1); L.wm_prof_reset()
     L.wm_dump_timers() if os.environ.get("WM_TIMING") else None
+    mp.reset_stats() if hasattr(mp, "reset_stats") else None
     phys, uuid = local, None  # NVML numbers the physical devices: honour CUDA_VISIBLE_DEVICES
     vis = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
     if local < len(vis):
@@ -300,11 +404,9 @@ def main():
             phys = int(vis[local])
         elif vis[local].startswith("GPU-"):
             uuid = vis[local]
+    bases = sum(len(s) for _, s in timed)
+    upload(timed)
     sampler = ClockSampler(phys, uuid); sampler.start()
-    # the K timed steps are submitted together (K batches of reads_per_step reads, all resident in HBM): the orchestration
-    # lanes pull chunks of reads from the whole pool, so the steps pipeline instead of draining the GPU at every step end
-    timed = [r for s in range(a.warmup, a.warmup + a.steps) for r in batches[s]]
-    bases = upload(timed)
     barrier()
     t_steps = map_uploaded()
     barrier()
@@ -312,20 +414,21 @@ def main():
     if os.environ.get("WM_TIMING"):
         log(f"timers over {a.steps} timed steps:")
         L.wm_dump_timers()
-    prof = (C.c_double * 8)(); L.wm_prof_get(prof)
+    prof = (C.c_double * 13)(); L.wm_prof_get(prof)
     L.wm_prof_enable(0)
-    # end to end through the host-buffer API (fresh batches)
-    e2e_recs = [r for s in range(a.steps) for r in make_batch(contigs, a.reads, seed0 + 500 + s)]
+    st = mp.stats()
+    tmpd = tempfile.mkdtemp(prefix="wm_bench_")
+    n_par = min(a.cpu_reads, len(timed))
+    paf_res, paf_host = os.path.join(tmpd, "resident.paf"), os.path.join(tmpd, "host.paf")
+    L.wm_bench_write(mp.ctx, C.byref(mp.mo), n_par, paf_res.encode())  # the records of the timed pass itself
+    # end to end through the host-buffer API: the same K steps, host buffers in, alignment records out
     L.wm_prof_reset()  # zeroes the library's host<->device byte counters
-    e2e_t, e2e_b, d2h_b = map_host(e2e_recs)  # K steps in one call: host buffers in, alignment records out
-    h2d_step, d2h_step = int(e2e_b / a.steps), int(d2h_b / a.steps)
-    try:  # what the library actually copied: reads and job tables in; chains, DP results and CIGARs out
-        cp = (C.c_double * 2)()
-        L.wm_prof_get_copies(cp)
-        if cp[0] > 0:
-            h2d_step, d2h_step = int(cp[0] / a.steps), int(cp[1] / a.steps)
-    except AttributeError:
-        pass
+    barrier()
+    e2e_t, d2h_b = map_host(timed, n_par, paf_host)
+    barrier()
+    cp = (C.c_double * 2)(); L.wm_prof_get_copies(cp)
+    h2d_step, d2h_step = int(cp[0] / a.steps), int(cp[1] / a.steps)
+    e2e_b = bases
     if dist is not None:
         import torch
         t = torch.tensor([t_steps, e2e_t], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,37 +444,64 @@ def main():
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
-    # lanes launch their fill kernels concurrently: the denominator is the time during which at least one of them ran
-    k_ms = prof[7] if prof[7] > 0 else prof[1]
-    ach = prof[3] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    cpu = None
-    try:  # the reference beside it (N = 1 only), bounded sample, all host cores
+
+    def roof(kind):
+        ms_sum, ms_uni, n_l, alg, units, units2 = [prof[1 + 6 * kind + i] for i in range(6)]
+        k_ms = ms_uni if ms_uni > 0 else ms_sum
+        ach = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        r = {"bound": "hbm", "kernel": ["wm_extd2_fill_kernel", "wm_chain_fill_kernel"][kind], "achieved": ach, "peak": peak, "unit": "GB/s",
+             "frac": ach / peak, "traffic": None, "of": "measured" if peaks else "fallback", "launches": int(n_l), "kernel_ms": k_ms,
+             "kernel_ms_sum_over_launches": ms_sum, "algorithmic_bytes": alg}
+        if kind == 0:
+            r.update({"block_cells": units, "jobs": int(units2), "block_cells_per_s": units / (k_ms * 1e-3) if k_ms > 0 else 0.0})
+        else:
+            r.update({"anchors": units, "anchors_per_s": units / (k_ms * 1e-3) if k_ms > 0 else 0.0})
+        return r
+    r_fill, r_chain = roof(0), roof(1)
+    dom, other = (r_fill, r_chain) if r_fill["kernel_ms"] >= r_chain["kernel_ms"] else (r_chain, r_fill)
+
+    cpu, parity, parity_note = None, False, ""
+    try:  # the reference beside it (N = 1 only), bounded sample, all host threads; its output is the parity oracle
         if world > 1:
             raise RuntimeError("reported by the N=1 run only")
-        recs = make_batch(contigs, a.cpu_reads, 777)
-        with tempfile.TemporaryDirectory() as td:
-            fa = os.path.join(td, "cpu.fa"); gen_data.write_fasta(fa, recs)
-            dt, _ = run_reference(refbin, ref, wf, fa, cores)
-        nb = sum(len(x) for _, x in recs)
+        if os.environ.get("WM_BENCH_NO_CPU"):
+            raise RuntimeError("WM_BENCH_NO_CPU set (profiling run)")
+        sample = (timed + warm)[:a.cpu_reads]
+        fa = os.path.join(tmpd, "cpu.fa"); write_reads(fa, sample)
+        ref_paf = os.path.join(tmpd, "ref.paf")
+        t_idx, stamps = run_reference(refbin, ref, wf, fa, cores, ref_paf)
+        dt = stamps[-1][0] - t_idx
+        nb = sum(len(s) for _, s in sample)
         cpu = {"value": nb / dt, "unit": "bases/s", "cores": cores, "kind": "reference",
-               "sample": f"{a.cpu_reads} reads ({nb / 1e6:.1f} Mbase) of the same distribution, winnowmap -t {cores}, mapping phase only"}
+               "sample": f"{len(sample)} reads ({nb / 1e6:.1f} Mbase) of the timed + warm-up steps in {dt:.1f}s, winnowmap -t {cores}, mapping phase only "
+                         f"(index build {t_idx:.0f}s excluded)"}
+        want = paf_by_read(ref_paf)
+        names = [nm.encode() for nm, _ in timed[:n_par]]
+        bad = 0
+        for got_path in (paf_res, paf_host):
+            got = paf_by_read(got_path)
+            bad += sum(1 for nm in names if got.get(nm, []) != want.get(nm, []))
+        parity = bad == 0 and n_par > 0
+        parity_note = f"{n_par} reads x 2 passes (resident, host-buffer) vs oracle/_ref/winnowmap: {bad} reads differ"
     except Exception as e:  # noqa: BLE001
-        cpu = {"value": None, "unit": "bases/s", "cores": cores, "kind": "reference", "sample": f"unavailable: {e}"}
-    st = mp.stats()
+        if cpu is None:
+            cpu = {"value": None, "unit": "bases/s", "cores": cores, "kind": "reference", "sample": f"unavailable: {e}"}
+        parity_note = parity_note or f"not checked: {e}"
+    try:
+        import shutil
+        shutil.rmtree(tmpd, ignore_errors=True)
+    except Exception:
+        pass
     print(json.dumps({
         "metric": "mapped bases/sec", "value": bases / t_steps, "unit": "bases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * t_steps / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": {"workload": f"{REF_LEN / 1e6:.0f} Mbp random ref, ONT reads N50=20kb 5% err, -x map-ont -W top-0.02% k=15 -c (BASELINE configs[1]); "
-                               f"{a.reads} fresh reads per step per GPU, working set >> L2", "reads_per_step": a.reads, "host_threads": n_thr,
-                   "lanes": int(os.environ.get("WM_LANES", max(2, min(8, n_thr // 8))))},
+        "config": {"workload": workload_name() + f"; {a.reads} fresh reads per step per GPU, working set >> L2", "reads_per_step": a.reads,
+                   "host_threads": n_thr, "lanes": int(os.environ.get("WM_LANES", max(2, min(8, n_thr // 8)))),
+                   "chunk_bases": int(os.environ["WM_CHUNK_BASES"]), "steps_per_submission": GROUP, "index_build_s": t_index},
         "e2e": {"value": e2e_b / e2e_t, "unit": "bases/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step},
         "gpu_launches": int(prof[0]),
-        "roofline": {"bound": "hbm", "kernel": "wm_extd2_fill_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": 5.196e9, "traffic_of": "dram read+write of one captured launch of 4.3e9 block cells (ncu --set full, "
-                     "profiles/r01_ncu_fill_v3_summary.txt): 1.2 B per algorithmic byte", "of": "measured" if peaks else "fallback", "launches": int(prof[2]), "kernel_ms": k_ms, "kernel_ms_sum_over_launches": prof[1],
-                     "block_cells_per_s": prof[4] / (k_ms * 1e-3) if k_ms > 0 else 0.0,
-                     "jobs": int(prof[5]), "block_cells": prof[4], "frac_cells_in_16x2_path": prof[6] / prof[4] if prof[4] > 0 else 0.0},
-        "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": dom, "roofline_other": other,
+        "cpu_baseline": cpu, "parity_checked": parity, "parity": parity_note, "clocks": clocks,
         "breakdown_s": {"seed_chain": st["t_seed"], "dp_rounds": st["t_dp"], "host_glue": st["t_host"]},
     }))
 

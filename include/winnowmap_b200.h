@@ -257,15 +257,23 @@ uint32_t wm_idx_seq_len(const wm_gpu_ctx *ctx, int rid);
 
 /* frees what wm_gpu_map_batch returned (the reference's output step does this itself, src/map.c:1210-1211) */
 void wm_free_regs(int n, const int32_t *n_reg, wm_reg1_t **reg);
-/* bench: upload a batch (not timed), then map it with the reads resident in HBM; *ms = CUDA-event time of the step */
+/* the records wm_gpu_map_batch returned, as PAF (or SAM when opt->flag has MM_F_OUT_SAM) lines in input order: the writer
+ * wm_map_file uses, i.e. what the output step of the reference prints for these reads (src/map.c:1189-1206) */
+int wm_format_batch(const wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_seq, const char *const *names, const char *const *seqs, const int32_t *lens,
+                    const int32_t *n_reg, wm_reg1_t *const *reg, const int32_t *rep_len, const char *out_fn);
+/* bench: upload a batch (not timed), then map it with the reads resident in HBM; *ms = CUDA-event time of the pass.  The
+ * reads are submitted group_reads at a time (<= 0: all at once).  The records of the pass stay in the context until the next pass; wm_bench_write formats those of the first n_first reads. */
 int wm_bench_upload(wm_gpu_ctx *ctx, int n_seq, const char *const *names, const char *const *seqs, const int32_t *lens);
-int wm_bench_map_resident(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_threads, double *ms);
+int wm_bench_map_resident(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_threads, int group_reads, double *ms);
+int wm_bench_write(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_first, const char *out_fn);
 
-/* bench instrumentation: launch counter and CUDA-event timing of the dominant (DP fill) kernel */
+/* bench instrumentation (csrc/prof.cu): launch counter and CUDA-event timing of the two dominant kernel classes */
 void wm_prof_enable(int on);
 void wm_prof_reset(void);
-void wm_prof_get(double *out8); /* launches, sum of fill-kernel ms, fill launches, fill algorithmic bytes, fill block cells, fill jobs,
-                                   block cells in the 16x2 path, ms during which at least one fill kernel ran (launches of concurrent lanes overlap) */
+/* out[0] = kernel launches; then six values per class (DP fill at out[1], chaining forward pass at out[7]): sum of launch
+ * ms, ms during which at least one kernel of the class ran (launches of concurrent lanes overlap), launches, algorithmic
+ * bytes, units (block cells / anchors), DP jobs */
+void wm_prof_get(double *out13);
 void wm_prof_get_copies(double *out2); /* bytes copied host-to-device / device-to-host by the mapping path since wm_prof_reset */
 int wm_device_synchronize(void);
 void wm_dump_timers(void); /* prints and resets the orchestration wall-clock accumulators (stderr) */

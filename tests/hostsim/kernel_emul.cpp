@@ -110,8 +110,27 @@ extern "C" int wmt_emul_extd2(const uint8_t *query, int qlen, const uint8_t *tar
 	return 0;
 }
 
+// the shared-memory-ring formulation (wm_chain_fill_warp_ring): window starts first (closed form), then the sweep.  The
+// small ring (64 slots) forces the scans through the older-than-the-ring path that reads global memory.
+template <int RING>
+static void run_ring(const wm128_dev *a, int n, const wm_chain_params *P, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int lane)
+{
+	static thread_local wm_chain_ring<RING> *ring = 0;
+	if (lane == 0) { if (!ring) ring = new wm_chain_ring<RING>(); memset(ring, 0xff, sizeof(*ring)); }
+	for (int i = lane; i < n; i += 32) v[i] = wm_chain_window_start(a, i, *P);
+	__syncwarp();
+	wm_chain_fill_warp_ring<RING>(a, n, *P, f, p, t, v, ring, lane);
+}
+static void run_fill(int mode, const wm128_dev *a, int n, const wm_chain_params *P, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int32_t *D, int lane)
+{
+	if (mode == 1) wm_chain_fill_warp_dense(a, n, *P, f, p, t, v, D, lane);
+	else if (mode == 2) run_ring<64>(a, n, P, f, p, t, v, lane);
+	else if (mode == 3) run_ring<1024>(a, n, P, f, p, t, v, lane);
+	else wm_chain_fill_warp(a, n, *P, f, p, t, v, lane);
+}
+
 // The chaining forward pass (csrc/chain_dev.cuh) on the software warp: dense = 0 the production formulation (32
-// predecessors per step), dense = 1 the dense-candidate formulation.  Outputs the f / p / v arrays the backtracking
+// predecessors per step), dense = 1 the dense-candidate formulation, 2 / 3 the shared-memory ring (64 / 1024 slots).  Outputs the f / p / v arrays the backtracking
 // kernel consumes (a is `n` anchors, x then y).
 extern "C" int wmt_emul_chain_fill(const uint64_t *a_xy, int n, int max_dist_x, int min_dist_x, int max_dist_y, int bw, int max_skip, int max_iter,
                                    float gap_scale, int dense, int32_t *f, int32_t *p, int32_t *v)
@@ -126,8 +145,7 @@ extern "C" int wmt_emul_chain_fill(const uint64_t *a_xy, int n, int max_dist_x, 
 	if (n <= 0) return 0;
 	wm_emul::run_warp([](int l, void *q) {
 		Args &x = *(Args*)q;
-		if (x.dense) wm_chain_fill_warp_dense(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, x.D, l);
-		else wm_chain_fill_warp(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, l);
+		run_fill(x.dense, x.a, x.n, x.P, x.f, x.p, x.t, x.v, x.D, l);
 	}, &A);
 	return 0;
 }
@@ -208,8 +226,7 @@ extern "C" int wmt_emul_chain(uint64_t *a_xy, int n, int max_dist_x, int min_dis
 		A = { a.data(), w.data(), b.data(), n, &P, f.data(), p.data(), t.data(), v.data(), D.data(), u.data(), u2.data(), &stack, dense, n_u_out, n_b_out };
 	wm_emul::run_warp([](int l, void *q) {
 		Args &x = *(Args*)q;
-		if (x.dense) wm_chain_fill_warp_dense(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, x.D, l);
-		else wm_chain_fill_warp(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, l);
+		run_fill(x.dense, x.a, x.n, x.P, x.f, x.p, x.t, x.v, x.D, l);
 		__syncwarp();
 		wm_chain_backtrack_warp(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, x.u, x.u2, x.w, x.b, x.stk, x.n_u, x.n_b, l);
 	}, &A);

@@ -166,20 +166,59 @@ def kmer_to_str(v, k):
     return "".join("ACGT"[(int(v) >> (2 * (k - 1 - i))) & 3] for i in range(k))
 
 
-def write_top_kmers(path, contigs, k, distinct=0.9998):
+def _tools_lib():
+    """tools/libwm_tools.so (built by __graft_entry__.build() from tools/wm_tools.c), or None."""
+    import ctypes as C
+    import os
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libwm_tools.so")
+    if not os.path.exists(so):
+        return None
+    L = C.CDLL(so)
+    L.wm_tools_count.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    L.wm_tools_hist.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.wm_tools_hist.restype = C.c_int64
+    L.wm_tools_above.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64]
+    L.wm_tools_above.restype = C.c_int64
+    return L
+
+
+def top_kmers(contigs, k, distinct=0.9998):
+    """(kmers, counts, threshold): canonical k-mers with count > threshold, ascending.
+    meryl rule: threshold = smallest count whose cumulative number of distinct k-mers reaches distinct * total
+    distinct (ext/meryl/src/meryl/merylOp-nextMer.C:103-115)."""
+    L = _tools_lib() if k <= 15 else None
+    if L is not None:  # direct-index table in C (4^k uint32 counters): seconds per Gbp
+        table = np.zeros(1 << (2 * k), dtype=np.uint32)
+        for _, seq in contigs:
+            seq = np.ascontiguousarray(seq)
+            L.wm_tools_count(seq.ctypes.data, len(seq), k, table.ctypes.data)
+        hist = np.zeros(1 << 20, dtype=np.int64)
+        n_distinct = L.wm_tools_hist(table.ctypes.data, k, hist.ctypes.data, len(hist))
+        cum = np.cumsum(hist)
+        vals = np.nonzero(hist)[0]
+        ti = int(np.searchsorted(cum[vals], distinct * n_distinct, side="left"))
+        thr = int(vals[min(ti, len(vals) - 1)]) if len(vals) else 0
+        m = L.wm_tools_above(table.ctypes.data, k, thr, None, None, 0)
+        kmers = np.zeros(m, dtype=np.uint64); counts = np.zeros(m, dtype=np.uint32)
+        if m:
+            L.wm_tools_above(table.ctypes.data, k, thr, kmers.ctypes.data, counts.ctypes.data, m)
+        return kmers, counts, thr
     kmers, counts = count_kmers(contigs, k)
-    # meryl rule: threshold = smallest count whose cumulative number of distinct k-mers
-    # reaches distinct * total distinct; print k-mers with count > threshold
     vals, hist = np.unique(counts, return_counts=True)
     cum = np.cumsum(hist)
     target = distinct * len(kmers)
     ti = int(np.searchsorted(cum, target, side="left"))
     thr = int(vals[min(ti, len(vals) - 1)])
     sel = counts > thr
+    return kmers[sel], counts[sel], thr
+
+
+def write_top_kmers(path, contigs, k, distinct=0.9998):
+    kmers, counts, thr = top_kmers(contigs, k, distinct)
     with open(path, "w") as f:
-        for v, c in zip(kmers[sel], counts[sel]):
+        for v, c in zip(kmers, counts):
             f.write(f"{kmer_to_str(v, k)}\t{int(c)}\n")
-    return int(sel.sum()), thr
+    return len(kmers), thr
 
 
 def main():

@@ -29,6 +29,7 @@ struct wm_gpu_ctx_s {
 	int64_t n_keys, n_pos;
 	std::vector<wm_read> resident; // bench: reads already uploaded by wm_bench_upload ...
 	char *d_resident = 0;          // ... their bases, one device pool (wm_read::dev_off)
+	std::vector<std::vector<wm_reg1_t>> res_regs; std::vector<int> res_rl; // records of the last wm_bench_map_resident pass (wm_bench_write)
 	std::string sam_cl;            // command line recorded in the @PG line of SAM output (wm_set_sam_cl)
 	std::vector<Backend*> lanes;   // lanes[0] == be; further lanes share the index and own a stream + workspaces
 	// host copy of the flattened index, kept for the one-time fan-out to the other GPUs (wm_idx_blob_*)
@@ -37,6 +38,7 @@ struct wm_gpu_ctx_s {
 	uint64_t bloom_bits;
 };
 
+static void free_reg_vectors(std::vector<std::vector<wm_reg1_t>> &regs);
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 static void require_device(const char *who)
@@ -157,6 +159,7 @@ extern "C" void wm_gpu_destroy(wm_gpu_ctx_s *c)
 	for (size_t i = 1; i < c->lanes.size(); ++i) gpu_backend_destroy(c->lanes[i]);
 	gpu_backend_destroy(c->be);
 	if (c->d_resident) cudaFree(c->d_resident);
+	free_reg_vectors(c->res_regs);
 	delete c;
 }
 
@@ -433,13 +436,17 @@ extern "C" void wm_reset_stats(wm_gpu_ctx_s *c) { memset(&c->stats, 0, sizeof(c-
 
 // ---- bench instrumentation ----
 extern "C" void wm_prof_enable(int on) { g_wm_prof.enabled = on; }
-extern "C" void wm_prof_reset(void) { int e = g_wm_prof.enabled; memset(&g_wm_prof, 0, sizeof(g_wm_prof)); g_wm_prof.enabled = e; wm_prof_fill_begin(); }
+extern "C" void wm_prof_reset(void) { int e = g_wm_prof.enabled; memset(&g_wm_prof, 0, sizeof(g_wm_prof)); g_wm_prof.enabled = e; wm_prof_region_begin(); }
 extern "C" void wm_prof_get(double *o)
-{ // o[0..7]: launches, sum of fill-kernel ms, fill launches, algorithmic bytes, block cells, jobs, block cells in the 16x2 path, union of fill-kernel ms
-	wm_prof_fill_collect();
-	o[0] = (double)g_wm_prof.n_launches; o[1] = g_wm_prof.fill_ms; o[2] = (double)g_wm_prof.fill_launches;
-	o[3] = g_wm_prof.fill_alg_bytes; o[4] = g_wm_prof.fill_cells; o[5] = g_wm_prof.fill_jobs; o[6] = g_wm_prof.fill_cells_v2;
-	o[7] = g_wm_prof.fill_union_ms;
+{ // o[0]: kernel launches; then per kernel class (0 = DP fill at o[1..6], 1 = chaining forward pass at o[7..12]):
+  // sum of launch ms, union of launch intervals ms, launches, algorithmic bytes, units (block cells / anchors), units2 (DP jobs)
+	wm_prof_collect();
+	o[0] = (double)g_wm_prof.n_launches;
+	for (int k = 0; k < WM_PK_N; ++k) {
+		const wm_prof_kind &K = g_wm_prof.k[k];
+		double *q = o + 1 + 6 * k;
+		q[0] = K.ms, q[1] = K.union_ms, q[2] = (double)K.launches, q[3] = K.alg_bytes, q[4] = K.units, q[5] = K.units2;
+	}
 }
 // host<->device traffic of the mapping path since wm_prof_reset: o[0] = host-to-device bytes, o[1] = device-to-host bytes
 extern "C" void wm_prof_get_copies(double *o) { o[0] = (double)g_wm_prof.h2d_bytes; o[1] = (double)g_wm_prof.d2h_bytes; }
@@ -479,21 +486,87 @@ extern "C" int wm_bench_upload(wm_gpu_ctx_s *c, int n_seq, const char *const *na
 
 // ... and map them with the device copies already resident; *ms = device time between two events that bracket the
 // whole step (recorded on the legacy default stream, which orders against the backend's blocking stream).
-extern "C" int wm_bench_map_resident(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, int n_threads, double *ms)
+static void free_reg_vectors(std::vector<std::vector<wm_reg1_t>> &regs)
 {
+	for (auto &v : regs) for (auto &r : v) free(r.p);
+	regs.clear();
+}
+
+extern "C" int wm_bench_map_resident(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, int n_threads, int group_reads, double *ms)
+{ // the resident reads are submitted in groups of group_reads reads (<= 0: all at once); two events bracket the whole pass
 	static cudaEvent_t e0 = 0, e1 = 0;
 	if (!e0) { WM_CUDA_CHECK(cudaEventCreate(&e0)); WM_CUDA_CHECK(cudaEventCreate(&e1)); }
-	std::vector<const wm_read*> reads(c->resident.size());
-	for (size_t i = 0; i < reads.size(); ++i) reads[i] = &c->resident[i];
-	std::vector<std::vector<wm_reg1_t>> regs; std::vector<int> rl, fg;
+	const int n = (int)c->resident.size();
+	free_reg_vectors(c->res_regs);
+	c->res_regs.resize(n); c->res_rl.assign(n, 0);
+	if (group_reads <= 0) group_reads = n > 0 ? n : 1;
 	WM_CUDA_CHECK(cudaEventRecord(e0, 0));
-	map_lanes(c, opt, reads, regs, rl, fg, n_threads, true);
+	for (int g0 = 0; g0 < n; g0 += group_reads) {
+		const int g1 = std::min(n, g0 + group_reads);
+		std::vector<const wm_read*> reads(g1 - g0);
+		for (int i = g0; i < g1; ++i) reads[i - g0] = &c->resident[i];
+		std::vector<std::vector<wm_reg1_t>> regs; std::vector<int> rl, fg;
+		map_lanes(c, opt, reads, regs, rl, fg, n_threads, true);
+		for (int i = g0; i < g1; ++i) { c->res_regs[i].swap(regs[i - g0]); c->res_rl[i] = rl[i - g0]; }
+	}
 	WM_CUDA_CHECK(cudaEventRecord(e1, 0));
 	WM_CUDA_CHECK(cudaEventSynchronize(e1));
 	float f = 0.f;
 	WM_CUDA_CHECK(cudaEventElapsedTime(&f, e0, e1));
 	*ms = f;
-	for (auto &v : regs) for (auto &r : v) free(r.p);
+	return 0;
+}
+
+// One read's output lines (PAF, or SAM when opt->flag says so), as the output step of the reference prints them (src/map.c:1189-1206)
+static void format_read(std::string &dst, const wm_host_idx *mi, const wm_mapopt_t *opt, const wm_read *t, int n_reg, const wm_reg1_t *regs, int rep_len)
+{
+	std::string line;
+	const bool sam = (opt->flag & WM_F_OUT_SAM) != 0;
+	auto emit = [&](int j) {
+		if (sam) write_sam(line, mi, t, j, n_reg, regs, opt->flag, rep_len, "");
+		else write_paf(line, mi, t, j >= 0 ? &regs[j] : 0, opt->flag, rep_len);
+		dst += line; dst += '\n';
+	};
+	if (n_reg > 0) {
+		for (int j = 0; j < n_reg; ++j) {
+			if ((opt->flag & WM_F_NO_PRINT_2ND) && regs[j].id != regs[j].parent) continue;
+			emit(j);
+		}
+	} else if ((opt->flag & WM_F_PAF_NO_HIT) || (sam && !(opt->flag & WM_F_SAM_HIT_ONLY))) emit(-1);
+}
+
+// bench: the records of the last resident pass, formatted for the first n_first reads in input order (parity check of the timed path)
+extern "C" int wm_bench_write(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, int n_first, const char *out_fn)
+{
+	FILE *out = fopen(out_fn, "wb");
+	if (!out) return -1;
+	const int n = std::min<int>(n_first, (int)c->res_regs.size());
+	std::string buf;
+	for (int i = 0; i < n; ++i) {
+		buf.clear();
+		format_read(buf, &c->hidx, opt, &c->resident[i], (int)c->res_regs[i].size(), c->res_regs[i].data(), c->res_rl[i]);
+		fwrite(buf.data(), 1, buf.size(), out);
+	}
+	fclose(out);
+	return n;
+}
+
+// The records wm_gpu_map_batch returned, formatted in input order with the writer wm_map_file uses (mm_write_paf3 / mm_write_sam3)
+extern "C" int wm_format_batch(const wm_gpu_ctx_s *c, const wm_mapopt_t *opt, int n_seq, const char *const *names, const char *const *seqs, const int32_t *lens,
+                               const int32_t *n_reg, wm_reg1_t *const *reg, const int32_t *rep_len, const char *out_fn)
+{
+	FILE *out = fopen(out_fn, "wb");
+	if (!out) return -1;
+	std::string buf;
+	wm_read t;
+	for (int i = 0; i < n_seq; ++i) {
+		t.name = names && names[i] ? names[i] : "";
+		t.seq.assign(seqs[i], lens[i]);
+		buf.clear();
+		format_read(buf, &c->hidx, opt, &t, n_reg[i], reg[i], rep_len[i]);
+		fwrite(buf.data(), 1, buf.size(), out);
+	}
+	fclose(out);
 	return 0;
 }
 

@@ -68,6 +68,57 @@ wm_chain_fill_dense_kernel(const wm128_dev *__restrict__ a_all, const int64_t *_
 	}
 }
 
+// Window start of every anchor (src/chain.c:49-55 in closed form, chain_dev.cuh), one thread per anchor, into v[].
+__global__ void wm_chain_window_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, int n_tasks, int64_t n_a,
+                                       wm_chain_params2 PP, const uint8_t *__restrict__ set_id, int32_t *__restrict__ v_all)
+{
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n_a) return;
+	int lo = 0, hi = n_tasks; // the task that holds anchor g: last t with off[t] <= g
+	while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (off[m] <= g) lo = m; else hi = m; }
+	const int64_t base = off[lo];
+	v_all[g] = wm_chain_window_start(a_all + base, (int)(g - base), PP.p[set_id ? set_id[lo] : 0]);
+}
+
+// The forward pass with the sliding window of each warp's task in a shared-memory ring (chain_dev.cuh).  Tasks
+// order[first .. last), one warp per task, pulled from a counter.
+template <int RING, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+wm_chain_fill_ring_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ order, int first, int last,
+                          wm_chain_params2 PP, const uint8_t *__restrict__ set_id, int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all,
+                          int32_t *__restrict__ v_all, int *counter)
+{
+	const unsigned FULL = 0xffffffffu;
+	extern __shared__ __align__(16) unsigned char wm_chain_smem[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	wm_chain_ring<RING> *R = (wm_chain_ring<RING>*)wm_chain_smem + wid;
+	for (;;) {
+		int ti = 0;
+		if (lane == 0) ti = first + atomicAdd(counter, 1);
+		ti = __shfl_sync(FULL, ti, 0);
+		if (ti >= last) break;
+		const int task = order[ti];
+		const int64_t base = off[task];
+		const int n = (int)(off[task + 1] - base);
+		if (n <= 0) continue;
+		wm_chain_fill_warp_ring<RING>(a_all + base, n, PP.p[set_id ? set_id[task] : 0], f_all + base, p_all + base, t_all + base, v_all + base, R, lane);
+		__syncwarp();
+	}
+}
+
+#define WM_CHAIN_SMALL_N 128    // tasks up to this many anchors: ring of the same size, eight warps per CTA
+template <int RING, int WARPS>
+static void wm_chain_launch_ring(int grid, cudaStream_t st, const wm128_dev *a, const int64_t *off, const int32_t *order, int first, int last,
+                                 const wm_chain_params2 &PP, const uint8_t *set_id, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int *counter)
+{
+	const size_t smem = sizeof(wm_chain_ring<RING>) * WARPS;
+	static bool attr_set = false;
+	if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_chain_fill_ring_kernel<RING, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+	wm_count_launch();
+	wm_chain_fill_ring_kernel<RING, WARPS><<<grid, WARPS * 32, smem, st>>>(a, off, order, first, last, PP, set_id, f, p, t, v, counter);
+	WM_CUDA_CHECK(cudaGetLastError());
+}
+
 __global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
 wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, int n_tasks, wm_chain_params2 PP, const uint8_t *__restrict__ set_id,
                           int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
@@ -105,8 +156,8 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	wm128_dev *w = (wm128_dev*)ws->w.need(sizeof(wm128_dev) * (n_a + 1)), *b = (wm128_dev*)ws->b.need(sizeof(wm128_dev) * (n_a + 1));
 	int32_t *n_u = (int32_t*)ws->n_u.need(sizeof(int32_t) * (n_tasks + 1));
 	int64_t *n_b = (int64_t*)ws->n_b.need(sizeof(int64_t) * (n_tasks + 1));
-	int *counter = (int*)ws->counter.need(2 * sizeof(int));
-	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));
+	int *counter = (int*)ws->counter.need(4 * sizeof(int));
+	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, 4 * sizeof(int), st));
 	// largest tasks first
 	std::vector<int32_t> order(n_tasks);
 	for (int i = 0; i < n_tasks; ++i) order[i] = i;
@@ -120,12 +171,60 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	const int need = (n_tasks + WM_CHAIN_WARPS - 1) / WM_CHAIN_WARPS;
 	if (grid > need) grid = need;
 	wm_rs_stack *stk = (wm_rs_stack*)ws->stacks.need(sizeof(wm_rs_stack) * (size_t)grid * WM_CHAIN_WARPS);
-	static int dense = -1; // experimental formulation, off unless WM_CHAIN_DENSE=1 (same results, see chain_dev.cuh)
-	if (dense < 0) { const char *e = getenv("WM_CHAIN_DENSE"); dense = (e && *e == '1') ? 1 : 0; }
-	wm_count_launch();
-	if (dense) wm_chain_fill_dense_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
-	else wm_chain_fill_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
-	WM_CUDA_CHECK(cudaGetLastError());
+	// formulation of the forward pass: 0 = plain warp loop, 1 = dense candidates, 2 = shared-memory ring (default)
+	static int mode = -1, ring_big = 1024;
+	if (mode < 0) {
+		const char *e = getenv("WM_CHAIN_DENSE"), *m = getenv("WM_CHAIN_MODE"), *r = getenv("WM_CHAIN_RING");
+		mode = m ? atoi(m) : (e && *e == '1') ? 1 : 2;
+		if (r) ring_big = atoi(r);
+		if (ring_big != 512 && ring_big != 1024 && ring_big != 2048) ring_big = 1024;
+	}
+	const int pslot = wm_prof_launch_begin(WM_PK_CHAIN, st, st, 0);
+	wm_prof_add(WM_PK_CHAIN, 32.0 * (double)n_a, (double)n_a, 0); // 16 A in (anchors) + 16 A out (f, p, t, v)
+	if (mode == 2) {
+		if (!ws->side_st) {
+			int lo = 0, hi = 0;
+			WM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+			WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->side_st, cudaStreamNonBlocking, hi));
+			WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
+			WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming));
+		}
+		int *counter2 = (int*)ws->counter.p + 2; // counters: [0] big tasks, [1] backtrack, [2] small tasks
+		wm_count_launch();
+		wm_chain_window_kernel<<<(unsigned)((n_a + 255) / 256), 256, 0, st>>>(d_a, d_off, n_tasks, n_a, PP, d_set_id, v);
+		WM_CUDA_CHECK(cudaGetLastError());
+		int n_big = 0; // order[] is by size, descending
+		while (n_big < n_tasks && h_off[order[n_big] + 1] - h_off[order[n_big]] > WM_CHAIN_SMALL_N) ++n_big;
+		const int n_small = n_tasks - n_big;
+		if (n_small > 0 && n_big > 0) {
+			WM_CUDA_CHECK(cudaEventRecord(ws->ev_fork, st));
+			WM_CUDA_CHECK(cudaStreamWaitEvent(ws->side_st, ws->ev_fork, 0));
+		}
+		if (n_big > 0) {
+			const int per_sm = ring_big == 512 ? 3 : ring_big == 1024 ? 2 : 1; // CTAs of 4 warps
+			int g = n_sm * per_sm; const int need_b = (n_big + 3) / 4;
+			if (g > need_b) g = need_b;
+			if (ring_big == 512) wm_chain_launch_ring<512, 4>(g, st, d_a, d_off, d_order, 0, n_big, PP, d_set_id, f, p, t, v, counter);
+			else if (ring_big == 1024) wm_chain_launch_ring<1024, 4>(g, st, d_a, d_off, d_order, 0, n_big, PP, d_set_id, f, p, t, v, counter);
+			else wm_chain_launch_ring<2048, 4>(g, st, d_a, d_off, d_order, 0, n_big, PP, d_set_id, f, p, t, v, counter);
+		}
+		if (n_small > 0) {
+			cudaStream_t s2 = n_big > 0 ? ws->side_st : st;
+			int g = n_sm * 6; const int need_s = (n_small + 7) / 8;
+			if (g > need_s) g = need_s;
+			wm_chain_launch_ring<WM_CHAIN_SMALL_N, 8>(g, s2, d_a, d_off, d_order, n_big, n_tasks, PP, d_set_id, f, p, t, v, counter2);
+			if (n_big > 0) {
+				WM_CUDA_CHECK(cudaEventRecord(ws->ev_join, ws->side_st));
+				WM_CUDA_CHECK(cudaStreamWaitEvent(st, ws->ev_join, 0));
+			}
+		}
+	} else {
+		wm_count_launch();
+		if (mode == 1) wm_chain_fill_dense_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
+		else wm_chain_fill_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_tasks, PP, d_set_id, f, p, t, v, counter);
+		WM_CUDA_CHECK(cudaGetLastError());
+	}
+	wm_prof_launch_end(pslot, st);
 	wm_count_launch(); wm_chain_backtrack_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, n_tasks, PP, d_set_id, f, p, t, v, u, u2, w, b, n_u, n_b, stk, counter + 1);
 	WM_CUDA_CHECK(cudaGetLastError());
 }

@@ -12,8 +12,12 @@ struct wm_chain_params2 { wm_chain_params p[2]; }; // stage-1/fallback and stage
 
 struct wm_chain_ws {
 	wm_dbuf f, p, t, v, u, u2, w, b, n_u, n_b, counter, order, stacks;
-	void release() { f.release(); p.release(); t.release(); v.release(); u.release(); u2.release(); w.release(); b.release();
-	                 n_u.release(); n_b.release(); counter.release(); order.release(); stacks.release(); }
+	cudaStream_t side_st = 0; cudaEvent_t ev_fork = 0, ev_join = 0; // the small-task forward pass runs beside the big-task one
+	void release() {
+		if (side_st) { cudaStreamDestroy(side_st); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); side_st = 0; }
+ f.release(); p.release(); t.release(); v.release(); u.release(); u2.release(); w.release(); b.release();
+	                 n_u.release(); n_b.release(); counter.release(); order.release(); stacks.release();
+	}
 };
 
 void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_tasks, const wm_chain_params2 &PP, const uint8_t *d_set_id, cudaStream_t st);

@@ -208,6 +208,129 @@ __device__ void wm_chain_fill_warp_dense(const wm128_dev *__restrict__ a, int n,
 	}
 }
 
+// ---- third formulation: sliding window in shared memory ----------------------------------------------------
+// The plain warp loop above is latency bound: every 32-predecessor step waits for two dependent global-memory round
+// trips (a[j] / f[j] / p[j], then the t[] marks), and the window start is found with one dependent load per step.
+// Here (1) the window start of every anchor is computed beforehand, in parallel (wm_chain_window_start: the serial
+// `while` loops of src/chain.c:49-55 have a closed form because a[] is sorted), (2) the last RING anchors' (x, q, f, p,
+// t-mark, v) live in a per-warp shared-memory ring, so a step costs shared-memory latency; predecessors older than the
+// ring are rare (the scan usually stops after ~100 candidates) and are read from global memory as before, (3) anchors are
+// loaded and f / p / v written back 32 at a time, coalesced, and (4) a step examines 64 predecessors: the loads and the
+// score arithmetic of both halves are issued together, the order-dependent part (running maximum, n_skip replay) is
+// resolved half by half.  Marks t[p[j]] = i written for the second half cannot touch an entry of the first half
+// (p[j] < j), so publishing them early does not change which entries the first half sees marked.
+//
+// st[i] of src/chain.c:49-55.  The reference advances st (which persists across i) while ri > a[st].x + max_dist_x,
+// then, if i - st > max_iter, while that still holds and ri > a[st].x + min_dist_x.  Both conditions are monotone in
+// st and in i (a[] ascending), so st_i = max(lb(max_dist_x), min(i - max_iter, lb(min_dist_x))) with lb(d) = the first s
+// whose a[s].x + d >= ri.
+__device__ __forceinline__ int wm_chain_window_start(const wm128_dev *__restrict__ a, int i, const wm_chain_params &P)
+{
+	const uint64_t ri = a[i].x;
+	int lo = 0, hi = i; // first s in [0, i] with !(ri > a[s].x + max_dist_x); s = i always qualifies
+	while (lo < hi) { const int m = (lo + hi) >> 1; if (ri > a[m].x + (uint64_t)(int64_t)P.max_dist_x) lo = m + 1; else hi = m; }
+	int st = lo;
+	if (i - st > P.max_iter) {
+		hi = i - P.max_iter; // lo = st: the answer lies in [st, i - max_iter]
+		while (lo < hi) { const int m = (lo + hi) >> 1; if (ri > a[m].x + (uint64_t)(int64_t)P.min_dist_x) lo = m + 1; else hi = m; }
+		st = lo;
+	}
+	return st;
+}
+
+// per-warp ring of RING anchors (RING a power of two >= 64): 28 bytes per slot
+template <int RING> struct wm_chain_ring {
+	uint64_t x[RING];
+	int32_t q[RING], f[RING], p[RING], t[RING], v[RING];
+};
+
+// One warp, one task.  v[] holds st[] on entry (wm_chain_window_start of every anchor) and the peak scores on return.
+template <int RING>
+__device__ void wm_chain_fill_warp_ring(const wm128_dev *__restrict__ a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v,
+                                        wm_chain_ring<RING> *R, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	constexpr int MASK = RING - 1;
+	unsigned long long sum = 0;
+	for (int i = lane; i < n; i += 32) { sum += a[i].y >> 32 & 0xff; t[i] = 0; }
+	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+	const float avg_qspan = __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n));
+	const double avg_d = (double)avg_qspan, scale_d = (double)P.gap_scale;
+	__syncwarp();
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		// this block's anchors and window starts, one per lane
+		const int il = i0 + lane;
+		wm128_dev al; al.x = al.y = 0; int stl = 0;
+		if (il < n) { al = a[il]; stl = v[il]; }
+		const int nb = n - i0 < 32 ? n - i0 : 32;
+		for (int k = 0; k < nb; ++k) {
+			const int i = i0 + k;
+			const uint64_t ri = __shfl_sync(FULL, al.x, k), yi = __shfl_sync(FULL, al.y, k);
+			const int st = __shfl_sync(FULL, stl, k);
+			const int32_t qi = (int32_t)yi, q_span = (int32_t)(yi >> 32 & 0xff);
+			const int ring_lo = i - RING; // anchors [max(0, i - RING), i) are in the ring
+			int max_f = q_span, max_j = -1, n_skip = 0;
+			bool brk_out = false;
+			for (int jb = i - 1; jb >= st && !brk_out; jb -= 64) {
+				bool cand[2]; int sc[2], jj[2];
+				#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					const int j = jb - 32 * h - lane;
+					jj[h] = j; cand[h] = false; sc[h] = INT_MIN;
+					if (j >= st) {
+						wm128_dev aj; int fj, pj;
+						if (j >= ring_lo) { const int s = j & MASK; aj.x = R->x[s]; aj.y = (uint64_t)(uint32_t)R->q[s]; fj = R->f[s]; pj = R->p[s]; }
+						else { aj = a[j]; fj = f[j]; pj = p[j]; }
+						int s0;
+						if (wm_chain_score(aj, ri, qi, q_span, P, avg_d, scale_d, &s0)) {
+							cand[h] = true; sc[h] = s0 + fj;
+							if (pj >= 0) { if (pj >= ring_lo) R->t[pj & MASK] = i; else t[pj] = i; } // src/chain.c:87
+						}
+					}
+				}
+				__syncwarp();
+				#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					if (h == 1 && jb - 32 < st) break; // the second half is empty
+					const int j = jj[h];
+					const bool marked = cand[h] && (j >= ring_lo ? R->t[j & MASK] : t[j]) == i;
+					const unsigned G = __ballot_sync(FULL, cand[h] && sc[h] > max_f);
+					unsigned Rm = G;
+					if (G & (G - 1)) { // two or more lanes beat the running maximum: the records are the prefix maxima among them
+						const int incl = wm_warp_incl_max(cand[h] ? sc[h] : INT_MIN, lane);
+						int excl = __shfl_up_sync(FULL, incl, 1);
+						if (lane == 0) excl = INT_MIN;
+						excl = max(excl, max_f);
+						Rm = __ballot_sync(FULL, cand[h] && sc[h] > excl);
+					}
+					const unsigned K = __ballot_sync(FULL, marked) & ~Rm;
+					const int brk = wm_chain_replay(Rm, K, &n_skip, P.max_skip);
+					const unsigned Rv = brk < 32 ? (Rm & ((1u << brk) - 1u)) : Rm;
+					if (Rv) {
+						const int top = 31 - __clz(Rv);
+						max_f = __shfl_sync(FULL, sc[h], top);
+						max_j = jb - 32 * h - top;
+					}
+					if (brk < 32) { brk_out = true; break; }
+				}
+			}
+			// anchor i enters the ring (its slot held anchor i - RING, which is no longer addressed through the ring)
+			int vj = INT_MIN;
+			if (max_j >= 0) vj = max_j >= ring_lo ? R->v[max_j & MASK] : v[max_j];
+			const int vi = (max_j >= 0 && vj > max_f) ? vj : max_f; // src/chain.c:89
+			__syncwarp();
+			if (lane == 0) {
+				const int s = i & MASK;
+				R->x[s] = ri; R->q[s] = qi; R->f[s] = max_f; R->p[s] = max_j; R->t[s] = 0; R->v[s] = vi;
+			}
+			__syncwarp();
+		}
+		// write the block's results back, coalesced (RING >= 64: the whole block is still in the ring)
+		if (il < n) { const int s = il & MASK; f[il] = R->f[s]; p[il] = R->p[s]; v[il] = R->v[s]; }
+		__syncwarp();
+	}
+}
+
 // descending bitonic sort of m (power of two) uint64 keys by one warp
 __device__ void wm_warp_bitonic_desc(uint64_t *x, int m, int lane)
 {

@@ -563,12 +563,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		g.h_cig.resize(base + o_off[m]);
 		for (int i = 0; i < m; ++i) cig_base[done + i] = (int64_t)base + o_off[i];
 		g_timers.add("dp.cigar_d2h", Timers::now() - tr0);
-		if (g_wm_prof.enabled) { // + 4 n_cigar
-			static std::mutex mu;
-			std::lock_guard<std::mutex> lk(mu);
-			g_wm_prof.fill_alg_bytes += prof_bytes + 4.0 * (double)o_off[m];
-			g_wm_prof.fill_jobs += m;
-		}
+		wm_prof_add(WM_PK_FILL, prof_bytes + 4.0 * (double)o_off[m], 0, m); // + 4 n_cigar
 		done = end;
 	}
 	g.h_cig.push_back(0);

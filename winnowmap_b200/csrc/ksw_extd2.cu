@@ -259,18 +259,6 @@ size_t wm_extd2_bt_bytes(int qlen, int tlen, int w)
 	return ((size_t)(qlen + tlen - 1) * n + 1) * 16;
 }
 
-// jobs/seq/bt/ez/cigar are device pointers; max_tlen = largest tlen among the jobs.
-wm_prof_t g_wm_prof = {0, 0, 0.0, 0, 0.0, 0.0, 0.0, 0.0, 0.0};
-thread_local cudaStream_t wm_dbuf_stream = 0;
-thread_local bool wm_dbuf_async = false;
-
-#define WM_PROF_SLOTS 65536
-struct wm_prof_launch { cudaEvent_t e0, e1; int slot; };
-static std::vector<wm_prof_launch> g_prof_launches;
-static std::mutex g_prof_mu;
-static cudaEvent_t g_prof_base = 0;
-static unsigned long long *g_prof_cells = 0;
-
 static int wm_use_v2(void)
 {
 	static int use_v2 = -1;
@@ -324,28 +312,15 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const
 		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_extd2_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	// bench mode: an event pair and a cell-counter slot per launch, read back by wm_prof_fill_collect(); nothing is
-	// synchronised here, so the timed region runs exactly as it does without profiling
-	const bool prof = g_wm_prof.enabled != 0;
-	unsigned long long *cell_ctr = 0;
-	wm_prof_launch pl; pl.e0 = pl.e1 = 0; pl.slot = -1;
-	if (prof) {
-		std::lock_guard<std::mutex> lk(g_prof_mu);
-		if (!g_prof_cells) { WM_CUDA_CHECK(cudaMalloc((void**)&g_prof_cells, sizeof(unsigned long long) * 2 * WM_PROF_SLOTS)); }
-		if ((int)g_prof_launches.size() < WM_PROF_SLOTS) pl.slot = (int)g_prof_launches.size();
-		if (pl.slot >= 0) {
-			WM_CUDA_CHECK(cudaEventCreate(&pl.e0)); WM_CUDA_CHECK(cudaEventCreate(&pl.e1));
-			cell_ctr = g_prof_cells + 2 * pl.slot;
-			g_prof_launches.push_back(pl);
-		}
-	}
-	if (pl.slot >= 0) WM_CUDA_CHECK(cudaMemsetAsync(cell_ctr, 0, 2 * sizeof(unsigned long long), stream));
 	WM_CUDA_CHECK(cudaEventRecord(ws->ev_ready, stream));
 	WM_CUDA_CHECK(cudaStreamWaitEvent(ws->fill_st, ws->ev_ready, 0));
-	if (pl.slot >= 0) WM_CUDA_CHECK(cudaEventRecord(pl.e0, ws->fill_st));
+	// bench mode: an event pair and a cell-counter slot per launch (prof.cu); nothing is synchronised here, so the
+	// timed region runs exactly as it does without profiling
+	unsigned long long *cell_ctr = 0;
+	const int pslot = wm_prof_launch_begin(WM_PK_FILL, ws->fill_st, ws->fill_st, &cell_ctr);
 	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, ws->fill_st>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, tcap, plan.max_qlen, use_v2, cell_ctr);
 	WM_CUDA_CHECK(cudaGetLastError());
-	if (pl.slot >= 0) WM_CUDA_CHECK(cudaEventRecord(pl.e1, ws->fill_st));
+	wm_prof_launch_end(pslot, ws->fill_st);
 	WM_CUDA_CHECK(cudaEventRecord(ws->ev_done, ws->fill_st));
 	WM_CUDA_CHECK(cudaStreamWaitEvent(stream, ws->ev_done, 0));
 	wm_zd_params Z; memset(&Z, 0, sizeof(Z));
@@ -354,47 +329,3 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const
 	WM_CUDA_CHECK(cudaGetLastError());
 }
 
-// start of a profiled region: a base event on the legacy stream gives all launches a common time axis
-void wm_prof_fill_begin(void)
-{
-	std::lock_guard<std::mutex> lk(g_prof_mu);
-	for (auto &l : g_prof_launches) { cudaEventDestroy(l.e0); cudaEventDestroy(l.e1); }
-	g_prof_launches.clear();
-	if (!g_prof_base) WM_CUDA_CHECK(cudaEventCreate(&g_prof_base));
-	WM_CUDA_CHECK(cudaDeviceSynchronize());
-	WM_CUDA_CHECK(cudaEventRecord(g_prof_base, 0));
-	WM_CUDA_CHECK(cudaEventSynchronize(g_prof_base));
-}
-
-// Fold the recorded launches into g_wm_prof: fill_ms is the sum of the launch durations, fill_union_ms the time during
-// which at least one fill kernel was running (launches of concurrent lanes overlap and slow each other down).
-void wm_prof_fill_collect(void)
-{
-	std::lock_guard<std::mutex> lk(g_prof_mu);
-	if (g_prof_launches.empty()) return;
-	WM_CUDA_CHECK(cudaDeviceSynchronize());
-	std::vector<std::pair<float, float>> iv;
-	std::vector<unsigned long long> cells(2 * g_prof_launches.size());
-	WM_CUDA_CHECK(cudaMemcpy(cells.data(), g_prof_cells, sizeof(unsigned long long) * cells.size(), cudaMemcpyDeviceToHost));
-	for (size_t i = 0; i < g_prof_launches.size(); ++i) {
-		wm_prof_launch &l = g_prof_launches[i];
-		float t0 = 0.f, t1 = 0.f;
-		WM_CUDA_CHECK(cudaEventElapsedTime(&t0, g_prof_base, l.e0));
-		WM_CUDA_CHECK(cudaEventElapsedTime(&t1, g_prof_base, l.e1));
-		iv.push_back(std::make_pair(t0, t1));
-		g_wm_prof.fill_ms += t1 - t0; ++g_wm_prof.fill_launches;
-		const double c = (double)(cells[2 * i] + cells[2 * i + 1]);
-		g_wm_prof.fill_cells += c; g_wm_prof.fill_alg_bytes += c; // 1 B of backtrack per block cell
-		g_wm_prof.fill_cells_v2 += (double)cells[2 * i + 1];
-		cudaEventDestroy(l.e0); cudaEventDestroy(l.e1);
-	}
-	g_prof_launches.clear();
-	std::sort(iv.begin(), iv.end());
-	float cur0 = iv[0].first, cur1 = iv[0].second; double uni = 0;
-	for (size_t i = 1; i < iv.size(); ++i) {
-		if (iv[i].first > cur1) { uni += cur1 - cur0; cur0 = iv[i].first; cur1 = iv[i].second; }
-		else if (iv[i].second > cur1) cur1 = iv[i].second;
-	}
-	uni += cur1 - cur0;
-	g_wm_prof.fill_union_ms += uni;
-}

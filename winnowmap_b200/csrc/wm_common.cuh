@@ -16,13 +16,16 @@
 
 #define WM_NEG_INF (-0x40000000)
 
-// Lightweight instrumentation used by bench.py: number of kernel launches and, when enabled, the device time and
-// algorithmic bytes of the dominant kernel (the extension-DP fill kernel), measured with CUDA events on the
-// launching stream.
+// Lightweight instrumentation used by bench.py (prof.cu): number of kernel launches and, when enabled, the device time
+// and algorithmic bytes of the two kernel classes that dominate the path (the extension-DP fill kernel and the
+// chaining forward pass), measured with CUDA events on the launching stream.  Nothing is synchronised inside a
+// profiled region: every launch gets an event pair that is read afterwards against a common base event.
+enum { WM_PK_FILL = 0, WM_PK_CHAIN = 1, WM_PK_N = 2 };
+struct wm_prof_kind { double ms, union_ms, alg_bytes, units, units2; long long launches; };
 struct wm_prof_t {
 	long long n_launches;
 	int enabled;
-	double fill_ms; long long fill_launches; double fill_alg_bytes, fill_cells, fill_jobs, fill_cells_v2, fill_union_ms;
+	wm_prof_kind k[WM_PK_N];        // units: block cells (fill) / anchors (chain); units2: DP jobs (fill)
 	long long h2d_bytes, d2h_bytes; // every host<->device copy of the mapping path (wm_memcpy_async)
 };
 extern wm_prof_t g_wm_prof;
@@ -33,8 +36,13 @@ static inline cudaError_t wm_memcpy_async(void *dst, const void *src, size_t byt
 	else if (kind == cudaMemcpyDeviceToHost) __atomic_fetch_add(&g_wm_prof.d2h_bytes, (long long)bytes, __ATOMIC_RELAXED);
 	return cudaMemcpyAsync(dst, src, bytes, kind, st);
 }
-void wm_prof_fill_begin(void);   // ksw_extd2.cu
-void wm_prof_fill_collect(void);
+void wm_prof_region_begin(void);  // start of a profiled region (base event)
+void wm_prof_collect(void);       // fold the recorded launches into g_wm_prof
+// Around one launch of kind `kind` on stream `st`: begin returns a slot (-1 = not profiling) and, if ctr is non-null,
+// a zeroed pair of device counters the kernel may add work units to (counted as units / algorithmic bytes at collect).
+int wm_prof_launch_begin(int kind, cudaStream_t st, cudaStream_t zero_st, unsigned long long **ctr);
+void wm_prof_launch_end(int slot, cudaStream_t st);
+void wm_prof_add(int kind, double alg_bytes, double units, double units2);
 static inline void wm_count_launch() { __atomic_fetch_add(&g_wm_prof.n_launches, 1LL, __ATOMIC_RELAXED); }
 
 // One extension-DP job; sequences live in a device byte pool (0..4 codes).
@@ -123,13 +131,18 @@ cudaStream_t wm_stream_create_high_priority(void);
 // Wait for a stream without burning a core: an orchestration lane spends most of its time waiting for the GPU, and
 // with several lanes per process and several processes per node the spinning waits of cudaStreamSynchronize compete
 // with the OpenMP workers.  (WM_SPIN_SYNC=1 restores the spinning wait.)
+struct wm_sync_event { // one blocking event per waiting thread, destroyed with the thread
+	cudaEvent_t ev;
+	wm_sync_event() : ev(0) {}
+	~wm_sync_event() { if (ev) cudaEventDestroy(ev); }
+};
 static inline void wm_stream_sync(cudaStream_t st)
 {
-	static thread_local cudaEvent_t ev = 0;
+	static thread_local wm_sync_event h;
 	static int spin = -1;
 	if (spin < 0) { const char *e = getenv("WM_SPIN_SYNC"); spin = (e && *e == '1') ? 1 : 0; }
 	if (spin) { WM_CUDA_CHECK(cudaStreamSynchronize(st)); return; }
-	if (!ev) WM_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming));
-	WM_CUDA_CHECK(cudaEventRecord(ev, st));
-	WM_CUDA_CHECK(cudaEventSynchronize(ev));
+	if (!h.ev) WM_CUDA_CHECK(cudaEventCreateWithFlags(&h.ev, cudaEventBlockingSync | cudaEventDisableTiming));
+	WM_CUDA_CHECK(cudaEventRecord(h.ev, st));
+	WM_CUDA_CHECK(cudaEventSynchronize(h.ev));
 }
