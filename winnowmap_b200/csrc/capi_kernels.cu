@@ -61,8 +61,6 @@ extern "C" int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qof
 	WM_CUDA_CHECK(cudaDeviceSynchronize());
 	WM_CUDA_CHECK(cudaMemcpy(ez, d_ez, sizeof(wm_extz_dev) * n, cudaMemcpyDeviceToHost));
 	if (cigar_off[n] > 0) WM_CUDA_CHECK(cudaMemcpy(cigar, d_cig, sizeof(uint32_t) * cigar_off[n], cudaMemcpyDeviceToHost));
-	ws.scratch.release();
-	if (ws.fill_st) { cudaStreamDestroy(ws.fill_st); cudaEventDestroy(ws.ev_ready); cudaEventDestroy(ws.ev_done); }
 	cudaFree(d_seq); cudaFree(d_bt); cudaFree(d_jobs); cudaFree(d_ez); cudaFree(d_cig);
 	return 0;
 }

@@ -1,6 +1,7 @@
 // C-ABI of the drop-in boundary (include/winnowmap_b200.h): index upload / construction, batch mapping
 // (the replacement of kt_for(worker_for), reference src/map.c:1162-1165) and the file-level driver that mirrors
 // mm_map_file (src/map.c:1244-1276) for PAF output.
+#include <stddef.h>
 #include <string.h>
 #include <algorithm>
 #include <atomic>
@@ -130,9 +131,18 @@ static void map_lanes(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const std::vector
 	}
 }
 
+// the sketch kernels size their shared arrays for the reference's own limits (assert at src/sketch.c:140)
+static bool kw_ok(const char *who, int k, int w)
+{
+	if (w > 0 && w < 256 && k > 0 && k <= 28) return true;
+	fprintf(stderr, "[ERROR] %s: k = %d, w = %d outside the supported range (0 < w < 256, 0 < k <= 28; src/sketch.c:140)\n", who, k, w);
+	return false;
+}
+
 extern "C" wm_gpu_ctx_s *wm_gpu_idx_upload(const wm_idx_view_t *v, int device)
 {
 	require_device("wm_gpu_idx_upload");
+	if (!kw_ok("wm_gpu_idx_upload", v->k, v->w)) return 0;
 	wm_gpu_ctx_s *c = new wm_gpu_ctx_s();
 	memset(&c->stats, 0, sizeof(c->stats));
 	c->device = device; c->t_index = c->t_map = 0;
@@ -156,9 +166,10 @@ extern "C" wm_gpu_ctx_s *wm_gpu_idx_upload(const wm_idx_view_t *v, int device)
 extern "C" void wm_gpu_destroy(wm_gpu_ctx_s *c)
 {
 	if (!c) return;
-	for (size_t i = 1; i < c->lanes.size(); ++i) gpu_backend_destroy(c->lanes[i]);
+	for (size_t i = 1; i < c->lanes.size(); ++i) gpu_backend_destroy(c->lanes[i]); // clones first: they borrow the owner's index
 	gpu_backend_destroy(c->be);
 	if (c->d_resident) cudaFree(c->d_resident);
+	gpu_backend_trim_pool(c->device);
 	free_reg_vectors(c->res_regs);
 	delete c;
 }
@@ -168,6 +179,7 @@ extern "C" void wm_gpu_destroy(wm_gpu_ctx_s *c)
 extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_freq_fn, int k, int w, int device)
 {
 	require_device("wm_index_build");
+	if (!kw_ok("wm_index_build", k, w)) return 0;
 	WM_CUDA_CHECK(cudaSetDevice(device));
 	const double t0 = now_s();
 	SeqReader rd;
@@ -246,6 +258,33 @@ extern "C" int wm_set_opt(const char *preset, wm_idxopt_t *io, wm_mapopt_t *mo) 
 extern "C" int wm_check_opt(const wm_idxopt_t *io, const wm_mapopt_t *mo) { return check_opt(io, mo); }
 extern "C" int wm_sizeof_mapopt(void) { return (int)sizeof(wm_mapopt_t); }
 extern "C" int wm_sizeof_reg1(void) { return (int)sizeof(wm_reg1_t); }
+extern "C" int wm_abi_layout(int64_t *out, int cap)
+{
+	int n = 0;
+#define PUT(v) do { if (n < cap) out[n] = (int64_t)(v); ++n; } while (0)
+	PUT(sizeof(wm_mapopt_t)); PUT(sizeof(wm_reg1_t)); PUT(sizeof(wm_extra_t)); PUT(sizeof(wm_idxopt_t));
+#define MO(f) PUT(offsetof(wm_mapopt_t, f))
+	MO(flag); MO(seed); MO(sdust_thres); MO(max_qlen); MO(bw); MO(max_gap); MO(max_gap_ref); MO(min_gap_ref); MO(max_frag_len); MO(max_chain_skip);
+	MO(max_chain_iter); MO(min_cnt); MO(min_chain_score); MO(chain_gap_scale); MO(SVaware); MO(SVawareMinReadLength); MO(suffixSampleOffset);
+	MO(min_mapq); MO(min_qcov); MO(minPrefixLength); MO(maxPrefixLength); MO(prefixIncrementFactor); MO(stage2_bw); MO(stage2_zdrop_inv);
+	MO(stage2_max_gap); MO(stage2_extension_inc); MO(mask_level); MO(mask_len); MO(pri_ratio); MO(best_n); MO(max_join_long); MO(max_join_short);
+	MO(min_join_flank_sc); MO(min_join_flank_ratio); MO(alt_drop); MO(a); MO(b); MO(q); MO(e); MO(q2); MO(e2); MO(sc_ambi); MO(noncan); MO(junc_bonus);
+	MO(zdrop); MO(zdrop_inv); MO(end_bonus); MO(min_dp_max); MO(min_ksw_len); MO(anchor_ext_len); MO(anchor_ext_shift); MO(max_clip_ratio);
+	MO(pe_ori); MO(pe_bonus); MO(mid_occ_frac); MO(min_mid_occ); MO(mid_occ); MO(max_occ); MO(mini_batch_size); MO(max_sw_mat);
+	MO(kmer_freq_filename); MO(split_prefix);
+#define RG(f) PUT(offsetof(wm_reg1_t, f))
+	RG(id); RG(cnt); RG(rid); RG(score); RG(qs); RG(qe); RG(rs); RG(re); RG(parent); RG(subsc); RG(as); RG(mlen); RG(blen); RG(n_sub); RG(score0); RG(hash); RG(div); RG(p);
+#define EX(f) PUT(offsetof(wm_extra_t, f))
+	EX(capacity); EX(dp_score); EX(dp_max); EX(dp_max2); EX(n_cigar); EX(cigar);
+#define IO(f) PUT(offsetof(wm_idxopt_t, f))
+	IO(k); IO(w); IO(flag); IO(bucket_bits); IO(mini_batch_size); IO(batch_size);
+#undef PUT
+#undef MO
+#undef RG
+#undef EX
+#undef IO
+	return n;
+}
 
 // The GPU replacement of kt_for(n_threads, worker_for, ...) (src/map.c:1164): fills n_reg/reg/rep_len/frag_gap of
 // every sequence exactly as worker_for does (:1025-1034).  reg[i] and each reg[i][j].p are malloc()ed; the caller
@@ -274,6 +313,24 @@ extern "C" int wm_gpu_map_batch(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, int n_s
 		rep_len[i] = rl[i], frag_gap[i] = fg[i];
 	}
 	return 0;
+}
+
+// mm_tbuf_t / mm_map (src/map.c:18-38, :976-984): the per-thread buffer only carries rep_len and frag_gap of the last call here
+// (device workspaces belong to the context's lanes).  One read = a batch of one through the same path as wm_gpu_map_batch.
+struct wm_tbuf_s { int rep_len, frag_gap; };
+extern "C" wm_tbuf_s *wm_tbuf_init(void) { return (wm_tbuf_s*)calloc(1, sizeof(wm_tbuf_s)); }
+extern "C" void wm_tbuf_destroy(wm_tbuf_s *b) { free(b); }
+extern "C" int wm_tbuf_rep_len(const wm_tbuf_s *b) { return b->rep_len; }
+extern "C" int wm_tbuf_frag_gap(const wm_tbuf_s *b) { return b->frag_gap; }
+extern "C" wm_reg1_t *wm_map(wm_gpu_ctx_s *c, int l_seq, const char *seq, int *n_regs, wm_tbuf_s *b, const wm_mapopt_t *opt, const char *name)
+{
+	int32_t n_reg = 0, rl = 0, fg = 0, len = l_seq;
+	wm_reg1_t *reg = 0;
+	const char *nm = name ? name : "";
+	wm_gpu_map_batch(c, opt, 1, &nm, &seq, &len, &n_reg, &reg, &rl, &fg, 1);
+	if (b) b->rep_len = rl, b->frag_gap = fg;
+	*n_regs = n_reg;
+	return reg;
 }
 
 // mm_map_file for PAF output.  Reads are taken in the reference's mini-batches (src/bseq.c:80-119), sorted by
@@ -611,17 +668,27 @@ extern "C" wm_gpu_ctx_s *wm_idx_blob_load(const uint8_t *buf, int64_t size, int 
 	require_device("wm_idx_blob_load");
 	const uint64_t *h = (const uint64_t*)buf;
 	if (size < 64 || h[0] != 0x31584449424d57ULL) { fprintf(stderr, "[ERROR] wm_idx_blob_load: bad blob\n"); return 0; }
-	const size_t n_seq = h[2], names = h[3], s_words = h[4], n_keys = h[5], n_pos = h[6];
+	const size_t n_seq = h[2], names = h[3], s_words = h[4], n_keys = h[5], n_pos = h[6], bloom_bytes = (size_t)(h[7] / 8);
+	{ // every section length comes from the header: the total must be exactly the buffer (a truncated or foreign broadcast is refused)
+		const unsigned __int128 need = (unsigned __int128)64 + pad8(n_seq * 4) + (unsigned __int128)n_seq * 8 + pad8(names) + pad8(s_words * 4) +
+			(unsigned __int128)n_keys * 8 + ((unsigned __int128)n_keys + 1) * 8 + (unsigned __int128)n_pos * 8 + pad8(bloom_bytes);
+		if (need != (unsigned __int128)size) { fprintf(stderr, "[ERROR] wm_idx_blob_load: blob of %lld bytes does not match its header\n", (long long)size); return 0; }
+	}
 	const uint8_t *p = buf + 64;
 	const uint32_t *len = (const uint32_t*)p; p += pad8(n_seq * 4);
 	const uint64_t *off = (const uint64_t*)p; p += n_seq * 8;
-	const char *nm = (const char*)p; p += pad8(names);
+	const char *nm = (const char*)p, *nm_end = nm + names; p += pad8(names);
 	const uint32_t *S = (const uint32_t*)p; p += pad8(s_words * 4);
 	const uint64_t *keys = (const uint64_t*)p; p += n_keys * 8;
 	const uint64_t *pos_off = (const uint64_t*)p; p += (n_keys + 1) * 8;
 	const uint64_t *pos = (const uint64_t*)p; p += n_pos * 8;
+	if (pos_off[n_keys] != n_pos) { fprintf(stderr, "[ERROR] wm_idx_blob_load: occurrence table does not match its header\n"); return 0; }
 	std::vector<const char*> name_ptr(n_seq);
-	for (size_t i = 0; i < n_seq; ++i) { name_ptr[i] = nm; nm += strlen(nm) + 1; }
+	for (size_t i = 0; i < n_seq; ++i) {
+		const void *z = nm < nm_end ? memchr(nm, 0, (size_t)(nm_end - nm)) : 0;
+		if (!z) { fprintf(stderr, "[ERROR] wm_idx_blob_load: sequence name table is truncated\n"); return 0; }
+		name_ptr[i] = nm; nm = (const char*)z + 1;
+	}
 	wm_idx_view_t v;
 	v.k = (int32_t)(h[1] >> 32), v.w = (int32_t)(uint32_t)h[1], v.n_seq = (int32_t)n_seq;
 	v.seq_name = name_ptr.data(), v.seq_len = len, v.seq_offset = off, v.S = S, v.S_words = s_words;

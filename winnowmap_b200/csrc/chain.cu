@@ -106,6 +106,88 @@ wm_chain_fill_ring_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__
 	}
 }
 
+// Giant tasks: one CTA per task, a tile of 32 consecutive anchors per round, one warp per anchor (chain_dev.cuh).
+__global__ void __launch_bounds__(WM_CT_WARPS * 32, 1)
+wm_chain_fill_tile_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ order, int first, int last,
+                          wm_chain_params2 PP, const uint8_t *__restrict__ set_id, int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all,
+                          int32_t *__restrict__ v_all, int *counter)
+{
+	const unsigned FULL = 0xffffffffu;
+	constexpr int MASK = WM_CT_RING - 1;
+	extern __shared__ __align__(16) unsigned char wm_chain_smem[];
+	wm_chain_tile_sm *S = (wm_chain_tile_sm*)wm_chain_smem;
+	__shared__ int s_task;
+	__shared__ unsigned long long s_sum[WM_CT_WARPS];
+	const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
+	for (;;) {
+		if (tid == 0) s_task = first + atomicAdd(counter, 1);
+		__syncthreads();
+		const int ti = s_task;
+		__syncthreads();
+		if (ti >= last) break;
+		const int task = order[ti];
+		const int64_t base = off[task];
+		const int n = (int)(off[task + 1] - base);
+		if (n <= 0) continue;
+		const wm128_dev *a = a_all + base;
+		int32_t *f = f_all + base, *p = p_all + base, *t = t_all + base, *v = v_all + base;
+		const wm_chain_params P = PP.p[set_id ? set_id[task] : 0];
+		// avg_qspan (src/chain.c:41-42); t[] is only used by the locked deep path
+		unsigned long long sum = 0;
+		for (int i = tid; i < n; i += WM_CT_WARPS * 32) { sum += a[i].y >> 32 & 0xff; t[i] = 0; }
+		for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+		if (lane == 0) s_sum[k] = sum;
+		if (tid == 0) S->done = 0, S->lock = 0;
+		__syncthreads();
+		sum = 0;
+		for (int w = 0; w < WM_CT_WARPS; ++w) sum += s_sum[w];
+		const float avg_qspan = __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n));
+		const double avg_d = (double)avg_qspan, scale_d = (double)P.gap_scale;
+		uint32_t *mk = S->marks[k];
+		for (int i0 = 0; i0 < n; i0 += 32) {
+			const int il = i0 + lane;
+			wm128_dev al; al.x = al.y = 0; int stl = 0;
+			if (il < n) { al = a[il]; stl = v[il]; }
+			const int i = i0 + k;
+			if (i < n) {
+				const int st = __shfl_sync(FULL, stl, k);
+				const int ring_lo = i0 + 32 - WM_CT_RING; // slots below are being overwritten by this tile's anchors
+				const uint64_t ri = __shfl_sync(FULL, al.x, k); const int32_t qi = (int32_t)__shfl_sync(FULL, al.y, k);
+				// the anchors of the tile this one depends on: its candidate predecessors (a geometric property)
+				const unsigned C = __ballot_sync(FULL, lane < k && il >= st && wm_chain_is_cand(al, ri, qi, P));
+				if (C) {
+					volatile unsigned *done = &S->done;
+					while ((*done & C) != C) { }
+					__threadfence_block();
+				}
+				int max_f, max_j;
+				if (!wm_chain_tile_scan(a, P, f, p, t, S, mk, al, i0, k, st, ring_lo, false, avg_d, scale_d, lane, &max_f, &max_j)) {
+					if (lane == 0) { while (atomicCAS(&S->lock, 0, 1) != 0) { } }
+					__syncwarp();
+					__threadfence_block();
+					wm_chain_tile_scan(a, P, f, p, t, S, mk, al, i0, k, st, ring_lo, true, avg_d, scale_d, lane, &max_f, &max_j);
+					__syncwarp();
+					__threadfence_block();
+					if (lane == 0) atomicExch(&S->lock, 0);
+				}
+				int vj = INT_MIN;
+				if (max_j >= 0) vj = max_j >= ring_lo ? S->v[max_j & MASK] : v[max_j];
+				const int vi = (max_j >= 0 && vj > max_f) ? vj : max_f; // src/chain.c:89
+				if (lane == 0) {
+					const int s = i & MASK;
+					S->x[s] = ri; S->q[s] = qi; S->f[s] = max_f; S->p[s] = max_j; S->v[s] = vi;
+					__threadfence_block();
+					atomicOr(&S->done, 1u << k);
+				}
+			}
+			__syncthreads();
+			if (k == 0 && il < n) { const int s = il & MASK; f[il] = S->f[s]; p[il] = S->p[s]; v[il] = S->v[s]; }
+			if (tid == 0) S->done = 0;
+			__syncthreads();
+		}
+	}
+}
+
 #define WM_CHAIN_SMALL_N 128    // tasks up to this many anchors: ring of the same size, eight warps per CTA
 template <int RING, int WARPS>
 static void wm_chain_launch_ring(int grid, cudaStream_t st, const wm128_dev *a, const int64_t *off, const int32_t *order, int first, int last,
@@ -156,8 +238,8 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	wm128_dev *w = (wm128_dev*)ws->w.need(sizeof(wm128_dev) * (n_a + 1)), *b = (wm128_dev*)ws->b.need(sizeof(wm128_dev) * (n_a + 1));
 	int32_t *n_u = (int32_t*)ws->n_u.need(sizeof(int32_t) * (n_tasks + 1));
 	int64_t *n_b = (int64_t*)ws->n_b.need(sizeof(int64_t) * (n_tasks + 1));
-	int *counter = (int*)ws->counter.need(4 * sizeof(int));
-	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, 4 * sizeof(int), st));
+	int *counter = (int*)ws->counter.need(8 * sizeof(int));
+	WM_CUDA_CHECK(cudaMemsetAsync(counter, 0, 8 * sizeof(int), st));
 	// largest tasks first
 	std::vector<int32_t> order(n_tasks);
 	for (int i = 0; i < n_tasks; ++i) order[i] = i;
@@ -172,9 +254,10 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	if (grid > need) grid = need;
 	wm_rs_stack *stk = (wm_rs_stack*)ws->stacks.need(sizeof(wm_rs_stack) * (size_t)grid * WM_CHAIN_WARPS);
 	// formulation of the forward pass: 0 = plain warp loop, 1 = dense candidates, 2 = shared-memory ring (default)
-	static int mode = -1, ring_big = 1024;
+	static int mode = -1, ring_big = 1024, tile_min = 2048;
 	if (mode < 0) {
-		const char *e = getenv("WM_CHAIN_DENSE"), *m = getenv("WM_CHAIN_MODE"), *r = getenv("WM_CHAIN_RING");
+		const char *e = getenv("WM_CHAIN_DENSE"), *m = getenv("WM_CHAIN_MODE"), *r = getenv("WM_CHAIN_RING"), *tm = getenv("WM_CHAIN_TILE_MIN");
+		if (tm && atoi(tm) > 0) tile_min = atoi(tm);
 		mode = m ? atoi(m) : (e && *e == '1') ? 1 : 2;
 		if (r) ring_big = atoi(r);
 		if (ring_big != 512 && ring_big != 1024 && ring_big != 2048) ring_big = 1024;
@@ -182,41 +265,63 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	const int pslot = wm_prof_launch_begin(WM_PK_CHAIN, st, st, 0);
 	wm_prof_add(WM_PK_CHAIN, 32.0 * (double)n_a, (double)n_a, 0); // 16 A in (anchors) + 16 A out (f, p, t, v)
 	if (mode == 2) {
-		if (!ws->side_st) {
+		if (!ws->side_st[0]) {
 			int lo = 0, hi = 0;
 			WM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-			WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->side_st, cudaStreamNonBlocking, hi));
+			for (int i = 0; i < 2; ++i) {
+				WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->side_st[i], cudaStreamNonBlocking, hi));
+				WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_join[i], cudaEventDisableTiming));
+			}
 			WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
-			WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming));
 		}
-		int *counter2 = (int*)ws->counter.p + 2; // counters: [0] big tasks, [1] backtrack, [2] small tasks
+		// counters: [0] giant tasks, [1] backtrack, [2] medium tasks, [3] small tasks
 		wm_count_launch();
 		wm_chain_window_kernel<<<(unsigned)((n_a + 255) / 256), 256, 0, st>>>(d_a, d_off, n_tasks, n_a, PP, d_set_id, v);
 		WM_CUDA_CHECK(cudaGetLastError());
-		int n_big = 0; // order[] is by size, descending
+		// order[] is by size, descending: giant tasks (tile kernel, one CTA each), medium (one warp each, ring), small
+		int n_giant = 0, n_big = 0;
+		while (n_giant < n_tasks && h_off[order[n_giant] + 1] - h_off[order[n_giant]] > tile_min) ++n_giant;
+		n_big = n_giant;
 		while (n_big < n_tasks && h_off[order[n_big] + 1] - h_off[order[n_big]] > WM_CHAIN_SMALL_N) ++n_big;
-		const int n_small = n_tasks - n_big;
-		if (n_small > 0 && n_big > 0) {
-			WM_CUDA_CHECK(cudaEventRecord(ws->ev_fork, st));
-			WM_CUDA_CHECK(cudaStreamWaitEvent(ws->side_st, ws->ev_fork, 0));
+		const int n_medium = n_big - n_giant, n_small = n_tasks - n_big;
+		const int n_classes = (n_giant > 0) + (n_medium > 0) + (n_small > 0);
+		if (n_classes > 1) WM_CUDA_CHECK(cudaEventRecord(ws->ev_fork, st));
+		int side = 0; bool main_used = false;
+		cudaStream_t joined[2]; int n_joined = 0;
+		auto pick = [&]() -> cudaStream_t { // the first class present runs on the caller's stream, the others beside it
+			if (!main_used) { main_used = true; return st; }
+			cudaStream_t s2 = ws->side_st[side++];
+			WM_CUDA_CHECK(cudaStreamWaitEvent(s2, ws->ev_fork, 0));
+			joined[n_joined++] = s2;
+			return s2;
+		};
+		if (n_giant > 0) {
+			cudaStream_t s2 = pick();
+			static bool attr_set = false;
+			const size_t smem = sizeof(wm_chain_tile_sm);
+			if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_chain_fill_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+			wm_count_launch();
+			wm_chain_fill_tile_kernel<<<n_giant < n_sm ? n_giant : n_sm, WM_CT_WARPS * 32, smem, s2>>>(d_a, d_off, d_order, 0, n_giant, PP, d_set_id, f, p, t, v, counter);
+			WM_CUDA_CHECK(cudaGetLastError());
 		}
-		if (n_big > 0) {
+		if (n_medium > 0) {
+			cudaStream_t s2 = pick();
 			const int per_sm = ring_big == 512 ? 3 : ring_big == 1024 ? 2 : 1; // CTAs of 4 warps
-			int g = n_sm * per_sm; const int need_b = (n_big + 3) / 4;
+			int g = n_sm * per_sm; const int need_b = (n_medium + 3) / 4;
 			if (g > need_b) g = need_b;
-			if (ring_big == 512) wm_chain_launch_ring<512, 4>(g, st, d_a, d_off, d_order, 0, n_big, PP, d_set_id, f, p, t, v, counter);
-			else if (ring_big == 1024) wm_chain_launch_ring<1024, 4>(g, st, d_a, d_off, d_order, 0, n_big, PP, d_set_id, f, p, t, v, counter);
-			else wm_chain_launch_ring<2048, 4>(g, st, d_a, d_off, d_order, 0, n_big, PP, d_set_id, f, p, t, v, counter);
+			if (ring_big == 512) wm_chain_launch_ring<512, 4>(g, s2, d_a, d_off, d_order, n_giant, n_big, PP, d_set_id, f, p, t, v, counter + 2);
+			else if (ring_big == 1024) wm_chain_launch_ring<1024, 4>(g, s2, d_a, d_off, d_order, n_giant, n_big, PP, d_set_id, f, p, t, v, counter + 2);
+			else wm_chain_launch_ring<2048, 4>(g, s2, d_a, d_off, d_order, n_giant, n_big, PP, d_set_id, f, p, t, v, counter + 2);
 		}
 		if (n_small > 0) {
-			cudaStream_t s2 = n_big > 0 ? ws->side_st : st;
+			cudaStream_t s2 = pick();
 			int g = n_sm * 6; const int need_s = (n_small + 7) / 8;
 			if (g > need_s) g = need_s;
-			wm_chain_launch_ring<WM_CHAIN_SMALL_N, 8>(g, s2, d_a, d_off, d_order, n_big, n_tasks, PP, d_set_id, f, p, t, v, counter2);
-			if (n_big > 0) {
-				WM_CUDA_CHECK(cudaEventRecord(ws->ev_join, ws->side_st));
-				WM_CUDA_CHECK(cudaStreamWaitEvent(st, ws->ev_join, 0));
-			}
+			wm_chain_launch_ring<WM_CHAIN_SMALL_N, 8>(g, s2, d_a, d_off, d_order, n_big, n_tasks, PP, d_set_id, f, p, t, v, counter + 3);
+		}
+		for (int i = 0; i < n_joined; ++i) {
+			WM_CUDA_CHECK(cudaEventRecord(ws->ev_join[i], joined[i]));
+			WM_CUDA_CHECK(cudaStreamWaitEvent(st, ws->ev_join[i], 0));
 		}
 	} else {
 		wm_count_launch();

@@ -12,9 +12,16 @@ struct wm_chain_params2 { wm_chain_params p[2]; }; // stage-1/fallback and stage
 
 struct wm_chain_ws {
 	wm_dbuf f, p, t, v, u, u2, w, b, n_u, n_b, counter, order, stacks;
-	cudaStream_t side_st = 0; cudaEvent_t ev_fork = 0, ev_join = 0; // the small-task forward pass runs beside the big-task one
+	// the forward passes of the three task classes (giant / medium / small) run side by side
+	cudaStream_t side_st[2] = {0, 0}; cudaEvent_t ev_fork = 0, ev_join[2] = {0, 0};
+	void drop_streams() {
+		if (!side_st[0]) return;
+		for (int i = 0; i < 2; ++i) { cudaStreamDestroy(side_st[i]); cudaEventDestroy(ev_join[i]); side_st[i] = 0; }
+		cudaEventDestroy(ev_fork);
+	}
+	~wm_chain_ws() { drop_streams(); }
 	void release() {
-		if (side_st) { cudaStreamDestroy(side_st); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); side_st = 0; }
+		drop_streams();
  f.release(); p.release(); t.release(); v.release(); u.release(); u2.release(); w.release(); b.release();
 	                 n_u.release(); n_b.release(); counter.release(); order.release(); stacks.release();
 	}

@@ -331,6 +331,144 @@ __device__ void wm_chain_fill_warp_ring(const wm128_dev *__restrict__ a, int n, 
 	}
 }
 
+// ---- fourth formulation: a tile of 32 consecutive anchors, one warp per anchor --------------------------------
+// Giant tasks (a read inside a tandem array: 10^5..10^6 anchors) are serial in the formulations above: one warp walks
+// the anchors one by one.  But anchor i depends on anchor j only if j is a CANDIDATE predecessor of i (it passes the
+// three `continue`s of src/chain.c:61-73) -- a purely geometric property of a[] -- because a non-candidate touches
+// neither max_f nor n_skip nor t[].  In a tandem lattice consecutive anchors mostly lie on different diagonals and
+// are not candidates of each other.  So the CTA takes 32 consecutive anchors at a time, warp k owns anchor i0 + k,
+// finds with one ballot which anchors of the tile are candidates for it, waits until exactly those have published
+// f / p / v (a done-mask in shared memory), and then runs the same exact scan as the ring formulation: first the
+// predecessors inside the tile (coordinates from registers, scores from the ring), then the ring, which holds only
+// finished anchors.  The t[p[j]] = i marks of the reference are per-anchor state, so every warp keeps its own in a bitset
+// over the ring window.  A scan that runs past the ring (rare: the ring covers the last ~4000 anchors) is redone under
+// a CTA-wide lock with the global arrays, exactly like the single-warp ring formulation.
+#define WM_CT_WARPS 32
+#ifndef WM_CT_RING
+#define WM_CT_RING 4096 // (the CPU emulation harness of the tests builds with a small ring to force the locked deep path)
+#endif
+struct wm_chain_tile_sm {
+	uint64_t x[WM_CT_RING];
+	int32_t q[WM_CT_RING], f[WM_CT_RING], p[WM_CT_RING], v[WM_CT_RING];
+	uint32_t marks[WM_CT_WARPS][WM_CT_RING / 32];
+	unsigned done; int lock;
+};
+
+// The scan of anchor i = i0 + k by one warp.  al / (tile registers): lane l holds a[i0 + l].  Entries j >= ring_lo are read from the
+// ring (intra-tile ones only if they are candidates, which the caller has waited for); older ones from global memory, and only
+// when deep_ok (the caller holds the lock: the global t[] marks are then this anchor's alone).  Returns false if it would have
+// had to go below the ring without deep_ok; on success *mf / *mj hold f[i] / p[i].
+__device__ __forceinline__ bool wm_chain_tile_scan(const wm128_dev *__restrict__ a, const wm_chain_params &P, const int32_t *f, const int32_t *p, int32_t *t,
+                                                   wm_chain_tile_sm *S, uint32_t *mk, wm128_dev al, int i0, int k, int st, int ring_lo, bool deep_ok,
+                                                   double avg_d, double scale_d, int lane, int *mf, int *mj)
+{
+	const unsigned FULL = 0xffffffffu;
+	constexpr int MASK = WM_CT_RING - 1;
+	const int i = i0 + k;
+	const uint64_t ri = __shfl_sync(FULL, al.x, k), yi = __shfl_sync(FULL, al.y, k);
+	const int32_t qi = (int32_t)yi, q_span = (int32_t)(yi >> 32 & 0xff);
+	int max_f = q_span, max_j = -1, n_skip = 0;
+	for (int w = lane; w < WM_CT_RING / 32; w += 32) mk[w] = 0;
+	__syncwarp();
+	bool brk_out = false;
+	// (1) predecessors inside the tile: lane m looks at j = i - 1 - m (tile slot k - 1 - m)
+	if (k > 0 && i - 1 >= st) {
+		const int src = k - 1 - lane;
+		const uint64_t xj = __shfl_sync(FULL, al.x, src < 0 ? 0 : src), yj = __shfl_sync(FULL, al.y, src < 0 ? 0 : src);
+		const int j = i - 1 - lane;
+		bool cand = false; int sc = INT_MIN;
+		if (src >= 0 && j >= st) {
+			wm128_dev aj; aj.x = xj, aj.y = (uint64_t)(uint32_t)yj;
+			int s0;
+			if (wm_chain_score(aj, ri, qi, q_span, P, avg_d, scale_d, &s0)) {
+				const int s = j & MASK;
+				cand = true; sc = s0 + S->f[s];
+				const int pj = S->p[s];
+				if (pj >= 0) {
+					if (pj >= ring_lo) atomicOr(&mk[(pj & MASK) >> 5], 1u << (pj & 31));
+					else if (deep_ok) t[pj] = i;
+					else brk_out = true; // a mark below the ring: only the locked path can keep it
+				}
+			}
+		}
+		if (__ballot_sync(FULL, brk_out)) return false;
+		__syncwarp();
+		const bool marked = cand && (mk[(j & MASK) >> 5] >> (j & 31) & 1); // j >= i0 > ring_lo
+		const unsigned G = __ballot_sync(FULL, cand && sc > max_f);
+		unsigned Rm = G;
+		if (G & (G - 1)) {
+			const int incl = wm_warp_incl_max(cand ? sc : INT_MIN, lane);
+			int excl = __shfl_up_sync(FULL, incl, 1);
+			if (lane == 0) excl = INT_MIN;
+			excl = max(excl, max_f);
+			Rm = __ballot_sync(FULL, cand && sc > excl);
+		}
+		const unsigned K = __ballot_sync(FULL, marked) & ~Rm;
+		const int brk = wm_chain_replay(Rm, K, &n_skip, P.max_skip);
+		const unsigned Rv = brk < 32 ? (Rm & ((1u << brk) - 1u)) : Rm;
+		if (Rv) {
+			const int top = 31 - __clz(Rv);
+			max_f = __shfl_sync(FULL, sc, top);
+			max_j = i - 1 - top;
+		}
+		if (brk < 32) brk_out = true;
+	}
+	// (2) below the tile: 64 predecessors per step, as in the ring formulation
+	for (int jb = i0 - 1; jb >= st && !brk_out; jb -= 64) {
+		if (!deep_ok && jb - 63 < ring_lo && ring_lo > st) return false; // this step would reach below the ring
+		bool cand[2]; int sc[2], jj[2];
+		bool need_deep = false;
+		#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			const int j = jb - 32 * h - lane;
+			jj[h] = j; cand[h] = false; sc[h] = INT_MIN;
+			if (j >= st) {
+				wm128_dev aj; int fj, pj;
+				if (j >= ring_lo) { const int s = j & MASK; aj.x = S->x[s]; aj.y = (uint64_t)(uint32_t)S->q[s]; fj = S->f[s]; pj = S->p[s]; }
+				else { aj = a[j]; fj = f[j]; pj = p[j]; }
+				int s0;
+				if (wm_chain_score(aj, ri, qi, q_span, P, avg_d, scale_d, &s0)) {
+					cand[h] = true; sc[h] = s0 + fj;
+					if (pj >= 0) {
+						if (pj >= ring_lo) atomicOr(&mk[(pj & MASK) >> 5], 1u << (pj & 31));
+						else if (deep_ok) t[pj] = i;
+						else need_deep = true;
+					}
+				}
+			}
+		}
+		if (__ballot_sync(FULL, need_deep)) return false;
+		__syncwarp();
+		#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			if (h == 1 && jb - 32 < st) break;
+			const int j = jj[h];
+			bool marked = false;
+			if (cand[h]) marked = j >= ring_lo ? (mk[(j & MASK) >> 5] >> (j & 31) & 1) != 0 : t[j] == i;
+			const unsigned G = __ballot_sync(FULL, cand[h] && sc[h] > max_f);
+			unsigned Rm = G;
+			if (G & (G - 1)) {
+				const int incl = wm_warp_incl_max(cand[h] ? sc[h] : INT_MIN, lane);
+				int excl = __shfl_up_sync(FULL, incl, 1);
+				if (lane == 0) excl = INT_MIN;
+				excl = max(excl, max_f);
+				Rm = __ballot_sync(FULL, cand[h] && sc[h] > excl);
+			}
+			const unsigned K = __ballot_sync(FULL, marked) & ~Rm;
+			const int brk = wm_chain_replay(Rm, K, &n_skip, P.max_skip);
+			const unsigned Rv = brk < 32 ? (Rm & ((1u << brk) - 1u)) : Rm;
+			if (Rv) {
+				const int top = 31 - __clz(Rv);
+				max_f = __shfl_sync(FULL, sc[h], top);
+				max_j = jb - 32 * h - top;
+			}
+			if (brk < 32) { brk_out = true; break; }
+		}
+	}
+	*mf = max_f, *mj = max_j;
+	return true;
+}
+
 // descending bitonic sort of m (power of two) uint64 keys by one warp
 __device__ void wm_warp_bitonic_desc(uint64_t *x, int m, int lane)
 {

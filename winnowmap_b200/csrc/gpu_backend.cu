@@ -110,13 +110,25 @@ struct GpuBackendImpl {
 	std::vector<uint64_t> h_u; std::vector<wm_pair_t> h_b; std::vector<int32_t> h_nu; std::vector<int64_t> h_nb;
 	std::vector<uint32_t> h_cig; std::vector<wm_extz_dev> h_ez; std::vector<int32_t> h_zd; wm_dbuf zd;
 	size_t bt_budget;
+	bool owns_index = false; // the lane that uploaded the index frees it; clones only borrow the pointers
 };
 
 class GpuBackend : public Backend {
 public:
 	GpuBackendImpl g;
 	GpuBackend() {}
-	~GpuBackend() { if (g.h_stage) cudaFreeHost(g.h_stage); }
+	~GpuBackend()
+	{ // workspaces (wm_dbuf members) free themselves; here: the stream, the pinned staging buffer and, for the owner lane, the index
+		cudaSetDevice(g.device);
+		if (g.st) { cudaStreamSynchronize(g.st); }
+		if (g.dpws.fill_st) cudaStreamSynchronize(g.dpws.fill_st);
+		if (g.h_stage) cudaFreeHost(g.h_stage);
+		if (g.owns_index) {
+			cudaFree((void*)g.ix.keys); cudaFree((void*)g.ix.pos_off); cudaFree((void*)g.ix.pos); cudaFree((void*)g.ix.S);
+			cudaFree((void*)g.ix.ht_key); cudaFree((void*)g.ix.ht_val); cudaFree((void*)g.bf.table);
+		}
+		if (g.st) cudaStreamDestroy(g.st);
+	}
 	void begin_batch(const std::vector<const wm_read*> &reads) override;
 	void set_resident_pool(const char *device_ascii) override { g.resident_pool = device_ascii; }
 	void seed_chain(const std::vector<SeedTask> &tasks, const int32_t *mask_pool, const wm_pair_t *pre_pool, const ChainParams cp[2], int max_occ, std::vector<SeedOut> &out) override;
@@ -646,6 +658,7 @@ Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64
 	g.ix.n_keys = n_keys, g.ix.keys = d_keys, g.ix.pos_off = d_poff, g.ix.pos = d_pos, g.ix.S = d_S;
 	wm_idx_dev_build_ht(&g.ix, g.st);
 	wm_bloom_dev_from_table(&g.bf, d_bt, bloom_bits);
+	g.owns_index = true;
 	wm_stream_sync(g.st);
 	size_t free_b = 0, total_b = 0;
 	WM_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
@@ -678,5 +691,11 @@ void gpu_backend_set_budget(Backend *be, size_t bytes) { static_cast<GpuBackend*
 size_t gpu_backend_get_budget(Backend *be) { return static_cast<GpuBackend*>(be)->g.bt_budget; }
 
 void gpu_backend_destroy(Backend *be) { delete be; }
+
+void gpu_backend_trim_pool(int device)
+{ // give the stream-ordered allocator's cached blocks back to the device (the release threshold is "never" while mapping)
+	cudaMemPool_t pool;
+	if (cudaSetDevice(device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); }
+}
 
 } // namespace wmh

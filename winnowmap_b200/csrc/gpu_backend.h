@@ -13,4 +13,5 @@ namespace wmh {
 Backend *gpu_backend_clone(Backend *base, int n_lanes);
 void gpu_backend_set_budget(Backend *be, size_t bytes);
 size_t gpu_backend_get_budget(Backend *be);
+void gpu_backend_trim_pool(int device);
 }

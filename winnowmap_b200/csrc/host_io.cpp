@@ -92,6 +92,7 @@ int check_opt(const wm_idxopt_t *io, const wm_mapopt_t *mo)
 { // mm_check_opt :133-188 (same return codes)
 	if (mo->split_prefix && (mo->flag & (WM_F_OUT_CS | WM_F_OUT_MD))) return -6;
 	if (io->k <= 0 || io->w <= 0) return -5;
+	if (io->k > 28 || io->w >= 256) return -5; // the sketch asserts 0 < w < 256 && 0 < k <= 28 (src/sketch.c:140); refused here instead of aborting later
 	if (mo->best_n < 0) return -4;
 	if (mo->pri_ratio < 0.0f || mo->pri_ratio > 1.0f) return -4;
 	if ((mo->flag & WM_F_FOR_ONLY) && (mo->flag & WM_F_REV_ONLY)) return -3;
@@ -204,12 +205,12 @@ int read_kmer_list(const char *fn, int k, std::vector<uint64_t> &out)
 	if (fn == 0) return 0;
 	std::ifstream idt(fn);
 	std::string kmer; uint64_t freq;
-	while (idt >> kmer >> freq) {
-		if ((int)kmer.size() != k) {
-			fprintf(stderr, "ERROR: input list of k-mers and winnowmap parameter k are inconsistent\n");
-			return -1;
-		}
-		out.push_back(encode_kmer(kmer));
+	while (idt >> kmer >> freq) out.push_back(encode_kmer(kmer));
+	// like the reference (:399-406), only the LAST k-mer read is checked against k; entries of another length are
+	// encoded over their own length, as encodeKmer does
+	if (!out.empty() && (int)kmer.size() != k) {
+		fprintf(stderr, "ERROR: input list of k-mers and winnowmap parameter k are inconsistent\n");
+		return -1;
 	}
 	return 0;
 }

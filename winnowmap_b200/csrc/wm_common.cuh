@@ -85,6 +85,10 @@ static inline void wm_dbuf_use_stream(cudaStream_t st) { wm_dbuf_stream = st; wm
 struct wm_dbuf {
 	void *p; size_t cap; bool async; cudaStream_t st;
 	wm_dbuf() : p(0), cap(0), async(false), st(0) {}
+	wm_dbuf(const wm_dbuf&) = delete;
+	wm_dbuf &operator=(const wm_dbuf&) = delete;
+	// cudaFree also takes stream-ordered allocations (it synchronises), so the owner's stream may be gone already
+	~wm_dbuf() { if (p) cudaFree(p); }
 	void drop() {
 		if (!p) return;
 		if (async) WM_CUDA_CHECK(cudaFreeAsync(p, st)); else WM_CUDA_CHECK(cudaFree(p));
@@ -113,6 +117,7 @@ struct wm_extd2_ws {
 	wm_dbuf scratch;
 	cudaStream_t fill_st; cudaEvent_t ev_ready, ev_done;
 	wm_extd2_ws() : fill_st(0), ev_ready(0), ev_done(0) {}
+	~wm_extd2_ws() { if (fill_st) { cudaStreamDestroy(fill_st); cudaEventDestroy(ev_ready); cudaEventDestroy(ev_done); } }
 };
 struct wm_extd2_plan_t { int n_slots, max_tlen, max_qlen; };
 void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2);

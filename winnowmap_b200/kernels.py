@@ -47,6 +47,23 @@ def ksw_extd2_batch(queries, targets, mat, q, e, q2, e2, w, zdrop, end_bonus, fl
     return out, cigs
 
 
+def ksw_ll_batch(queries, targets, mat, gapo, gape):
+    """Batched ksw_ll_qinit + ksw_ll_i16 (reference src/ksw2_ll_sse.c:32,80).  Returns (n,3) int32: score, query end, target end."""
+    n = len(queries)
+    qb, qoff = _concat(queries)
+    tb, toff = _concat(targets)
+    if len(qb) == 0:
+        qb = np.zeros(1, np.uint8)
+    if len(tb) == 0:
+        tb = np.zeros(1, np.uint8)
+    mat = np.ascontiguousarray(mat, dtype=np.int8)
+    sc, qe, te = (np.zeros(max(n, 1), np.int32) for _ in range(3))
+    L = lib()
+    L.wm_ksw_ll_batch.argtypes = [C.c_int, u8p, i64p, u8p, i64p, i8p, C.c_int, C.c_int, i32p, i32p, i32p]
+    L.wm_ksw_ll_batch(n, _p(qb, u8p), _p(qoff, i64p), _p(tb, u8p), _p(toff, i64p), _p(mat, i8p), gapo, gape, _p(sc, i32p), _p(qe, i32p), _p(te, i32p))
+    return np.stack([sc, qe, te], axis=1)[:n]
+
+
 _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
 
