@@ -354,7 +354,7 @@ def main():
         lens = (C.c_int32 * n)(*[len(s) for _, s in recs])
         return n, names, seqs, lens
 
-    group_reads = GROUP * a.reads
+    group_reads = max(GROUP * a.reads, 1)
 
     def map_host(recs, keep_first=0, out_path=None):
         """recs through wm_gpu_map_batch in groups of GROUP steps; wall time of the calls; optionally formats the first keep_first reads."""
@@ -389,11 +389,18 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    # warm-up in the shape of the timed passes: W steps, device-resident and through the host API
+    # warm-up in the shape of the timed passes: the W steps, device-resident and through the host API.  Every orchestration
+    # lane must have sized its workspaces for a full chunk before the timed region, so when W steps hold fewer than about
+    # one chunk per lane the same W steps are submitted several times over in one submission (no extra reads are made).
     if warm:
-        upload(warm)
+        lanes = int(os.environ.get("WM_LANES", max(2, min(8, n_thr // 8))))
+        warm_bases = sum(len(s) for _, s in warm)
+        n_rep = max(1, -(-int(1.25 * lanes * int(os.environ["WM_CHUNK_BASES"])) // max(1, warm_bases)))
+        warm_sub = warm * n_rep
+        upload(warm_sub)
         map_uploaded()
-        map_host(warm)
+        map_host(warm_sub)
+        del warm_sub
     L.wm_prof_enable(1); L.wm_prof_reset()
     L.wm_dump_timers() if os.environ.get("WM_TIMING") else None
     mp.reset_stats() if hasattr(mp, "reset_stats") else None

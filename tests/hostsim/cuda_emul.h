@@ -62,6 +62,7 @@ template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 3
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return wm_emul::exchange(v, wm_emul::lane ^ m); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
 inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 
 // ---- integer SIMD-in-a-word intrinsics (CUDA math API semantics) ----

@@ -257,14 +257,14 @@ extern "C" int wmt_emul_chain(uint64_t *a_xy, int n, int max_dist_x, int min_dis
 	P.min_cnt = min_cnt, P.min_sc = min_sc, P.gap_scale = gap_scale;
 	std::vector<int32_t> f((size_t)n + 1), p((size_t)n + 1), t((size_t)n + 1, 0), v((size_t)n + 1), D(WM_CHAIN_DENSE_CAP, 0);
 	std::vector<uint64_t> u(2 * (size_t)n + 2), u2((size_t)n + 1);
-	wm_rs_stack stack;
-	struct Args { wm128_dev *a, *w, *b; int n; const wm_chain_params *P; int32_t *f, *p, *t, *v, *D; uint64_t *u, *u2; wm_rs_stack *stk; int dense; int32_t *n_u; int64_t *n_b; }
+	wm_rs_warp_ws stack; memset(&stack, 0, sizeof(stack));
+	struct Args { wm128_dev *a, *w, *b; int n; const wm_chain_params *P; int32_t *f, *p, *t, *v, *D; uint64_t *u, *u2; wm_rs_warp_ws *stk; int dense; int32_t *n_u; int64_t *n_b; }
 		A = { a.data(), w.data(), b.data(), n, &P, f.data(), p.data(), t.data(), v.data(), D.data(), u.data(), u2.data(), &stack, dense, n_u_out, n_b_out };
 	wm_emul::run_warp([](int l, void *q) {
 		Args &x = *(Args*)q;
 		run_fill(x.dense, x.a, x.n, x.P, x.f, x.p, x.t, x.v, x.D, l);
 		__syncwarp();
-		wm_chain_backtrack_warp(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, x.u, x.u2, x.w, x.b, x.stk, x.n_u, x.n_b, l);
+		wm_chain_backtrack_grp<false>(x.a, x.n, *x.P, x.f, x.p, x.t, x.v, x.u, x.u2, x.w, x.b, x.stk, x.n_u, x.n_b, l, 32, 0);
 	}, &A);
 	for (int i = 0; i < *n_u_out; ++i) u_out[i] = u2[i];
 	for (int64_t i = 0; i < *n_b_out; ++i) a_xy[2 * i] = a[i].x, a_xy[2 * i + 1] = a[i].y;

@@ -201,27 +201,53 @@ static void wm_chain_launch_ring(int grid, cudaStream_t st, const wm128_dev *a, 
 	WM_CUDA_CHECK(cudaGetLastError());
 }
 
+// Backtracking (chain_dev.cuh): tasks order[first .. last), one warp per task ...
 __global__ void __launch_bounds__(WM_CHAIN_WARPS * 32)
-wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, int n_tasks, wm_chain_params2 PP, const uint8_t *__restrict__ set_id,
+wm_chain_backtrack_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ order, int first, int last,
+                          wm_chain_params2 PP, const uint8_t *__restrict__ set_id,
                           int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
                           uint64_t *__restrict__ u_all, uint64_t *__restrict__ u2_all, wm128_dev *__restrict__ w_all, wm128_dev *__restrict__ b_all,
-                          int32_t *__restrict__ n_u_out, int64_t *__restrict__ n_b_out, wm_rs_stack *__restrict__ stacks, int *counter)
+                          int32_t *__restrict__ n_u_out, int64_t *__restrict__ n_b_out, int *counter)
 {
 	const unsigned FULL = 0xffffffffu;
-	const int lane = threadIdx.x & 31;
-	const int wslot = blockIdx.x * WM_CHAIN_WARPS + (threadIdx.x >> 5);
+	__shared__ wm_rs_warp_ws W[WM_CHAIN_WARPS];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	for (;;) {
-		int task = 0;
-		if (lane == 0) task = atomicAdd(counter, 1);
-		task = __shfl_sync(FULL, task, 0);
-		if (task >= n_tasks) break;
+		int ti = 0;
+		if (lane == 0) ti = first + atomicAdd(counter, 1);
+		ti = __shfl_sync(FULL, ti, 0);
+		if (ti >= last) break;
+		const int task = order[ti];
 		const int64_t base = off[task];
 		const int n = (int)(off[task + 1] - base);
 		if (lane == 0) n_u_out[task] = 0, n_b_out[task] = 0;
 		if (n <= 0) continue;
 		__syncwarp();
-		wm_chain_backtrack_warp(a_all + base, n, PP.p[set_id ? set_id[task] : 0], f_all + base, p_all + base, t_all + base, v_all + base,
-		                        u_all + 2 * base, u2_all + base, w_all + base, b_all + base, stacks + wslot, n_u_out + task, n_b_out + task, lane);
+		wm_chain_backtrack_grp<false>(a_all + base, n, PP.p[set_id ? set_id[task] : 0], f_all + base, p_all + base, t_all + base, v_all + base,
+		                              u_all + 2 * base, u2_all + base, w_all + base, b_all + base, &W[wid], n_u_out + task, n_b_out + task, lane, 32, 0);
+	}
+}
+
+// ... and one CTA per giant task
+__global__ void __launch_bounds__(1024)
+wm_chain_backtrack_cta_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ order, int n_giant,
+                              wm_chain_params2 PP, const uint8_t *__restrict__ set_id,
+                              int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all, int32_t *__restrict__ v_all,
+                              uint64_t *__restrict__ u_all, uint64_t *__restrict__ u2_all, wm128_dev *__restrict__ w_all, wm128_dev *__restrict__ b_all,
+                              int32_t *__restrict__ n_u_out, int64_t *__restrict__ n_b_out)
+{
+	__shared__ wm_rs_warp_ws W;
+	__shared__ int sm[64];
+	for (int ti = blockIdx.x; ti < n_giant; ti += gridDim.x) {
+		const int task = order[ti];
+		const int64_t base = off[task];
+		const int n = (int)(off[task + 1] - base);
+		if (threadIdx.x == 0) n_u_out[task] = 0, n_b_out[task] = 0;
+		__syncthreads();
+		if (n <= 0) continue;
+		wm_chain_backtrack_grp<true>(a_all + base, n, PP.p[set_id ? set_id[task] : 0], f_all + base, p_all + base, t_all + base, v_all + base,
+		                             u_all + 2 * base, u2_all + base, w_all + base, b_all + base, &W, n_u_out + task, n_b_out + task, (int)threadIdx.x, (int)blockDim.x, sm);
+		__syncthreads();
 	}
 }
 
@@ -252,12 +278,12 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 	int grid = n_sm * (32 / WM_CHAIN_WARPS);
 	const int need = (n_tasks + WM_CHAIN_WARPS - 1) / WM_CHAIN_WARPS;
 	if (grid > need) grid = need;
-	wm_rs_stack *stk = (wm_rs_stack*)ws->stacks.need(sizeof(wm_rs_stack) * (size_t)grid * WM_CHAIN_WARPS);
 	// formulation of the forward pass: 0 = plain warp loop, 1 = dense candidates, 2 = shared-memory ring (default)
-	static int mode = -1, ring_big = 1024, tile_min = 2048;
+	static int mode = -1, ring_big = 1024, tile_min = 2048, bt_cta_min = 4096;
 	if (mode < 0) {
 		const char *e = getenv("WM_CHAIN_DENSE"), *m = getenv("WM_CHAIN_MODE"), *r = getenv("WM_CHAIN_RING"), *tm = getenv("WM_CHAIN_TILE_MIN");
 		if (tm && atoi(tm) > 0) tile_min = atoi(tm);
+		if (getenv("WM_CHAIN_BT_CTA_MIN") && atoi(getenv("WM_CHAIN_BT_CTA_MIN")) > 0) bt_cta_min = atoi(getenv("WM_CHAIN_BT_CTA_MIN"));
 		mode = m ? atoi(m) : (e && *e == '1') ? 1 : 2;
 		if (r) ring_big = atoi(r);
 		if (ring_big != 512 && ring_big != 1024 && ring_big != 2048) ring_big = 1024;
@@ -330,8 +356,20 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	wm_prof_launch_end(pslot, st);
-	wm_count_launch(); wm_chain_backtrack_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, n_tasks, PP, d_set_id, f, p, t, v, u, u2, w, b, n_u, n_b, stk, counter + 1);
-	WM_CUDA_CHECK(cudaGetLastError());
+	{ // backtracking: giant tasks by a CTA each, the others by a warp each (order[] is by size, descending)
+		int n_giant = 0;
+		while (n_giant < n_tasks && h_off[order[n_giant] + 1] - h_off[order[n_giant]] > bt_cta_min) ++n_giant;
+		if (n_giant > 0) {
+			wm_count_launch();
+			wm_chain_backtrack_cta_kernel<<<n_giant < 2 * n_sm ? n_giant : 2 * n_sm, 1024, 0, st>>>(d_a, d_off, d_order, n_giant, PP, d_set_id, f, p, t, v, u, u2, w, b, n_u, n_b);
+			WM_CUDA_CHECK(cudaGetLastError());
+		}
+		if (n_tasks > n_giant) {
+			wm_count_launch();
+			wm_chain_backtrack_kernel<<<grid, WM_CHAIN_WARPS * 32, 0, st>>>(d_a, d_off, d_order, n_giant, n_tasks, PP, d_set_id, f, p, t, v, u, u2, w, b, n_u, n_b, counter + 1);
+			WM_CUDA_CHECK(cudaGetLastError());
+		}
+	}
 }
 
 // ---- C ABI ----

@@ -469,12 +469,22 @@ __device__ __forceinline__ bool wm_chain_tile_scan(const wm128_dev *__restrict__
 	return true;
 }
 
-// descending bitonic sort of m (power of two) uint64 keys by one warp
-__device__ void wm_warp_bitonic_desc(uint64_t *x, int m, int lane)
+// ---- backtracking (src/chain.c:92-165) by a group of threads: one warp (tasks of ordinary size) or one CTA (giant tasks) ----
+template <bool CTA> __device__ __forceinline__ void wm_grp_sync()
+{
+#ifndef WM_HOST_EMUL
+	if (CTA) __syncthreads(); else
+#endif
+	__syncwarp();
+}
+
+// descending bitonic sort of m (power of two) uint64 keys by the group
+template <bool CTA>
+__device__ void wm_grp_bitonic_desc(uint64_t *x, int m, int tid, int G)
 {
 	for (int k = 2; k <= m; k <<= 1)
 		for (int j = k >> 1; j > 0; j >>= 1) {
-			for (int i = lane; i < m; i += 32) {
+			for (int i = tid; i < m; i += G) {
 				const int l = i ^ j;
 				if (l > i) {
 					const uint64_t a = x[i], b = x[l];
@@ -482,91 +492,139 @@ __device__ void wm_warp_bitonic_desc(uint64_t *x, int m, int lane)
 					if (up ? a < b : a > b) x[i] = b, x[l] = a;
 				}
 			}
-			__syncwarp();
+			wm_grp_sync<CTA>();
 		}
 }
 
-// Backtracking of one task by one warp (src/chain.c:92-165): chain ends, greedy claim walk (serial, lane 0), chains
-// written out in ascending anchor order and re-ordered by the position of their first anchor.  On return a[] holds the
-// chained anchors (*n_b_out of them), u2[] the (score << 32 | count) words (*n_u_out); both counts are 0 if there is no chain
-// (the caller zeroes them first).  u has room for the power-of-two padding of the bitonic sort (2n entries).
-__device__ __forceinline__ void wm_chain_backtrack_warp(wm128_dev *a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v,
-                                               uint64_t *u, uint64_t *u2, wm128_dev *w, wm128_dev *b, wm_rs_stack *stack, int32_t *n_u_out, int64_t *n_b_out, int lane)
+// exclusive prefix of (a, b) over the threads of the group; *ta / *tb receive the totals.  sm: 64 ints of shared memory (CTA only)
+template <bool CTA>
+__device__ __forceinline__ void wm_grp_scan2(int &a, int &b, int *ta, int *tb, int tid, int *sm)
 {
 	const unsigned FULL = 0xffffffffu;
-	// chain ends (src/chain.c:93-98): anchors that are nobody's predecessor and whose peak score passes
-	for (int i = lane; i < n; i += 32) t[i] = 0;
-	__syncwarp();
-	for (int i = lane; i < n; i += 32) if (p[i] >= 0) t[p[i]] = 1;
-	__syncwarp();
-	int n_u = 0;
-	for (int ib = 0; ib < n; ib += 32) {
-		const int i = ib + lane;
-		const bool is_end = i < n && t[i] == 0 && v[i] >= P.min_sc;
-		const unsigned m = __ballot_sync(FULL, is_end);
-		if (is_end) { // :104-110: walk back to the peak that maximises f[]
+	const int lane = tid & 31;
+	int ia = a, ib = b;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int xa = __shfl_up_sync(FULL, ia, o), xb = __shfl_up_sync(FULL, ib, o);
+		if (lane >= o) ia += xa, ib += xb;
+	}
+	int base_a = 0, base_b = 0, tot_a = __shfl_sync(FULL, ia, 31), tot_b = __shfl_sync(FULL, ib, 31);
+#ifndef WM_HOST_EMUL
+	if (CTA) {
+		const int w = tid >> 5, nw = (int)(blockDim.x >> 5);
+		if (lane == 31) sm[w] = ia, sm[32 + w] = ib;
+		__syncthreads();
+		tot_a = tot_b = 0;
+		for (int k = 0; k < nw; ++k) { if (k == w) base_a = tot_a, base_b = tot_b; tot_a += sm[k]; tot_b += sm[32 + k]; }
+		__syncthreads();
+	}
+#endif
+	a = base_a + ia - a, b = base_b + ib - b;
+	*ta = tot_a, *tb = tot_b;
+}
+
+// Backtracking of one task (src/chain.c:92-165).  On return a[] holds the chained anchors (*n_b_out of them), u2[] the
+// (score << 32 | count) words (*n_u_out); both counts are 0 if there is no chain.  u has 2n entries, *n_u_out must be 0 on entry
+// (it serves as the counter of the chain starts).
+// The reference takes the chain starts in score order and lets each claim its path of predecessors up to the first anchor
+// that is claimed already (:118-135).  That walk is order dependent only through "claimed by a better start": anchor x ends up
+// with the best-ranked start among those whose path reaches it, so every start walks its path concurrently with an atomicMin
+// of its rank and stops at the first anchor that already carries a better one.  The first anchor of a start is taken even
+// when it is claimed (the do-while of :121-125).
+template <bool CTA>
+__device__ void wm_chain_backtrack_grp(wm128_dev *a, int n, const wm_chain_params &P, int32_t *f, int32_t *p, int32_t *t, int32_t *v,
+                                       uint64_t *u, uint64_t *u2, wm128_dev *w, wm128_dev *b, wm_rs_warp_ws *W, int32_t *n_u_out, int64_t *n_b_out,
+                                       int tid, int G, int *sm)
+{
+	// chain starts (:93-110): anchors that are nobody's predecessor and whose peak score passes; from each, back to the peak of f[]
+	for (int i = tid; i < n; i += G) t[i] = 0;
+	wm_grp_sync<CTA>();
+	for (int i = tid; i < n; i += G) if (p[i] >= 0) t[p[i]] = 1;
+	wm_grp_sync<CTA>();
+	for (int i = tid; i < n; i += G)
+		if (t[i] == 0 && v[i] >= P.min_sc) {
 			int j = i;
 			while (j >= 0 && f[j] < v[j]) j = p[j];
 			if (j < 0) j = i;
-			u[n_u + __popc(m & ((1u << lane) - 1u))] = (uint64_t)(uint32_t)f[j] << 32 | (uint32_t)j;
+			u[atomicAdd(n_u_out, 1)] = (uint64_t)(uint32_t)f[j] << 32 | (uint32_t)j;
 		}
-		n_u += __popc(m);
+	wm_grp_sync<CTA>();
+	const int n_e = *n_u_out;
+	wm_grp_sync<CTA>();
+	if (tid == 0) *n_u_out = 0, *n_b_out = 0;
+	if (n_e == 0) { wm_grp_sync<CTA>(); return; } // :99-102
+	{ // :112-116 best first.  Equal words are the same (score, anchor) pair, so any correct sort gives the reference's sequence.
+		int m = 1; while (m < n_e) m <<= 1;
+		for (int i = n_e + tid; i < m; i += G) u[i] = 0;
+		wm_grp_sync<CTA>();
+		wm_grp_bitonic_desc<CTA>(u, m, tid, G);
 	}
-	__syncwarp();
-	if (n_u == 0) { __syncwarp(); return; } // :99-102
-	{ // :112-116 sort by (score, index) descending; keys are distinct so any correct sort gives the reference order
-		int m = 1; while (m < n_u) m <<= 1;
-		for (int i = n_u + lane; i < m; i += 32) u[i] = 0;
-		__syncwarp();
-		wm_warp_bitonic_desc(u, m, lane);
-	}
-	for (int i = lane; i < n; i += 32) t[i] = 0;
-	__syncwarp();
-	int n_v = 0, k = 0;
-	if (lane == 0) { // :118-135 greedy claim walk, serial by construction
-		for (int i = 0; i < n_u; ++i) {
-			const int n_v0 = n_v, k0 = k;
-			int j = (int32_t)u[i];
-			do { v[n_v++] = j; t[j] = 1; j = p[j]; } while (j >= 0 && t[j] == 0);
-			if (j < 0) {
-				if (n_v - n_v0 >= P.min_cnt) u[k++] = u[i] >> 32 << 32 | (uint32_t)(n_v - n_v0);
-			} else if ((int32_t)(u[i] >> 32) - f[j] >= P.min_sc) {
-				if (n_v - n_v0 >= P.min_cnt) u[k++] = ((u[i] >> 32) - (uint64_t)f[j]) << 32 | (uint32_t)(n_v - n_v0);
-			}
-			if (k0 == k) n_v = n_v0;
+	// owners: t[x] = rank of the best start that claims x
+	for (int i = tid; i < n; i += G) t[i] = INT_MAX;
+	wm_grp_sync<CTA>();
+	for (int r = tid; r < n_e; r += G) {
+		int j = (int32_t)u[r];
+		while (j >= 0) {
+			if (atomicMin(&t[j], r) < r) break;
+			j = p[j];
 		}
 	}
-	n_v = __shfl_sync(FULL, n_v, 0); k = __shfl_sync(FULL, k, 0);
-	n_u = k;
-	__syncwarp();
-	// :141-147 write chains to b[] in ascending anchor order; :150-154 build the re-sort keys
+	wm_grp_sync<CTA>();
+	// length, score and fate of every start (:119-134); w[r] = { score << 32 | count (0: dropped), first anchor }
+	for (int r = tid; r < n_e; r += G) {
+		const int s0 = (int32_t)u[r];
+		int cnt = 1, j = p[s0];
+		if (t[s0] == r) while (j >= 0 && t[j] == r) ++cnt, j = p[j];
+		const int32_t sc = j < 0 ? (int32_t)(u[r] >> 32) : (int32_t)(u[r] >> 32) - f[j];
+		const bool keep = (j < 0 || sc >= P.min_sc) && cnt >= P.min_cnt;
+		w[r].x = keep ? (uint64_t)(uint32_t)sc << 32 | (uint32_t)cnt : 0;
+		w[r].y = (uint64_t)(uint32_t)s0;
+	}
+	wm_grp_sync<CTA>();
+	// chain index and anchor offset of the kept starts, in rank order (:130-133, :141-147): a prefix over contiguous blocks of
+	// ranks, kept per rank (t[r] = chain index, upper half of w[r].y = offset) so that the copies below can be dealt round-robin
+	// (the best-ranked chains are the longest: a block of consecutive ranks per thread would leave all of them to thread 0)
+	int n_u = 0, n_v = 0;
 	{
-		int kk = 0;
-		for (int i = 0; i < n_u; ++i) {
-			const int ni = (int32_t)u[i];
-			for (int j = lane; j < ni; j += 32) b[kk + j] = a[v[kk + (ni - j - 1)]];
-			kk += ni;
-		}
-		__syncwarp();
-		if (lane == 0) {
-			int k2 = 0;
-			for (int i = 0; i < n_u; ++i) { w[i].x = b[k2].x, w[i].y = (uint64_t)k2 << 32 | (uint32_t)i; k2 += (int32_t)u[i]; }
-			wm_radix_sort_emul(w, n_u, stack); // :155, tie order matters
-		}
-		__syncwarp();
+		const int L = (n_e + G - 1) / G, r0 = tid * L < n_e ? tid * L : n_e, r1 = r0 + L < n_e ? r0 + L : n_e;
+		int kc = 0, ac = 0;
+		for (int r = r0; r < r1; ++r) if (w[r].x) ++kc, ac += (int32_t)w[r].x;
+		wm_grp_scan2<CTA>(kc, ac, &n_u, &n_v, tid, sm);
+		for (int r = r0; r < r1; ++r)
+			if (w[r].x) { t[r] = kc; w[r].y |= (uint64_t)(uint32_t)ac << 32; ++kc; ac += (int32_t)w[r].x; }
 	}
-	{ // :156-164 chains re-ordered by the position of their first anchor
-		int kk = 0;
-		for (int i = 0; i < n_u; ++i) {
-			const int j = (int32_t)w[i].y, nn = (int32_t)u[j];
-			const wm128_dev *src = b + (w[i].y >> 32);
-			if (lane == 0) u2[i] = u[j];
-			for (int l = lane; l < nn; l += 32) a[kk + l] = src[l];
-			kk += nn;
+	wm_grp_sync<CTA>();
+	if (n_u == 0) { wm_grp_sync<CTA>(); return; }
+	// the chains into b[], each in ascending anchor order (:141-147); u[k] / v[k]: (score << 32 | count) and offset of chain k
+	for (int r = tid; r < n_e; r += G)
+		if (w[r].x) {
+			const int cnt = (int32_t)w[r].x, off = (int32_t)(w[r].y >> 32), k = t[r];
+			int j = (int32_t)w[r].y;
+			for (int m = cnt - 1; m >= 0; --m) { b[off + m] = a[j]; j = p[j]; }
+			u2[k] = w[r].x; v[k] = off;
 		}
-		__syncwarp();
-		if (lane == 0) *n_u_out = n_u, *n_b_out = kk;
+	wm_grp_sync<CTA>();
+	// :150-155 chains ordered by the position of their first anchor (tie-exact sort of the reference)
+	for (int k = tid; k < n_u; k += G) { w[k].x = b[v[k]].x; w[k].y = (uint64_t)(uint32_t)v[k] << 32 | (uint32_t)k; u[k] = u2[k]; }
+	wm_grp_sync<CTA>();
+	if (tid < 32) wm_radix_sort_warp(w, n_u, W, (wm_rs_range*)(u + n), tid);
+	wm_grp_sync<CTA>();
+	// :156-164 the chains in that order: offsets by a second prefix (t[i] = where chain i of the new order starts), then the copies
+	{
+		const int L2 = (n_u + G - 1) / G, k0 = tid * L2 < n_u ? tid * L2 : n_u, k1 = k0 + L2 < n_u ? k0 + L2 : n_u;
+		int dummy = 0, off = 0, td, toff;
+		for (int i = k0; i < k1; ++i) off += (int32_t)u[(int32_t)w[i].y];
+		wm_grp_scan2<CTA>(dummy, off, &td, &toff, tid, sm);
+		for (int i = k0; i < k1; ++i) { t[i] = off; off += (int32_t)u[(int32_t)w[i].y]; }
 	}
-	__syncwarp();
+	wm_grp_sync<CTA>();
+	for (int i = tid; i < n_u; i += G) {
+		const int j = (int32_t)w[i].y, nn = (int32_t)u[j], off = t[i];
+		const wm128_dev *src = b + (w[i].y >> 32);
+		u2[i] = u[j];
+		for (int l = 0; l < nn; ++l) a[off + l] = src[l];
+	}
+	wm_grp_sync<CTA>();
+	if (tid == 0) *n_u_out = n_u, *n_b_out = n_v;
+	wm_grp_sync<CTA>();
 }
-

@@ -68,13 +68,14 @@ __device__ void wm_rs_pass(T *a, wm_rs_frame &F, int *b)
 struct wm_rs_range { int beg, end, s; };
 struct wm_rs_warp_ws { int e[256], b[256]; };
 
+// s0: the byte the first pass looks at (56 for a whole array; lower when the caller has done the upper passes itself)
 template <typename T>
-__device__ void wm_radix_sort_warp(T *a, int n, wm_rs_warp_ws *W, wm_rs_range *wl, int lane)
+__device__ void wm_radix_sort_warp_from(T *a, int n, int s0, wm_rs_warp_ws *W, wm_rs_range *wl, int lane)
 {
 	const unsigned FULL = 0xffffffffu;
 	if (n <= WM_RS_MIN_SIZE) { if (lane == 0) wm_rs_insertsort(a, a + n); __syncwarp(); return; }
 	int n_wl = 0;
-	int beg = 0, end = n, s = 56;
+	int beg = 0, end = n, s = s0;
 	for (;;) {
 		// histogram of byte s>>3 (ksort.h:121-122)
 		#pragma unroll
@@ -136,6 +137,9 @@ __device__ void wm_radix_sort_warp(T *a, int n, wm_rs_warp_ws *W, wm_rs_range *w
 	}
 	__syncwarp();
 }
+
+template <typename T>
+__device__ __forceinline__ void wm_radix_sort_warp(T *a, int n, wm_rs_warp_ws *W, wm_rs_range *wl, int lane) { wm_radix_sort_warp_from(a, n, 56, W, wl, lane); }
 
 // radix_sort_##name (ksort.h:146-150) on a[0,n)
 template <typename T>

@@ -158,6 +158,171 @@ wm_anchor_sort_big_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__
 	}
 }
 
+// ---- giant arrays (a read inside a tandem array: 10^5..10^6 anchors) ----
+// The permutation walk of a radix pass (ksort.h:126-138) is a serial chain: the element in hand decides the bucket, the
+// bucket's write position gives the next element in hand.  One observation makes it fast: every position of the array
+// is written exactly once, when its bucket's write pointer passes it, so until then it still holds its ORIGINAL element
+// -- the upcoming elements of every bucket can be prefetched.  One CTA per array: thread 0 walks, three feeder warps keep
+// a FIFO of the next WM_GS_F original elements of each of the 256 buckets in shared memory, the walker never waits for
+// global memory.  Sub-buckets that need another big pass go back on the array's work list; the smaller ones are sorted
+// by the four warps in parallel (staged in shared memory, rsort.cuh); the <= 64-element ones by one thread each.
+#define WM_GS_THREADS 128
+#define WM_GS_F 16                 // FIFO depth per bucket (power of two)
+#define WM_GS_STAGE 2048           // sub-ranges up to this many elements are sorted by one warp in shared memory
+struct wm_gs_sm {
+	int B[256], E[256];            // bucket bounds of the current pass
+	int b[256];                    // write pointers (walker)
+	int filled[256];               // originals loaded so far, per bucket (feeders)
+	int hist[256];
+	int n_big, n_small, next_small, walk_done;
+	wm_rs_warp_ws W[4];
+	wm_rs_range swl[4][40];        // per-warp work list of phase 2 (disjoint sub-ranges of > 64 elements of a <= 2048-element range)
+	union {
+		wm128_dev fifo[256][WM_GS_F];
+		wm128_dev stage[4][WM_GS_STAGE];
+	} u;
+};
+
+__global__ void __launch_bounds__(WM_GS_THREADS)
+wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ ids, int n_arr,
+                            wm_rs_range *__restrict__ wl_all)
+{
+	extern __shared__ __align__(16) unsigned char wm_gs_smem[];
+	wm_gs_sm *S = (wm_gs_sm*)wm_gs_smem;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	for (int ai = blockIdx.x; ai < n_arr; ai += gridDim.x) {
+		const int task = ids[ai];
+		const int64_t base = off[task];
+		const int n = (int)(off[task + 1] - base);
+		wm128_dev *a = a_all + base;
+		// work lists in global memory (the array's slice of wl_all: n / 64 + 1 entries): big ranges grow from the front,
+		// small ones from the back
+		wm_rs_range *wl = wl_all + (base >> 6) + task;
+		const int wl_cap = (n >> 6) + 1;
+		if (tid == 0) { S->n_big = 0, S->n_small = 0; wm_rs_range r; r.beg = 0, r.end = n, r.s = 56; wl[0] = r; S->n_big = 1; }
+		__syncthreads();
+		// ---- phase 1: big passes, one at a time ----
+		for (;;) {
+			if (S->n_big == 0) break;
+			__syncthreads();
+			wm_rs_range R = wl[S->n_big - 1];
+			__syncthreads();
+			if (tid == 0) --S->n_big;
+			int beg = R.beg, end = R.end, s = R.s;
+			bool single;
+			for (;;) { // histogram of byte s >> 3; identity passes (one bucket holds everything) are skipped (ksort.h:121-125)
+				for (int k = tid; k < 256; k += WM_GS_THREADS) S->hist[k] = 0;
+				__syncthreads();
+				for (int i = beg + tid; i < end; i += WM_GS_THREADS) atomicAdd(&S->hist[a[i].x >> s & 255], 1);
+				__syncthreads();
+				single = false;
+				for (int k = 0; k < 256; ++k) if (S->hist[k] == end - beg) single = true; // (uniform: every thread scans the same table)
+				if (!single || s == 0) break;
+				s = s > 8 ? s - 8 : 0;
+				__syncthreads();
+			}
+			if (single) { __syncthreads(); continue; } // all keys equal down to the last byte: nothing moves
+			if (wid == 0) { // bucket bounds: exclusive prefix over 256 counts
+				int cnt[8], sum = 0;
+				#pragma unroll
+				for (int k = 0; k < 8; ++k) { cnt[k] = S->hist[lane * 8 + k]; sum += cnt[k]; }
+				int incl = sum;
+				#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+				int acc = beg + incl - sum;
+				#pragma unroll
+				for (int k = 0; k < 8; ++k) { S->B[lane * 8 + k] = acc; S->b[lane * 8 + k] = acc; S->filled[lane * 8 + k] = acc; acc += cnt[k]; S->E[lane * 8 + k] = acc; }
+				if (lane == 0) S->walk_done = 0;
+			}
+			__syncthreads();
+			if (tid == 0) { // the walker (ksort.h:126-138); b[] are its pointers, filled[] the feeders'
+				volatile int *filled = S->filled; int *b = S->b; const int *E = S->E;
+				for (int k = 0; k < 256;) {
+					const int bk = b[k];
+					if (bk != E[k]) {
+						while (filled[k] <= bk) { }
+						asm volatile("" ::: "memory");
+						wm128_dev tmp = S->u.fifo[k][bk & (WM_GS_F - 1)];
+						int l = (int)(tmp.x >> s & 255);
+						if (l != k) {
+							do {
+								const int bl = b[l];
+								while (filled[l] <= bl) { }
+								asm volatile("" ::: "memory");
+								const wm128_dev nxt = S->u.fifo[l][bl & (WM_GS_F - 1)];
+								a[bl] = tmp;
+								*(volatile int*)&b[l] = bl + 1;
+								tmp = nxt;
+								l = (int)(tmp.x >> s & 255);
+							} while (l != k);
+							a[bk] = tmp;
+						}
+						*(volatile int*)&b[k] = bk + 1;
+					} else ++k;
+				}
+				__threadfence_block();
+				*(volatile int*)&S->walk_done = 1;
+			} else if (wid > 0) { // feeders: 96 threads, buckets tid - 32, + 96, + 192
+				volatile int *bv = S->b; volatile int *done = &S->walk_done;
+				for (;;) {
+					bool any = false;
+					for (int k = tid - 32; k < 256; k += WM_GS_THREADS - 32) {
+						const int fl = S->filled[k], Ek = S->E[k];
+						if (fl >= Ek) continue;
+						any = true;
+						const int pending = fl - bv[k];   // loaded, not yet taken by the walker
+						int room = WM_GS_F - pending;
+						if (room > Ek - fl) room = Ek - fl;
+						if (room > 8) room = 8;
+						if (room >= 4 || (room > 0 && (room == Ek - fl || pending < 4))) { // refill in batches unless the FIFO runs low
+							wm128_dev r[8];
+							#pragma unroll
+							for (int m = 0; m < 8; ++m) if (m < room) r[m] = a[fl + m];
+							#pragma unroll
+							for (int m = 0; m < 8; ++m) if (m < room) S->u.fifo[k][(fl + m) & (WM_GS_F - 1)] = r[m];
+							__threadfence_block();
+							*(volatile int*)&S->filled[k] = fl + room;
+						}
+					}
+					if (!any || *done) break;
+				}
+			}
+			__syncthreads();
+			// sub-buckets (ksort.h:140-145)
+			if (s > 0) {
+				const int ns = s > 8 ? s - 8 : 0;
+				for (int k = tid; k < 256; k += WM_GS_THREADS) {
+					const int cb = S->B[k], ce = S->E[k], sz = ce - cb;
+					if (sz > WM_GS_STAGE) { const int q = atomicAdd(&S->n_big, 1); wm_rs_range r; r.beg = cb, r.end = ce, r.s = ns; wl[q] = r; }
+					else if (sz > WM_RS_MIN_SIZE) { const int q = atomicAdd(&S->n_small, 1); wm_rs_range r; r.beg = cb, r.end = ce, r.s = ns; wl[wl_cap - 1 - q] = r; }
+					else if (sz > 1) wm_rs_insertsort(a + cb, a + ce);
+				}
+			}
+			__syncthreads();
+		}
+		// ---- phase 2: the small ranges, one warp each, staged in shared memory ----
+		if (tid == 0) S->next_small = 0;
+		__syncthreads();
+		{
+			wm128_dev *st = S->u.stage[wid];
+			for (;;) {
+				int q = 0;
+				if (lane == 0) q = atomicAdd(&S->next_small, 1);
+				q = __shfl_sync(0xffffffffu, q, 0);
+				if (q >= S->n_small) break;
+				const wm_rs_range R = wl[wl_cap - 1 - q];
+				const int m = R.end - R.beg;
+				for (int j = lane; j < m; j += 32) st[j] = a[R.beg + j];
+				__syncwarp();
+				wm_radix_sort_warp_from(st, m, R.s, &S->W[wid], S->swl[wid], lane);
+				for (int j = lane; j < m; j += 32) a[R.beg + j] = st[j];
+				__syncwarp();
+			}
+		}
+		__syncthreads();
+	}
+}
+
 // sort n_arr arrays (device); h_off is the host copy of the offsets
 void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_arr, cudaStream_t st)
 {
@@ -183,7 +348,16 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 		int32_t *d_big = (int32_t*)ws->big_ids.need(sizeof(int32_t) * big.size());
 		wm_rs_range *d_wl = (wm_rs_range*)ws->rs_stacks.need(sizeof(wm_rs_range) * (size_t)((h_off[n_arr] >> 6) + n_arr + 2));
 		WM_CUDA_CHECK(wm_memcpy_async(d_big, big.data(), sizeof(int32_t) * big.size(), cudaMemcpyHostToDevice, st));
-		if (n_l) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_l, 32, 0, st>>>(d_a, d_off, d_big, (int)n_l, d_wl, 0); }
+		if (n_l) {
+			static int giant = -1; // WM_SORT_GIANT=0: the single-warp walk in global memory (kept for comparison)
+			if (giant < 0) { const char *e = getenv("WM_SORT_GIANT"); giant = (e && *e == '0') ? 0 : 1; }
+			wm_count_launch();
+			if (giant) {
+				static bool attr_set = false;
+				if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(wm_gs_sm))); attr_set = true; }
+				wm_anchor_sort_giant_kernel<<<(unsigned)(n_l < 296 ? n_l : 296), WM_GS_THREADS, sizeof(wm_gs_sm), st>>>(d_a, d_off, d_big, (int)n_l, d_wl);
+			} else wm_anchor_sort_big_kernel<<<(unsigned)n_l, 32, 0, st>>>(d_a, d_off, d_big, (int)n_l, d_wl, 0);
+		}
 		if (n_m) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_m, 32, cap_m * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, cap_m); }
 		if (n_s) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_s, 32, cap_s * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l + n_m, (int)n_s, d_wl, cap_s); }
 		WM_CUDA_CHECK(cudaGetLastError());
