@@ -708,6 +708,175 @@ int wmo_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 }
 
 /* ------------------------------------------------------------------------------------
+ * ksw_extz2_sse: src/ksw2_extz2_sse.c:23-304 (single affine gap), the SSE4.1
+ * code path (what ksw2_dispatch.c selects on the hosts used here).  Same skeleton as extd2, but the
+ * state rows hold UNSIGNED offsets (u, v, x, y are the differences plus q + e resp. shifted so that
+ * they are >= 0, rows start at 0 thanks to kcalloc, :106), the score is z = s + 2(q+e) (:27), the
+ * three-way maximum mixes a signed compare for `a` with an unsigned maximum for `b` (:40, :163-166)
+ * and the clamp with max_sc_ is unsigned (:41).  Every operation below is the 8-bit operation of the
+ * reference (wrap-around add/sub, signed or unsigned compare as written there), so out-of-range
+ * parameter sets misbehave identically.  One more artefact is kept: x1 / v1 are int8_t and go through
+ * _mm_cvtsi32_si128 WITHOUT a cast (:153-154), so a negative value ORs 0xff into the next three
+ * cells of the first block (:30,:34).
+ * ---------------------------------------------------------------------------------- */
+int wmo_ksw_extz2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                  int q, int e, int w, int zdrop, int end_bonus, int flag,
+                  wmo_ez_t *ez, uint32_t *cigar_out, int max_cigar)
+{
+	const int m = 5;
+	int r, t, qe = q + e, n_col_, *off = 0, *off_end = 0, tlen_, qlen_, last_st, last_en, max_sc, min_sc;
+	int approx_max = !!(flag & WMO_EZ_APPROX_MAX), right = !!(flag & WMO_EZ_RIGHT);
+	int32_t *H = 0, H0 = 0, last_H0_t = 0;
+	uint8_t *mem, *u, *v, *x, *y, *sf, *qr, *p, max_sc_u8, qe2_u8 = (uint8_t)((q + e) * 2);
+	int8_t *s, sc_N;
+	wmo_cig_t cig = {0, 0, 0};
+
+	wmo_reset_ez(ez);
+	if (qlen <= 0 || tlen <= 0) return 0;
+	sc_N = mat[m*m-1] == 0 ? -e : mat[m*m-1]; /* :79 */
+	max_sc_u8 = (uint8_t)(mat[0] + (q + e) * 2); /* :81 */
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	tlen_ = (tlen + 15) / 16;
+	n_col_ = qlen < tlen ? qlen : tlen;
+	n_col_ = ((n_col_ < w + 1 ? n_col_ : w + 1) + 15) / 16 + 1;
+	qlen_ = (qlen + 15) / 16;
+	for (t = 1, max_sc = mat[0], min_sc = mat[1]; t < m * m; ++t) {
+		max_sc = max_sc > mat[t] ? max_sc : mat[t];
+		min_sc = min_sc < mat[t] ? min_sc : mat[t];
+	}
+	if (-min_sc > 2 * (q + e)) return 0; /* :94 */
+
+	mem = (uint8_t*)calloc((size_t)tlen_ * 6 + qlen_ + 1, 16); /* :96-98: zero initialised */
+	u = mem; v = u + tlen_ * 16; x = v + tlen_ * 16; y = x + tlen_ * 16; s = (int8_t*)(y + tlen_ * 16);
+	sf = (uint8_t*)(s + tlen_ * 16); qr = sf + tlen_ * 16;
+	if (!approx_max) {
+		H = (int32_t*)malloc((size_t)tlen_ * 16 * 4);
+		for (t = 0; t < tlen_ * 16; ++t) H[t] = WMO_NEG_INF;
+	}
+	p = (uint8_t*)malloc(((size_t)(qlen + tlen - 1) * n_col_ + 1) * 16);
+	off = (int*)malloc((size_t)(qlen + tlen - 1) * sizeof(int) * 2);
+	off_end = off + qlen + tlen - 1;
+	for (t = 0; t < qlen; ++t) qr[t] = query[qlen - 1 - t];
+	memcpy(sf, target, tlen);
+
+	for (r = 0, last_st = last_en = -1; r < qlen + tlen - 1; ++r) {
+		int st = 0, en = tlen - 1, st0, en0;
+		int8_t x1, v1;
+		uint8_t *qrr = qr + (qlen - 1 - r);
+		if (st < r - qlen + 1) st = r - qlen + 1;
+		if (en > r) en = r;
+		if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+		if (en > (r + w) >> 1) en = (r + w) >> 1;
+		if (st > en) { ez->zdropped = 1; break; }
+		st0 = st, en0 = en;
+		st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;
+		if (st > 0) { /* :133-139 */
+			if (st - 1 >= last_st && st - 1 <= last_en) x1 = (int8_t)x[st - 1], v1 = (int8_t)v[st - 1];
+			else x1 = v1 = 0;
+		} else x1 = 0, v1 = r ? q : 0;
+		if (en >= r) y[r] = 0, u[r] = r ? q : 0;
+		for (t = st0; t <= en0; t += 16) { /* :142-160 */
+			int kk;
+			for (kk = 0; kk < 16; ++kk) {
+				uint8_t sq = sf[t + kk], sq2 = qrr[t + kk];
+				s[t + kk] = (sq == m - 1 || sq2 == m - 1) ? sc_N : (sq == sq2 ? mat[0] : mat[1]);
+			}
+		}
+		off[r] = st, off_end[r] = en;
+		{
+			uint8_t cx = (uint8_t)x1, cv = (uint8_t)v1; /* cells t-1 of the previous diagonal */
+			uint8_t orx = x1 < 0 ? 0xff : 0, orv = v1 < 0 ? 0xff : 0; /* sign bytes of _mm_cvtsi32_si128(int8_t) */
+			uint8_t *pr = p + (size_t)r * n_col_ * 16;
+			for (t = st; t <= en; ++t) {
+				uint8_t xo = x[t], vo = v[t], ut = u[t], xt1 = cx, vt1 = cv, z, a, b, d, zq;
+				if (t - st >= 1 && t - st <= 3) xt1 |= orx, vt1 |= orv;
+				z = (uint8_t)((uint8_t)s[t] + qe2_u8);
+				a = (uint8_t)(xt1 + vt1);
+				b = (uint8_t)(y[t] + ut);
+				if (!right) { /* :212-221 */
+					d = (int8_t)a > (int8_t)z ? 1 : 0;
+					z = (int8_t)z > (int8_t)a ? z : a;
+					d = (int8_t)b > (int8_t)z ? 2 : d;
+				} else { /* :247-256 */
+					d = (int8_t)z > (int8_t)a ? 0 : 1;
+					z = (int8_t)z > (int8_t)a ? z : a;
+					d = (int8_t)z > (int8_t)b ? d : 2;
+				}
+				z = z > b ? z : b;                     /* _mm_max_epu8 (:40) */
+				z = z < max_sc_u8 ? z : max_sc_u8;     /* _mm_min_epu8 (:41) */
+				u[t] = (uint8_t)(z - vt1); v[t] = (uint8_t)(z - ut);
+				zq = (uint8_t)(z - (uint8_t)q); a = (uint8_t)(a - zq); b = (uint8_t)(b - zq);
+				if (!right) { /* :223-229 */
+					x[t] = (int8_t)a > 0 ? a : 0; d |= (int8_t)a > 0 ? 0x08 : 0;
+					y[t] = (int8_t)b > 0 ? b : 0; d |= (int8_t)b > 0 ? 0x10 : 0;
+				} else { /* :258-264 */
+					x[t] = 0 > (int8_t)a ? 0 : a; d |= 0 > (int8_t)a ? 0 : 0x08;
+					y[t] = 0 > (int8_t)b ? 0 : b; d |= 0 > (int8_t)b ? 0 : 0x10;
+				}
+				pr[t - st] = d;
+				cx = xo, cv = vo;
+			}
+		}
+		if (!approx_max) { /* :267-321 */
+			int32_t max_H, max_t;
+			if (r > 0) {
+				int32_t HH[4], tt[4], en1 = st0 + (en0 - st0) / 4 * 4, i;
+				max_H = H[en0] = en0 > 0 ? H[en0 - 1] + u[en0] - qe : H[en0] + v[en0] - qe;
+				max_t = en0;
+				for (i = 0; i < 4; ++i) HH[i] = max_H, tt[i] = max_t;
+				for (t = st0; t < en1; t += 4)
+					for (i = 0; i < 4; ++i) {
+						H[t + i] += (int32_t)v[t + i] - qe;
+						if (H[t + i] > HH[i]) HH[i] = H[t + i], tt[i] = t;
+					}
+				for (i = 0; i < 4; ++i)
+					if (max_H < HH[i]) max_H = HH[i], max_t = tt[i] + i;
+				for (; t < en0; ++t) {
+					H[t] += (int32_t)v[t] - qe;
+					if (H[t] > max_H) max_H = H[t], max_t = t;
+				}
+			} else H[0] = v[0] - qe - qe, max_H = H[0], max_t = 0;
+			if (en0 == tlen - 1 && H[en0] > ez->mte) ez->mte = H[en0], ez->mte_q = r - en;
+			if (r - st0 == qlen - 1 && H[st0] > ez->mqe) ez->mqe = H[st0], ez->mqe_t = st0;
+			if (wmo_apply_zdrop(ez, max_H, r, max_t, zdrop, e)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez->score = H[tlen - 1];
+		} else { /* :322-338 */
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					int32_t d0 = v[last_H0_t] - qe, d1 = u[last_H0_t + 1] - qe;
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
+					H0 += v[last_H0_t] - qe;
+				} else {
+					++last_H0_t, H0 += u[last_H0_t] - qe;
+				}
+				if ((flag & WMO_EZ_APPROX_DROP) && wmo_apply_zdrop(ez, H0, r, last_H0_t, zdrop, e)) break;
+			} else H0 = v[0] - qe - qe, last_H0_t = 0;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez->score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+	free(mem); free(H);
+	{ /* :343-355 */
+		int rev_cigar = !!(flag & WMO_EZ_REV_CIGAR);
+		if (!ez->zdropped && !(flag & WMO_EZ_EXTZ_ONLY)) {
+			wmo_backtrack(rev_cigar, p, off, off_end, n_col_ * 16, tlen - 1, qlen - 1, &cig);
+		} else if (!ez->zdropped && (flag & WMO_EZ_EXTZ_ONLY) && ez->mqe + end_bonus > ez->max) {
+			ez->reach_end = 1;
+			wmo_backtrack(rev_cigar, p, off, off_end, n_col_ * 16, ez->mqe_t, qlen - 1, &cig);
+		} else if (ez->max_t >= 0 && ez->max_q >= 0) {
+			wmo_backtrack(rev_cigar, p, off, off_end, n_col_ * 16, ez->max_t, ez->max_q, &cig);
+		}
+	}
+	free(p); free(off);
+	ez->n_cigar = cig.n;
+	if (cigar_out) memcpy(cigar_out, cig.a, (size_t)(cig.n < max_cigar ? cig.n : max_cigar) * 4);
+	free(cig.a);
+	return ez->n_cigar;
+}
+
+/* ------------------------------------------------------------------------------------
  * ksw_ll_i16: src/ksw2_ll_sse.c:32-147 (score, qe, te of a striped int16 local SW).
  * Restated as the row-by-row Gotoh recurrence the striped kernel evaluates, over the
  * padded query (slen*8 columns, padding scores 0, :70-75), with the same tie rules:

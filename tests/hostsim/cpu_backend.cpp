@@ -28,6 +28,8 @@ int wmo_chain_dp(int max_dist_x, int min_dist_x, int max_dist_y, int bw, int max
 typedef struct { int max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar; } wmo_ez_t;
 int wmo_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int q, int e, int q2, int e2, int w, int zdrop,
                   int end_bonus, int flag, wmo_ez_t *ez, uint32_t *cigar_out, int max_cigar);
+int wmo_ksw_extz2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int q, int e, int w, int zdrop,
+                  int end_bonus, int flag, wmo_ez_t *ez, uint32_t *cigar_out, int max_cigar);
 int wmo_ksw_ll(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int gapo, int gape, int *qe_, int *te_);
 }
 
@@ -130,7 +132,10 @@ public:
 			fetch(J.q, wins[J.task], q); fetch(J.t, wins[J.task], t);
 			wmo_ez_t ez;
 			cigs[i].resize(J.q.len + J.t.len + 2);
-			wmo_ksw_extd2(J.q.len, q.data(), J.t.len, t.data(), sc.mat, sc.q, sc.e, sc.q2, sc.e2, J.w, J.zdrop, J.end_bonus, J.flag, &ez, cigs[i].data(), (int)cigs[i].size());
+			if (sc.q == sc.q2 && sc.e == sc.e2) // src/align.c:328-331
+				wmo_ksw_extz2(J.q.len, q.data(), J.t.len, t.data(), sc.mat, sc.q, sc.e, J.w, J.zdrop, J.end_bonus, J.flag, &ez, cigs[i].data(), (int)cigs[i].size());
+			else
+				wmo_ksw_extd2(J.q.len, q.data(), J.t.len, t.data(), sc.mat, sc.q, sc.e, sc.q2, sc.e2, J.w, J.zdrop, J.end_bonus, J.flag, &ez, cigs[i].data(), (int)cigs[i].size());
 			DpRes &r = res[i];
 			r.max = ez.max, r.zdropped = ez.zdropped, r.max_q = ez.max_q, r.max_t = ez.max_t, r.mqe = ez.mqe, r.mqe_t = ez.mqe_t, r.mte = ez.mte, r.mte_q = ez.mte_q;
 			r.score = ez.score, r.reach_end = ez.reach_end, r.n_cigar = ez.n_cigar, r.cigar = cigs[i].data();
@@ -149,6 +154,9 @@ public:
 	}
 };
 
+static int g_gap_override[4] = {0, 0, 0, 0}; // -O / -E of the next run (0 = keep the preset's)
+extern "C" void wmt_set_gap(int q, int e, int q2, int e2) { g_gap_override[0] = q, g_gap_override[1] = e, g_gap_override[2] = q2, g_gap_override[3] = e2; }
+
 static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *preset, const char *reads_fn, const char *out_fn, int n_threads, int sam, int64_t extra_flags = 0)
 {
 	wm_idxopt_t io; wm_mapopt_t mo;
@@ -157,6 +165,8 @@ static int map_file_impl(const char *ref_fn, const char *kmer_fn, const char *pr
 	if (sam) mo.flag |= WM_F_OUT_SAM | WM_F_CIGAR; // -a (src/main.c)
 	else mo.flag |= WM_F_OUT_CG | WM_F_CIGAR;      // -c
 	mo.flag |= extra_flags;                        // --cs / --cs=long / --MD (src/main.c:227,249-266)
+	if (g_gap_override[0] > 0) mo.q = g_gap_override[0], mo.e = g_gap_override[1], mo.q2 = g_gap_override[2], mo.e2 = g_gap_override[3]; // -O / -E (src/main.c)
+	g_gap_override[0] = 0; // one shot
 	if (check_opt(&io, &mo) < 0) return -2;
 	wm_host_idx H; H.k = io.k, H.w = io.w;
 	std::vector<uint64_t> kmers;

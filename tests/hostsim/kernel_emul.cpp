@@ -9,6 +9,7 @@
 #include "../../winnowmap_b200/csrc/wm_common.cuh"
 #include "../../winnowmap_b200/csrc/ksw_extd2_common.cuh"
 #include "../../winnowmap_b200/csrc/ksw_extd2_v2.cuh"
+#include "../../winnowmap_b200/csrc/ksw_extz2.cuh"
 #include "../../winnowmap_b200/csrc/chain_dev.cuh"
 #include "../../winnowmap_b200/csrc/rsort.cuh"
 
@@ -107,6 +108,34 @@ extern "C" int wmt_emul_extd2(const uint8_t *query, int qlen, const uint8_t *tar
 		Z.q = q, Z.e = e; memcpy(Z.mat, mat, 25);
 		wm_extd2_backtrack_job(J, &ez, bt.data(), cigar, seq.data(), Z, zd_out);
 	}
+	memcpy(ez_out, &ez, sizeof(ez));
+	return 0;
+}
+
+// one ksw_extz2 call (single gap pair) through the product's sweep (csrc/ksw_extz2.cuh) + the shared traceback
+extern "C" int wmt_emul_extz2(const uint8_t *query, int qlen, const uint8_t *target, int tlen, const int8_t *mat, int q, int e,
+                              int w, int zdrop, int end_bonus, int flag, int32_t *ez_out, uint32_t *cigar, int cig_cap, int32_t *zd_out)
+{
+	wm_dp_params P; params_init(&P, mat, q, e, q, e);
+	P.single = 1;
+	std::vector<uint8_t> seq((size_t)qlen + tlen + 64, 0);
+	if (qlen > 0) memcpy(seq.data(), query, qlen);
+	if (tlen > 0) memcpy(seq.data() + qlen, target, tlen);
+	wm_dp_job J; memset(&J, 0, sizeof(J));
+	J.q_off = 0, J.t_off = qlen, J.p_off = 0, J.cig_off = 0;
+	J.qlen = qlen, J.tlen = tlen, J.w = w, J.zdrop = zdrop, J.end_bonus = end_bonus, J.flag = flag, J.cig_cap = cig_cap, J.pad = -1;
+	wm_extz_dev ez; memset(&ez, 0, sizeof(ez));
+	const int tlen16 = (tlen + 15) / 16 * 16;
+	int ww = w < 0 ? (tlen > qlen ? tlen : qlen) : w;
+	const size_t bt_bytes = (qlen > 0 && tlen > 0) ? ((size_t)(qlen + tlen - 1) * (size_t)(wm_ncol16(qlen, tlen, ww) / 16) + 1) * 16 : 16;
+	std::vector<uint8_t> bt(bt_bytes + 64, 0);
+	std::vector<uint64_t> state((size_t)tlen16 * 9 / 8 + 16, 0);
+	struct Args { const wm_dp_job *J; const uint8_t *seq; uint8_t *bt; wm_extz_dev *ez; const wm_dp_params *P; int8_t *state; }
+		A = { &J, seq.data(), bt.data(), &ez, &P, (int8_t*)state.data() };
+	wm_emul::run_warp([](int l, void *p) { Args &a = *(Args*)p; wm_extz2_fill_job(*a.J, a.seq, a.bt, a.ez, *a.P, a.state, l, 0); }, &A);
+	wm_zd_params Z; memset(&Z, 0, sizeof(Z));
+	Z.q = q, Z.e = e; memcpy(Z.mat, mat, 25);
+	wm_extd2_backtrack_job(J, &ez, bt.data(), cigar, seq.data(), Z, zd_out);
 	memcpy(ez_out, &ez, sizeof(ez));
 	return 0;
 }

@@ -59,6 +59,7 @@ def oracle():
         L.wmo_collect_seed_hits.argtypes = [C.c_void_p, C.c_int, _u64p, C.c_long, C.c_int, _u64p, C.c_long, _i32p, _u64p, _i32p]
         L.wmo_chain_dp.argtypes = [C.c_int] * 8 + [C.c_float, C.c_long, _u64p, _u64p, _u64p, C.POINTER(C.c_long)]
         L.wmo_ksw_extd2.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p] + [C.c_int] * 8 + [_i32p, _u32p, C.c_int]
+        L.wmo_ksw_extz2.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p] + [C.c_int] * 6 + [_i32p, _u32p, C.c_int]
         L.wmo_ksw_ll.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p, C.c_int, C.c_int, _i32p, _i32p]
         L.wmo_counters_get.argtypes = [_u64p]
         _oracle = L
@@ -111,6 +112,25 @@ def _extd2(fn, q, t, mat, go, ge, go2, ge2, w, zdrop, end_bonus, flag):
     n = fn(len(q), _ptr(q, _u8p), len(t), _ptr(t, _u8p), _ptr(mat, _i8p), go, ge, go2, ge2, w, zdrop, end_bonus, flag,
            _ptr(ez, _i32p), _ptr(cig, _u32p), cap)
     return ez, cig[:n].copy()
+
+
+def _extz2(fn, q, t, mat, go, ge, w, zdrop, end_bonus, flag):
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    ez = np.zeros(11, dtype=np.int32)
+    cap = len(q) + len(t) + 8
+    cig = np.zeros(cap, dtype=np.uint32)
+    n = fn(len(q), _ptr(q, _u8p), len(t), _ptr(t, _u8p), _ptr(mat, _i8p), go, ge, w, zdrop, end_bonus, flag,
+           _ptr(ez, _i32p), _ptr(cig, _u32p), cap)
+    return ez, cig[:n].copy()
+
+
+def oracle_extz2(*a):
+    return _extz2(oracle().wmo_ksw_extz2, *a)
+
+
+def ref_extz2(*a):
+    return _extz2(ref().ref_ksw_extz2, *a)
 
 
 def oracle_extd2(*a):

@@ -33,6 +33,8 @@ def test_paf_matches_reference(name, tmp_path):
     assert make_golden.md5(ref) == m["ref_md5"] and make_golden.md5(reads) == m["reads_md5"], "synthetic input generator drifted"
     exp = gzip.open(os.path.join(ROOT, "tests", "golden", name + ".paf.gz")).read()
     mp = Mapper(ref, wfile, preset=m["params"]["preset"], cigar=True)
+    if "gap" in m["params"]:  # -O4 -E2: a single gap pair, every DP call is the single-affine kernel (ksw_extz2)
+        mp.mo.q, mp.mo.e, mp.mo.q2, mp.mo.e2 = m["params"]["gap"]
     out = str(tmp_path / "out.paf")
     mp.map_file(reads, out)
     got = open(out, "rb").read()

@@ -61,3 +61,30 @@ def test_cigar_capacity_overflow_is_reported():
     e0, c0 = ol.oracle_extd2(q, t, mat, 4, 2, 24, 1, 751, 400, -1, 0)
     ez, cigs = kernels.ksw_extd2_batch([q], [t], mat, 4, 2, 24, 1, 751, 400, -1, 0, cigar_cap=4)
     assert ez[0, 10] == len(c0) and len(c0) > 4
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_extz2_single_gap_pair_batch(seed):
+    """Equal gap pairs route to the single-affine kernel (ksw_extz2_sse, src/ksw2_extz2_sse.c:23; dispatch src/align.c:328-331):
+    the extd2 matrix of sizes / bands / flags, several scoring sets incl. ones that strain the unsigned-offset encoding,
+    a 9 kb end extension (state rows in the global slice) and empty inputs, against the oracle's extz2."""
+    from winnowmap_b200 import kernels
+    rng = np.random.default_rng(950 + seed)
+    for a, b, go, ge in [(2, 4, 4, 2), (1, 4, 6, 2), (1, 9, 16, 2), (5, 4, 40, 20)]:
+        mat = ol.simple_mat(a, b, 1)
+        Q, T, W, Z, E, F = [], [], [], [], [], []
+        for it in range(150):
+            tlen = int(rng.choice([1, 5, 16, 17, 33, 100, 250, 300, 700, 1100, 2500]))
+            q, t = rand_pair(rng, tlen, err=float(rng.choice([0.02, 0.1, 0.3])), drift=int(rng.choice([0, 0, 30, 120, 400])), n_runs=int(rng.integers(0, 3)))
+            Q.append(q); T.append(t)
+            W.append(int(rng.choice([5, 20, 50, 100, 751, 3001, -1]))); Z.append(int(rng.choice([400, 200, 50, -1])))
+            E.append(int(rng.choice([-1, 0, 10]))); F.append(FLAGS[int(rng.integers(0, len(FLAGS)))] | (0x10 if it % 7 == 0 else 0))
+        if seed == 0 and (a, b) == (2, 4):
+            q, t = rand_pair(rng, 9000, err=0.08, drift=300)
+            Q += [q, np.zeros(0, np.uint8), q[:300]]; T += [t, t[:10], np.zeros(0, np.uint8)]
+            W += [3001, 751, 751]; Z += [400, 400, 400]; E += [-1, -1, -1]; F += [0x40, 0, 0]
+        ez, cigs = kernels.ksw_extd2_batch(Q, T, mat, go, ge, go, ge, np.array(W), np.array(Z), np.array(E), np.array(F))
+        for i in range(len(Q)):
+            e0, c0 = ol.oracle_extz2(Q[i], T[i], mat, go, ge, W[i], Z[i], E[i], F[i])
+            assert np.array_equal(e0, ez[i]), (i, (a, b, go, ge), len(Q[i]), len(T[i]), W[i], hex(F[i]), e0, ez[i])
+            assert np.array_equal(c0, cigs[i]), (i, (a, b, go, ge), len(Q[i]), len(T[i]), W[i], hex(F[i]))

@@ -27,12 +27,13 @@ def hostsim():
     return L
 
 
-@pytest.mark.parametrize("name", ["ont_small", "hifi_small", "ont_sv", "ont_tandem"])
+@pytest.mark.parametrize("name", ["ont_small", "hifi_small", "ont_sv", "ont_tandem", "asm20_small", "ont_single_gap"])
 def test_host_pipeline_matches_reference_golden(hostsim, name, tmp_path):
     m = MANIFEST[name]
     ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
     assert make_golden.md5(ref) == m["ref_md5"] and make_golden.md5(reads) == m["reads_md5"]
     out = str(tmp_path / "o.paf")
+    hostsim.wmt_set_gap(*m["params"].get("gap", (0, 0, 0, 0)))  # -O / -E: one gap pair routes every DP call to ksw_extz2
     rc = hostsim.wmt_map_file(ref.encode(), wfile.encode() if wfile else None, m["params"]["preset"].encode(), reads.encode(), out.encode(), 8)
     assert rc == 0
     exp = gzip.open(os.path.join(ROOT, "tests", "golden", name + ".paf.gz")).read()

@@ -56,6 +56,28 @@ def test_fill_and_traceback_match_oracle(emul, seed):
         _check(emul, q, t, mat, (4, 2, 24, 1), w, zdrop, eb, flag, global_state=bool(it & 1))
 
 
+def test_single_affine_sweep_matches_oracle(emul):
+    """csrc/ksw_extz2.cuh (ksw_extz2_sse: unsigned-offset state, mixed signed / unsigned maxima) on the software warp against the
+    oracle's restatement, which tests/test_oracle_vs_ref.py pins to the reference's function."""
+    emul.wmt_emul_extz2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(4300)
+    for it in range(48):
+        tlen = int(rng.choice([1, 5, 16, 17, 33, 64, 100, 130, 250, 300, 480, 900]))
+        q, t = rand_pair(rng, tlen, err=float(rng.choice([0.02, 0.1, 0.3])), drift=int(rng.choice([0, 0, 30, 120])), n_runs=int(rng.integers(0, 3)))
+        w = int(rng.choice([5, 20, 50, 100, 751, -1])); zdrop = int(rng.choice([400, 200, 50, -1])); eb = int(rng.choice([-1, 0, 10]))
+        flag = FLAGS[int(rng.integers(0, len(FLAGS)))] | (0x10 if it % 5 == 0 else 0)
+        a, b, go, ge = [(2, 4, 4, 2), (1, 4, 6, 2), (1, 9, 16, 2), (5, 4, 40, 20), (3, 6, 50, 13)][it % 5]
+        mat = np.ascontiguousarray(ol.simple_mat(a, b, 1), dtype=np.int8)
+        qq = np.ascontiguousarray(q, dtype=np.uint8); tt = np.ascontiguousarray(t, dtype=np.uint8)
+        cap = len(qq) + len(tt) + 2
+        ez = np.zeros(12, np.int32); cig = np.zeros(cap, np.uint32); zd = np.zeros(5, np.int32)
+        assert emul.wmt_emul_extz2(qq.ctypes.data, len(qq), tt.ctypes.data, len(tt), mat.ctypes.data, go, ge, w, zdrop, eb, flag,
+                                   ez.ctypes.data, cig.ctypes.data, cap, zd.ctypes.data) == 0
+        e0, c0 = ol.oracle_extz2(qq, tt, mat, go, ge, w, zdrop, eb, flag)
+        assert np.array_equal(e0[:11], ez[:11]), (it, len(qq), len(tt), w, hex(flag), (a, b, go, ge), e0, ez)
+        assert np.array_equal(c0, cig[:max(0, ez[10])]), (it, len(qq), len(tt), w, hex(flag))
+
+
 def test_other_scorings_and_a_long_target(emul):
     rng = np.random.default_rng(4200)
     for a, b, q_, e_, q2, e2 in [(1, 4, 6, 2, 26, 1), (2, 4, 24, 1, 4, 2)]:  # asm-like scoring; gap pair given in swapped order

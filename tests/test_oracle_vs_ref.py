@@ -65,6 +65,30 @@ def test_extd2_matches_reference(seed):
     assert n == 60
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_extz2_matches_reference(seed):
+    """The single-affine restatement (oracle wmo_ksw_extz2) against the reference's ksw_extz2_sse (src/ksw2_extz2_sse.c:23), over the
+    extd2 matrix plus scoring sets that push the unsigned-offset encoding (large gap costs, asm-like matrices)."""
+    rng = np.random.default_rng(300 + seed)
+    n = 0
+    for it in range(70):
+        tlen = int(rng.choice([1, 5, 17, 33, 100, 250, 300, 700, 1500]))
+        w = int(rng.choice([5, 20, 50, 100, 751, 3001, -1]))
+        drift = int(rng.choice([0, 0, 30, 120, 400]))
+        q, t = rand_pair(rng, tlen, err=float(rng.choice([0.02, 0.1, 0.3])), drift=drift, n_runs=int(rng.integers(0, 3)))
+        flag = FLAGS[int(rng.integers(0, len(FLAGS)))] | (0x10 if rng.random() < 0.3 else 0)
+        zdrop = int(rng.choice([400, 200, 50, -1]))
+        end_bonus = int(rng.choice([-1, 0, 10]))
+        a, b, go, ge = [(2, 4, 4, 2), (2, 4, 4, 2), (1, 4, 6, 2), (1, 9, 16, 2), (2, 8, 12, 2), (5, 4, 40, 20), (3, 6, 50, 13)][int(rng.integers(0, 7))]
+        mat = ol.simple_mat(a, b, 1)
+        e1, c1 = ol.ref_extz2(q, t, mat, go, ge, w, zdrop, end_bonus, flag)
+        e2, c2 = ol.oracle_extz2(q, t, mat, go, ge, w, zdrop, end_bonus, flag)
+        assert np.array_equal(e1, e2), (it, tlen, len(q), w, flag, zdrop, (a, b, go, ge), e1, e2)
+        assert np.array_equal(c1, c2), (it, tlen, len(q), w, flag)
+        n += 1
+    assert n == 70
+
+
 def test_extd2_swapped_gap_and_asm_scoring():
     rng = np.random.default_rng(7)
     for a, b, q, e, q2, e2 in [(1, 4, 6, 2, 26, 1), (1, 9, 16, 2, 41, 1), (2, 4, 24, 1, 4, 2)]:

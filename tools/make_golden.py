@@ -30,6 +30,10 @@ CASES = {
     # a 300-bp family present > 5000 times: minimizers above mid_occ are skipped and rl:i: becomes non-zero
     "ont_highocc": dict(ref_len=2600000, contigs=1, tandem=False, ref_seed=1022, n_reads=40, n50=9000, err=0.05, read_seed=2022, min_len=1500,
                         preset="map-ont", use_W=True, k=15, highocc=True),
+    # -O4 -E2: one gap pair (q == q2, e == e2), every DP call is ksw_extz2_sse (src/align.c:328-331)
+    # (the structural-variant reads: long gaps are where one gap pair and two differ)
+    "ont_single_gap": dict(ref_len=400000, contigs=2, tandem=False, ref_seed=1021, n_reads=60, n50=14000, err=0.04, read_seed=2021, min_len=2000,
+                           preset="map-ont", use_W=False, k=15, sv=True, extra=["-O4", "-E2"], gap=(4, 2, 4, 2)),
     "asm20_small": dict(ref_len=300000, contigs=1, tandem=True, ref_seed=1014, n_reads=12, n50=40000, err=0.02, read_seed=2014, min_len=5000,
                         preset="asm20", use_W=True, k=19, w_distinct=0.99),
 }
@@ -198,7 +202,7 @@ def main():
     manifest = {}
     for name, c in CASES.items():
         ref, reads, wfile = make_inputs(name, tmp)
-        cmd = [refbin, "-t", "4", "-c", "-x", c["preset"]]
+        cmd = [refbin, "-t", "4", "-c", "-x", c["preset"]] + c.get("extra", [])
         if wfile:
             cmd += ["-W", wfile]
         cmd += [ref, reads]

@@ -46,7 +46,7 @@ extern "C" int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qof
 		J.p_off = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.qlen, J.tlen, J.w);
 		J.cig_off = cigar_off[i]; J.cig_cap = (int32_t)(cigar_off[i + 1] - cigar_off[i]); J.pad = -1;
 	}
-	const wm_extd2_plan_t plan = wm_extd2_plan(jobs.data(), n);
+	const wm_extd2_plan_t plan = wm_extd2_plan(jobs.data(), n, q == q2 && e == e2);
 	uint8_t *d_seq = wm_dev_alloc<uint8_t>(qtot + ttot + 16);
 	uint8_t *d_bt = wm_dev_alloc<uint8_t>(p_off + 16);
 	wm_dp_job *d_jobs = wm_dev_alloc<wm_dp_job>(n);

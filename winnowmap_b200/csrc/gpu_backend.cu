@@ -505,7 +505,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			D.p_off = h_poff[i];
 			D.cig_off = h_coff[i]; D.cig_cap = J.q.len + J.t.len + 2; D.pad = -1;
 		}
-		const wm_extd2_plan_t plan = wm_extd2_plan(dj.data(), m);
+		const wm_extd2_plan_t plan = wm_extd2_plan(dj.data(), m, P.single != 0);
 		g_timers.add("dp.host_prep", Timers::now() - tp0);
 		if (getenv("WM_DP_STATS")) {
 			int n_big = 0, mq = 0, mt = 0, mw = 0; double cells = 0, big_cells = 0;

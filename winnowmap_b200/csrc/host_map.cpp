@@ -107,10 +107,6 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		fprintf(stderr, "[ERROR] winnowmap-b200: splice/sr/heap-sort/-X/--for-only/--rev-only modes are outside the accelerated path\n");
 		exit(1);
 	}
-	if (opt->q == opt->q2 && opt->e == opt->e2) {
-		fprintf(stderr, "[ERROR] winnowmap-b200: single-affine scoring (ksw_extz2) is not built yet\n");
-		exit(1);
-	}
 	be->begin_batch(reads);
 	// 0..4 codes of every read, both strands, once per batch: the alignment tasks of all windows of a read slice them
 	std::vector<int64_t> code_off(n_reads + 1, 0);

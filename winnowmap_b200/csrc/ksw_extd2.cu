@@ -198,6 +198,7 @@ __device__ void wm_extd2_fill_job(const wm_dp_job &J, const uint8_t *__restrict_
 }
 
 #include "ksw_extd2_v2.cuh"
+#include "ksw_extz2.cuh"
 
 __global__ void __launch_bounds__(WM_FILL_WARPS * 32, 4)
 wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
@@ -215,7 +216,8 @@ wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8
 	const wm_dp_job J = jobs[j];
 	int8_t *my_g = J.pad >= 0 ? gscratch + (size_t)J.pad * gscratch_stride : (int8_t*)0;
 	const int tlen16 = (J.tlen + 15) / 16 * 16;
-	if (use_v2 && J.qlen > 0 && J.tlen > 0 && !P.early_out) {
+	if (P.single) wm_extz2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane, cell_ctr);
+	else if (use_v2 && J.qlen > 0 && J.tlen > 0 && !P.early_out) {
 		if (J.pad < 0) wm_extd2_fill_job_v2<true>(J, seq, bt, ez + j, P, (uint8_t*)my_smem, 0, 0, lane, cell_ctr ? cell_ctr + 1 : 0);
 		else wm_extd2_fill_job_v2<false>(J, seq, bt, ez + j, P, (uint8_t*)my_g, g_tcap, g_qcap, lane, cell_ctr ? cell_ctr + 1 : 0);
 	} else
@@ -236,6 +238,7 @@ __global__ void wm_extd2_backtrack_kernel(const wm_dp_job *__restrict__ jobs, in
 
 void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2)
 { // src/ksw2_extd2_sse.c:61-97
+	P->single = q == q2 && e == e2; // src/align.c:328-331: ksw_extz2_sse(q, e) instead
 	P->qe_h = q + e;
 	if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
 	P->q = q, P->e = e, P->q2 = q2, P->e2 = e2;
@@ -266,10 +269,10 @@ static int wm_use_v2(void)
 	return use_v2;
 }
 
-wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n)
+wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n, bool single)
 {
 	wm_extd2_plan_t pl; pl.n_slots = 0, pl.max_tlen = 0, pl.max_qlen = 0;
-	const int use_v2 = wm_use_v2();
+	const int use_v2 = single ? 0 : wm_use_v2();
 	for (int i = 0; i < n; ++i) {
 		wm_dp_job &J = h_jobs[i];
 		const int tlen16 = (J.tlen + 15) / 16 * 16;
@@ -294,7 +297,7 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const
 {
 	if (n_jobs <= 0) return;
 	const size_t smem = (size_t)WM_FILL_WARPS * WM_FILL_SLICE;
-	const int use_v2 = wm_use_v2();
+	const int use_v2 = P.single ? 0 : wm_use_v2();
 	const int grid = (n_jobs + WM_FILL_WARPS - 1) / WM_FILL_WARPS;
 	// global state slices of the jobs that do not fit the shared-memory slice (wm_extd2_plan gave them slots)
 	const int tcap = (plan.max_tlen + 15) / 16 * 16;

@@ -61,6 +61,7 @@ struct wm_dp_params {
 	int32_t sc_mch, sc_mis, sc_N;
 	int32_t long_thres, long_diff;
 	int32_t early_out;         // -min_sc > 2*(q+e) (:92)
+	int32_t single;            // q == q2 && e == e2: the call is ksw_extz2_sse (src/align.c:328-331), csrc/ksw_extz2.cuh
 };
 
 struct wm_extz_dev {
@@ -122,8 +123,9 @@ struct wm_extd2_ws {
 struct wm_extd2_plan_t { int n_slots, max_tlen, max_qlen; };
 void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2);
 size_t wm_extd2_bt_bytes(int qlen, int tlen, int w);
-// sets h_jobs[i].pad (global-scratch slot or -1) for the n jobs of one launch, in launch order
-wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n);
+// sets h_jobs[i].pad (global-scratch slot or -1) for the n jobs of one launch, in launch order; single: the jobs run the
+// single-affine sweep (wm_dp_params::single), whose state slice is 9 bytes per target cell
+wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n, bool single = false);
 // Jobs flagged WM_DP_SCAN_ZDROP also get the score walk of mm_test_zdrop (src/align.c:32-70) over their CIGAR: five
 // int32 per job in d_zd (max_zdrop, t0, t1, q0, q1; max_zdrop = -1: no result).  zp / d_zd may be null.
 #define WM_DP_SCAN_ZDROP 0x10000
