@@ -164,25 +164,25 @@ static void run_tile(const wm128_dev *a, int n, const wm_chain_params *P, int32_
 	const float avg_qspan = (float)sum / (float)(long long)n;
 	const double avg_d = (double)avg_qspan, scale_d = (double)P->gap_scale;
 	__syncwarp();
+	wm128_dev prev; prev.x = prev.y = 0;
 	for (int i0 = 0; i0 < n; i0 += 32) {
 		const int il = i0 + lane;
 		wm128_dev al; al.x = al.y = 0; int stl = 0;
 		if (il < n) { al = a[il]; stl = v[il]; }
 		for (int k = 0; k < 32 && i0 + k < n; ++k) {
-			const int i = i0 + k, st = __shfl_sync(0xffffffffu, stl, k), ring_lo = i0 + 32 - WM_CT_RING;
+			const int i = i0 + k, st = __shfl_sync(0xffffffffu, stl, k), ring_lo = i0 + 64 - WM_CT_RING;
 			int max_f = 0, max_j = -1;
-			if (!wm_chain_tile_scan(a, *P, f, p, t, S, S->marks[k], al, i0, k, st, ring_lo, false, avg_d, scale_d, lane, &max_f, &max_j))
-				wm_chain_tile_scan(a, *P, f, p, t, S, S->marks[k], al, i0, k, st, ring_lo, true, avg_d, scale_d, lane, &max_f, &max_j);
+			if (!wm_chain_tile_scan(a, *P, f, p, t, S, S->marks[k], al, prev, i0, k, st, ring_lo, false, avg_d, scale_d, lane, &max_f, &max_j))
+				wm_chain_tile_scan(a, *P, f, p, t, S, S->marks[k], al, prev, i0, k, st, ring_lo, true, avg_d, scale_d, lane, &max_f, &max_j);
 			int vj = INT_MIN;
 			if (max_j >= 0) vj = max_j >= ring_lo ? S->v[max_j & MASK] : v[max_j];
 			const int vi = (max_j >= 0 && vj > max_f) ? vj : max_f;
+			const uint64_t xi = __shfl_sync(0xffffffffu, al.x, k), yi = __shfl_sync(0xffffffffu, al.y, k);
 			__syncwarp();
-			if (lane == 0) { const int s = i & MASK; S->x[s] = __shfl_sync(0xffffffffu, al.x, k), S->q[s] = (int32_t)__shfl_sync(0xffffffffu, al.y, k), S->f[s] = max_f, S->p[s] = max_j, S->v[s] = vi; }
-			else { __shfl_sync(0xffffffffu, al.x, k); __shfl_sync(0xffffffffu, al.y, k); }
+			if (lane == 0) { const int s = i & MASK; S->x[s] = xi, S->q[s] = (int32_t)yi, S->f[s] = max_f, S->p[s] = max_j, S->v[s] = vi; f[i] = max_f; p[i] = max_j; v[i] = vi; }
 			__syncwarp();
 		}
-		if (il < n) { const int s = il & MASK; f[il] = S->f[s]; p[il] = S->p[s]; v[il] = S->v[s]; }
-		__syncwarp();
+		prev = al;
 	}
 }
 static void run_fill(int mode, const wm128_dev *a, int n, const wm_chain_params *P, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int32_t *D, int lane)

@@ -47,6 +47,12 @@ extern "C" int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qof
 		J.cig_off = cigar_off[i]; J.cig_cap = (int32_t)(cigar_off[i + 1] - cigar_off[i]); J.pad = -1;
 	}
 	const wm_extd2_plan_t plan = wm_extd2_plan(jobs.data(), n, q == q2 && e == e2);
+	std::vector<int32_t> coop; // the big jobs go to the CTA-cooperative sweep, as in the mapping pipeline (gpu_backend.cu)
+	if (!(q == q2 && e == e2) && !(getenv("WM_DP_COOP") && *getenv("WM_DP_COOP") == '0') && !(getenv("WM_DP_V1") && *getenv("WM_DP_V1") == '1'))
+		for (int i = 0; i < n; ++i)
+			if (jobs[i].pad >= 0 && wm_dp_is_coop(jobs[i].qlen, jobs[i].tlen, jobs[i].w)) { jobs[i].flag |= WM_DP_COOP; coop.push_back(i); }
+	int32_t *d_coop = wm_dev_alloc<int32_t>(coop.size() + 1);
+	if (!coop.empty()) WM_CUDA_CHECK(cudaMemcpy(d_coop, coop.data(), sizeof(int32_t) * coop.size(), cudaMemcpyHostToDevice));
 	uint8_t *d_seq = wm_dev_alloc<uint8_t>(qtot + ttot + 16);
 	uint8_t *d_bt = wm_dev_alloc<uint8_t>(p_off + 16);
 	wm_dp_job *d_jobs = wm_dev_alloc<wm_dp_job>(n);
@@ -57,10 +63,10 @@ extern "C" int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qof
 	WM_CUDA_CHECK(cudaMemcpy(d_jobs, jobs.data(), sizeof(wm_dp_job) * n, cudaMemcpyHostToDevice));
 	wm_dp_params P; wm_dp_params_init(&P, mat, q, e, q2, e2);
 	wm_extd2_ws ws;
-	wm_extd2_launch(&ws, d_jobs, n, plan, d_seq, d_bt, d_ez, d_cig, P, 0);
+	wm_extd2_launch(&ws, d_jobs, n, plan, d_seq, d_bt, d_ez, d_cig, P, 0, 0, 0, d_coop, (int)coop.size());
 	WM_CUDA_CHECK(cudaDeviceSynchronize());
 	WM_CUDA_CHECK(cudaMemcpy(ez, d_ez, sizeof(wm_extz_dev) * n, cudaMemcpyDeviceToHost));
 	if (cigar_off[n] > 0) WM_CUDA_CHECK(cudaMemcpy(cigar, d_cig, sizeof(uint32_t) * cigar_off[n], cudaMemcpyDeviceToHost));
-	cudaFree(d_seq); cudaFree(d_bt); cudaFree(d_jobs); cudaFree(d_ez); cudaFree(d_cig);
+	cudaFree(d_seq); cudaFree(d_bt); cudaFree(d_jobs); cudaFree(d_ez); cudaFree(d_cig); cudaFree(d_coop);
 	return 0;
 }

@@ -106,7 +106,7 @@ wm_chain_fill_ring_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__
 	}
 }
 
-// Giant tasks: one CTA per task, a tile of 32 consecutive anchors per round, one warp per anchor (chain_dev.cuh).
+// Giant tasks: one CTA per task, warp k owns anchor k of every 32-anchor tile, dataflow between the warps (chain_dev.cuh).
 __global__ void __launch_bounds__(WM_CT_WARPS * 32, 1)
 wm_chain_fill_tile_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ order, int first, int last,
                           wm_chain_params2 PP, const uint8_t *__restrict__ set_id, int32_t *__restrict__ f_all, int32_t *__restrict__ p_all, int32_t *__restrict__ t_all,
@@ -137,54 +137,59 @@ wm_chain_fill_tile_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__
 		for (int i = tid; i < n; i += WM_CT_WARPS * 32) { sum += a[i].y >> 32 & 0xff; t[i] = 0; }
 		for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
 		if (lane == 0) s_sum[k] = sum;
-		if (tid == 0) S->done = 0, S->lock = 0;
+		if (tid < 8) S->done[tid] = 0;
+		if (tid == 0) S->lock = 0;
 		__syncthreads();
 		sum = 0;
 		for (int w = 0; w < WM_CT_WARPS; ++w) sum += s_sum[w];
 		const float avg_qspan = __fdiv_rn(__ull2float_rn(sum), __ll2float_rn((long long)n));
 		const double avg_d = (double)avg_qspan, scale_d = (double)P.gap_scale;
 		uint32_t *mk = S->marks[k];
-		for (int i0 = 0; i0 < n; i0 += 32) {
+		volatile unsigned *done = S->done;
+		wm128_dev prev; prev.x = prev.y = 0;
+		for (int T = 0, i0 = 0; i0 < n; ++T, i0 += 32) {
 			const int il = i0 + lane;
-			wm128_dev al; al.x = al.y = 0; int stl = 0;
-			if (il < n) { al = a[il]; stl = v[il]; }
+			wm128_dev cur; cur.x = cur.y = 0; int stl = 0;
+			if (il < n) { cur = a[il]; stl = v[il]; }
 			const int i = i0 + k;
 			if (i < n) {
+				// tile T - 2 and everything before it must be complete; its done-slot + 6 (tile T - 4's) is free for tile T + 4
+				if (T >= 2) { while (done[(T - 2) & 7] != FULL) { } }
+				if (lane == 0) done[(T + 4) & 7] = 0;
 				const int st = __shfl_sync(FULL, stl, k);
-				const int ring_lo = i0 + 32 - WM_CT_RING; // slots below are being overwritten by this tile's anchors
-				const uint64_t ri = __shfl_sync(FULL, al.x, k); const int32_t qi = (int32_t)__shfl_sync(FULL, al.y, k);
-				// the anchors of the tile this one depends on: its candidate predecessors (a geometric property)
-				const unsigned C = __ballot_sync(FULL, lane < k && il >= st && wm_chain_is_cand(al, ri, qi, P));
-				if (C) {
-					volatile unsigned *done = &S->done;
-					while ((*done & C) != C) { }
-					__threadfence_block();
-				}
+				const int ring_lo = i0 + 64 - WM_CT_RING; // older slots are being overwritten by the anchors of the two active tiles
+				const uint64_t ri = __shfl_sync(FULL, cur.x, k); const int32_t qi = (int32_t)__shfl_sync(FULL, cur.y, k);
+				// the anchors of this tile and of the one before that this one depends on: its candidate predecessors (a geometric property)
+				const unsigned Cc = __ballot_sync(FULL, lane < k && il >= st && wm_chain_is_cand(cur, ri, qi, P));
+				const unsigned Cp = T > 0 ? __ballot_sync(FULL, il - 32 >= st && wm_chain_is_cand(prev, ri, qi, P)) : 0u;
+				if (Cp) { while ((done[(T - 1) & 7] & Cp) != Cp) { } }
+				if (Cc) { while ((done[T & 7] & Cc) != Cc) { } }
+				__threadfence_block();
 				int max_f, max_j;
-				if (!wm_chain_tile_scan(a, P, f, p, t, S, mk, al, i0, k, st, ring_lo, false, avg_d, scale_d, lane, &max_f, &max_j)) {
+				if (!wm_chain_tile_scan(a, P, f, p, t, S, mk, cur, prev, i0, k, st, ring_lo, false, avg_d, scale_d, lane, &max_f, &max_j)) {
 					if (lane == 0) { while (atomicCAS(&S->lock, 0, 1) != 0) { } }
 					__syncwarp();
 					__threadfence_block();
-					wm_chain_tile_scan(a, P, f, p, t, S, mk, al, i0, k, st, ring_lo, true, avg_d, scale_d, lane, &max_f, &max_j);
+					wm_chain_tile_scan(a, P, f, p, t, S, mk, cur, prev, i0, k, st, ring_lo, true, avg_d, scale_d, lane, &max_f, &max_j);
 					__syncwarp();
 					__threadfence_block();
 					if (lane == 0) atomicExch(&S->lock, 0);
 				}
 				int vj = INT_MIN;
-				if (max_j >= 0) vj = max_j >= ring_lo ? S->v[max_j & MASK] : v[max_j];
+				if (max_j >= 0) vj = max_j >= ring_lo ? S->v[max_j & MASK] : __ldcg(v + max_j);
 				const int vi = (max_j >= 0 && vj > max_f) ? vj : max_f; // src/chain.c:89
 				if (lane == 0) {
 					const int s = i & MASK;
 					S->x[s] = ri; S->q[s] = qi; S->f[s] = max_f; S->p[s] = max_j; S->v[s] = vi;
+					f[i] = max_f; p[i] = max_j; v[i] = vi;
 					__threadfence_block();
-					atomicOr(&S->done, 1u << k);
+					atomicOr(&S->done[T & 7], 1u << k);
 				}
+				__syncwarp();
 			}
-			__syncthreads();
-			if (k == 0 && il < n) { const int s = il & MASK; f[il] = S->f[s]; p[il] = S->p[s]; v[il] = S->v[s]; }
-			if (tid == 0) S->done = 0;
-			__syncthreads();
+			prev = cur;
 		}
+		__syncthreads();
 	}
 }
 

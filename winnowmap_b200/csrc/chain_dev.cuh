@@ -331,19 +331,27 @@ __device__ void wm_chain_fill_warp_ring(const wm128_dev *__restrict__ a, int n, 
 	}
 }
 
-// ---- fourth formulation: a tile of 32 consecutive anchors, one warp per anchor --------------------------------
+// ---- fourth formulation: tiles of 32 consecutive anchors, one warp per anchor, dataflow between the warps -------------
 // Giant tasks (a read inside a tandem array: 10^5..10^6 anchors) are serial in the formulations above: one warp walks
 // the anchors one by one.  But anchor i depends on anchor j only if j is a CANDIDATE predecessor of i (it passes the
 // three `continue`s of src/chain.c:61-73) -- a purely geometric property of a[] -- because a non-candidate touches
 // neither max_f nor n_skip nor t[].  In a tandem lattice consecutive anchors mostly lie on different diagonals and
-// are not candidates of each other.  So the CTA takes 32 consecutive anchors at a time, warp k owns anchor i0 + k,
-// finds with one ballot which anchors of the tile are candidates for it, waits until exactly those have published
-// f / p / v (a done-mask in shared memory), and then runs the same exact scan as the ring formulation: first the
-// predecessors inside the tile (coordinates from registers, scores from the ring), then the ring, which holds only
-// finished anchors.  The t[p[j]] = i marks of the reference are per-anchor state, so every warp keeps its own in a bitset
-// over the ring window.  A scan that runs past the ring (rare: the ring covers the last ~4000 anchors) is redone under
-// a CTA-wide lock with the global arrays, exactly like the single-warp ring formulation.
+// are not candidates of each other.  So the CTA runs 32 warps; warp k owns anchors k, k + 32, k + 64, ... (anchor
+// i0 + k of every 32-anchor tile).  Before it scans anchor i it finds, with two ballots over coordinates it holds in
+// registers, which anchors of its own tile and of the tile before are candidates for i, and waits until exactly those have
+// published f / p / v (done-masks in shared memory); anchors two tiles back and older are complete by construction (a
+// warp enters tile T only when tile T - 2 is complete).  Then it runs the same exact scan as the ring formulation: the
+// predecessors inside its tile and in the tile before with coordinates from registers and scores from the ring, then the
+// ring, which below that holds only finished anchors.  There is no barrier in the loop: the warps drift apart as far as the
+// dependencies allow.  The t[p[j]] = i marks of the reference are per-anchor state, so every warp keeps its own in a
+// bitset over the ring window.  A scan that runs past the ring (rare: it covers the last ~4000 anchors) is redone under a
+// CTA-wide lock with the global arrays, exactly like the single-warp ring formulation.
 #define WM_CT_WARPS 32
+#ifdef WM_HOST_EMUL
+#define WM_LDCG(p) (*(p))
+#else
+#define WM_LDCG(p) __ldcg(p)
+#endif
 #ifndef WM_CT_RING
 #define WM_CT_RING 4096 // (the CPU emulation harness of the tests builds with a small ring to force the locked deep path)
 #endif
@@ -351,70 +359,105 @@ struct wm_chain_tile_sm {
 	uint64_t x[WM_CT_RING];
 	int32_t q[WM_CT_RING], f[WM_CT_RING], p[WM_CT_RING], v[WM_CT_RING];
 	uint32_t marks[WM_CT_WARPS][WM_CT_RING / 32];
-	unsigned done; int lock;
+	unsigned done[8];  // done[T & 7]: which anchors of tile T have published
+	int lock;
 };
 
-// The scan of anchor i = i0 + k by one warp.  al / (tile registers): lane l holds a[i0 + l].  Entries j >= ring_lo are read from the
-// ring (intra-tile ones only if they are candidates, which the caller has waited for); older ones from global memory, and only
-// when deep_ok (the caller holds the lock: the global t[] marks are then this anchor's alone).  Returns false if it would have
-// had to go below the ring without deep_ok; on success *mf / *mj hold f[i] / p[i].
+// per-scan state of one anchor
+struct wm_chain_scan {
+	uint64_t ri; int32_t qi, q_span;
+	int i, max_f, max_j, n_skip;
+};
+
+// the order-dependent part of a 32-predecessor step (running maximum with strict ">", n_skip replay): lane m holds the m-th
+// predecessor in scan order (index jtop - m), its score sc if it is a candidate, and whether it carries this anchor's mark.
+// Returns true when the reference leaves its loop inside this step.
+__device__ __forceinline__ bool wm_chain_resolve(wm_chain_scan &A, bool cand, int sc, bool marked, int jtop, int max_skip, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	const unsigned G = __ballot_sync(FULL, cand && sc > A.max_f);
+	unsigned Rm = G;
+	if (G & (G - 1)) { // two or more lanes beat the running maximum: the records are the prefix maxima among them
+		const int incl = wm_warp_incl_max(cand ? sc : INT_MIN, lane);
+		int excl = __shfl_up_sync(FULL, incl, 1);
+		if (lane == 0) excl = INT_MIN;
+		excl = max(excl, A.max_f);
+		Rm = __ballot_sync(FULL, cand && sc > excl);
+	}
+	const unsigned K = __ballot_sync(FULL, marked) & ~Rm;
+	const int brk = wm_chain_replay(Rm, K, &A.n_skip, max_skip);
+	const unsigned Rv = brk < 32 ? (Rm & ((1u << brk) - 1u)) : Rm;
+	if (Rv) {
+		const int top = 31 - __clz(Rv);
+		A.max_f = __shfl_sync(FULL, sc, top);
+		A.max_j = jtop - top;
+	}
+	return brk < 32;
+}
+
+// a step over predecessors whose coordinates the warp holds in registers (`tile`: lane l holds anchor tbase + l): lane m looks at
+// j = jtop - m.  Scores / predecessors of candidates come from the ring (the caller has waited for them).  Returns 0 = go on,
+// 1 = the reference's loop ended here, 2 = a mark below the ring is needed (only the locked path can keep it).
+__device__ __forceinline__ int wm_chain_reg_step(wm_chain_scan &A, const wm_chain_params &P, wm_chain_tile_sm *S, uint32_t *mk, int32_t *t, wm128_dev tile, int tbase,
+                                                 int jtop, int st, int ring_lo, bool deep_ok, double avg_d, double scale_d, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	constexpr int MASK = WM_CT_RING - 1;
+	const int j = jtop - lane, src = j - tbase;
+	const bool in = src >= 0 && src < 32 && j >= st;
+	const uint64_t xj = __shfl_sync(FULL, tile.x, in ? src : 0), yj = __shfl_sync(FULL, tile.y, in ? src : 0);
+	bool cand = false, deep = false; int sc = INT_MIN;
+	if (in) {
+		wm128_dev aj; aj.x = xj, aj.y = (uint64_t)(uint32_t)yj;
+		int s0;
+		if (wm_chain_score(aj, A.ri, A.qi, A.q_span, P, avg_d, scale_d, &s0)) {
+			const int s = j & MASK;
+			cand = true; sc = s0 + S->f[s];
+			const int pj = S->p[s];
+			if (pj >= 0) {
+				if (pj >= ring_lo) atomicOr(&mk[(pj & MASK) >> 5], 1u << (pj & 31));
+				else if (deep_ok) t[pj] = A.i;
+				else deep = true;
+			}
+		}
+	}
+	if (__ballot_sync(FULL, deep)) return 2;
+	__syncwarp();
+	const bool marked = cand && (mk[(j & MASK) >> 5] >> (j & 31) & 1); // register tiles lie above ring_lo
+	return wm_chain_resolve(A, cand, sc, marked, jtop, P.max_skip, lane) ? 1 : 0;
+}
+
+// The scan of anchor i = i0 + k by one warp.  cur / prev: lane l holds a[i0 + l] / a[i0 - 32 + l].  Entries j >= ring_lo are read
+// from the ring (those of the two register tiles only if they are candidates, which the caller has waited for); older ones from
+// global memory, and only when deep_ok (the caller holds the lock: the global t[] marks are then this anchor's alone).  Returns
+// false if it would have had to go below the ring without deep_ok; on success *mf / *mj hold f[i] / p[i].
 __device__ __forceinline__ bool wm_chain_tile_scan(const wm128_dev *__restrict__ a, const wm_chain_params &P, const int32_t *f, const int32_t *p, int32_t *t,
-                                                   wm_chain_tile_sm *S, uint32_t *mk, wm128_dev al, int i0, int k, int st, int ring_lo, bool deep_ok,
+                                                   wm_chain_tile_sm *S, uint32_t *mk, wm128_dev cur, wm128_dev prev, int i0, int k, int st, int ring_lo, bool deep_ok,
                                                    double avg_d, double scale_d, int lane, int *mf, int *mj)
 {
 	const unsigned FULL = 0xffffffffu;
 	constexpr int MASK = WM_CT_RING - 1;
-	const int i = i0 + k;
-	const uint64_t ri = __shfl_sync(FULL, al.x, k), yi = __shfl_sync(FULL, al.y, k);
-	const int32_t qi = (int32_t)yi, q_span = (int32_t)(yi >> 32 & 0xff);
-	int max_f = q_span, max_j = -1, n_skip = 0;
+	wm_chain_scan A;
+	A.i = i0 + k;
+	A.ri = __shfl_sync(FULL, cur.x, k);
+	{ const uint64_t yi = __shfl_sync(FULL, cur.y, k); A.qi = (int32_t)yi, A.q_span = (int32_t)(yi >> 32 & 0xff); }
+	A.max_f = A.q_span, A.max_j = -1, A.n_skip = 0;
 	for (int w = lane; w < WM_CT_RING / 32; w += 32) mk[w] = 0;
 	__syncwarp();
 	bool brk_out = false;
-	// (1) predecessors inside the tile: lane m looks at j = i - 1 - m (tile slot k - 1 - m)
-	if (k > 0 && i - 1 >= st) {
-		const int src = k - 1 - lane;
-		const uint64_t xj = __shfl_sync(FULL, al.x, src < 0 ? 0 : src), yj = __shfl_sync(FULL, al.y, src < 0 ? 0 : src);
-		const int j = i - 1 - lane;
-		bool cand = false; int sc = INT_MIN;
-		if (src >= 0 && j >= st) {
-			wm128_dev aj; aj.x = xj, aj.y = (uint64_t)(uint32_t)yj;
-			int s0;
-			if (wm_chain_score(aj, ri, qi, q_span, P, avg_d, scale_d, &s0)) {
-				const int s = j & MASK;
-				cand = true; sc = s0 + S->f[s];
-				const int pj = S->p[s];
-				if (pj >= 0) {
-					if (pj >= ring_lo) atomicOr(&mk[(pj & MASK) >> 5], 1u << (pj & 31));
-					else if (deep_ok) t[pj] = i;
-					else brk_out = true; // a mark below the ring: only the locked path can keep it
-				}
-			}
-		}
-		if (__ballot_sync(FULL, brk_out)) return false;
-		__syncwarp();
-		const bool marked = cand && (mk[(j & MASK) >> 5] >> (j & 31) & 1); // j >= i0 > ring_lo
-		const unsigned G = __ballot_sync(FULL, cand && sc > max_f);
-		unsigned Rm = G;
-		if (G & (G - 1)) {
-			const int incl = wm_warp_incl_max(cand ? sc : INT_MIN, lane);
-			int excl = __shfl_up_sync(FULL, incl, 1);
-			if (lane == 0) excl = INT_MIN;
-			excl = max(excl, max_f);
-			Rm = __ballot_sync(FULL, cand && sc > excl);
-		}
-		const unsigned K = __ballot_sync(FULL, marked) & ~Rm;
-		const int brk = wm_chain_replay(Rm, K, &n_skip, P.max_skip);
-		const unsigned Rv = brk < 32 ? (Rm & ((1u << brk) - 1u)) : Rm;
-		if (Rv) {
-			const int top = 31 - __clz(Rv);
-			max_f = __shfl_sync(FULL, sc, top);
-			max_j = i - 1 - top;
-		}
-		if (brk < 32) brk_out = true;
+	// (1) predecessors inside the tile, (2) the tile before: coordinates from registers
+	if (k > 0 && A.i - 1 >= st) {
+		const int r = wm_chain_reg_step(A, P, S, mk, t, cur, i0, A.i - 1, st, ring_lo, deep_ok, avg_d, scale_d, lane);
+		if (r == 2) return false;
+		brk_out = r == 1;
 	}
-	// (2) below the tile: 64 predecessors per step, as in the ring formulation
-	for (int jb = i0 - 1; jb >= st && !brk_out; jb -= 64) {
+	if (!brk_out && i0 > 0 && i0 - 1 >= st) {
+		const int r = wm_chain_reg_step(A, P, S, mk, t, prev, i0 - 32, i0 - 1, st, ring_lo, deep_ok, avg_d, scale_d, lane);
+		if (r == 2) return false;
+		brk_out = r == 1;
+	}
+	// (3) two tiles back and older: 64 predecessors per step, as in the ring formulation
+	for (int jb = i0 - 33; jb >= st && !brk_out; jb -= 64) {
 		if (!deep_ok && jb - 63 < ring_lo && ring_lo > st) return false; // this step would reach below the ring
 		bool cand[2]; int sc[2], jj[2];
 		bool need_deep = false;
@@ -425,13 +468,13 @@ __device__ __forceinline__ bool wm_chain_tile_scan(const wm128_dev *__restrict__
 			if (j >= st) {
 				wm128_dev aj; int fj, pj;
 				if (j >= ring_lo) { const int s = j & MASK; aj.x = S->x[s]; aj.y = (uint64_t)(uint32_t)S->q[s]; fj = S->f[s]; pj = S->p[s]; }
-				else { aj = a[j]; fj = f[j]; pj = p[j]; }
+				else { aj = a[j]; fj = WM_LDCG(f + j); pj = WM_LDCG(p + j); } // written by other warps of the CTA: read at L2
 				int s0;
-				if (wm_chain_score(aj, ri, qi, q_span, P, avg_d, scale_d, &s0)) {
+				if (wm_chain_score(aj, A.ri, A.qi, A.q_span, P, avg_d, scale_d, &s0)) {
 					cand[h] = true; sc[h] = s0 + fj;
 					if (pj >= 0) {
 						if (pj >= ring_lo) atomicOr(&mk[(pj & MASK) >> 5], 1u << (pj & 31));
-						else if (deep_ok) t[pj] = i;
+						else if (deep_ok) t[pj] = A.i;
 						else need_deep = true;
 					}
 				}
@@ -444,28 +487,11 @@ __device__ __forceinline__ bool wm_chain_tile_scan(const wm128_dev *__restrict__
 			if (h == 1 && jb - 32 < st) break;
 			const int j = jj[h];
 			bool marked = false;
-			if (cand[h]) marked = j >= ring_lo ? (mk[(j & MASK) >> 5] >> (j & 31) & 1) != 0 : t[j] == i;
-			const unsigned G = __ballot_sync(FULL, cand[h] && sc[h] > max_f);
-			unsigned Rm = G;
-			if (G & (G - 1)) {
-				const int incl = wm_warp_incl_max(cand[h] ? sc[h] : INT_MIN, lane);
-				int excl = __shfl_up_sync(FULL, incl, 1);
-				if (lane == 0) excl = INT_MIN;
-				excl = max(excl, max_f);
-				Rm = __ballot_sync(FULL, cand[h] && sc[h] > excl);
-			}
-			const unsigned K = __ballot_sync(FULL, marked) & ~Rm;
-			const int brk = wm_chain_replay(Rm, K, &n_skip, P.max_skip);
-			const unsigned Rv = brk < 32 ? (Rm & ((1u << brk) - 1u)) : Rm;
-			if (Rv) {
-				const int top = 31 - __clz(Rv);
-				max_f = __shfl_sync(FULL, sc[h], top);
-				max_j = jb - 32 * h - top;
-			}
-			if (brk < 32) { brk_out = true; break; }
+			if (cand[h]) marked = j >= ring_lo ? (mk[(j & MASK) >> 5] >> (j & 31) & 1) != 0 : t[j] == A.i;
+			if (wm_chain_resolve(A, cand[h], sc[h], marked, jb - 32 * h, P.max_skip, lane)) { brk_out = true; break; }
 		}
 	}
-	*mf = max_f, *mj = max_j;
+	*mf = A.max_f, *mj = A.max_j;
 	return true;
 }
 

@@ -104,7 +104,7 @@ struct GpuBackendImpl {
 	// workspaces
 	wm_sketch_ws sk; wm_seed_ws sd, sd2; wm_chain_ws ch; wm_extd2_ws dpws;
 	wm_dbuf masked, mask_tasks, mask_toff, mask_pool, qlen_buf, pre_buf, cat_tasks, cat_toff, cat_a, set_id, off_buf, nb_off, nu_off, b_out, u_out;
-	wm_dbuf g_jobs, g_joff, seq_pool, dp_jobs, bt, ez, cig, cig_off, cig_out, ll_jobs, ll_scr, ll_out, mat;
+	wm_dbuf coop_ids, g_jobs, g_joff, seq_pool, dp_jobs, bt, ez, cig, cig_off, cig_out, ll_jobs, ll_scr, ll_out, mat;
 	// host result pools
 	std::vector<uint32_t> h_mzpos; std::vector<int64_t> h_mz_off; std::vector<int32_t> h_rep;
 	std::vector<uint64_t> h_u; std::vector<wm_pair_t> h_b; std::vector<int32_t> h_nu; std::vector<int64_t> h_nb;
@@ -208,6 +208,8 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	out.assign(n, SeedOut());
 	if (n == 0) return;
 	const uint8_t *d_codes = (const uint8_t*)g.codes.p;
+	double t_mark = Timers::now();
+	auto lap = [&](const char *nm) { const double t = Timers::now(); g_timers.add(nm, t - t_mark); t_mark = t; };
 	// 1. masked copies
 	std::vector<wm_mask_task> mt; std::vector<int64_t> mtoff(1, 0);
 	int64_t n_mask_iv = 0, n_pre = 0;
@@ -232,6 +234,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		wm_count_launch(); wm_mask_copy_kernel<<<(unsigned)((mtoff.back() + 255) / 256), 256, 0, st>>>(d_codes, d_masked, d_mt, d_mtoff, (int)mt.size(), d_mp, mtoff.back());
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
+	lap("seed.a_mask");
 	// 2. sketch: tasks that sketch something.  The masked copies live in another buffer, so two passes.
 	std::vector<int> sk_of(n, -1);       // task -> index among the sketched tasks
 	std::vector<wm_sk_task> skt_plain, skt_mask;
@@ -286,6 +289,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 			mz_cnt[t] = pass_mzoff[pass][i + 1] - pass_mzoff[pass][i], mz_src[t] = pass_mzoff[pass][i];
 		}
 	}
+	lap("seed.b_sketch_seed");
 	// 3. final anchor arrays: [pre ; seeds] per task
 	std::vector<int64_t> f_off(n + 1, 0);
 	std::vector<wm_cat_task> ct(n);
@@ -353,6 +357,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 			}
 		}
 	}
+	lap("seed.c_concat_sort3");
 	// 4. chaining
 	uint8_t *d_set = (uint8_t*)g.set_id.need(n);
 	WM_CUDA_CHECK(wm_memcpy_async(d_set, set_id.data(), n, cudaMemcpyHostToDevice, st));
@@ -369,6 +374,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	WM_CUDA_CHECK(wm_memcpy_async(g.h_nb.data(), g.ch.n_b.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
 	wm_stream_sync(st);
 	g_timers.add("seed.chain", Timers::now() - t_chain0);
+	lap("seed.d_chain");
 	std::vector<int64_t> nb_off(n + 1, 0), nu_off(n + 1, 0);
 	for (int i = 0; i < n; ++i) nb_off[i + 1] = nb_off[i] + g.h_nb[i], nu_off[i + 1] = nu_off[i] + g.h_nu[i];
 	int64_t *d_nb = (int64_t*)g.nb_off.need(sizeof(int64_t) * (n + 1)), *d_nu = (int64_t*)g.nu_off.need(sizeof(int64_t) * (n + 1));
@@ -382,6 +388,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	if (nb_off[n] > 0) WM_CUDA_CHECK(wm_memcpy_async(g.h_b.data(), d_bo, sizeof(wm128_dev) * nb_off[n], cudaMemcpyDeviceToHost, st));
 	if (nu_off[n] > 0) WM_CUDA_CHECK(wm_memcpy_async(g.h_u.data(), d_uo, sizeof(uint64_t) * nu_off[n], cudaMemcpyDeviceToHost, st));
 	wm_stream_sync(st);
+	lap("seed.e_compact_d2h");
 	// 5. per task views
 	g.h_mz_off.assign(n + 1, 0);
 	for (int i = 0; i < n; ++i) g.h_mz_off[i + 1] = g.h_mz_off[i] + mz_cnt[i];
@@ -395,6 +402,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		o.n_u = g.h_nu[i], o.u = g.h_u.data() + nu_off[i];
 		o.n_b = g.h_nb[i], o.b = g.h_b.data() + nb_off[i];
 	}
+	lap("seed.f_views");
 }
 
 static inline wm_gather_job make_gather(const GpuBackendImpl &g, const SeqRef &s, const MapWin &w, int64_t dst_off)
@@ -449,6 +457,8 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 	g.h_cig.clear();
 	if (n == 0) return;
 	wm_dp_params P; wm_dp_params_init(&P, sc.mat, sc.q, sc.e, sc.q2, sc.e2);
+	static int coop_on = -1; // WM_DP_COOP=0: every job on one warp (for comparison)
+	if (coop_on < 0) { const char *e = getenv("WM_DP_COOP"); coop_on = (e && *e == '0') ? 0 : 1; if (getenv("WM_DP_V1") && *getenv("WM_DP_V1") == '1') coop_on = 0; }
 	std::vector<int64_t> cig_base(n + 1, 0); // offsets into h_cig, by execution slot
 	std::vector<int> slot_of(n, 0);           // job -> execution slot (jobs of a chunk run sorted by size)
 	g.h_ez.resize(n); g.h_zd.resize(5 * (size_t)n);
@@ -506,6 +516,10 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			D.cig_off = h_coff[i]; D.cig_cap = J.q.len + J.t.len + 2; D.pad = -1;
 		}
 		const wm_extd2_plan_t plan = wm_extd2_plan(dj.data(), m, P.single != 0);
+		std::vector<int32_t> coop; // the big jobs go to the CTA-cooperative sweep (not for the single-affine and first-generation paths)
+		if (!P.single && coop_on)
+			for (int i = 0; i < m && dj[i].qlen + dj[i].tlen >= 1600; ++i) // (sorted by qlen + tlen, descending)
+				if (dj[i].pad >= 0 && wm_dp_is_coop(dj[i].qlen, dj[i].tlen, dj[i].w)) { dj[i].flag |= WM_DP_COOP; coop.push_back(i); }
 		g_timers.add("dp.host_prep", Timers::now() - tp0);
 		if (getenv("WM_DP_STATS")) {
 			int n_big = 0, mq = 0, mt = 0, mw = 0; double cells = 0, big_cells = 0;
@@ -550,7 +564,12 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		int32_t *d_zd = (int32_t*)g.zd.need(sizeof(int32_t) * 5 * (size_t)m);
 		wm_zd_params zp; memset(&zp, 0, sizeof(zp));
 		zp.q = sc.q, zp.e = sc.e; memcpy(zp.mat, sc.mat, 25);
-		wm_extd2_launch(&g.dpws, d_dj, m, plan, d_pool, d_bt, d_ez, d_cig, P, st, &zp, d_zd);
+		int32_t *d_coop = 0;
+		if (!coop.empty()) {
+			d_coop = (int32_t*)g.coop_ids.need(sizeof(int32_t) * coop.size());
+			WM_CUDA_CHECK(wm_memcpy_async(d_coop, coop.data(), sizeof(int32_t) * coop.size(), cudaMemcpyHostToDevice, st));
+		}
+		wm_extd2_launch(&g.dpws, d_dj, m, plan, d_pool, d_bt, d_ez, d_cig, P, st, &zp, d_zd, d_coop, (int)coop.size());
 		WM_CUDA_CHECK(wm_memcpy_async(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
 		WM_CUDA_CHECK(wm_memcpy_async(g.h_zd.data() + 5 * (size_t)done, d_zd, sizeof(int32_t) * 5 * m, cudaMemcpyDeviceToHost, st));
 		wm_stream_sync(st);

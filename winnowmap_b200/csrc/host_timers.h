@@ -8,7 +8,7 @@
 
 namespace wmh {
 struct Timers {
-	enum { MAXT = 48 };
+	enum { MAXT = 64 };
 	const char *name[MAXT]; double sec[MAXT], cpu[MAXT]; long cnt[MAXT]; int n;
 	Timers() : n(0) {}
 	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

@@ -214,6 +214,7 @@ wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8
 	const int j = blockIdx.x * WM_FILL_WARPS + wid;
 	if (j >= n_jobs) return;
 	const wm_dp_job J = jobs[j];
+	if (J.flag & WM_DP_COOP) return; // swept by a whole CTA in wm_extd2_fill_coop_kernel
 	int8_t *my_g = J.pad >= 0 ? gscratch + (size_t)J.pad * gscratch_stride : (int8_t*)0;
 	const int tlen16 = (J.tlen + 15) / 16 * 16;
 	if (P.single) wm_extz2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane, cell_ctr);
@@ -222,6 +223,20 @@ wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8
 		else wm_extd2_fill_job_v2<false>(J, seq, bt, ez + j, P, (uint8_t*)my_g, g_tcap, g_qcap, lane, cell_ctr ? cell_ctr + 1 : 0);
 	} else
 		wm_extd2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane, cell_ctr);
+}
+
+// the big jobs, one CTA each (ksw_extd2_v2.cuh: wm_extd2_fill_job_v2_cta)
+__global__ void __launch_bounds__(WM_V2_CTA_WARPS * 32)
+wm_extd2_fill_coop_kernel(const wm_dp_job *__restrict__ jobs, const int32_t *__restrict__ ids, int n_ids, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
+                          wm_extz_dev *__restrict__ ez, wm_dp_params P, int8_t *gscratch, size_t gscratch_stride, int g_tcap, int g_qcap, unsigned long long *cell_ctr)
+{
+	__shared__ wm_v2_cta_sm SM;
+	for (int i = blockIdx.x; i < n_ids; i += gridDim.x) {
+		const int j = ids[i];
+		const wm_dp_job J = jobs[j];
+		wm_extd2_fill_job_v2_cta(J, seq, bt, ez + j, P, (uint8_t*)(gscratch + (size_t)J.pad * gscratch_stride), g_tcap, g_qcap, &SM, cell_ctr ? cell_ctr + 1 : 0);
+		__syncthreads();
+	}
 }
 
 __global__ void wm_extd2_backtrack_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ bt,
@@ -293,7 +308,8 @@ cudaStream_t wm_stream_create_high_priority(void)
 }
 
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
-                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream, const wm_zd_params *zp, int32_t *d_zd)
+                     wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream, const wm_zd_params *zp, int32_t *d_zd,
+                     const int32_t *d_coop_ids, int n_coop)
 {
 	if (n_jobs <= 0) return;
 	const size_t smem = (size_t)WM_FILL_WARPS * WM_FILL_SLICE;
@@ -307,8 +323,10 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const
 		int lo = 0, hi = 0;
 		WM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
 		WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->fill_st, cudaStreamNonBlocking, lo));
+		WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->coop_st, cudaStreamNonBlocking, lo));
 		WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_ready, cudaEventDisableTiming));
 		WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_done, cudaEventDisableTiming));
+		WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_coop, cudaEventDisableTiming));
 	}
 	static bool attr_set = false;
 	if (!attr_set) {
@@ -321,8 +339,15 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const
 	// timed region runs exactly as it does without profiling
 	unsigned long long *cell_ctr = 0;
 	const int pslot = wm_prof_launch_begin(WM_PK_FILL, ws->fill_st, ws->fill_st, &cell_ctr);
+	if (n_coop > 0 && use_v2) { // the big jobs first, on their own stream: they set the length of the launch
+		WM_CUDA_CHECK(cudaStreamWaitEvent(ws->coop_st, ws->ev_ready, 0));
+		wm_count_launch(); wm_extd2_fill_coop_kernel<<<n_coop, WM_V2_CTA_WARPS * 32, 0, ws->coop_st>>>(d_jobs, d_coop_ids, n_coop, d_seq, d_bt, d_ez, P, gs, stride, tcap, plan.max_qlen, cell_ctr);
+		WM_CUDA_CHECK(cudaGetLastError());
+		WM_CUDA_CHECK(cudaEventRecord(ws->ev_coop, ws->coop_st));
+	}
 	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, ws->fill_st>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, tcap, plan.max_qlen, use_v2, cell_ctr);
 	WM_CUDA_CHECK(cudaGetLastError());
+	if (n_coop > 0 && use_v2) WM_CUDA_CHECK(cudaStreamWaitEvent(ws->fill_st, ws->ev_coop, 0));
 	wm_prof_launch_end(pslot, ws->fill_st);
 	WM_CUDA_CHECK(cudaEventRecord(ws->ev_done, ws->fill_st));
 	WM_CUDA_CHECK(cudaStreamWaitEvent(stream, ws->ev_done, 0));

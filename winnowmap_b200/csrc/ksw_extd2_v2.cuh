@@ -284,3 +284,166 @@ __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restri
 	}
 	if (lane == 0) { *out = ez; if (cell_ctr) atomicAdd(cell_ctr, (unsigned long long)cells_acc); }
 }
+
+
+// ---- CTA-cooperative sweep for the few big jobs ------------------------------------------------------------------
+// One warp per job leaves a launch waiting for its largest job: an end extension of 16 kb x 17 kb at w = 3001 is ~10^8
+// cells on one warp.  Here the NW warps of a CTA share one job: the 128-cell steps of a diagonal are dealt round-robin to
+// the warps.  A step needs the (x, v, x2) values of the cell left of it on the PREVIOUS diagonal, which the neighbouring
+// step is about to overwrite, so every diagonal starts by saving those carry-in values (one per step) in shared memory;
+// then: barrier, steps, barrier, H tracking (spread over all threads, reduced through shared memory), barrier.  State
+// rows live in the job's global (L2-resident) slice, as for every job that does not fit a warp's shared-memory slice.
+#define WM_V2_CTA_WARPS 8
+#define WM_V2_CTA_MAXSTEPS 1024 // diagonals of up to 131072 cells
+struct wm_v2_cta_sm {
+	int16_t cx[WM_V2_CTA_MAXSTEPS], cv[WM_V2_CTA_MAXSTEPS], cx2[WM_V2_CTA_MAXSTEPS];
+	long long best[WM_V2_CTA_WARPS];
+};
+
+__device__ void wm_extd2_fill_job_v2_cta(const wm_dp_job &J, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
+                                         wm_extz_dev *out, const wm_dp_params &P, uint8_t *S8, int tcap, int qcap, wm_v2_cta_sm *SM, unsigned long long *cell_ctr)
+{
+	constexpr int NW = WM_V2_CTA_WARPS, NT = NW * 32;
+	const unsigned FULL = 0xffffffffu;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int ts = tcap + 8;
+	const uint8_t *query = seq + J.q_off, *target = seq + J.t_off;
+	const int qlen = J.qlen, tlen = J.tlen, flag = J.flag;
+	int w = J.w;
+	wm_extz_dev ez;
+	ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+	ez.max = 0, ez.score = ez.mqe = ez.mte = WM_NEG_INF;
+	ez.n_cigar = 0, ez.zdropped = 0, ez.reach_end = 0, ez.reserved = 0;
+	const int q = P.q, e = P.e, q2 = P.q2, e2 = P.e2;
+	const bool approx_max = (flag & 0x08) != 0, right = (flag & 0x02) != 0;
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	const int tlen16 = (tlen + 15) / 16 * 16;
+	const int n_col16 = wm_ncol16(qlen, tlen, w);
+	wm_v2_k K;
+	K.U = (int16_t*)S8, K.V = K.U + ts, K.X = K.V + ts, K.Y = K.X + ts, K.X2 = K.Y + ts, K.Y2 = K.X2 + ts, K.SK = K.Y2 + ts;
+	int16_t *const U = K.U, *const V = K.V, *const X = K.X, *const Y = K.Y, *const X2 = K.X2, *const Y2 = K.Y2, *const SK = K.SK;
+	int32_t *H = (int32_t*)(SK + ts);
+	uint8_t *tg = (uint8_t*)(H + tcap);
+	uint8_t *qr = tg + tcap + 16 + 16;
+	K.tg = tg, K.qr16 = qr - 16;
+	{
+		const int TAG_S = right ? 0 : 7, TAG_A = right ? 1 : 6, TAG_B = right ? 2 : 5, TAG_A2 = right ? 3 : 4, TAG_B2 = right ? 4 : 3;
+		K.KEY_MCH = wm_rep2(P.sc_mch * 8 + TAG_S), K.KEY_MIS = wm_rep2(P.sc_mis * 8 + TAG_S), K.KEY_N = wm_rep2(P.sc_N * 8 + TAG_S);
+		K.TA = wm_rep2(TAG_A), K.TB = wm_rep2(TAG_B), K.TA2 = wm_rep2(TAG_A2), K.TB2 = wm_rep2(TAG_B2);
+		K.MCH8 = wm_rep2(P.sc_mch * 8);
+		K.DTX = right ? 0u : 0x00070007u;
+		K.NZ1X = wm_rep2(-e * 8 + 1 + 1), K.NZ1Y = wm_rep2(-e * 8 + 1 + 2), K.NZ2X = wm_rep2(-e2 * 8 + 1 + 1), K.NZ2Y = wm_rep2(-e2 * 8 + 1 + 2);
+		K.C1X = wm_rep2(-(q + e) * 8 + (right ? 0 : 6)), K.C1Y = wm_rep2(-(q + e) * 8 + (right ? 0 : 5));
+		K.C2X = wm_rep2(-(q2 + e2) * 8 + (right ? 0 : 6)), K.C2Y = wm_rep2(-(q2 + e2) * 8 + (right ? 0 : 5));
+		const int16_t i1 = (int16_t)(-(q + e) * 8), i2 = (int16_t)(-(q2 + e2) * 8), s0 = (int16_t)TAG_S;
+		for (int i = tid; i < tlen16; i += NT) {
+			U[i] = V[i] = X[i] = Y[i] = i1; X2[i] = Y2[i] = i2; SK[i] = s0;
+			if (!approx_max) H[i] = WM_NEG_INF;
+		}
+		for (int i = tid; i < tcap + 16; i += NT) tg[i] = i < tlen ? target[i] : 0;
+		for (int i = tid; i < qcap + 48; i += NT) { const int j = i - 16; (qr - 16)[i] = (j >= 0 && j < qlen) ? query[qlen - 1 - j] : 0; }
+	}
+	__syncthreads();
+
+	const int NQE = -(q + e) * 8, NQE2 = -(q2 + e2) * 8;
+	const int bnd_lt = -e * 8, bnd_eq = P.long_diff * 8, bnd_gt = -e2 * 8, long_thres = P.long_thres;
+	int32_t H0 = 0, last_H0_t = 0;
+	int last_st = -1, last_en = -1;
+	unsigned long long cells_acc = 0;
+	const int n_diag = qlen + tlen - 1;
+	for (int r = 0; r < n_diag; ++r) {
+		const int st0 = wm_band_st(r, qlen, w), en0 = wm_band_en(r, tlen, w);
+		if (st0 > en0) { ez.zdropped = 1; break; }
+		const int st = st0 & ~15, en = en0 | 15;
+		const int lim = st0 + (((en0 - st0) >> 4) + 1) * 16;
+		cells_acc += (unsigned long long)(en - st + 1);
+		const int bnd = r == 0 ? NQE : r < long_thres ? bnd_lt : r == long_thres ? bnd_eq : bnd_gt;
+		const int last = lim - 1 > en ? lim - 1 : en;
+		const int nf = last - st >= 64 ? (last - st - 64) / 128 + 1 : 0; // full 128-cell steps; then at most one 64-cell step
+		const int c_tail = st + 128 * nf, n_steps = nf + (c_tail <= last ? 1 : 0);
+		// carry-in of every step: the (x, v, x2) of the cell left of it, previous diagonal (src/ksw2_extd2_sse.c:141-151 for step 0)
+		for (int sidx = tid; sidx < n_steps; sidx += NT) {
+			int x1 = NQE, x21 = NQE2, v1 = st > 0 ? NQE : bnd;
+			const int c = st + 128 * sidx;
+			if (sidx == 0) { if (st > 0 && st - 1 >= last_st && st - 1 <= last_en) x1 = X[st - 1], x21 = X2[st - 1], v1 = V[st - 1]; }
+			else if (c - 1 <= en) x1 = X[c - 1], x21 = X2[c - 1], v1 = V[c - 1];
+			else x1 = x21 = v1 = 0;
+			SM->cx[sidx] = (int16_t)x1, SM->cx2[sidx] = (int16_t)x21, SM->cv[sidx] = (int16_t)v1;
+		}
+		const int32_t Hm1 = (!approx_max && r > 0 && en0 > 0) ? H[en0 - 1] : 0, Hen = (!approx_max && r > 0) ? H[en0] : 0; // before anybody adds to H[]
+		if (en >= r && tid == 0) { Y[r] = (int16_t)NQE, Y2[r] = (int16_t)NQE2; U[r] = (int16_t)bnd; } // :152-155
+		__syncthreads();
+		{
+			uint8_t *pr = bt + J.p_off + (size_t)r * n_col16;
+			const int qoff = qlen - 1 - r;
+			for (int sidx = wid; sidx < n_steps; sidx += NW) {
+				uint32_t cx = (uint32_t)(uint16_t)SM->cx[sidx] << 16, cv = (uint32_t)(uint16_t)SM->cv[sidx] << 16, cx2 = (uint32_t)(uint16_t)SM->cx2[sidx] << 16;
+				const int c = st + 128 * sidx;
+				if (sidx < nf) wm_v2_step<2>(K, c, lane, st, en, st0, lim, tlen16, qoff, pr, cx, cv, cx2);
+				else wm_v2_step<1>(K, c, lane, st, en, st0, lim, tlen16, qoff, pr, cx, cv, cx2);
+			}
+		}
+		__syncthreads();
+		if (!approx_max) {
+			int32_t max_H, max_t;
+			if (r > 0) {
+				const int en1 = st0 + (en0 - st0) / 4 * 4;
+				long long best = (long long)0x8000000000000000LL;
+				for (int t = st0 + tid; t < en0; t += NT) {
+					const int32_t h = H[t] + (V[t] >> 3);
+					H[t] = h;
+					const uint32_t prio = t < en1 ? 1u + ((uint32_t)((t - st0) & 3) << 24) + (uint32_t)((t - st0) >> 2 << 2)
+					                              : (1u << 27) + (uint32_t)(t - st0);
+					const long long key = ((long long)h << 32) | (long long)(0xffffffffu - prio);
+					best = key > best ? key : best;
+				}
+				if (tid == 0) {
+					const int32_t Hn = en0 > 0 ? Hm1 + (U[en0] >> 3) : Hen + (V[en0] >> 3);
+					H[en0] = Hn;
+					const long long key = ((long long)Hn << 32) | (long long)0xffffffffu;
+					best = key > best ? key : best;
+				}
+				#pragma unroll
+				for (int o = 16; o; o >>= 1) {
+					const long long other = __shfl_xor_sync(FULL, best, o);
+					best = other > best ? other : best;
+				}
+				if (lane == 0) SM->best[wid] = best;
+				__syncthreads();
+				best = SM->best[0];
+				#pragma unroll
+				for (int k2 = 1; k2 < NW; ++k2) { const long long other = SM->best[k2]; best = other > best ? other : best; }
+				max_H = (int32_t)(best >> 32);
+				const uint32_t prio = 0xffffffffu - (uint32_t)(best & 0xffffffffLL);
+				if (prio == 0) max_t = en0;
+				else if (prio < (1u << 27)) max_t = st0 + (int)((prio - 1) & 0xffffffu) + (int)((prio - 1) >> 24);
+				else max_t = st0 + (int)(prio - (1u << 27));
+			} else {
+				max_H = (V[0] >> 3) - P.qe_h, max_t = 0;
+				if (tid == 0) H[0] = max_H;
+				__syncthreads();
+			}
+			const int32_t Hen0 = H[en0], Hst0 = H[st0];
+			if (en0 == tlen - 1 && Hen0 > ez.mte) ez.mte = Hen0, ez.mte_q = r - en;
+			if (r - st0 == qlen - 1 && Hst0 > ez.mqe) ez.mqe = Hst0, ez.mqe_t = st0;
+			if (wm_apply_zdrop(ez, max_H, r, max_t, J.zdrop, e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
+		} else {
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					const int32_t d0 = V[last_H0_t] >> 3, d1 = U[last_H0_t + 1] >> 3;
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
+					H0 += V[last_H0_t] >> 3;
+				} else {
+					++last_H0_t, H0 += U[last_H0_t] >> 3;
+				}
+			} else H0 = (V[0] >> 3) - P.qe_h, last_H0_t = 0;
+			if ((flag & 0x10) && wm_apply_zdrop(ez, H0, r, last_H0_t, J.zdrop, e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+	if (tid == 0) { *out = ez; if (cell_ctr) atomicAdd(cell_ctr, cells_acc); }
+}

@@ -185,8 +185,13 @@ struct wm_gs_sm {
 
 __global__ void __launch_bounds__(WM_GS_THREADS)
 wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ ids, int n_arr,
-                            wm_rs_range *__restrict__ wl_all)
+                            wm_rs_range *__restrict__ wl_all, unsigned long long *dbg)
 {
+	// dbg (tuning aid, WM_SORT_DEBUG=1): clocks spent by thread 0 in [0] histograms, [1] the walk, [2] sub-bucket dispatch + tiny sorts,
+	// [3] phase 2, [4] walker steps, [5] walker waits (polls of an empty FIFO)
+	long long t_dbg = dbg ? clock64() : 0;
+	unsigned long long n_steps_dbg = 0, n_wait_dbg = 0;
+#define WM_GS_LAP(i) do { if (dbg && tid == 0) { const long long t2 = clock64(); atomicAdd(dbg + (i), (unsigned long long)(t2 - t_dbg)); t_dbg = t2; } } while (0)
 	extern __shared__ __align__(16) unsigned char wm_gs_smem[];
 	wm_gs_sm *S = (wm_gs_sm*)wm_gs_smem;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -221,6 +226,7 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 				s = s > 8 ? s - 8 : 0;
 				__syncthreads();
 			}
+			WM_GS_LAP(0);
 			if (single) { __syncthreads(); continue; } // all keys equal down to the last byte: nothing moves
 			if (wid == 0) { // bucket bounds: exclusive prefix over 256 counts
 				int cnt[8], sum = 0;
@@ -240,14 +246,16 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 				for (int k = 0; k < 256;) {
 					const int bk = b[k];
 					if (bk != E[k]) {
-						while (filled[k] <= bk) { }
+						while (filled[k] <= bk) { ++n_wait_dbg; }
 						asm volatile("" ::: "memory");
 						wm128_dev tmp = S->u.fifo[k][bk & (WM_GS_F - 1)];
+						++n_steps_dbg;
 						int l = (int)(tmp.x >> s & 255);
 						if (l != k) {
 							do {
 								const int bl = b[l];
-								while (filled[l] <= bl) { }
+								while (filled[l] <= bl) { ++n_wait_dbg; }
+								++n_steps_dbg;
 								asm volatile("" ::: "memory");
 								const wm128_dev nxt = S->u.fifo[l][bl & (WM_GS_F - 1)];
 								a[bl] = tmp;
@@ -288,6 +296,7 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 				}
 			}
 			__syncthreads();
+			WM_GS_LAP(1);
 			// sub-buckets (ksort.h:140-145)
 			if (s > 0) {
 				const int ns = s > 8 ? s - 8 : 0;
@@ -300,6 +309,7 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 			}
 			__syncthreads();
 		}
+		WM_GS_LAP(2);
 		// ---- phase 2: the small ranges, one warp each, staged in shared memory ----
 		if (tid == 0) S->next_small = 0;
 		__syncthreads();
@@ -320,7 +330,10 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 			}
 		}
 		__syncthreads();
+		WM_GS_LAP(3);
 	}
+	if (dbg && tid == 0) { atomicAdd(dbg + 4, n_steps_dbg); atomicAdd(dbg + 5, n_wait_dbg); }
+#undef WM_GS_LAP
 }
 
 // sort n_arr arrays (device); h_off is the host copy of the offsets
@@ -338,7 +351,9 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 	WM_CUDA_CHECK(cudaGetLastError());
 	if (!big.empty()) {
 		// three launches by size class: the shared-memory stage of the array sets the occupancy
-		const int cap_s = 2048, cap_m = 13312; // 32 KB and 208 KB of anchors
+		static int cap_m_env = -1; // WM_SORT_GIANT_MIN: arrays above this many anchors go to the giant kernel (default: what fits the 208 KB stage)
+		if (cap_m_env < 0) { const char *e = getenv("WM_SORT_GIANT_MIN"); cap_m_env = e && atoi(e) >= 2048 && atoi(e) <= 13312 ? atoi(e) : 13312; }
+		const int cap_s = 2048, cap_m = cap_m_env; // 32 KB and up to 208 KB of anchors
 		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_m * (int)sizeof(wm128_dev)));
 		std::stable_sort(big.begin(), big.end(), [&](int x, int y) { return h_off[x + 1] - h_off[x] > h_off[y + 1] - h_off[y]; });
 		size_t n_l = 0, n_m = 0;
@@ -355,7 +370,16 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 			if (giant) {
 				static bool attr_set = false;
 				if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(wm_gs_sm))); attr_set = true; }
-				wm_anchor_sort_giant_kernel<<<(unsigned)(n_l < 296 ? n_l : 296), WM_GS_THREADS, sizeof(wm_gs_sm), st>>>(d_a, d_off, d_big, (int)n_l, d_wl);
+				unsigned long long *dbg = 0;
+				if (getenv("WM_SORT_DEBUG")) { WM_CUDA_CHECK(cudaMalloc((void**)&dbg, 64)); WM_CUDA_CHECK(cudaMemset(dbg, 0, 64)); }
+				wm_anchor_sort_giant_kernel<<<(unsigned)(n_l < 296 ? n_l : 296), WM_GS_THREADS, sizeof(wm_gs_sm), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, dbg);
+				if (dbg) {
+					unsigned long long h[8];
+					WM_CUDA_CHECK(cudaStreamSynchronize(st));
+					WM_CUDA_CHECK(cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost));
+					fprintf(stderr, "[sort-debug] arrays=%d clocks: hist %llu walk %llu dispatch %llu phase2 %llu | walker steps %llu wait polls %llu\n", (int)n_l, h[0], h[1], h[2], h[3], h[4], h[5]);
+					cudaFree(dbg);
+				}
 			} else wm_anchor_sort_big_kernel<<<(unsigned)n_l, 32, 0, st>>>(d_a, d_off, d_big, (int)n_l, d_wl, 0);
 		}
 		if (n_m) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_m, 32, cap_m * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, cap_m); }

@@ -116,9 +116,9 @@ struct wm_dbuf {
 // the highest priority) take the freed slots first instead of queueing behind a whole DP launch.
 struct wm_extd2_ws {
 	wm_dbuf scratch;
-	cudaStream_t fill_st; cudaEvent_t ev_ready, ev_done;
-	wm_extd2_ws() : fill_st(0), ev_ready(0), ev_done(0) {}
-	~wm_extd2_ws() { if (fill_st) { cudaStreamDestroy(fill_st); cudaEventDestroy(ev_ready); cudaEventDestroy(ev_done); } }
+	cudaStream_t fill_st, coop_st; cudaEvent_t ev_ready, ev_done, ev_coop; // coop_st: the CTA-cooperative sweep of the big jobs, beside the others
+	wm_extd2_ws() : fill_st(0), coop_st(0), ev_ready(0), ev_done(0), ev_coop(0) {}
+	~wm_extd2_ws() { if (fill_st) { cudaStreamDestroy(fill_st); cudaStreamDestroy(coop_st); cudaEventDestroy(ev_ready); cudaEventDestroy(ev_done); cudaEventDestroy(ev_coop); } }
 };
 struct wm_extd2_plan_t { int n_slots, max_tlen, max_qlen; };
 void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2);
@@ -129,10 +129,20 @@ wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n, bool single = false);
 // Jobs flagged WM_DP_SCAN_ZDROP also get the score walk of mm_test_zdrop (src/align.c:32-70) over their CIGAR: five
 // int32 per job in d_zd (max_zdrop, t0, t1, q0, q1; max_zdrop = -1: no result).  zp / d_zd may be null.
 #define WM_DP_SCAN_ZDROP 0x10000
+// Jobs flagged WM_DP_COOP are skipped by the warp-per-job kernel and swept by a whole CTA (d_coop_ids lists them): the few big
+// jobs (millions of cells) that would otherwise keep a launch waiting on one warp.  wm_dp_is_coop is the host's rule.
+#define WM_DP_COOP 0x20000
+static inline bool wm_dp_is_coop(int qlen, int tlen, int w)
+{
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	const int diag = qlen < tlen ? (qlen < w + 1 ? qlen : w + 1) : (tlen < w + 1 ? tlen : w + 1);
+	const long long cells = (long long)tlen * (qlen < 2 * w + 1 ? qlen : 2 * w + 1);
+	return diag >= 384 && cells >= 1500000;
+}
 struct wm_zd_params { int32_t q, e; int8_t mat[25]; int8_t pad[3]; };
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream,
-                     const wm_zd_params *zp = 0, int32_t *d_zd = 0);
+                     const wm_zd_params *zp = 0, int32_t *d_zd = 0, const int32_t *d_coop_ids = 0, int n_coop = 0);
 cudaStream_t wm_stream_create_high_priority(void);
 
 // Wait for a stream without burning a core: an orchestration lane spends most of its time waiting for the GPU, and
