@@ -13,7 +13,7 @@ One "step" = one pass of the hot path (stage-1 MCAS waves + stage-2 remap: sketc
 chaining, extension DP with traceback, host glue) over --reads fresh reads (~26.5 Mbase; working set -- read pool,
 anchors, backtrack matrices, multi-GB index -- far larger than L2).  Steps are submitted to the library in groups of
 at most WM_BENCH_GROUP steps (default 8) and the library cuts each submission into chunks of WM_CHUNK_BASES bases
-(pinned here to 16 Mbase), so device and host footprints do not grow with --steps.
+(pinned here to 32 Mbase), so device and host footprints do not grow with --steps.
 
   value : bases/s with the raw reads of all K steps already resident in one HBM pool (wm_bench_upload); CUDA events
           bracket the whole pass (ASCII -> 2-bit codes is inside: it is part of the path)
@@ -42,7 +42,7 @@ import threading
 import time
 
 os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")  # before anything loads libgomp: idle workers must not spin (see _lib.py)
-os.environ.setdefault("WM_CHUNK_BASES", "16000000")  # fixed chunk size: footprint independent of --steps
+os.environ.setdefault("WM_CHUNK_BASES", "32000000")  # fixed chunk size: footprint independent of --steps
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -393,7 +393,7 @@ def main():
     # lane must have sized its workspaces for a full chunk before the timed region, so when W steps hold fewer than about
     # one chunk per lane the same W steps are submitted several times over in one submission (no extra reads are made).
     if warm:
-        lanes = int(os.environ.get("WM_LANES", max(2, min(8, n_thr // 8))))
+        lanes = int(os.environ.get("WM_LANES", max(2, min(8, n_thr))))
         warm_bases = sum(len(s) for _, s in warm)
         n_rep = max(1, -(-int(1.25 * lanes * int(os.environ["WM_CHUNK_BASES"])) // max(1, warm_bases)))
         warm_sub = warm * n_rep
@@ -503,7 +503,7 @@ def main():
         "metric": "mapped bases/sec", "value": bases / t_steps, "unit": "bases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * t_steps / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
         "config": {"workload": workload_name() + f"; {a.reads} fresh reads per step per GPU, working set >> L2", "reads_per_step": a.reads,
-                   "host_threads": n_thr, "lanes": int(os.environ.get("WM_LANES", max(2, min(8, n_thr // 8)))),
+                   "host_threads": n_thr, "lanes": int(os.environ.get("WM_LANES", max(2, min(8, n_thr)))),
                    "chunk_bases": int(os.environ["WM_CHUNK_BASES"]), "steps_per_submission": GROUP, "index_build_s": t_index},
         "e2e": {"value": e2e_b / e2e_t, "unit": "bases/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step},
         "gpu_launches": int(prof[0]),

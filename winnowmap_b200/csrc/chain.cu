@@ -154,7 +154,8 @@ wm_chain_fill_tile_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__
 			const int i = i0 + k;
 			if (i < n) {
 				// tile T - 2 and everything before it must be complete; its done-slot + 6 (tile T - 4's) is free for tile T + 4
-				if (T >= 2) { while (done[(T - 2) & 7] != FULL) { } }
+				// (the polls sleep a little: 32 warps spinning on shared memory slow the loads of the warps that are scanning)
+				if (T >= 2) { while (done[(T - 2) & 7] != FULL) __nanosleep(64); }
 				if (lane == 0) done[(T + 4) & 7] = 0;
 				const int st = __shfl_sync(FULL, stl, k);
 				const int ring_lo = i0 + 64 - WM_CT_RING; // older slots are being overwritten by the anchors of the two active tiles
@@ -162,12 +163,12 @@ wm_chain_fill_tile_kernel(const wm128_dev *__restrict__ a_all, const int64_t *__
 				// the anchors of this tile and of the one before that this one depends on: its candidate predecessors (a geometric property)
 				const unsigned Cc = __ballot_sync(FULL, lane < k && il >= st && wm_chain_is_cand(cur, ri, qi, P));
 				const unsigned Cp = T > 0 ? __ballot_sync(FULL, il - 32 >= st && wm_chain_is_cand(prev, ri, qi, P)) : 0u;
-				if (Cp) { while ((done[(T - 1) & 7] & Cp) != Cp) { } }
-				if (Cc) { while ((done[T & 7] & Cc) != Cc) { } }
+				if (Cp) { while ((done[(T - 1) & 7] & Cp) != Cp) __nanosleep(32); }
+				if (Cc) { while ((done[T & 7] & Cc) != Cc) __nanosleep(32); }
 				__threadfence_block();
 				int max_f, max_j;
 				if (!wm_chain_tile_scan(a, P, f, p, t, S, mk, cur, prev, i0, k, st, ring_lo, false, avg_d, scale_d, lane, &max_f, &max_j)) {
-					if (lane == 0) { while (atomicCAS(&S->lock, 0, 1) != 0) { } }
+					if (lane == 0) { while (atomicCAS(&S->lock, 0, 1) != 0) __nanosleep(64); }
 					__syncwarp();
 					__threadfence_block();
 					wm_chain_tile_scan(a, P, f, p, t, S, mk, cur, prev, i0, k, st, ring_lo, true, avg_d, scale_d, lane, &max_f, &max_j);

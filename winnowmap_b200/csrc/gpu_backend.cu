@@ -337,23 +337,12 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		// sort #3 (src/map.c:831): only arrays that really merged two sorted runs can change
 		std::vector<int64_t> s_off(n + 1);
 		{
-			// sort only the tasks with both parts; others are already sorted -> give them empty ranges via a filtered offset list
-			std::vector<int64_t> offs; std::vector<int> which;
+			// sort only the tasks with both parts (the others are already sorted), all of them in one set of launches
+			std::vector<int32_t> which;
 			for (int i = 0; i < n; ++i) if (tasks[i].n_pre > 0 && seed_cnt[i] > 0) which.push_back(i);
 			if (!which.empty()) {
-				// build a compact offset table of (begin,end) pairs by sorting each as its own array
-				std::vector<int64_t> pair_off;
-				for (int i : which) { pair_off.push_back(f_off[i]); pair_off.push_back(f_off[i + 1]); }
-				// wm_anchor_sort_run expects contiguous offsets; call it per maximal run of adjacent tasks
-				size_t a0 = 0;
-				while (a0 < which.size()) {
-					size_t a1 = a0;
-					while (a1 + 1 < which.size() && which[a1 + 1] == which[a1] + 1) ++a1;
-					const int first = which[a0], cnt = (int)(a1 - a0 + 1);
-					wm_anchor_sort_run(&g.sd, d_A, d_foff + first, f_off.data() + first, cnt, st);
-					wm_stream_sync(st);
-					a0 = a1 + 1;
-				}
+				wm_anchor_sort_run(&g.sd, d_A, d_foff, f_off.data(), n, st, which.data(), (int)which.size());
+				wm_stream_sync(st);
 			}
 		}
 	}

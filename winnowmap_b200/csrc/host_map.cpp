@@ -107,6 +107,19 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		fprintf(stderr, "[ERROR] winnowmap-b200: splice/sr/heap-sort/-X/--for-only/--rev-only modes are outside the accelerated path\n");
 		exit(1);
 	}
+	// options the reference honours on this path that are not implemented here are refused, not silently ignored
+	if (opt->max_occ > opt->mid_occ) { // re-chaining with a higher occurrence threshold (src/map.c:391-415, :563-590, :892-915)
+		fprintf(stderr, "[ERROR] winnowmap-b200: max_occ > mid_occ (re-chaining of repetitive reads) is not implemented; the CLI cannot set it either (src/main.c:278)\n");
+		exit(1);
+	}
+	if (opt->max_qlen > 0) { // stage-1 / stage-2 length cut-off (src/map.c:356, :528, :725)
+		fprintf(stderr, "[ERROR] winnowmap-b200: max_qlen is not implemented\n");
+		exit(1);
+	}
+	if (opt->mid_occ_frac >= 0.0f && opt->mid_occ_frac < 1.0f) { // -f: mm_mapopt_update would derive mid_occ from the index (src/options.c:75-76)
+		fprintf(stderr, "[ERROR] winnowmap-b200: mid_occ_frac (-f) is not implemented: set mid_occ itself\n");
+		exit(1);
+	}
 	be->begin_batch(reads);
 	// 0..4 codes of every read, both strands, once per batch: the alignment tasks of all windows of a read slice them
 	std::vector<int64_t> code_off(n_reads + 1, 0);

@@ -293,6 +293,7 @@ __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restri
 // step is about to overwrite, so every diagonal starts by saving those carry-in values (one per step) in shared memory;
 // then: barrier, steps, barrier, H tracking (spread over all threads, reduced through shared memory), barrier.  State
 // rows live in the job's global (L2-resident) slice, as for every job that does not fit a warp's shared-memory slice.
+#ifndef WM_HOST_EMUL // (CTA-level code: not part of the single-warp CPU emulation of the tests; checked on the device)
 #define WM_V2_CTA_WARPS 8
 #define WM_V2_CTA_MAXSTEPS 1024 // diagonals of up to 131072 cells
 struct wm_v2_cta_sm {
@@ -447,3 +448,4 @@ __device__ void wm_extd2_fill_job_v2_cta(const wm_dp_job &J, const uint8_t *__re
 	}
 	if (tid == 0) { *out = ez; if (cell_ctr) atomicAdd(cell_ctr, cells_acc); }
 }
+#endif // WM_HOST_EMUL

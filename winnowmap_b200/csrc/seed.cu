@@ -124,10 +124,11 @@ __global__ void wm_seed_task_kernel(const wm128_dev *__restrict__ mz, const int6
 }
 
 // tie-exact radix_sort_128x of each task's anchors (src/map.c:252)
-__global__ void wm_anchor_sort_small_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__ off, int n_arr)
+__global__ void wm_anchor_sort_small_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__ off, int n_arr, const int32_t *__restrict__ ids)
 {
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n_arr) return;
+	if (ids) t = ids[t];
 	const int64_t n = off[t + 1] - off[t];
 	if (n <= WM_RS_MIN_SIZE) wm_rs_insertsort(a + off[t], a + off[t] + n);
 }
@@ -167,8 +168,10 @@ wm_anchor_sort_big_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__
 // global memory.  Sub-buckets that need another big pass go back on the array's work list; the smaller ones are sorted
 // by the four warps in parallel (staged in shared memory, rsort.cuh); the <= 64-element ones by one thread each.
 #define WM_GS_THREADS 128
-#define WM_GS_F 16                 // FIFO depth per bucket (power of two)
-#define WM_GS_STAGE 2048           // sub-ranges up to this many elements are sorted by one warp in shared memory
+// WM_GS_F: FIFO depth per bucket (power of two); WM_GS_STAGE: sub-ranges up to this many elements are sorted by one warp in
+// shared memory.  Two instantiations: <16, 2048> (142 KB of shared memory, one CTA per SM) for the giant arrays and
+// <8, 512> (46 KB, four CTAs per SM) for the medium ones, of which there are thousands per wave.
+template <int WM_GS_F, int WM_GS_STAGE>
 struct wm_gs_sm {
 	int B[256], E[256];            // bucket bounds of the current pass
 	int b[256];                    // write pointers (walker)
@@ -183,6 +186,7 @@ struct wm_gs_sm {
 	} u;
 };
 
+template <int WM_GS_F, int WM_GS_STAGE>
 __global__ void __launch_bounds__(WM_GS_THREADS)
 wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ ids, int n_arr,
                             wm_rs_range *__restrict__ wl_all, unsigned long long *dbg)
@@ -193,7 +197,8 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 	unsigned long long n_steps_dbg = 0, n_wait_dbg = 0;
 #define WM_GS_LAP(i) do { if (dbg && tid == 0) { const long long t2 = clock64(); atomicAdd(dbg + (i), (unsigned long long)(t2 - t_dbg)); t_dbg = t2; } } while (0)
 	extern __shared__ __align__(16) unsigned char wm_gs_smem[];
-	wm_gs_sm *S = (wm_gs_sm*)wm_gs_smem;
+	typedef wm_gs_sm<WM_GS_F, WM_GS_STAGE> sm_t;
+	sm_t *S = (sm_t*)wm_gs_smem;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (int ai = blockIdx.x; ai < n_arr; ai += gridDim.x) {
 		const int task = ids[ai];
@@ -273,7 +278,7 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 			} else if (wid > 0) { // feeders: 96 threads, buckets tid - 32, + 96, + 192
 				volatile int *bv = S->b; volatile int *done = &S->walk_done;
 				for (;;) {
-					bool any = false;
+					bool any = false, fed = false;
 					for (int k = tid - 32; k < 256; k += WM_GS_THREADS - 32) {
 						const int fl = S->filled[k], Ek = S->E[k];
 						if (fl >= Ek) continue;
@@ -282,7 +287,8 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 						int room = WM_GS_F - pending;
 						if (room > Ek - fl) room = Ek - fl;
 						if (room > 8) room = 8;
-						if (room >= 4 || (room > 0 && (room == Ek - fl || pending < 4))) { // refill in batches unless the FIFO runs low
+						if (room > WM_GS_F) room = WM_GS_F;
+						if (room >= WM_GS_F / 4 || (room > 0 && (room == Ek - fl || pending < WM_GS_F / 4))) { // refill in batches unless the FIFO runs low
 							wm128_dev r[8];
 							#pragma unroll
 							for (int m = 0; m < 8; ++m) if (m < room) r[m] = a[fl + m];
@@ -290,9 +296,13 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 							for (int m = 0; m < 8; ++m) if (m < room) S->u.fifo[k][(fl + m) & (WM_GS_F - 1)] = r[m];
 							__threadfence_block();
 							*(volatile int*)&S->filled[k] = fl + room;
+							fed = true;
 						}
 					}
 					if (!any || *done) break;
+					// nothing to load right now: do not hammer shared memory with polls (the walker's own loads queue behind them;
+					// measured: 300 clocks per step with spinning feeders)
+					if (!fed) __nanosleep(256);
 				}
 			}
 			__syncthreads();
@@ -337,17 +347,25 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 }
 
 // sort n_arr arrays (device); h_off is the host copy of the offsets
-void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_arr, cudaStream_t st)
-{
-	if (n_arr <= 0) return;
-	std::vector<int32_t> big;
-	for (int i = 0; i < n_arr; ++i) if (h_off[i + 1] - h_off[i] > WM_RS_MIN_SIZE) big.push_back(i);
+void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, const int64_t *h_off, int n_arr, cudaStream_t st, const int32_t *only, int n_only)
+{ // only != null: just the arrays only[0 .. n_only) of the n_arr
+	if (n_arr <= 0 || (only && n_only <= 0)) return;
+	std::vector<int32_t> big, small_ids;
+	if (only) {
+		for (int q = 0; q < n_only; ++q) { const int i = only[q]; if (h_off[i + 1] - h_off[i] > WM_RS_MIN_SIZE) big.push_back(i); else if (h_off[i + 1] - h_off[i] > 1) small_ids.push_back(i); }
+	} else for (int i = 0; i < n_arr; ++i) if (h_off[i + 1] - h_off[i] > WM_RS_MIN_SIZE) big.push_back(i);
 	if (getenv("WM_DP_STATS")) {
 		int64_t mx = 0, n_2k = 0, n_10k = 0;
 		for (int i = 0; i < n_arr; ++i) { int64_t n = h_off[i + 1] - h_off[i]; mx = n > mx ? n : mx; n_2k += n > 2560; n_10k += n > 10240; }
 		fprintf(stderr, "[sort-stats] arrays=%d big=%d >2560:%ld >10240:%ld max=%ld total=%ld\n", n_arr, (int)big.size(), (long)n_2k, (long)n_10k, (long)mx, (long)h_off[n_arr]);
 	}
-	wm_count_launch(); wm_anchor_sort_small_kernel<<<(n_arr + 127) / 128, 128, 0, st>>>(d_a, d_off, n_arr);
+	if (!only) { wm_count_launch(); wm_anchor_sort_small_kernel<<<(n_arr + 127) / 128, 128, 0, st>>>(d_a, d_off, n_arr, 0); }
+	else if (!small_ids.empty()) {
+		int32_t *d_small = (int32_t*)ws->small_ids.need(sizeof(int32_t) * small_ids.size());
+		WM_CUDA_CHECK(wm_memcpy_async(d_small, small_ids.data(), sizeof(int32_t) * small_ids.size(), cudaMemcpyHostToDevice, st));
+		wm_count_launch(); wm_anchor_sort_small_kernel<<<(unsigned)((small_ids.size() + 127) / 128), 128, 0, st>>>(d_a, d_off, (int)small_ids.size(), d_small);
+		wm_stream_sync(st); // small_ids is a local
+	}
 	WM_CUDA_CHECK(cudaGetLastError());
 	if (!big.empty()) {
 		// three launches by size class: the shared-memory stage of the array sets the occupancy
@@ -363,16 +381,17 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 		int32_t *d_big = (int32_t*)ws->big_ids.need(sizeof(int32_t) * big.size());
 		wm_rs_range *d_wl = (wm_rs_range*)ws->rs_stacks.need(sizeof(wm_rs_range) * (size_t)((h_off[n_arr] >> 6) + n_arr + 2));
 		WM_CUDA_CHECK(wm_memcpy_async(d_big, big.data(), sizeof(int32_t) * big.size(), cudaMemcpyHostToDevice, st));
+		static int giant = -1, medium_coop = -1; // WM_SORT_GIANT=0 / WM_SORT_MEDIUM=0: the single-warp kernels (kept for comparison)
+		if (giant < 0) { const char *e = getenv("WM_SORT_GIANT"); giant = (e && *e == '0') ? 0 : 1; e = getenv("WM_SORT_MEDIUM"); medium_coop = (e && *e == '0') ? 0 : 1; }
 		if (n_l) {
-			static int giant = -1; // WM_SORT_GIANT=0: the single-warp walk in global memory (kept for comparison)
-			if (giant < 0) { const char *e = getenv("WM_SORT_GIANT"); giant = (e && *e == '0') ? 0 : 1; }
 			wm_count_launch();
 			if (giant) {
+				typedef wm_gs_sm<16, 2048> sm_t;
 				static bool attr_set = false;
-				if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(wm_gs_sm))); attr_set = true; }
+				if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<16, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t))); attr_set = true; }
 				unsigned long long *dbg = 0;
 				if (getenv("WM_SORT_DEBUG")) { WM_CUDA_CHECK(cudaMalloc((void**)&dbg, 64)); WM_CUDA_CHECK(cudaMemset(dbg, 0, 64)); }
-				wm_anchor_sort_giant_kernel<<<(unsigned)(n_l < 296 ? n_l : 296), WM_GS_THREADS, sizeof(wm_gs_sm), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, dbg);
+				wm_anchor_sort_giant_kernel<16, 2048><<<(unsigned)(n_l < 296 ? n_l : 296), WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, dbg);
 				if (dbg) {
 					unsigned long long h[8];
 					WM_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -382,7 +401,15 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 				}
 			} else wm_anchor_sort_big_kernel<<<(unsigned)n_l, 32, 0, st>>>(d_a, d_off, d_big, (int)n_l, d_wl, 0);
 		}
-		if (n_m) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_m, 32, cap_m * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, cap_m); }
+		if (n_m) {
+			wm_count_launch();
+			if (medium_coop) { // thousands of arrays per wave: the light instantiation, four CTAs per SM
+				typedef wm_gs_sm<8, 512> sm_t;
+				static bool attr_set = false;
+				if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t))); attr_set = true; }
+				wm_anchor_sort_giant_kernel<8, 512><<<(unsigned)(n_m < 592 ? n_m : 592), WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, 0);
+			} else wm_anchor_sort_big_kernel<<<(unsigned)n_m, 32, cap_m * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, cap_m);
+		}
 		if (n_s) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_s, 32, cap_s * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l + n_m, (int)n_s, d_wl, cap_s); }
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
