@@ -12,7 +12,7 @@ N50 = 30 kb at 5 % error, `-x map-ont -W <top-0.02 % 15-mers> -c`.  WM_BENCH_REF
 One "step" = one pass of the hot path (stage-1 MCAS waves + stage-2 remap: sketch, seed lookup, anchor sort,
 chaining, extension DP with traceback, host glue) over --reads fresh reads (~26.5 Mbase; working set -- read pool,
 anchors, backtrack matrices, multi-GB index -- far larger than L2).  Steps are submitted to the library in groups of
-at most WM_BENCH_GROUP steps (default 8) and the library cuts each submission into chunks of WM_CHUNK_BASES bases
+at most WM_BENCH_GROUP steps (default 32) and the library cuts each submission into chunks of WM_CHUNK_BASES bases
 (pinned here to 32 Mbase), so device and host footprints do not grow with --steps.
 
   value : bases/s with the raw reads of all K steps already resident in one HBM pool (wm_bench_upload); CUDA events
@@ -52,7 +52,7 @@ import numpy as np  # noqa: E402
 
 CACHE = os.environ.get("WM_BENCH_CACHE", "/tmp/wm_bench_cache")
 REF_LEN = int(os.environ.get("WM_BENCH_REF_LEN", 500_000_000))
-GROUP = max(1, int(os.environ.get("WM_BENCH_GROUP", 8)))
+GROUP = max(1, int(os.environ.get("WM_BENCH_GROUP", 32)))
 N50, ERR, K = 30000, 0.05, 15
 CONTIGS = None  # set by load_workload(); read by the forked read generators
 

@@ -35,17 +35,25 @@ extern "C" int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qof
 	wm_require_device("wm_ksw_extd2_batch");
 	if (n <= 0) return 0;
 	static_assert(sizeof(wm_extz_t) == sizeof(wm_extz_dev), "ez layout");
-	const int64_t qtot = qoff[n], ttot = toff[n];
+	// the sequence pool in the layout of the mapping pipeline (gpu_backend.cu): every sequence on a 16-byte boundary, zero padded
+	// (the fill kernel stages aligned sequences with bulk copies; odd-numbered jobs are shifted by one byte here so that the
+	// plain staging loop is exercised as well)
 	std::vector<wm_dp_job> jobs(n);
+	std::vector<uint8_t> pool;
 	int64_t p_off = 0;
 	for (int i = 0; i < n; ++i) {
 		wm_dp_job &J = jobs[i];
-		J.q_off = qoff[i]; J.t_off = qtot + toff[i];
 		J.qlen = (int32_t)(qoff[i + 1] - qoff[i]); J.tlen = (int32_t)(toff[i + 1] - toff[i]);
+		const size_t shift = (i & 1) ? 1 : 0;
+		pool.resize((pool.size() + 15) / 16 * 16 + shift, 0);
+		J.q_off = (int64_t)pool.size(); pool.insert(pool.end(), qseq + qoff[i], qseq + qoff[i + 1]);
+		pool.resize((pool.size() + 15) / 16 * 16 + shift, 0);
+		J.t_off = (int64_t)pool.size(); pool.insert(pool.end(), tseq + toff[i], tseq + toff[i + 1]);
 		J.w = w[i]; J.zdrop = zdrop[i]; J.end_bonus = end_bonus[i]; J.flag = flag[i];
 		J.p_off = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.qlen, J.tlen, J.w);
 		J.cig_off = cigar_off[i]; J.cig_cap = (int32_t)(cigar_off[i + 1] - cigar_off[i]); J.pad = -1;
 	}
+	pool.resize((pool.size() + 15) / 16 * 16 + 32, 0);
 	const wm_extd2_plan_t plan = wm_extd2_plan(jobs.data(), n, q == q2 && e == e2);
 	std::vector<int32_t> coop; // the big jobs go to the CTA-cooperative sweep, as in the mapping pipeline (gpu_backend.cu)
 	if (!(q == q2 && e == e2) && !(getenv("WM_DP_COOP") && *getenv("WM_DP_COOP") == '0') && !(getenv("WM_DP_V1") && *getenv("WM_DP_V1") == '1'))
@@ -53,13 +61,12 @@ extern "C" int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qof
 			if (jobs[i].pad >= 0 && wm_dp_is_coop(jobs[i].qlen, jobs[i].tlen, jobs[i].w)) { jobs[i].flag |= WM_DP_COOP; coop.push_back(i); }
 	int32_t *d_coop = wm_dev_alloc<int32_t>(coop.size() + 1);
 	if (!coop.empty()) WM_CUDA_CHECK(cudaMemcpy(d_coop, coop.data(), sizeof(int32_t) * coop.size(), cudaMemcpyHostToDevice));
-	uint8_t *d_seq = wm_dev_alloc<uint8_t>(qtot + ttot + 16);
+	uint8_t *d_seq = wm_dev_alloc<uint8_t>(pool.size() + 16);
 	uint8_t *d_bt = wm_dev_alloc<uint8_t>(p_off + 16);
 	wm_dp_job *d_jobs = wm_dev_alloc<wm_dp_job>(n);
 	wm_extz_dev *d_ez = wm_dev_alloc<wm_extz_dev>(n);
 	uint32_t *d_cig = wm_dev_alloc<uint32_t>(cigar_off[n] + 1);
-	WM_CUDA_CHECK(cudaMemcpy(d_seq, qseq, qtot, cudaMemcpyHostToDevice));
-	WM_CUDA_CHECK(cudaMemcpy(d_seq + qtot, tseq, ttot, cudaMemcpyHostToDevice));
+	WM_CUDA_CHECK(cudaMemcpy(d_seq, pool.data(), pool.size(), cudaMemcpyHostToDevice));
 	WM_CUDA_CHECK(cudaMemcpy(d_jobs, jobs.data(), sizeof(wm_dp_job) * n, cudaMemcpyHostToDevice));
 	wm_dp_params P; wm_dp_params_init(&P, mat, q, e, q2, e2);
 	wm_extd2_ws ws;

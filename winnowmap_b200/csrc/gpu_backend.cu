@@ -428,6 +428,7 @@ __global__ void wm_gather2_kernel(const wm_gather_job *__restrict__ jobs, const 
 	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (joff[m] <= gidx) lo = m; else hi = m; }
 	const wm_gather_job J = jobs[lo];
 	const int p = (int)(gidx - joff[lo]);
+	if (p >= J.len) { dst[gidx] = 0; return; } // padding up to the next 16-byte boundary
 	const int64_t s = J.src_off + (J.reversed ? J.len - 1 - p : p);
 	uint8_t c;
 	if (J.kind == 0) c = codes[s];
@@ -486,8 +487,9 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		for (int i = 0; i < m; ++i) {
 			const DpJob &J = jobs[done + perm[i]];
 			slot_of[done + perm[i]] = done + i;
-			joff[2 * i] = pool_off; pool_off += J.q.len;
-			joff[2 * i + 1] = pool_off; pool_off += J.t.len;
+			// every sequence starts on a 16-byte boundary and is zero padded to one: the fill kernel stages it with bulk copies
+			joff[2 * i] = pool_off; pool_off += (J.q.len + 15) & ~15;
+			joff[2 * i + 1] = pool_off; pool_off += (J.t.len + 15) & ~15;
 			h_poff[i] = p_off; p_off += (int64_t)wm_extd2_bt_bytes(J.q.len, J.t.len, J.w);
 			h_coff[i] = c_off; c_off += J.q.len + J.t.len + 2;
 			prof_bytes += 2.0 * (J.q.len + J.t.len) + 48; // qlen + tlen (codes in) + (qlen + tlen) (traceback) + 48; C_block is counted on the device

@@ -24,7 +24,7 @@
 #define WM_FILL_WARPS 4
 #define WM_SMEM_CELLS 1024   // first-generation path: per-warp shared-memory slice covers tlen <= 1024
 #define WM_FILL_SLICE (WM_SMEM_CELLS * 11 > WM_V2_SLICE_C ? WM_SMEM_CELLS * 11 : WM_V2_SLICE_C)
-#define WM_V2_SLICE_C ((7 * 2 * (512 + 8) + 4 * 512 + (512 + 16) + (640 + 64) + 15) / 16 * 16)
+#define WM_V2_SLICE_C ((7 * 2 * (512 + 8) + 4 * 512 + (512 + 16) + (640 + 64) + 640 + 16 + 15) / 16 * 16)
 
 #include "ksw_extd2_common.cuh"
 

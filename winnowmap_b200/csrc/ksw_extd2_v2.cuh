@@ -17,7 +17,37 @@
 #define WM_V2_T 512      // max tlen16 handled in shared memory
 #define WM_V2_Q 640      // max qlen
 #define WM_V2_TS (WM_V2_T + 8)
-#define WM_V2_SLICE (7 * 2 * WM_V2_TS + 4 * WM_V2_T + (WM_V2_T + 16) + (WM_V2_Q + 64))
+// state rows + H + target + reversed query, then (shared-memory slices only) the landing zone of the query's bulk copy and the
+// warp's mbarrier
+#define WM_V2_SLICE (7 * 2 * WM_V2_TS + 4 * WM_V2_T + (WM_V2_T + 16) + (WM_V2_Q + 64) + WM_V2_Q + 16)
+
+#ifndef WM_HOST_EMUL
+// ---- bulk-asynchronous (TMA) staging of a job's sequences: cp.async.bulk global -> shared, completion on an mbarrier ----
+// One lane arms the warp's mbarrier with the byte count and issues the two copies (target, query); the copy engine moves the
+// bytes while the 32 lanes initialise the state rows; everybody then waits on the barrier's phase.  Source and destination
+// must be 16-byte aligned and the sizes multiples of 16: the gather kernel lays the pool out that way (gpu_backend.cu).
+__device__ __forceinline__ uint32_t wm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wm_mbar_init(uint64_t *mbar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(wm_smem_u32(mbar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void wm_mbar_expect_tx(uint64_t *mbar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(wm_smem_u32(mbar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void wm_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *mbar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(wm_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(wm_smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void wm_mbar_wait(uint64_t *mbar, uint32_t phase)
+{
+	uint32_t ok = 0;
+	while (!ok)
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+		             : "=r"(ok) : "r"(wm_smem_u32(mbar)), "r"(phase) : "memory");
+}
+#endif
+
 
 __device__ __forceinline__ uint32_t wm_pack2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 __device__ __forceinline__ uint32_t wm_rep2(int v) { return wm_pack2(v, v); }
@@ -191,8 +221,29 @@ __device__ void wm_extd2_fill_job_v2(const wm_dp_job &J, const uint8_t *__restri
 			U[i] = V[i] = X[i] = Y[i] = i1; X2[i] = Y2[i] = i2; SK[i] = s0;
 			if (!approx_max) H[i] = WM_NEG_INF;
 		}
-		for (int i = lane; i < tcap + 16; i += 32) tg[i] = i < tlen ? target[i] : 0;
-		for (int i = lane; i < qcap + 48; i += 32) { const int j = i - 16; (qr - 16)[i] = (j >= 0 && j < qlen) ? query[qlen - 1 - j] : 0; }
+#ifndef WM_HOST_EMUL
+		if (SM && ((J.q_off | J.t_off) & 15) == 0) {
+			// bulk copies of the 16-byte padded target and query (the pool's padding bytes are zero); the state rows above were
+			// being initialised while the copies were in flight
+			uint8_t *stage = qr + qcap + 48;                       // landing zone of the forward query
+			uint64_t *mbar = (uint64_t*)(stage + qcap);
+			const uint32_t tb = (uint32_t)((tlen + 15) & ~15), qb = (uint32_t)((qlen + 15) & ~15);
+			if (lane == 0) {
+				wm_mbar_init(mbar, 1);
+				wm_mbar_expect_tx(mbar, tb + qb);
+				wm_bulk_g2s(tg, target, tb, mbar);
+				wm_bulk_g2s(stage, query, qb, mbar);
+			}
+			for (int i = (int)tb + lane; i < tcap + 16; i += 32) tg[i] = 0;
+			__syncwarp();
+			wm_mbar_wait(mbar, 0);
+			for (int i = lane; i < qcap + 48; i += 32) { const int j = i - 16; (qr - 16)[i] = (j >= 0 && j < qlen) ? stage[qlen - 1 - j] : 0; }
+		} else
+#endif
+		{
+			for (int i = lane; i < tcap + 16; i += 32) tg[i] = i < tlen ? target[i] : 0;
+			for (int i = lane; i < qcap + 48; i += 32) { const int j = i - 16; (qr - 16)[i] = (j >= 0 && j < qlen) ? query[qlen - 1 - j] : 0; }
+		}
 	}
 	__syncwarp();
 

@@ -186,6 +186,16 @@ struct wm_gs_sm {
 	} u;
 };
 
+// a FIFO entry, read in place of a plain load so that the compiler keeps it after the (volatile) poll of `filled` without a
+// "memory" clobber in the walker's loop (which made it re-derive the shared-memory base, an S2UR, on every step)
+__device__ __forceinline__ wm128_dev wm_gs_fifo_read(const wm128_dev *p)
+{
+	wm128_dev r; uint32_t x0, x1, y0, y1;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(y0), "=r"(y1) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+	r.x = (uint64_t)x1 << 32 | x0, r.y = (uint64_t)y1 << 32 | y0;
+	return r;
+}
+
 template <int WM_GS_F, int WM_GS_STAGE>
 __global__ void __launch_bounds__(WM_GS_THREADS)
 wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ ids, int n_arr,
@@ -205,6 +215,7 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 		const int64_t base = off[task];
 		const int n = (int)(off[task + 1] - base);
 		wm128_dev *a = a_all + base;
+		asm volatile("" : "+l"(a)); // keep the pointer in registers: the walker's loop was re-deriving it from the parameter bank (an LDC per step)
 		// work lists in global memory (the array's slice of wl_all: n / 64 + 1 entries): big ranges grow from the front,
 		// small ones from the back
 		wm_rs_range *wl = wl_all + (base >> 6) + task;
@@ -252,8 +263,7 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 					const int bk = b[k];
 					if (bk != E[k]) {
 						while (filled[k] <= bk) { ++n_wait_dbg; }
-						asm volatile("" ::: "memory");
-						wm128_dev tmp = S->u.fifo[k][bk & (WM_GS_F - 1)];
+						wm128_dev tmp = wm_gs_fifo_read(&S->u.fifo[k][bk & (WM_GS_F - 1)]);
 						++n_steps_dbg;
 						int l = (int)(tmp.x >> s & 255);
 						if (l != k) {
@@ -261,8 +271,7 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 								const int bl = b[l];
 								while (filled[l] <= bl) { ++n_wait_dbg; }
 								++n_steps_dbg;
-								asm volatile("" ::: "memory");
-								const wm128_dev nxt = S->u.fifo[l][bl & (WM_GS_F - 1)];
+								const wm128_dev nxt = wm_gs_fifo_read(&S->u.fifo[l][bl & (WM_GS_F - 1)]);
 								a[bl] = tmp;
 								*(volatile int*)&b[l] = bl + 1;
 								tmp = nxt;
