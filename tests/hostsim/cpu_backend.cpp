@@ -256,6 +256,8 @@ extern "C" void wmt_dump_timers(void) { wmh::g_timers.dump(stderr); wmh::g_timer
 
 // unit hook: the index builder's parallel (hash, position) sort on an interleaved x,y array
 #include "../../winnowmap_b200/csrc/host_index.h"
+// unit hook: the index builder's 4-bit packing of a sequence placed at base offset o0 (S: zeroed words)
+extern "C" void wmt_pack_seq4(uint32_t *S, uint64_t o0, const char *seq, uint64_t L) { wmh::pack_seq4(S, o0, seq, L); }
 extern "C" void wmt_sort_index_pairs(uint64_t *xy, int64_t n, int n_threads)
 {
 	std::vector<wm_pair_t> a((size_t)n);

@@ -116,3 +116,24 @@ def test_index_pair_sort_is_the_sorted_order(hostsim):
         hostsim.wmt_sort_index_pairs(a.ctypes.data, n, threads)
         order = np.lexsort((y, x >> np.uint64(8)))
         assert np.array_equal(a, np.stack([x[order], y[order]], axis=1)), (n, key_bits, threads)
+
+
+def test_reference_packing_matches_the_plain_loop(hostsim):
+    """pack_seq4 (csrc/host_index.h: whole words in parallel, shared edge words serially) against mm_seq4_set applied base by base
+    (src/mmpriv.h:29): several sequences back to back at odd offsets, lengths around the word size, IUPAC and lower case."""
+    import numpy as np
+    rng = np.random.default_rng(12)
+    hostsim.wmt_pack_seq4.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    alphabet = np.frombuffer(b"ACGTacgtNnRYU", dtype=np.uint8)
+    code = {ord("A"): 0, ord("a"): 0, ord("C"): 1, ord("c"): 1, ord("G"): 2, ord("g"): 2, ord("T"): 3, ord("t"): 3}
+    lens = [0, 1, 3, 7, 8, 9, 15, 16, 17, 5, 64, 100, 40000, 2, 33000, 6]
+    seqs = [alphabet[rng.integers(0, len(alphabet), size=n)].tobytes() for n in lens]
+    total = sum(lens)
+    S = np.zeros((total + 7) // 8 + 1, np.uint32); E = np.zeros_like(S)
+    o = 0
+    for sq in seqs:
+        hostsim.wmt_pack_seq4(S.ctypes.data, o, sq, len(sq))
+        for j, ch in enumerate(sq):
+            E[(o + j) >> 3] |= np.uint32(code.get(ch, 4) << (((o + j) & 7) << 2))
+        o += len(sq)
+    assert np.array_equal(S, E)

@@ -13,6 +13,7 @@
 #include <vector>
 #include "wm_common.cuh"
 #include "sketch.cuh"
+#include "index_dev.cuh"
 #include "gpu_backend.h"
 #include "host_io.h"
 #include "host_index.h"
@@ -196,8 +197,9 @@ extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_fre
 	uint8_t *d_table = wm_dev_alloc<uint8_t>(wm_bloom_bits(bloom) / 8 + 16);
 	WM_CUDA_CHECK(cudaMemcpy(d_table, wm_bloom_table(bloom), wm_bloom_bits(bloom) / 8, cudaMemcpyHostToDevice));
 	wm_bloom_dev bf; wm_bloom_dev_from_table(&bf, d_table, wm_bloom_bits(bloom));
-	// read the reference, pack it 4 bits per base (mm_seq4_set, src/mmpriv.h:29) and sketch it in groups
-	std::vector<wm128_dev> mz;
+	// read the reference, pack it 4 bits per base (mm_seq4_set, src/mmpriv.h:29) and sketch it in groups; the minimizers stay
+	// on the device: they are sorted and cut into the CSR there (index_dev.cu)
+	std::vector<std::pair<wm128_dev*, int64_t>> parts; int64_t n_mz_total = 0;
 	wm_sketch_ws ws;
 	std::vector<wm_sk_task> tasks; std::string group; uint64_t sum_len = 0;
 	wm_dbuf d_ascii, d_codes;
@@ -210,9 +212,11 @@ extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_fre
 		int64_t n_mz = 0;
 		wm_sketch_run(&ws, bf, dc, tasks.data(), (int)tasks.size(), w, k, &n_mz, 0);
 		WM_CUDA_CHECK(cudaDeviceSynchronize());
-		const size_t old = mz.size();
-		mz.resize(old + n_mz);
-		if (n_mz > 0) WM_CUDA_CHECK(cudaMemcpy(mz.data() + old, ws.mz.p, sizeof(wm128_dev) * n_mz, cudaMemcpyDeviceToHost));
+		if (n_mz > 0) {
+			wm128_dev *part = wm_dev_alloc<wm128_dev>(n_mz);
+			WM_CUDA_CHECK(cudaMemcpy(part, ws.mz.p, sizeof(wm128_dev) * n_mz, cudaMemcpyDeviceToDevice));
+			parts.push_back(std::make_pair(part, n_mz)); n_mz_total += n_mz;
+		}
 		tasks.clear(); group.clear();
 	};
 	wm_read r;
@@ -221,13 +225,7 @@ extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_fre
 		H.name.push_back(r.name); H.len.push_back((uint32_t)r.seq.size()); H.offset.push_back(sum_len);
 		const uint64_t need_words = (sum_len + r.seq.size() + 7) / 8;
 		if (H.S.size() < need_words) H.S.resize(need_words, 0);
-		for (size_t j = 0; j < r.seq.size(); ++j) {
-			int cc;
-			switch (r.seq[j]) { case 'A': case 'a': cc = 0; break; case 'C': case 'c': cc = 1; break; case 'G': case 'g': cc = 2; break;
-				case 'T': case 't': cc = 3; break; default: cc = 4; }
-			const uint64_t o = sum_len + j;
-			H.S[o >> 3] |= (uint32_t)cc << ((o & 7) << 2);
-		}
+		pack_seq4(H.S.data(), sum_len, r.seq.data(), r.seq.size());
 		sum_len += r.seq.size();
 		if (!r.seq.empty()) {
 			wm_sk_task t; t.seq_off = (int64_t)group.size(); t.len = (int32_t)r.seq.size(); t.rid = rid;
@@ -237,19 +235,18 @@ extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_fre
 	}
 	flush();
 	ws.release(); d_ascii.release(); d_codes.release(); cudaFree(d_table);
-	// (hash, position) pairs sorted by hash then position: the occurrence lists mm_idx_get returns (src/index.c:239)
-	sort_index_pairs(mz, std::min(32, omp_get_max_threads()));
-	std::vector<uint64_t> keys, pos_off, pos(mz.size());
-	for (size_t i = 0; i < mz.size(); ++i) {
-		if (i == 0 || (mz[i].x >> 8) != (mz[i - 1].x >> 8)) { keys.push_back(mz[i].x >> 8); pos_off.push_back(i); }
-		pos[i] = mz[i].y;
+	// one array in position order, then sort + CSR on the device
+	wm128_dev *d_all = wm_dev_alloc<wm128_dev>(n_mz_total + 1);
+	{
+		int64_t o = 0;
+		for (auto &pp : parts) { WM_CUDA_CHECK(cudaMemcpy(d_all + o, pp.first, sizeof(wm128_dev) * pp.second, cudaMemcpyDeviceToDevice)); o += pp.second; cudaFree(pp.first); }
 	}
-	pos_off.push_back(mz.size());
-	c->n_keys = (int64_t)keys.size(), c->n_pos = (int64_t)pos.size();
-	c->be = gpu_backend_create(&H, keys.data(), (int64_t)keys.size(), pos_off.data(), pos.data(), wm_bloom_bits(bloom), wm_bloom_table(bloom), device);
+	uint64_t *d_keys = 0, *d_poff = 0, *d_pos = 0; int64_t n_keys = 0;
+	wm_index_build_dev(d_all, n_mz_total, k, &d_keys, &d_poff, &d_pos, &n_keys, 0);
+	c->n_keys = n_keys, c->n_pos = n_mz_total;
+	c->be = gpu_backend_create_dev(&H, d_keys, n_keys, d_poff, d_pos, wm_bloom_bits(bloom), wm_bloom_table(bloom), device);
 	c->bloom_bits = wm_bloom_bits(bloom);
 	c->bloom.assign(wm_bloom_table(bloom), wm_bloom_table(bloom) + c->bloom_bits / 8);
-	c->keys.swap(keys); c->pos_off.swap(pos_off); c->pos.swap(pos);
 	wm_bloom_destroy(bloom);
 	c->t_index = now_s() - t0;
 	return c;
@@ -637,8 +634,23 @@ extern "C" void wm_dump_timers(void) { wmh::g_timers.dump(stderr); wmh::g_timers
 // every other rank re-creates its context from it.  Layout: 8 x uint64 header, then the arrays, each 8-byte aligned.
 static inline size_t pad8(size_t x) { return (x + 7) & ~(size_t)7; }
 
-extern "C" int64_t wm_idx_blob_size(const wm_gpu_ctx_s *c)
+// the host copies of keys / pos_off / pos exist only when the index came through wm_gpu_idx_upload; an index built on the
+// device (wm_index_build) is fetched when the blob is first asked for
+static void fetch_index_arrays(wm_gpu_ctx_s *c)
 {
+	if (!c->keys.empty() || c->n_keys == 0) return;
+	const uint64_t *dk, *dpo, *dp;
+	gpu_backend_index_arrays(c->be, &dk, &dpo, &dp);
+	c->keys.resize(c->n_keys); c->pos_off.resize(c->n_keys + 1); c->pos.resize(c->n_pos);
+	WM_CUDA_CHECK(cudaMemcpy(c->keys.data(), dk, sizeof(uint64_t) * c->n_keys, cudaMemcpyDeviceToHost));
+	WM_CUDA_CHECK(cudaMemcpy(c->pos_off.data(), dpo, sizeof(uint64_t) * (c->n_keys + 1), cudaMemcpyDeviceToHost));
+	WM_CUDA_CHECK(cudaMemcpy(c->pos.data(), dp, sizeof(uint64_t) * c->n_pos, cudaMemcpyDeviceToHost));
+}
+
+extern "C" int64_t wm_idx_blob_size(const wm_gpu_ctx_s *c_)
+{
+	wm_gpu_ctx_s *c = const_cast<wm_gpu_ctx_s*>(c_);
+	fetch_index_arrays(c);
 	const wm_host_idx &H = c->hidx;
 	size_t names = 0;
 	for (auto &s : H.name) names += s.size() + 1;
@@ -646,8 +658,10 @@ extern "C" int64_t wm_idx_blob_size(const wm_gpu_ctx_s *c)
 	                 c->pos_off.size() * 8 + c->pos.size() * 8 + pad8(c->bloom.size()));
 }
 
-extern "C" int wm_idx_blob_write(const wm_gpu_ctx_s *c, uint8_t *buf)
+extern "C" int wm_idx_blob_write(const wm_gpu_ctx_s *c_, uint8_t *buf)
 {
+	wm_gpu_ctx_s *c = const_cast<wm_gpu_ctx_s*>(c_);
+	fetch_index_arrays(c);
 	const wm_host_idx &H = c->hidx;
 	size_t names = 0;
 	for (auto &s : H.name) names += s.size() + 1;

@@ -333,7 +333,10 @@ void wm_chain_run(wm_chain_ws *ws, wm128_dev *d_a, const int64_t *d_off, const i
 			const size_t smem = sizeof(wm_chain_tile_sm);
 			if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_chain_fill_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
 			wm_count_launch();
-			wm_chain_fill_tile_kernel<<<n_giant < n_sm ? n_giant : n_sm, WM_CT_WARPS * 32, smem, s2>>>(d_a, d_off, d_order, 0, n_giant, PP, d_set_id, f, p, t, v, counter);
+			static int tile_ctas = -1; // WM_CHAIN_TILE_CTAS: SMs the tile kernel may hold at once (a CTA takes a whole SM's registers)
+			if (tile_ctas < 0) { const char *e = getenv("WM_CHAIN_TILE_CTAS"); tile_ctas = e && atoi(e) > 0 ? atoi(e) : n_sm; }
+			const int g_t = n_giant < tile_ctas ? n_giant : tile_ctas;
+			wm_chain_fill_tile_kernel<<<g_t, WM_CT_WARPS * 32, smem, s2>>>(d_a, d_off, d_order, 0, n_giant, PP, d_set_id, f, p, t, v, counter);
 			WM_CUDA_CHECK(cudaGetLastError());
 		}
 		if (n_medium > 0) {

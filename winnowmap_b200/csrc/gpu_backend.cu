@@ -641,26 +641,17 @@ void GpuBackend::run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin
 }
 
 // ---- construction: upload the index to one device ----
-Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64_t n_keys, const uint64_t *pos_off, const uint64_t *pos,
-                            uint64_t bloom_bits, const uint8_t *bloom_table, int device)
+// the index arrays are device allocations handed over to the backend (which frees them when it is destroyed)
+Backend *gpu_backend_create_dev(const wm_host_idx *hidx, uint64_t *d_keys, int64_t n_keys, uint64_t *d_poff, uint64_t *d_pos,
+                                uint64_t bloom_bits, const uint8_t *bloom_table, int device)
 {
-	int ndev = 0;
-	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
-		fprintf(stderr, "[ERROR] winnowmap-b200: no CUDA device visible; there is no CPU fallback\n");
-		exit(1);
-	}
 	WM_CUDA_CHECK(cudaSetDevice(device));
 	GpuBackend *be = new GpuBackend();
 	GpuBackendImpl &g = be->g;
 	g.device = device; g.hidx = hidx; g.n_bases = 0;
 	g.st = wm_stream_create_high_priority(); // the DP fill kernels go to a lowest-priority side stream (wm_extd2_launch)
-	const uint64_t n_pos = pos_off[n_keys];
-	uint64_t *d_keys = wm_dev_alloc<uint64_t>(n_keys + 1), *d_poff = wm_dev_alloc<uint64_t>(n_keys + 2), *d_pos = wm_dev_alloc<uint64_t>(n_pos + 1);
 	uint32_t *d_S = wm_dev_alloc<uint32_t>(hidx->S.size() + 4);
 	uint8_t *d_bt = wm_dev_alloc<uint8_t>(bloom_bits / 8 + 16);
-	WM_CUDA_CHECK(cudaMemcpy(d_keys, keys, sizeof(uint64_t) * n_keys, cudaMemcpyHostToDevice));
-	WM_CUDA_CHECK(cudaMemcpy(d_poff, pos_off, sizeof(uint64_t) * (n_keys + 1), cudaMemcpyHostToDevice));
-	WM_CUDA_CHECK(cudaMemcpy(d_pos, pos, sizeof(uint64_t) * n_pos, cudaMemcpyHostToDevice));
 	WM_CUDA_CHECK(cudaMemcpy(d_S, hidx->S.data(), sizeof(uint32_t) * hidx->S.size(), cudaMemcpyHostToDevice));
 	WM_CUDA_CHECK(cudaMemcpy(d_bt, bloom_table, bloom_bits / 8, cudaMemcpyHostToDevice));
 	memset(&g.ix, 0, sizeof(g.ix));
@@ -681,6 +672,30 @@ Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64
 		WM_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
 	}
 	return be;
+}
+
+Backend *gpu_backend_create(const wm_host_idx *hidx, const uint64_t *keys, int64_t n_keys, const uint64_t *pos_off, const uint64_t *pos,
+                            uint64_t bloom_bits, const uint8_t *bloom_table, int device)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+		fprintf(stderr, "[ERROR] winnowmap-b200: no CUDA device visible; there is no CPU fallback\n");
+		exit(1);
+	}
+	WM_CUDA_CHECK(cudaSetDevice(device));
+	const uint64_t n_pos = pos_off[n_keys];
+	uint64_t *d_keys = wm_dev_alloc<uint64_t>(n_keys + 1), *d_poff = wm_dev_alloc<uint64_t>(n_keys + 2), *d_pos = wm_dev_alloc<uint64_t>(n_pos + 1);
+	WM_CUDA_CHECK(cudaMemcpy(d_keys, keys, sizeof(uint64_t) * n_keys, cudaMemcpyHostToDevice));
+	WM_CUDA_CHECK(cudaMemcpy(d_poff, pos_off, sizeof(uint64_t) * (n_keys + 1), cudaMemcpyHostToDevice));
+	WM_CUDA_CHECK(cudaMemcpy(d_pos, pos, sizeof(uint64_t) * n_pos, cudaMemcpyHostToDevice));
+	return gpu_backend_create_dev(hidx, d_keys, n_keys, d_poff, d_pos, bloom_bits, bloom_table, device);
+}
+
+// the resident index arrays of a backend (for the one-time fan-out blob)
+void gpu_backend_index_arrays(Backend *be_, const uint64_t **d_keys, const uint64_t **d_poff, const uint64_t **d_pos)
+{
+	GpuBackend *be = static_cast<GpuBackend*>(be_);
+	*d_keys = be->g.ix.keys, *d_poff = be->g.ix.pos_off, *d_pos = be->g.ix.pos;
 }
 
 // A second orchestration lane on the same device: shares the resident index, owns its stream and workspaces.

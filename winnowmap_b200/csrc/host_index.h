@@ -9,6 +9,33 @@
 
 namespace wmh {
 
+// mm_seq4_set for a whole sequence (src/mmpriv.h:29, src/index.c:321-332): bases [o0, o0 + L) of the concatenated reference, 4 bits
+// each, eight per 32-bit word; A C G T (either case) -> 0..3, everything else 4.  S must be zero where it is written.  Whole
+// words in parallel, the (at most two) words shared with a neighbouring sequence serially.
+static inline void pack_seq4(uint32_t *S, uint64_t o0, const char *seq, uint64_t L)
+{
+	static const uint8_t code4[256] = {
+#define WM_W4 4, 4, 4, 4
+#define WM_W16 WM_W4, WM_W4, WM_W4, WM_W4
+		WM_W16, WM_W16, WM_W16, WM_W16,
+		4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+		4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+		WM_W16, WM_W16, WM_W16, WM_W16, WM_W16, WM_W16, WM_W16, WM_W16
+#undef WM_W16
+#undef WM_W4
+	};
+	const uint64_t o1 = o0 + L, w0 = (o0 + 7) / 8, w1 = o1 / 8; // words [w0, w1) lie inside this sequence
+	const unsigned char *sq = (const unsigned char*)seq;
+	for (uint64_t o = o0; o < o1 && o < w0 * 8; ++o) S[o >> 3] |= (uint32_t)code4[sq[o - o0]] << ((o & 7) << 2);
+	#pragma omp parallel for schedule(static) if (w1 > w0 + 4096)
+	for (int64_t wi = (int64_t)w0; wi < (int64_t)w1; ++wi) {
+		const unsigned char *q = sq + ((uint64_t)wi * 8 - o0);
+		S[wi] = (uint32_t)code4[q[0]] | (uint32_t)code4[q[1]] << 4 | (uint32_t)code4[q[2]] << 8 | (uint32_t)code4[q[3]] << 12 |
+		        (uint32_t)code4[q[4]] << 16 | (uint32_t)code4[q[5]] << 20 | (uint32_t)code4[q[6]] << 24 | (uint32_t)code4[q[7]] << 28;
+	}
+	for (uint64_t o = w1 >= w0 ? w1 * 8 : o1; o < o1; ++o) S[o >> 3] |= (uint32_t)code4[sq[o - o0]] << ((o & 7) << 2);
+}
+
 // Sort by (x >> 8, y).  Keys are partitioned by their leading bits, the partitions are sorted concurrently; the result
 // is the unique sorted order (no two entries share hash and position), so it does not depend on the thread count.
 template <typename T>

@@ -378,10 +378,13 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 	WM_CUDA_CHECK(cudaGetLastError());
 	if (!big.empty()) {
 		// three launches by size class: the shared-memory stage of the array sets the occupancy
-		static int cap_m_env = -1; // WM_SORT_GIANT_MIN: arrays above this many anchors go to the giant kernel (default: what fits the 208 KB stage)
-		if (cap_m_env < 0) { const char *e = getenv("WM_SORT_GIANT_MIN"); cap_m_env = e && atoi(e) >= 2048 && atoi(e) <= 13312 ? atoi(e) : 13312; }
-		const int cap_s = 2048, cap_m = cap_m_env; // 32 KB and up to 208 KB of anchors
-		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap_m * (int)sizeof(wm128_dev)));
+		static int cap_m_env = -1; // WM_SORT_GIANT_MIN: arrays above this many anchors go to the <16, 2048> instantiation (default: none --
+		// measured on the tandem workload: everything on the light <8, 512> instantiation, four CTAs per SM, is 10 % faster end to end)
+		if (cap_m_env < 0) { const char *e = getenv("WM_SORT_GIANT_MIN"); cap_m_env = e && atoi(e) >= 2048 ? atoi(e) : (1 << 30); } // (above 13312 only with the walker kernels: the single-warp kernel stages the array in 208 KB)
+		static int giant = -1, medium_coop = -1; // WM_SORT_GIANT=0 / WM_SORT_MEDIUM=0: the single-warp kernels (kept for comparison)
+		if (giant < 0) { const char *e = getenv("WM_SORT_GIANT"); giant = (e && *e == '0') ? 0 : 1; e = getenv("WM_SORT_MEDIUM"); medium_coop = (e && *e == '0') ? 0 : 1; }
+		const int cap_s = 2048, cap_m = medium_coop || cap_m_env < 13312 ? cap_m_env : 13312; // 32 KB and up to 208 KB of anchors
+		WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (cap_m < 13312 ? cap_m : 13312) * (int)sizeof(wm128_dev)));
 		std::stable_sort(big.begin(), big.end(), [&](int x, int y) { return h_off[x + 1] - h_off[x] > h_off[y + 1] - h_off[y]; });
 		size_t n_l = 0, n_m = 0;
 		while (n_l < big.size() && h_off[big[n_l] + 1] - h_off[big[n_l]] > cap_m) ++n_l;
@@ -390,8 +393,6 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 		int32_t *d_big = (int32_t*)ws->big_ids.need(sizeof(int32_t) * big.size());
 		wm_rs_range *d_wl = (wm_rs_range*)ws->rs_stacks.need(sizeof(wm_rs_range) * (size_t)((h_off[n_arr] >> 6) + n_arr + 2));
 		WM_CUDA_CHECK(wm_memcpy_async(d_big, big.data(), sizeof(int32_t) * big.size(), cudaMemcpyHostToDevice, st));
-		static int giant = -1, medium_coop = -1; // WM_SORT_GIANT=0 / WM_SORT_MEDIUM=0: the single-warp kernels (kept for comparison)
-		if (giant < 0) { const char *e = getenv("WM_SORT_GIANT"); giant = (e && *e == '0') ? 0 : 1; e = getenv("WM_SORT_MEDIUM"); medium_coop = (e && *e == '0') ? 0 : 1; }
 		if (n_l) {
 			wm_count_launch();
 			if (giant) {
@@ -400,7 +401,9 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 				if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<16, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t))); attr_set = true; }
 				unsigned long long *dbg = 0;
 				if (getenv("WM_SORT_DEBUG")) { WM_CUDA_CHECK(cudaMalloc((void**)&dbg, 64)); WM_CUDA_CHECK(cudaMemset(dbg, 0, 64)); }
-				wm_anchor_sort_giant_kernel<16, 2048><<<(unsigned)(n_l < 296 ? n_l : 296), WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, dbg);
+				static int giant_ctas = -1; // WM_SORT_GIANT_CTAS
+				if (giant_ctas < 0) { const char *e = getenv("WM_SORT_GIANT_CTAS"); giant_ctas = e && atoi(e) > 0 ? atoi(e) : 148; }
+				wm_anchor_sort_giant_kernel<16, 2048><<<(unsigned)(n_l < (size_t)giant_ctas ? n_l : (size_t)giant_ctas), WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, dbg);
 				if (dbg) {
 					unsigned long long h[8];
 					WM_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -416,7 +419,9 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 				typedef wm_gs_sm<8, 512> sm_t;
 				static bool attr_set = false;
 				if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t))); attr_set = true; }
-				wm_anchor_sort_giant_kernel<8, 512><<<(unsigned)(n_m < 592 ? n_m : 592), WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, 0);
+				static int med_ctas = -1; // WM_SORT_MEDIUM_CTAS: resident CTAs of the medium class (47 KB of shared memory each)
+				if (med_ctas < 0) { const char *e = getenv("WM_SORT_MEDIUM_CTAS"); med_ctas = e && atoi(e) > 0 ? atoi(e) : 592; }
+				wm_anchor_sort_giant_kernel<8, 512><<<(unsigned)(n_m < (size_t)med_ctas ? n_m : (size_t)med_ctas), WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, 0);
 			} else wm_anchor_sort_big_kernel<<<(unsigned)n_m, 32, cap_m * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, cap_m);
 		}
 		if (n_s) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_s, 32, cap_s * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l + n_m, (int)n_s, d_wl, cap_s); }

@@ -130,14 +130,16 @@ wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n, bool single = false);
 // int32 per job in d_zd (max_zdrop, t0, t1, q0, q1; max_zdrop = -1: no result).  zp / d_zd may be null.
 #define WM_DP_SCAN_ZDROP 0x10000
 // Jobs flagged WM_DP_COOP are skipped by the warp-per-job kernel and swept by a whole CTA (d_coop_ids lists them): the few big
-// jobs (millions of cells) that would otherwise keep a launch waiting on one warp.  wm_dp_is_coop is the host's rule.
+// jobs (>= 300 k band cells, diagonals of >= 384 cells) that would otherwise keep a launch waiting on one warp.  wm_dp_is_coop is the host's rule.
 #define WM_DP_COOP 0x20000
 static inline bool wm_dp_is_coop(int qlen, int tlen, int w)
 {
+	static long long min_cells = -1; // WM_DP_COOP_MIN_CELLS (tuning)
+	if (min_cells < 0) { const char *e = getenv("WM_DP_COOP_MIN_CELLS"); min_cells = e && atoll(e) > 0 ? atoll(e) : 300000; }
 	if (w < 0) w = tlen > qlen ? tlen : qlen;
 	const int diag = qlen < tlen ? (qlen < w + 1 ? qlen : w + 1) : (tlen < w + 1 ? tlen : w + 1);
 	const long long cells = (long long)tlen * (qlen < 2 * w + 1 ? qlen : 2 * w + 1);
-	return diag >= 384 && cells >= 1500000;
+	return diag >= 384 && cells >= min_cells;
 }
 struct wm_zd_params { int32_t q, e; int8_t mat[25]; int8_t pad[3]; };
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
