@@ -663,8 +663,12 @@ Backend *gpu_backend_create_dev(const wm_host_idx *hidx, uint64_t *d_keys, int64
 	wm_stream_sync(g.st);
 	size_t free_b = 0, total_b = 0;
 	WM_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-	g.bt_budget = free_b / 4; // backtrack matrices of one DP chunk
+	g.bt_budget = free_b / 4; // backtrack matrices of the DP launches in flight (shared by the lanes)
 	if (g.bt_budget > ((size_t)32 << 30)) g.bt_budget = (size_t)32 << 30;
+	if (const char *e = getenv("WM_BT_BUDGET_GB")) { // tuning: bigger budgets mean fewer, larger fill launches per DP round
+		const size_t want = (size_t)atoll(e) << 30;
+		if (want > 0 && want < free_b * 3 / 4) g.bt_budget = want;
+	}
 	{ // workspaces grow through the stream-ordered allocator (wm_dbuf): keep freed blocks in the pool for reuse
 		cudaMemPool_t pool;
 		uint64_t thr = ~(uint64_t)0;

@@ -196,7 +196,7 @@ __device__ __forceinline__ wm128_dev wm_gs_fifo_read(const wm128_dev *p)
 	return r;
 }
 
-template <int WM_GS_F, int WM_GS_STAGE>
+template <int WM_GS_F, int WM_GS_STAGE, bool WM_GS_DBG>
 __global__ void __launch_bounds__(WM_GS_THREADS)
 wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ ids, int n_arr,
                             wm_rs_range *__restrict__ wl_all, unsigned long long *dbg)
@@ -262,15 +262,15 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 				for (int k = 0; k < 256;) {
 					const int bk = b[k];
 					if (bk != E[k]) {
-						while (filled[k] <= bk) { ++n_wait_dbg; }
+						while (filled[k] <= bk) { if (WM_GS_DBG) ++n_wait_dbg; }
 						wm128_dev tmp = wm_gs_fifo_read(&S->u.fifo[k][bk & (WM_GS_F - 1)]);
-						++n_steps_dbg;
+						if (WM_GS_DBG) ++n_steps_dbg;
 						int l = (int)(tmp.x >> s & 255);
 						if (l != k) {
 							do {
 								const int bl = b[l];
-								while (filled[l] <= bl) { ++n_wait_dbg; }
-								++n_steps_dbg;
+								while (filled[l] <= bl) { if (WM_GS_DBG) ++n_wait_dbg; }
+								if (WM_GS_DBG) ++n_steps_dbg;
 								const wm128_dev nxt = wm_gs_fifo_read(&S->u.fifo[l][bl & (WM_GS_F - 1)]);
 								a[bl] = tmp;
 								*(volatile int*)&b[l] = bl + 1;
@@ -398,12 +398,18 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 			if (giant) {
 				typedef wm_gs_sm<16, 2048> sm_t;
 				static bool attr_set = false;
-				if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<16, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t))); attr_set = true; }
+				if (!attr_set) {
+					WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<16, 2048, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t)));
+					WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<16, 2048, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t)));
+					attr_set = true;
+				}
 				unsigned long long *dbg = 0;
 				if (getenv("WM_SORT_DEBUG")) { WM_CUDA_CHECK(cudaMalloc((void**)&dbg, 64)); WM_CUDA_CHECK(cudaMemset(dbg, 0, 64)); }
 				static int giant_ctas = -1; // WM_SORT_GIANT_CTAS
 				if (giant_ctas < 0) { const char *e = getenv("WM_SORT_GIANT_CTAS"); giant_ctas = e && atoi(e) > 0 ? atoi(e) : 148; }
-				wm_anchor_sort_giant_kernel<16, 2048><<<(unsigned)(n_l < (size_t)giant_ctas ? n_l : (size_t)giant_ctas), WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, dbg);
+				const unsigned g_l = (unsigned)(n_l < (size_t)giant_ctas ? n_l : (size_t)giant_ctas);
+				if (dbg) wm_anchor_sort_giant_kernel<16, 2048, true><<<g_l, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, dbg);
+				else wm_anchor_sort_giant_kernel<16, 2048, false><<<g_l, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, 0);
 				if (dbg) {
 					unsigned long long h[8];
 					WM_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -418,10 +424,24 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 			if (medium_coop) { // thousands of arrays per wave: the light instantiation, four CTAs per SM
 				typedef wm_gs_sm<8, 512> sm_t;
 				static bool attr_set = false;
-				if (!attr_set) { WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t))); attr_set = true; }
+				if (!attr_set) {
+					WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<8, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t)));
+					WM_CUDA_CHECK(cudaFuncSetAttribute(wm_anchor_sort_giant_kernel<8, 512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(sm_t)));
+					attr_set = true;
+				}
+				unsigned long long *dbg = 0;
+				if (getenv("WM_SORT_DEBUG")) { WM_CUDA_CHECK(cudaMalloc((void**)&dbg, 64)); WM_CUDA_CHECK(cudaMemset(dbg, 0, 64)); }
 				static int med_ctas = -1; // WM_SORT_MEDIUM_CTAS: resident CTAs of the medium class (47 KB of shared memory each)
 				if (med_ctas < 0) { const char *e = getenv("WM_SORT_MEDIUM_CTAS"); med_ctas = e && atoi(e) > 0 ? atoi(e) : 592; }
-				wm_anchor_sort_giant_kernel<8, 512><<<(unsigned)(n_m < (size_t)med_ctas ? n_m : (size_t)med_ctas), WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, 0);
+				const unsigned g_m = (unsigned)(n_m < (size_t)med_ctas ? n_m : (size_t)med_ctas);
+				if (dbg) {
+					wm_anchor_sort_giant_kernel<8, 512, true><<<g_m, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, dbg);
+					unsigned long long h[8];
+					WM_CUDA_CHECK(cudaStreamSynchronize(st));
+					WM_CUDA_CHECK(cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost));
+					fprintf(stderr, "[sort-debug] arrays=%d clocks: hist %llu walk %llu dispatch %llu phase2 %llu | walker steps %llu wait polls %llu\n", (int)n_m, h[0], h[1], h[2], h[3], h[4], h[5]);
+					cudaFree(dbg);
+				} else wm_anchor_sort_giant_kernel<8, 512, false><<<g_m, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, 0);
 			} else wm_anchor_sort_big_kernel<<<(unsigned)n_m, 32, cap_m * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, cap_m);
 		}
 		if (n_s) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_s, 32, cap_s * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l + n_m, (int)n_s, d_wl, cap_s); }
