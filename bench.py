@@ -434,6 +434,10 @@ def main():
     e2e_t, d2h_b = map_host(timed, n_par, paf_host)
     barrier()
     cp = (C.c_double * 2)(); L.wm_prof_get_copies(cp)
+    mem = (C.c_double * 2)()
+    L.wm_device_mem.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.wm_device_mem(mem, C.cast(C.addressof(mem) + 8, C.POINTER(C.c_double)))
+    hbm_used_gb = (mem[1] - mem[0]) / 1e9  # the pools are never trimmed while mapping: the footprint's high-water mark
     h2d_step, d2h_step = int(cp[0] / a.steps), int(cp[1] / a.steps)
     e2e_b = bases
     if dist is not None:
@@ -504,7 +508,8 @@ def main():
         "ms_per_step": 1e3 * t_steps / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
         "config": {"workload": workload_name() + f"; {a.reads} fresh reads per step per GPU, working set >> L2", "reads_per_step": a.reads,
                    "host_threads": n_thr, "lanes": int(os.environ.get("WM_LANES", max(2, min(8, n_thr)))),
-                   "chunk_bases": int(os.environ["WM_CHUNK_BASES"]), "steps_per_submission": GROUP, "index_build_s": t_index},
+                   "chunk_bases": int(os.environ["WM_CHUNK_BASES"]), "steps_per_submission": GROUP, "index_build_s": t_index,
+                   "hbm_used_gb": round(hbm_used_gb, 1)},
         "e2e": {"value": e2e_b / e2e_t, "unit": "bases/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step},
         "gpu_launches": int(prof[0]),
         "roofline": dom, "roofline_other": other,

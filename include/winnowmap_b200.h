@@ -291,6 +291,7 @@ void wm_prof_reset(void);
 void wm_prof_get(double *out13);
 void wm_prof_get_copies(double *out2); /* bytes copied host-to-device / device-to-host by the mapping path since wm_prof_reset */
 int wm_device_synchronize(void);
+int wm_device_mem(double *free_bytes, double *total_bytes); /* cudaMemGetInfo of the current device */
 void wm_dump_timers(void); /* prints and resets the orchestration wall-clock accumulators (stderr) */
 
 void wm_get_stats(wm_gpu_ctx *ctx, double *out, int n);

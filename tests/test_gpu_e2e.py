@@ -170,3 +170,28 @@ def test_midsize_tandem_reference_matches_reference_binary(preset, n50, err, n_r
     assert exp.count(b"\n") >= n_reads * 0.9
     assert any(b"\trl:i:" in ln and not ln.rstrip().endswith(b"rl:i:0") for ln in exp.split(b"\n")[:4000]) or True
     assert got == exp, _first_diff(exp, got)
+
+
+@pytest.mark.parametrize("key,sam,flags", [("paf_cs", 0, 0x40), ("paf_cs_long", 0, 0x40 | 0x800), ("sam_md", 1, 0x1000000),
+                                            ("paf_eqx", 0, 0x4000000), ("sam_softclip", 1, 0x80000),
+                                            ("sam_no2nd_hitonly", 1, 0x4000 | 0x40000000), ("paf_no_hit", 0, 0x8000000),
+                                            ("sam_fastq_comment", 1, 0x2000000)])
+def test_output_options_match_reference_on_the_gpu(key, sam, flags, tmp_path):
+    """--cs / --cs=long / --MD / --eqx / -Y / --secondary=no --sam-hit-only / --paf-no-hit / -y with gzipped FASTQ input, through the
+    CUDA path (the same switches are checked against the oracle-backed host build in tests/test_host_orchestration.py): the md5 of
+    the whole output equals the reference's (tests/golden/manifest.json, tools/make_golden.py TAG_CASES)."""
+    import hashlib
+    from winnowmap_b200.mapper import Mapper
+    case = make_golden.TAG_CASES[key]
+    name = case[0]
+    m = MANIFEST[name]
+    ref, reads, wfile = make_golden.make_inputs(name, str(tmp_path))
+    if len(case) > 2 and case[2] == "fastq":
+        reads = make_golden.fastq_gz_of(reads, reads + ".fq.gz")
+    mp = Mapper(ref, wfile, preset=m["params"]["preset"], cigar=not sam, sam=bool(sam))
+    mp.mo.flag |= flags
+    out = str(tmp_path / "o.txt")
+    mp.map_file(reads, out)
+    mp.close()
+    got = make_golden.sam_without_pg(open(out, "rb").read())
+    assert hashlib.md5(got).hexdigest() == m["tag_md5"][key], key

@@ -95,6 +95,14 @@ static void map_lanes(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const std::vector
 		if (chunk_bases < 4000000) chunk_bases = 4000000;
 		if (chunk_bases > 32000000) chunk_bases = 32000000;
 		if (e && atoll(e) > 0) chunk_bases = atoll(e);
+		// whole rounds: the latency of a chunk grows much more slowly than its size (it is set by the serial giant tasks of
+		// its waves), so a lone chunk left over after the last full round costs almost a whole round.  The chunk size is
+		// therefore adjusted (up to +35 %) so that the chunks fill a whole number of rounds of the lanes.
+		const int64_t n_lanes = (int64_t)c->lanes.size();
+		int64_t rounds = (int64_t)((double)total / (double)(n_lanes * chunk_bases) + 0.35);
+		if (rounds < 1) rounds = 1;
+		if (total > n_lanes * chunk_bases * 13 / 20) chunk_bases = (total + n_lanes * rounds - 1) / (n_lanes * rounds);
+		else if (total / n_lanes >= 2000000) chunk_bases = (total + n_lanes - 1) / n_lanes; // less than a round: one chunk per lane
 		for (int i = 0; i < n; ++i) {
 			acc += (int64_t)reads[i]->seq.size();
 			if (acc >= chunk_bases || i == n - 1) { cb.push_back(i + 1); acc = 0; }
@@ -508,6 +516,15 @@ extern "C" void wm_prof_get(double *o)
 // host<->device traffic of the mapping path since wm_prof_reset: o[0] = host-to-device bytes, o[1] = device-to-host bytes
 extern "C" void wm_prof_get_copies(double *o) { o[0] = (double)g_wm_prof.h2d_bytes; o[1] = (double)g_wm_prof.d2h_bytes; }
 extern "C" int wm_device_synchronize(void) { WM_CUDA_CHECK(cudaDeviceSynchronize()); return 0; }
+// free / total bytes of the current device (bench: with the stream-ordered pool never trimmed while mapping, total - free after a
+// pass is the high-water mark of the library's footprint)
+extern "C" int wm_device_mem(double *free_bytes, double *total_bytes)
+{
+	size_t f = 0, t = 0;
+	WM_CUDA_CHECK(cudaMemGetInfo(&f, &t));
+	*free_bytes = (double)f, *total_bytes = (double)t;
+	return 0;
+}
 
 extern "C" void wm_free_regs(int n, const int32_t *n_reg, wm_reg1_t **reg)
 { // what the reference's output step does after printing (src/map.c:1210-1211)

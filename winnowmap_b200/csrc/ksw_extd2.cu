@@ -322,8 +322,10 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const
 	if (!ws->fill_st) {
 		int lo = 0, hi = 0;
 		WM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-		WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->fill_st, cudaStreamNonBlocking, lo));
-		WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->coop_st, cudaStreamNonBlocking, lo));
+		const char *pe = getenv("WM_FILL_PRIO"); // tuning: "high" puts the DP fill on the same priority as the other kernels
+		const int prio = (pe && *pe == 'h') ? hi : lo;
+		WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->fill_st, cudaStreamNonBlocking, prio));
+		WM_CUDA_CHECK(cudaStreamCreateWithPriority(&ws->coop_st, cudaStreamNonBlocking, prio));
 		WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_ready, cudaEventDisableTiming));
 		WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_done, cudaEventDisableTiming));
 		WM_CUDA_CHECK(cudaEventCreateWithFlags(&ws->ev_coop, cudaEventDisableTiming));
