@@ -418,6 +418,9 @@ def main():
     t_steps = map_uploaded()
     barrier()
     clocks = sampler.result()
+    if os.environ.get("WM_BENCH_VALUE_TWICE"):  # tuning aid: the same resident pass once more (not reported in the JSON line)
+        t2 = map_uploaded()
+        log(f"resident pass again: {bases / t2 / 1e6:.1f} Mbase/s (first: {bases / t_steps / 1e6:.1f})")
     if os.environ.get("WM_TIMING"):
         log(f"timers over {a.steps} timed steps:")
         L.wm_dump_timers()

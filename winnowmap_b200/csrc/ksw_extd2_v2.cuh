@@ -21,32 +21,7 @@
 // warp's mbarrier
 #define WM_V2_SLICE (7 * 2 * WM_V2_TS + 4 * WM_V2_T + (WM_V2_T + 16) + (WM_V2_Q + 64) + WM_V2_Q + 16)
 
-#ifndef WM_HOST_EMUL
-// ---- bulk-asynchronous (TMA) staging of a job's sequences: cp.async.bulk global -> shared, completion on an mbarrier ----
-// One lane arms the warp's mbarrier with the byte count and issues the two copies (target, query); the copy engine moves the
-// bytes while the 32 lanes initialise the state rows; everybody then waits on the barrier's phase.  Source and destination
-// must be 16-byte aligned and the sizes multiples of 16: the gather kernel lays the pool out that way (gpu_backend.cu).
-__device__ __forceinline__ uint32_t wm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void wm_mbar_init(uint64_t *mbar, int count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(wm_smem_u32(mbar)), "r"(count) : "memory");
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void wm_mbar_expect_tx(uint64_t *mbar, uint32_t bytes)
-{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(wm_smem_u32(mbar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void wm_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *mbar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             :: "r"(wm_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(wm_smem_u32(mbar)) : "memory");
-}
-__device__ __forceinline__ void wm_mbar_wait(uint64_t *mbar, uint32_t phase)
-{
-	uint32_t ok = 0;
-	while (!ok)
-		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-		             : "=r"(ok) : "r"(wm_smem_u32(mbar)), "r"(phase) : "memory");
-}
-#endif
+// (bulk-asynchronous staging helpers -- cp.async.bulk + mbarrier -- are in wm_common.cuh)
 
 
 __device__ __forceinline__ uint32_t wm_pack2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }

@@ -141,7 +141,11 @@ wm_anchor_sort_big_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__
 {
 	extern __shared__ __align__(16) unsigned char wm_sort_smem[];
 	__shared__ wm_rs_warp_ws W;
+	__shared__ __align__(8) uint64_t mbar;
 	const int lane = threadIdx.x;
+	uint32_t phase = 0;
+	if (lane == 0) wm_mbar_init(&mbar, 1);
+	__syncwarp();
 	for (int i = blockIdx.x; i < n_big; i += gridDim.x) {
 		const int t = big_ids[i];
 		const int64_t base = off[t];
@@ -149,11 +153,14 @@ wm_anchor_sort_big_kernel(wm128_dev *__restrict__ a, const int64_t *__restrict__
 		wm_rs_range *wl = wl_all + (base >> 6) + t;
 		wm128_dev *g = a + base;
 		if (n <= smem_cap) {
+			// the array into its shared-memory stage and back with bulk-asynchronous copies (16-byte elements: always aligned)
 			wm128_dev *s = (wm128_dev*)wm_sort_smem;
-			for (int j = lane; j < n; j += 32) s[j] = g[j];
-			__syncwarp();
+			const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(wm128_dev);
+			if (lane == 0) { wm_mbar_expect_tx(&mbar, bytes); wm_bulk_g2s(s, g, bytes, &mbar); }
+			wm_mbar_wait(&mbar, phase); phase ^= 1;
 			wm_radix_sort_warp(s, n, &W, wl, lane);
-			for (int j = lane; j < n; j += 32) g[j] = s[j];
+			__syncwarp();
+			if (lane == 0) { wm_bulk_s2g(g, s, bytes); wm_bulk_s2g_wait(); } // (the stage is reused by the next array)
 			__syncwarp();
 		} else wm_radix_sort_warp(g, n, &W, wl, lane);
 	}
@@ -180,7 +187,9 @@ struct wm_gs_sm {
 	int n_big, n_small, next_small, walk_done;
 	wm_rs_warp_ws W[4];
 	wm_rs_range swl[4][40];        // per-warp work list of phase 2 (disjoint sub-ranges of > 64 elements of a <= 2048-element range)
-	union {
+	uint64_t mbar[4];              // per-warp mbarriers of the bulk copies that stage a sub-range
+	uint32_t mbar_phase[4];
+	union alignas(16) { // (bulk copies land in `stage`: 16-byte aligned)
 		wm128_dev fifo[256][WM_GS_F];
 		wm128_dev stage[4][WM_GS_STAGE];
 	} u;
@@ -209,6 +218,8 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 	extern __shared__ __align__(16) unsigned char wm_gs_smem[];
 	typedef wm_gs_sm<WM_GS_F, WM_GS_STAGE> sm_t;
 	sm_t *S = (sm_t*)wm_gs_smem;
+	if (threadIdx.x < 4) { wm_mbar_init(&S->mbar[threadIdx.x], 1); S->mbar_phase[threadIdx.x] = 0; }
+	__syncthreads();
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (int ai = blockIdx.x; ai < n_arr; ai += gridDim.x) {
 		const int task = ids[ai];
@@ -334,6 +345,7 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 		__syncthreads();
 		{
 			wm128_dev *st = S->u.stage[wid];
+			uint32_t ph2 = S->mbar_phase[wid]; // the warp's barrier survives from array to array: remember its phase
 			for (;;) {
 				int q = 0;
 				if (lane == 0) q = atomicAdd(&S->next_small, 1);
@@ -341,12 +353,15 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 				if (q >= S->n_small) break;
 				const wm_rs_range R = wl[wl_cap - 1 - q];
 				const int m = R.end - R.beg;
-				for (int j = lane; j < m; j += 32) st[j] = a[R.beg + j];
-				__syncwarp();
+				const uint32_t bytes = (uint32_t)m * (uint32_t)sizeof(wm128_dev);
+				if (lane == 0) { wm_mbar_expect_tx(&S->mbar[wid], bytes); wm_bulk_g2s(st, a + R.beg, bytes, &S->mbar[wid]); }
+				wm_mbar_wait(&S->mbar[wid], ph2); ph2 ^= 1;
 				wm_radix_sort_warp_from(st, m, R.s, &S->W[wid], S->swl[wid], lane);
-				for (int j = lane; j < m; j += 32) a[R.beg + j] = st[j];
+				__syncwarp();
+				if (lane == 0) { wm_bulk_s2g(a + R.beg, st, bytes); wm_bulk_s2g_wait(); }
 				__syncwarp();
 			}
+			if (lane == 0) S->mbar_phase[wid] = ph2;
 		}
 		__syncthreads();
 		WM_GS_LAP(3);

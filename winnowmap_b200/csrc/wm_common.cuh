@@ -165,3 +165,39 @@ static inline void wm_stream_sync(cudaStream_t st)
 	WM_CUDA_CHECK(cudaEventRecord(h.ev, st));
 	WM_CUDA_CHECK(cudaEventSynchronize(h.ev));
 }
+
+#ifndef WM_HOST_EMUL
+// ---- bulk-asynchronous (TMA) copies: cp.async.bulk global <-> shared, completion on an mbarrier / a bulk group ----
+// One thread arms an mbarrier with the byte count and issues the copy; the copy engine moves the bytes while the other
+// threads do something else; everybody then waits on the barrier's phase.  Source and destination must be 16-byte aligned
+// and the size a multiple of 16.  Users: the DP fill kernel (a job's target and query), the anchor sort kernels (an array
+// into its shared-memory stage and back).
+__device__ __forceinline__ uint32_t wm_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wm_mbar_init(uint64_t *mbar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(wm_smem_u32(mbar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void wm_mbar_expect_tx(uint64_t *mbar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(wm_smem_u32(mbar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void wm_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *mbar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(wm_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(wm_smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void wm_mbar_wait(uint64_t *mbar, uint32_t phase)
+{
+	uint32_t ok = 0;
+	while (!ok)
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+		             : "=r"(ok) : "r"(wm_smem_u32(mbar)), "r"(phase) : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk group
+__device__ __forceinline__ void wm_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the generic-proxy writes of the stage must be visible to the copy engine
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst_gmem), "r"(wm_smem_u32(src_smem)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void wm_bulk_s2g_wait(void) { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#endif
