@@ -467,6 +467,10 @@ def main():
              "frac": ach / peak, "traffic": None, "of": "measured" if peaks else "fallback", "launches": int(n_l), "kernel_ms": k_ms,
              "kernel_ms_sum_over_launches": ms_sum, "algorithmic_bytes": alg}
         if kind == 0:
+            # the contract's `bound` is "hbm" | "tensor"; this kernel is neither: alone on the GPU it is integer-issue bound
+            r["limiter"] = ("integer ALU issue, not HBM: ncu --set full of the kernel alone shows ALU pipe 66 %, issue slots 68 %, DRAM 6 % of "
+                            "peak at 333 G cells/s (profiles/r02_ncu_wm_extd2_fill_kernel_summary.txt); in the bench its launches share the SMs "
+                            "with the other lanes' kernels")
             r.update({"block_cells": units, "jobs": int(units2), "block_cells_per_s": units / (k_ms * 1e-3) if k_ms > 0 else 0.0})
         else:
             r.update({"anchors": units, "anchors_per_s": units / (k_ms * 1e-3) if k_ms > 0 else 0.0})

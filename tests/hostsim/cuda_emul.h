@@ -79,6 +79,8 @@ inline unsigned __vmaxs2(unsigned a, unsigned b)
 inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vadd2(a, b), c); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift)
 { const uint64_t v = (uint64_t)hi << 32 | lo; return (uint32_t)(v >> (shift & 31)); }
+inline unsigned long long __brevll(unsigned long long x)
+{ unsigned long long r = 0; for (int i = 0; i < 64; ++i) r |= (x >> i & 1ULL) << (63 - i); return r; }
 // prmt.b32, default mode: byte i of the result is byte (sel nibble i & 7) of {b,a}; nibble bit 3 replicates that byte's sign
 inline uint32_t wm_emul_prmt(uint32_t a, uint32_t b, uint32_t sel)
 {

@@ -12,6 +12,7 @@
 #include "../../winnowmap_b200/csrc/ksw_extz2.cuh"
 #include "../../winnowmap_b200/csrc/chain_dev.cuh"
 #include "../../winnowmap_b200/csrc/rsort.cuh"
+#include "../../winnowmap_b200/csrc/pkseq.cuh"
 
 namespace wm_emul {
 thread_local Warp *warp = 0; thread_local int lane = 0;
@@ -297,5 +298,106 @@ extern "C" int wmt_emul_chain(uint64_t *a_xy, int n, int max_dist_x, int min_dis
 	}, &A);
 	for (int i = 0; i < *n_u_out; ++i) u_out[i] = u2[i];
 	for (int64_t i = 0; i < *n_b_out; ++i) a_xy[2 * i] = a[i].x, a_xy[2 * i + 1] = a[i].y;
+	return 0;
+}
+
+
+// ---- the packed read pool (csrc/pkseq.cuh): packing, k-mer windows, masked copies and the DP gather against a plain
+// byte-per-base restatement.  Returns 0, or the line of the first mismatch. ----
+static uint64_t pk_rng(uint64_t *s) { *s = *s * 6364136223846793005ULL + 1442695040888963407ULL; return *s >> 33; }
+extern "C" int wmt_pk_selftest(uint64_t seed, int64_t n, int k)
+{
+	uint8_t lut[256];
+	for (int c = 0; c < 256; ++c) { // seq_nt4_table (src/sketch.c:19-36)
+		uint8_t v = c < 4 ? (uint8_t)c : 4;
+		if (c == 'A' || c == 'a') v = 0; else if (c == 'C' || c == 'c') v = 1; else if (c == 'G' || c == 'g') v = 2;
+		else if (c == 'T' || c == 't' || c == 'U' || c == 'u') v = 3;
+		lut[c] = v;
+	}
+	static const char alphabet[] = "ACGTacgtNnUuRY\x01\x03-";
+	std::vector<unsigned char> ascii(n + 64, 'N');
+	for (int64_t i = 0; i < n; ++i) {
+		const uint64_t r = pk_rng(&seed);
+		ascii[i] = (r & 63) < 60 ? "ACGT"[r >> 8 & 3] : (unsigned char)alphabet[(r >> 8) % (sizeof(alphabet) - 1)];
+	}
+	std::vector<uint8_t> code(n + 64, 4);
+	for (int64_t i = 0; i < n; ++i) code[i] = lut[ascii[i]];
+	const int64_t ng = (n + 31) / 32;
+	std::vector<uint32_t> pk(2 * ng + WM_PK_SLACK + 4, 0), nm(ng + WM_PK_SLACK + 4, 0xffffffffu);
+	for (int64_t g = 0; g < ng; ++g) {
+		uint32_t raw[8];
+		for (int j = 0; j < 8; ++j) { uint32_t v = 0; for (int b = 0; b < 4; ++b) v |= (uint32_t)ascii[g * 32 + 4 * j + b] << 8 * b; raw[j] = v; }
+		uint64_t p; uint32_t m;
+		wm_pk_pack32(raw, lut, &p, &m);
+		pk[2 * g] = (uint32_t)p, pk[2 * g + 1] = (uint32_t)(p >> 32), nm[g] = m;
+	}
+	wm_pkseq S; S.pk = pk.data(), S.nm = nm.data();
+	for (int64_t i = 0; i < n; ++i) if (wm_pk_get(S, i) != code[i]) return __LINE__;
+	const uint32_t kmask = (1u << k) - 1u;
+	for (int64_t b = 0; b + k <= n; ++b) { // every k-mer: src/sketch.c:162-163 base by base
+		uint64_t f = 0, r = 0; bool amb = false;
+		for (int j = 0; j < k; ++j) {
+			const uint64_t c = code[b + j];
+			amb |= c > 3;
+			f = f << 2 | (c & 3);
+			r = r >> 2 | (3ULL ^ (c & 3)) << (2 * (k - 1));
+		}
+		if (((wm_pk_nwindow(S.nm, b) & kmask) != 0) != amb) return __LINE__;
+		uint64_t f2, r2;
+		wm_pk_kmer(wm_pk_window(S.pk, b), k, &f2, &r2);
+		if (!amb && (f2 != f || r2 != r)) return __LINE__;
+	}
+	// masked copies of random windows
+	for (int it = 0; it < 200; ++it) {
+		wm_mask_task T;
+		T.len = 1 + (int)(pk_rng(&seed) % 3000); if (T.len > n) T.len = (int)n;
+		T.src_off = (int64_t)(pk_rng(&seed) % (uint64_t)(n - T.len + 1)); T.dst_off = 0, T.mask_off = 3;
+		std::vector<int32_t> pool(6, 0);
+		int pos = (int)(pk_rng(&seed) % 40); T.n_mask = 0;
+		while (pos < T.len + 50 && T.n_mask < 64) {
+			const int e = pos + 1 + (int)(pk_rng(&seed) % 200);
+			pool.push_back(pos), pool.push_back(e); ++T.n_mask;
+			pos = e + (int)(pk_rng(&seed) % 300);
+		}
+		for (int p0 = 0; p0 < T.len; p0 += 32) {
+			uint64_t v; uint32_t m;
+			wm_pk_mask32(S, T, p0, pool.data(), &v, &m);
+			for (int j = 0; j < 32; ++j) {
+				const int p = p0 + j;
+				int c = 4;
+				if (p < T.len) {
+					c = code[T.src_off + p];
+					for (int a = 0; a < T.n_mask; ++a) if (p >= pool[6 + 2 * a] && p < pool[6 + 2 * a + 1]) c = 4;
+				}
+				const int got = (m >> j & 1) ? 4 : (int)(v >> 2 * j & 3);
+				if (got != c) return __LINE__;
+			}
+		}
+	}
+	// DP gather: slices of "reads" (both strands, both directions) and of a 4-bit packed reference
+	std::vector<uint32_t> S4((n + 7) / 8 + 4, 0);
+	for (int64_t i = 0; i < n; ++i) S4[i >> 3] |= (uint32_t)code[i] << ((i & 7) << 2);
+	for (int it = 0; it < 4000; ++it) {
+		const int64_t L = 1 + (int64_t)(pk_rng(&seed) % (uint64_t)(n < 5000 ? n : 5000)), r0 = (int64_t)(pk_rng(&seed) % (uint64_t)(n - L + 1));
+		wm_gather_job J;
+		J.len = 1 + (int)(pk_rng(&seed) % (uint64_t)L); if (it % 7 == 0 && J.len > 17) J.len = 1 + (int)(pk_rng(&seed) % 17);
+		const int64_t o = (int64_t)(pk_rng(&seed) % (uint64_t)(L - J.len + 1)); // offset of the slice on its strand
+		J.kind = (int)(pk_rng(&seed) % 3), J.reversed = (int)(pk_rng(&seed) & 1), J.pad = 0, J.dst_off = 0;
+		J.src_off = J.kind == 2 ? r0 + (L - 1 - o) : r0 + o;
+		for (int p0 = 0; p0 < J.len + 16; p0 += 16) {
+			uint32_t out[4];
+			wm_pk_gather16(J, p0, S, S4.data(), out);
+			for (int j = 0; j < 16; ++j) {
+				const int p = p0 + j;
+				int want = 0;
+				if (p < J.len) {
+					const int64_t q = o + (J.reversed ? J.len - 1 - p : p); // position on the slice's strand
+					if (J.kind == 2) { const int c = code[r0 + (L - 1 - q)]; want = c < 4 ? 3 - c : 4; } // src/align.c:874-876
+					else want = code[r0 + q];
+				}
+				if ((int)(out[j >> 2] >> 8 * (j & 3) & 255) != want) return __LINE__;
+			}
+		}
+	}
 	return 0;
 }

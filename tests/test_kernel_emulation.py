@@ -194,3 +194,12 @@ def test_chaining_end_to_end_matches_oracle(emul, dense):
             emul.wmt_emul_chain(buf.ctypes.data, n, *prm, 3, 40, 1.0, dense, u.ctypes.data, C.addressof(n_u), C.addressof(n_b))
             assert np.array_equal(ue, u[:n_u.value]), (n, prm, len(ue), n_u.value)
             assert np.array_equal(be, buf[:n_b.value]), (n, prm)
+
+
+@pytest.mark.parametrize("seed,n,k", [(1, 20000, 15), (2, 20000, 19), (3, 7777, 28), (4, 100, 5), (5, 33, 1), (6, 50000, 16)])
+def test_packed_read_pool_matches_bytewise_restatement(emul, seed, n, k):
+    """csrc/pkseq.cuh compiled for the host: ASCII -> 2-bit + ambiguity mask, every k-mer as one 64-bit window (forward and
+    reverse-complement words of src/sketch.c:162-163), masked copies (src/map.c:795-801) and the DP gather of both strands /
+    both directions / the 4-bit reference (src/align.c:874-876), each against a byte-per-base restatement."""
+    emul.wmt_pk_selftest.argtypes = [C.c_uint64, C.c_int64, C.c_int]
+    assert emul.wmt_pk_selftest(seed, n, k) == 0

@@ -210,15 +210,17 @@ extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_fre
 	std::vector<std::pair<wm128_dev*, int64_t>> parts; int64_t n_mz_total = 0;
 	wm_sketch_ws ws;
 	std::vector<wm_sk_task> tasks; std::string group; uint64_t sum_len = 0;
-	wm_dbuf d_ascii, d_codes;
+	wm_dbuf d_ascii, d_pk, d_nm;
 	auto flush = [&]() {
 		if (tasks.empty()) return;
 		char *da = (char*)d_ascii.need(group.size() + 16);
-		uint8_t *dc = (uint8_t*)d_codes.need(group.size() + 16);
+		wm_pkseq pks; // the group as a packed pool (pkseq.cuh)
+		pks.pk = (uint32_t*)d_pk.need(sizeof(uint32_t) * wm_pk_words((int64_t)group.size()));
+		pks.nm = (uint32_t*)d_nm.need(sizeof(uint32_t) * wm_nm_words((int64_t)group.size()));
 		WM_CUDA_CHECK(cudaMemcpy(da, group.data(), group.size(), cudaMemcpyHostToDevice));
-		wm_ascii_to_code(da, dc, (int64_t)group.size(), 0);
+		wm_pack_ascii(da, (int64_t)group.size(), (uint32_t*)pks.pk, (uint32_t*)pks.nm, 0);
 		int64_t n_mz = 0;
-		wm_sketch_run(&ws, bf, dc, tasks.data(), (int)tasks.size(), w, k, &n_mz, 0);
+		wm_sketch_run(&ws, bf, pks, tasks.data(), (int)tasks.size(), w, k, &n_mz, 0);
 		WM_CUDA_CHECK(cudaDeviceSynchronize());
 		if (n_mz > 0) {
 			wm128_dev *part = wm_dev_alloc<wm128_dev>(n_mz);
@@ -242,7 +244,7 @@ extern "C" wm_gpu_ctx_s *wm_index_build(const char *ref_fn, const char *kmer_fre
 		if (group.size() >= ((size_t)1 << 30)) flush();
 	}
 	flush();
-	ws.release(); d_ascii.release(); d_codes.release(); cudaFree(d_table);
+	ws.release(); d_ascii.release(); d_pk.release(); d_nm.release(); cudaFree(d_table);
 	// one array in position order, then sort + CSR on the device
 	wm128_dev *d_all = wm_dev_alloc<wm128_dev>(n_mz_total + 1);
 	{

@@ -21,37 +21,20 @@ void wm_ksw_ll_launch(const wm_ll_job *d_jobs, int n, const uint8_t *d_seq, cons
 using namespace wmh;
 
 // ---- small data-movement kernels ----
-__global__ void wm_revcomp_kernel(const uint8_t *__restrict__ fwd, uint8_t *__restrict__ rev, const int64_t *__restrict__ read_off, int n_reads, int64_t n)
-{ // strand 1 of every read (src/align.c:874-876): rev[L-1-i] = comp(fwd[i])
+// Masked copy of a window (src/map.c:795-801: covered bases become ambiguous) as a packed sequence of its own: one thread
+// per 32 bases takes the unaligned source windows and sets the flags of the covered bases.
+__global__ void wm_mask_pack_kernel(const wm_pkseq seq, const wm_mask_task *__restrict__ tasks, const int64_t *__restrict__ goff, int n_tasks,
+                                    const int32_t *__restrict__ mask_pool, int64_t n_groups, uint32_t *__restrict__ pk_out, uint32_t *__restrict__ nm_out)
+{
 	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (g >= n) return;
-	int lo = 0, hi = n_reads;
-	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (read_off[m] <= g) lo = m; else hi = m; }
-	const int64_t b = read_off[lo], L = read_off[lo + 1] - b;
-	const uint8_t c = fwd[g];
-	rev[b + (L - 1 - (g - b))] = c < 4 ? 3 - c : 4;
-}
-
-struct wm_mask_task { int64_t src_off, dst_off, mask_off; int32_t len, n_mask; };
-
-__global__ void wm_mask_copy_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ dst, const wm_mask_task *__restrict__ tasks, const int64_t *__restrict__ toff,
-                                    int n_tasks, const int32_t *__restrict__ mask_pool, int64_t n)
-{ // covered bases become ambiguous (src/map.c:795-801)
-	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (g >= n) return;
+	if (g >= n_groups) return;
 	int lo = 0, hi = n_tasks;
-	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (toff[m] <= g) lo = m; else hi = m; }
-	const wm_mask_task T = tasks[lo];
-	const int p = (int)(g - toff[lo]);
-	const int32_t *iv = mask_pool + 2 * T.mask_off;
-	int a = 0, b = T.n_mask; // last interval with start <= p
-	bool covered = false;
-	while (a < b) { int m = (a + b) >> 1; if (iv[2 * m] <= p) a = m + 1; else b = m; }
-	if (a > 0) covered = p < iv[2 * (a - 1) + 1];
-	dst[T.dst_off + p] = covered ? 4 : codes[T.src_off + p];
+	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (goff[m] <= g) lo = m; else hi = m; }
+	uint64_t v; uint32_t m;
+	wm_pk_mask32(seq, tasks[lo], (int)(g - goff[lo]) * 32, mask_pool, &v, &m);
+	((uint2*)pk_out)[g] = make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+	nm_out[g] = m;
 }
-
-struct wm_gather_job { int64_t src_off, dst_off; int32_t len, kind, reversed, pad; }; // kind 0: read strand 0, 2: read strand 1, 1: 4-bit packed reference
 
 struct wm_cat_task { int64_t pre_off, seed_off, dst_off; int32_t n_pre, n_seed; };
 
@@ -97,13 +80,13 @@ struct GpuBackendImpl {
 	const wm_host_idx *hidx;
 	// batch state
 	std::vector<int64_t> read_off; // host
-	wm_dbuf ascii, codes, rcodes, d_read_off, d_src_off;
+	wm_dbuf ascii, pk, nm, d_read_off, d_src_off; // the batch's reads: ASCII as uploaded, then the packed pool (pkseq.cuh)
 	int64_t n_bases;
 	const char *resident_pool = 0;         // device ASCII of reads that carry a dev_off (bench: inputs resident in HBM)
 	char *h_stage = 0; size_t h_stage_cap = 0; // pinned staging buffer of begin_batch
 	// workspaces
 	wm_sketch_ws sk; wm_seed_ws sd, sd2; wm_chain_ws ch; wm_extd2_ws dpws;
-	wm_dbuf masked, mask_tasks, mask_toff, mask_pool, qlen_buf, pre_buf, cat_tasks, cat_toff, cat_a, set_id, off_buf, nb_off, nu_off, b_out, u_out;
+	wm_dbuf masked_pk, masked_nm, mask_tasks, mask_toff, mask_pool, qlen_buf, pre_buf, cat_tasks, cat_toff, cat_a, set_id, off_buf, nb_off, nu_off, b_out, u_out;
 	wm_dbuf coop_ids, g_jobs, g_joff, seq_pool, dp_jobs, bt, ez, cig, cig_off, cig_out, ll_jobs, ll_scr, ll_out, mat;
 	// host result pools
 	std::vector<uint32_t> h_mzpos; std::vector<int64_t> h_mz_off; std::vector<int32_t> h_rep;
@@ -137,26 +120,6 @@ public:
 	void end_batch() override {}
 };
 
-// bases of reads scattered over a device ASCII pool -> contiguous 0..4 codes (seq_nt4_table, src/sketch.c:19-36)
-__global__ void wm_gather_code_kernel(const char *__restrict__ pool, const int64_t *__restrict__ src_off, const int64_t *__restrict__ dst_off, int n_reads,
-                                      uint8_t *__restrict__ out, int64_t n)
-{
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	int lo = 0, hi = n_reads;
-	while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (dst_off[m] <= i) lo = m; else hi = m; }
-	const unsigned char c = (unsigned char)pool[src_off[lo] + (i - dst_off[lo])];
-	uint8_t v;
-	switch (c) {
-		case 'A': case 'a': v = 0; break;
-		case 'C': case 'c': v = 1; break;
-		case 'G': case 'g': v = 2; break;
-		case 'T': case 't': case 'U': case 'u': v = 3; break;
-		default: v = c < 4 ? c : 4;
-	}
-	out[i] = v;
-}
-
 void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
 {
 	WM_CUDA_CHECK(cudaSetDevice(g.device));
@@ -165,20 +128,17 @@ void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
 	g.read_off.assign(n + 1, 0);
 	for (int i = 0; i < n; ++i) g.read_off[i + 1] = g.read_off[i] + (int64_t)reads[i]->seq.size();
 	g.n_bases = g.read_off[n];
-	uint8_t *d_codes = (uint8_t*)g.codes.need(g.n_bases + 16), *d_rc = (uint8_t*)g.rcodes.need(g.n_bases + 16);
+	uint32_t *d_pk = (uint32_t*)g.pk.need(sizeof(uint32_t) * wm_pk_words(g.n_bases)), *d_nm = (uint32_t*)g.nm.need(sizeof(uint32_t) * wm_nm_words(g.n_bases));
 	int64_t *d_off = (int64_t*)g.d_read_off.need(sizeof(int64_t) * (n + 1));
 	bool resident = g.resident_pool != 0;
 	for (int i = 0; i < n && resident; ++i) resident = reads[i]->dev_off >= 0;
 	WM_CUDA_CHECK(wm_memcpy_async(d_off, g.read_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, g.st));
-	if (resident) { // the bases are in HBM already: gather + encode on the device
+	if (resident) { // the bases are in HBM already: gather + pack on the device
 		std::vector<int64_t> src(n);
 		for (int i = 0; i < n; ++i) src[i] = reads[i]->dev_off;
 		int64_t *d_src = (int64_t*)g.d_src_off.need(sizeof(int64_t) * (n + 1));
 		WM_CUDA_CHECK(wm_memcpy_async(d_src, src.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, g.st));
-		if (g.n_bases > 0) {
-			wm_count_launch(); wm_gather_code_kernel<<<(unsigned)((g.n_bases + 255) / 256), 256, 0, g.st>>>(g.resident_pool, d_src, d_off, n, d_codes, g.n_bases);
-			WM_CUDA_CHECK(cudaGetLastError());
-		}
+		wm_pack_gather(g.resident_pool, d_src, d_off, n, g.n_bases, d_pk, d_nm, g.st);
 		wm_stream_sync(g.st); // src[] is a local
 	} else { // one host staging buffer (pinned), one copy
 		if ((size_t)g.n_bases + 16 > g.h_stage_cap) {
@@ -191,11 +151,7 @@ void GpuBackend::begin_batch(const std::vector<const wm_read*> &reads)
 			if (!reads[i]->seq.empty()) memcpy(g.h_stage + g.read_off[i], reads[i]->seq.data(), reads[i]->seq.size());
 		char *d_ascii = (char*)g.ascii.need(g.n_bases + 16);
 		if (g.n_bases > 0) WM_CUDA_CHECK(wm_memcpy_async(d_ascii, g.h_stage, g.n_bases, cudaMemcpyHostToDevice, g.st));
-		wm_ascii_to_code(d_ascii, d_codes, g.n_bases, g.st);
-	}
-	if (g.n_bases > 0) {
-		wm_count_launch(); wm_revcomp_kernel<<<(unsigned)((g.n_bases + 255) / 256), 256, 0, g.st>>>(d_codes, d_rc, d_off, n, g.n_bases);
-		WM_CUDA_CHECK(cudaGetLastError());
+		wm_pack_ascii(d_ascii, g.n_bases, d_pk, d_nm, g.st);
 	}
 }
 
@@ -207,23 +163,32 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	const int n = (int)tasks.size();
 	out.assign(n, SeedOut());
 	if (n == 0) return;
-	const uint8_t *d_codes = (const uint8_t*)g.codes.p;
+	wm_pkseq rd; rd.pk = (const uint32_t*)g.pk.p, rd.nm = (const uint32_t*)g.nm.p;
 	double t_mark = Timers::now();
 	auto lap = [&](const char *nm) { const double t = Timers::now(); g_timers.add(nm, t - t_mark); t_mark = t; };
 	// 1. masked copies
-	std::vector<wm_mask_task> mt; std::vector<int64_t> mtoff(1, 0);
+	std::vector<wm_mask_task> mt; std::vector<int64_t> mtoff(1, 0); // mtoff: in groups of 32 bases
 	int64_t n_mask_iv = 0, n_pre = 0;
 	for (int i = 0; i < n; ++i) {
 		const SeedTask &t = tasks[i];
 		if (t.flags & SEED_MASKED) {
 			wm_mask_task m;
-			m.src_off = g.read_off[t.win.read] + t.win.wb, m.dst_off = mtoff.back(), m.mask_off = t.mask_off, m.len = t.win.wl, m.n_mask = t.n_mask;
-			mt.push_back(m); mtoff.push_back(mtoff.back() + t.win.wl);
+			m.src_off = g.read_off[t.win.read] + t.win.wb, m.dst_off = mtoff.back() * 32, m.mask_off = t.mask_off, m.len = t.win.wl, m.n_mask = t.n_mask;
+			mt.push_back(m); mtoff.push_back(mtoff.back() + (t.win.wl + 31) / 32);
 			n_mask_iv = std::max<int64_t>(n_mask_iv, t.mask_off + t.n_mask);
 		}
 		n_pre = std::max<int64_t>(n_pre, t.pre_off + t.n_pre);
 	}
-	uint8_t *d_masked = (uint8_t*)g.masked.need(mtoff.back() + 16);
+	wm_pkseq rd_masked;
+	{
+		const int64_t nb = mtoff.back() * 32;
+		uint32_t *mpk = (uint32_t*)g.masked_pk.need(sizeof(uint32_t) * wm_pk_words(nb)), *mnm = (uint32_t*)g.masked_nm.need(sizeof(uint32_t) * wm_nm_words(nb));
+		rd_masked.pk = mpk, rd_masked.nm = mnm;
+		if (!mt.empty()) { // the look-ahead words
+			WM_CUDA_CHECK(cudaMemsetAsync(mpk + 2 * mtoff.back(), 0, sizeof(uint32_t) * WM_PK_SLACK, st));
+			WM_CUDA_CHECK(cudaMemsetAsync(mnm + mtoff.back(), 0xff, sizeof(uint32_t) * WM_PK_SLACK, st));
+		}
+	}
 	if (!mt.empty()) {
 		wm_mask_task *d_mt = (wm_mask_task*)g.mask_tasks.need(sizeof(wm_mask_task) * mt.size());
 		int64_t *d_mtoff = (int64_t*)g.mask_toff.need(sizeof(int64_t) * mtoff.size());
@@ -231,7 +196,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		WM_CUDA_CHECK(wm_memcpy_async(d_mt, mt.data(), sizeof(wm_mask_task) * mt.size(), cudaMemcpyHostToDevice, st));
 		WM_CUDA_CHECK(wm_memcpy_async(d_mtoff, mtoff.data(), sizeof(int64_t) * mtoff.size(), cudaMemcpyHostToDevice, st));
 		WM_CUDA_CHECK(wm_memcpy_async(d_mp, mask_pool, sizeof(int32_t) * 2 * n_mask_iv, cudaMemcpyHostToDevice, st));
-		wm_count_launch(); wm_mask_copy_kernel<<<(unsigned)((mtoff.back() + 255) / 256), 256, 0, st>>>(d_codes, d_masked, d_mt, d_mtoff, (int)mt.size(), d_mp, mtoff.back());
+		wm_count_launch(); wm_mask_pack_kernel<<<(unsigned)((mtoff.back() + 127) / 128), 128, 0, st>>>(rd, d_mt, d_mtoff, (int)mt.size(), d_mp, mtoff.back(), (uint32_t*)rd_masked.pk, (uint32_t*)rd_masked.nm);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	lap("seed.a_mask");
@@ -266,7 +231,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 		const int ns = (int)skt.size();
 		if (ns == 0) continue;
 		int64_t n_mz = 0;
-		{ WM_TIMED("seed.sketch"); wm_sketch_run(&g.sk, g.bf, pass == 0 ? d_codes : d_masked, skt.data(), ns, w, k, &n_mz, st); }
+		{ WM_TIMED("seed.sketch"); wm_sketch_run(&g.sk, g.bf, pass == 0 ? rd : rd_masked, skt.data(), ns, w, k, &n_mz, st); }
 		WM_TIMED("seed.lookup_sort");
 		std::vector<int32_t> qlen(ns);
 		for (int i = 0; i < ns; ++i) qlen[i] = skt[i].len;
@@ -398,43 +363,35 @@ static inline wm_gather_job make_gather(const GpuBackendImpl &g, const SeqRef &s
 {
 	wm_gather_job j;
 	j.len = s.len, j.reversed = s.reversed, j.pad = 0, j.dst_off = dst_off;
-	const int64_t L = g.read_off[w.read + 1] - g.read_off[w.read];
 	if (s.kind == SEQ_Q0) j.kind = 0, j.src_off = g.read_off[w.read] + w.wb + s.off;
-	else if (s.kind == SEQ_Q1) j.kind = 2, j.src_off = g.read_off[w.read] + (L - w.wb - w.wl) + s.off; // strand 1 of the window is a slice of strand 1 of the read
+	// base o of strand 1 of the window is the complement of base wl - 1 - o of its strand 0 (src/align.c:874-876)
+	else if (s.kind == SEQ_Q1) j.kind = 2, j.src_off = g.read_off[w.read] + w.wb + (w.wl - 1 - s.off);
 	else j.kind = 1, j.src_off = (int64_t)g.hidx->offset[s.rid] + s.off;
 	return j;
 }
 
-// query / target slices of a job -> gather descriptors
+// query / target slices of a job -> gather descriptors; every slice starts on a 16-byte boundary of the pool
 static inline void add_gather(std::vector<wm_gather_job> &gj, std::vector<int64_t> &joff, const GpuBackendImpl &g, const SeqRef &s, const MapWin &w, int64_t *pool_off)
 {
-	wm_gather_job j;
-	j.len = s.len, j.reversed = s.reversed, j.pad = 0, j.dst_off = *pool_off;
-	const int64_t L = g.read_off[w.read + 1] - g.read_off[w.read];
-	if (s.kind == SEQ_Q0) j.kind = 0, j.src_off = g.read_off[w.read] + w.wb + s.off;
-	else if (s.kind == SEQ_Q1) j.kind = 2, j.src_off = g.read_off[w.read] + (L - w.wb - w.wl) + s.off; // strand 1 of the window is a slice of strand 1 of the read
-	else j.kind = 1, j.src_off = (int64_t)g.hidx->offset[s.rid] + s.off;
-	gj.push_back(j);
-	joff.push_back(joff.back() + s.len);
-	*pool_off += s.len;
+	gj.push_back(make_gather(g, s, w, *pool_off));
+	*pool_off += (s.len + 15) & ~15;
+	joff.push_back(*pool_off);
 }
 
-__global__ void wm_gather2_kernel(const wm_gather_job *__restrict__ jobs, const int64_t *__restrict__ joff, int n_jobs, const uint8_t *__restrict__ codes,
-                                  const uint8_t *__restrict__ rcodes, const uint32_t *__restrict__ S, uint8_t *__restrict__ dst, int64_t n)
+// DP sequences out of the packed pools: one thread writes 16 bytes of 0..4 codes (one 128-bit store) from one unaligned
+// window -- 32 bits of the read pool or 64 bits of the 4-bit reference -- read forwards or backwards.  Slices start on
+// 16-byte boundaries of `dst` and are zero padded to one (the fill kernel stages them with bulk copies).
+__global__ void wm_gather2_kernel(const wm_gather_job *__restrict__ jobs, const int64_t *__restrict__ joff, int n_jobs, const wm_pkseq rd,
+                                  const uint32_t *__restrict__ S, uint8_t *__restrict__ dst, int64_t n16)
 {
 	const int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (gidx >= n) return;
+	if (gidx >= n16) return;
+	const int64_t byte0 = gidx * 16;
 	int lo = 0, hi = n_jobs;
-	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (joff[m] <= gidx) lo = m; else hi = m; }
-	const wm_gather_job J = jobs[lo];
-	const int p = (int)(gidx - joff[lo]);
-	if (p >= J.len) { dst[gidx] = 0; return; } // padding up to the next 16-byte boundary
-	const int64_t s = J.src_off + (J.reversed ? J.len - 1 - p : p);
-	uint8_t c;
-	if (J.kind == 0) c = codes[s];
-	else if (J.kind == 2) c = rcodes[s];
-	else { c = (uint8_t)(S[s >> 3] >> ((s & 7) << 2) & 0xf); if (c > 4) c = 4; }
-	dst[J.dst_off + p] = c;
+	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (joff[m] <= byte0) lo = m; else hi = m; }
+	uint32_t out[4];
+	wm_pk_gather16(jobs[lo], (int)(byte0 - joff[lo]), rd, S, out);
+	((uint4*)dst)[gidx] = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<DpRes> &res)
@@ -446,6 +403,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 	res.assign(n, DpRes());
 	g.h_cig.clear();
 	if (n == 0) return;
+	wm_pkseq rd; rd.pk = (const uint32_t*)g.pk.p, rd.nm = (const uint32_t*)g.nm.p;
 	wm_dp_params P; wm_dp_params_init(&P, sc.mat, sc.q, sc.e, sc.q2, sc.e2);
 	static int coop_on = -1; // WM_DP_COOP=0: every job on one warp (for comparison)
 	if (coop_on < 0) { const char *e = getenv("WM_DP_COOP"); coop_on = (e && *e == '0') ? 0 : 1; if (getenv("WM_DP_V1") && *getenv("WM_DP_V1") == '1') coop_on = 0; }
@@ -549,7 +507,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		WM_CUDA_CHECK(wm_memcpy_async(d_joff, joff.data(), sizeof(int64_t) * joff.size(), cudaMemcpyHostToDevice, st));
 		WM_CUDA_CHECK(wm_memcpy_async(d_dj, dj.data(), sizeof(wm_dp_job) * m, cudaMemcpyHostToDevice, st));
 		if (pool_off > 0) {
-			wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
+			wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off / 16 + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), rd, g.ix.S, d_pool, pool_off / 16);
 			WM_CUDA_CHECK(cudaGetLastError());
 		}
 		int32_t *d_zd = (int32_t*)g.zd.need(sizeof(int32_t) * 5 * (size_t)m);
@@ -610,6 +568,7 @@ void GpuBackend::run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin
 	const int n = (int)jobs.size();
 	res.assign(n, LlRes());
 	if (n == 0) return;
+	wm_pkseq rd; rd.pk = (const uint32_t*)g.pk.p, rd.nm = (const uint32_t*)g.nm.p;
 	std::vector<wm_gather_job> gj; std::vector<int64_t> joff(1, 0); std::vector<wm_ll_job> lj(n);
 	int64_t pool_off = 0, s_off = 0;
 	for (int i = 0; i < n; ++i) {
@@ -630,7 +589,7 @@ void GpuBackend::run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin
 	WM_CUDA_CHECK(wm_memcpy_async(d_lj, lj.data(), sizeof(wm_ll_job) * n, cudaMemcpyHostToDevice, st));
 	WM_CUDA_CHECK(wm_memcpy_async(d_mat, sc.mat, 25, cudaMemcpyHostToDevice, st));
 	if (pool_off > 0) {
-		wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), (const uint8_t*)g.codes.p, (const uint8_t*)g.rcodes.p, g.ix.S, d_pool, pool_off);
+		wm_count_launch(); wm_gather2_kernel<<<(unsigned)((pool_off / 16 + 255) / 256), 256, 0, st>>>(d_gj, d_joff, (int)gj.size(), rd, g.ix.S, d_pool, pool_off / 16);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	wm_ksw_ll_launch(d_lj, n, d_pool, d_mat, sc.q, sc.e, d_scr, d_out, st);

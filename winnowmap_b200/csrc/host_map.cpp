@@ -232,6 +232,7 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		std::vector<int> active;
 		for (int i = 0; i < n; ++i) if (mm[i].aligning) active.push_back(i);
 		dp_res.clear(), ll_res.clear();
+		double t_dp_wave = 0;
 		while (!active.empty()) {
 			double ta0 = Timers::now();
 			#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads)
@@ -266,6 +267,7 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			double t2 = now_s();
 			{ WM_TIMED("round.run_dp"); be->run_dp(dp_jobs, wins, sc, dp_res); }
 			{ WM_TIMED("round.run_ll"); be->run_ll(ll_jobs, wins, sc, ll_res); }
+			t_dp_wave += now_s() - t2;
 			if (st) {
 				st->t_dp += now_s() - t2, st->n_dp_jobs += (int64_t)dp_jobs.size(), st->n_ll_jobs += (int64_t)ll_jobs.size(), ++st->n_rounds;
 			}
@@ -284,7 +286,7 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 			set_mapq(M.regs, M.opt->min_chain_score, M.opt->a, M.rep_len, 0);
 		}
 		g_timers.add("wave.final_mapq", Timers::now() - tf0);
-		if (st) st->t_host += now_s() - t1;
+		if (st) st->t_host += now_s() - t1 - t_dp_wave; // the host's own share: the DP rounds are counted in t_dp
 	};
 
 	// ---------------- stage 1: minimal confidently-alignable substrings (src/map.c:314-700) ----------------

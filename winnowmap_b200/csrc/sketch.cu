@@ -12,12 +12,17 @@
 //
 // For odd k (the defaults 15/19) a k-mer cannot equal its reverse complement, so ring slots and
 // bases coincide (src/sketch.c:166 never fires); even k takes a sequential per-sequence kernel.
+//
+// The sequences are read from the packed pool (pkseq.cuh: 2 bits per base + ambiguity mask).  Pass A stages the packed
+// words of its tile with 128-bit loads, takes every k-mer as one unaligned 64-bit window of them (no per-base rebuild),
+// and finds the minimum of the w previous keys by doubling (log2 w rounds over shared memory) instead of scanning them.
 #include <math.h>
 #include <string.h>
 #include <vector>
 #include "wm_common.cuh"
 #include "scan.cuh"
 #include "sketch.cuh"
+#include "pkseq.cuh"
 
 #define WM_SK_TN 1024      // new positions per tile in pass A
 #define WM_SK_THREADS 256
@@ -63,64 +68,72 @@ __device__ __forceinline__ double wm_weight(uint64_t kmer, const wm_bloom_dev &b
 	return -x;
 }
 
-// canonical k-mer ending at position i of `c` (codes 0..4); returns false if it spans an N / the start
-__device__ __forceinline__ bool wm_kmer_at(const uint8_t *c, int k, uint64_t *fw, uint64_t *rv)
-{ // c points at the first base of the k-mer
-	uint64_t f = 0, r = 0;
-	bool ok = true;
-	for (int j = 0; j < k; ++j) {
-		uint64_t b = c[j];
-		ok &= b < 4;
-		f = f << 2 | (b & 3);
-		r = r >> 2 | (3ULL ^ (b & 3)) << (2 * (k - 1));
-	}
-	*fw = f, *rv = r;
-	return ok;
-}
-
 // ---- pass A ----
+#define WM_SK_NE (WM_SK_TN + 256)   // order keys held per tile: the w previous positions + the tile
+#define WM_SK_PKW 96                // packed words staged per tile (64-base aligned start, + the window's look-ahead)
+#define WM_SK_SMEM (3 * WM_SK_NE * 8 + WM_SK_PKW * 4 + WM_SK_PKW * 2)
+
 __global__ void __launch_bounds__(WM_SK_THREADS)
-wm_sketch_order_kernel(const uint8_t *__restrict__ codes, const wm_sk_task *__restrict__ tasks, const int64_t *__restrict__ tile_off,
+wm_sketch_order_kernel(const wm_pkseq seq, const wm_sk_task *__restrict__ tasks, const int64_t *__restrict__ tile_off,
                        const int64_t *__restrict__ base_off, int n_tasks, int w, int k, wm_bloom_dev bf,
                        double *__restrict__ ord, uint8_t *__restrict__ elig)
 {
 	extern __shared__ __align__(16) uint8_t sm_raw[];
-	double *s_ord = (double*)sm_raw;                       // WM_SK_TN + w entries, position p0 - w + j
-	uint8_t *s_code = sm_raw + (size_t)(WM_SK_TN + 256) * 8;  // WM_SK_TN + w + k - 1 codes, position p0 - w - (k-1) + j
+	double *s_ord = (double*)sm_raw;                 // position p0 - w + j
+	double *s_a = s_ord + WM_SK_NE, *s_b = s_a + WM_SK_NE; // window minima, ping-pong
+	uint32_t *s_pk = (uint32_t*)(s_b + WM_SK_NE);    // packed bases from pool base Gw on
+	uint32_t *s_nm = s_pk + WM_SK_PKW;
 	// which task does this tile belong to?
 	int lo = 0, hi = n_tasks;
 	const int64_t tile = blockIdx.x;
 	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (tile_off[m] <= tile) lo = m; else hi = m; }
 	const wm_sk_task T = tasks[lo];
 	const int p0 = (int)(tile - tile_off[lo]) * WM_SK_TN;
-	const uint8_t *seq = codes + T.seq_off;
-	const int n_code = WM_SK_TN + w + k - 1, c_start = p0 - w - (k - 1);
-	for (int j = threadIdx.x; j < n_code; j += WM_SK_THREADS) {
-		int p = c_start + j;
-		s_code[j] = (p >= 0 && p < T.len) ? seq[p] : 4;
+	// bases p0 - w - (k - 1) .. p0 + WM_SK_TN - 1 of the sequence, staged from the 64-base boundary below the first one
+	const int n_code = WM_SK_TN + w + k - 1;
+	const int64_t G0 = T.seq_off + p0 - w - (k - 1);
+	const int64_t Gw = (G0 >> 6) << 6; // (floors for a negative G0: the first sequence of the pool)
+	const int n_q = ((int)(G0 - Gw) + n_code + 63) / 64 + 1;
+	const int64_t q_last = (T.seq_off + T.len) >> 6; // nothing past the sequence is needed
+	for (int j = threadIdx.x; j < n_q; j += WM_SK_THREADS) {
+		const int64_t q = (Gw >> 6) + j;
+		const bool in = q >= 0 && q <= q_last;
+		((uint4*)s_pk)[j] = in ? ((const uint4*)seq.pk)[q] : make_uint4(0u, 0u, 0u, 0u);
+		((uint2*)s_nm)[j] = in ? ((const uint2*)seq.nm)[q] : make_uint2(~0u, ~0u);
 	}
 	__syncthreads();
-	for (int j = threadIdx.x; j < WM_SK_TN + w; j += WM_SK_THREADS) {
+	const uint32_t kmask = (1u << k) - 1u;
+	for (int j = threadIdx.x; j < WM_SK_NE; j += WM_SK_THREADS) {
 		const int p = p0 - w + j;
 		double o = 2.0;
-		if (p >= k - 1 && p < T.len) {
-			uint64_t f, r;
-			if (wm_kmer_at(s_code + j, k, &f, &r) && f != r) o = wm_weight(f < r ? f : r, bf);
+		if (j < WM_SK_TN + w && p >= k - 1 && p < T.len) {
+			const int64_t rel = T.seq_off + (p - (k - 1)) - Gw; // first base of the k-mer
+			if (!(wm_pk_nwindow(s_nm, rel) & kmask)) {
+				uint64_t f, r;
+				wm_pk_kmer(wm_pk_window(s_pk, rel), k, &f, &r);
+				if (f != r) o = wm_weight(f < r ? f : r, bf);
+			}
 		}
 		s_ord[j] = o;
 	}
 	__syncthreads();
+	// minimum over [j, j + w): levels of spans 2, 4, .. 2^t <= w, then two overlapping spans of 2^t
+	int t = 31 - __clz(w);
+	const double *cur = s_ord;
+	for (int l = 0; l < t; ++l) {
+		double *nxt = (l & 1) ? s_b : s_a;
+		const int d = 1 << l;
+		for (int j = threadIdx.x; j < WM_SK_NE; j += WM_SK_THREADS) nxt[j] = j + d < WM_SK_NE ? fmin(cur[j], cur[j + d]) : cur[j];
+		__syncthreads();
+		cur = nxt;
+	}
+	const int d2 = w - (1 << t);
 	const int64_t gb = base_off[lo];
 	for (int j = threadIdx.x; j < WM_SK_TN; j += WM_SK_THREADS) {
 		const int p = p0 + j;
 		if (p >= T.len) break;
 		const double o = s_ord[j + w];
-		bool e = o < 2.0;
-		if (e) {
-			double m = 2.0;
-			for (int d = 0; d < w; ++d) m = fmin(m, s_ord[j + d]);
-			e = o < m;
-		}
+		const bool e = o < 2.0 && o < fmin(cur[j], cur[j + d2]);
 		ord[gb + p] = o;
 		elig[gb + p] = e ? 1 : 0;
 	}
@@ -180,13 +193,12 @@ __global__ void wm_sketch_winnow_kernel(const wm_sk_task *__restrict__ tasks, co
 }
 
 // sequential pass for even k (symmetric k-mers make ring slots != bases): one thread per sequence
-__global__ void wm_sketch_seq_kernel(const uint8_t *__restrict__ codes, const wm_sk_task *__restrict__ tasks, const int64_t *__restrict__ base_off,
+__global__ void wm_sketch_seq_kernel(const wm_pkseq seq, const wm_sk_task *__restrict__ tasks, const int64_t *__restrict__ base_off,
                                      int n_tasks, int w, int k, wm_bloom_dev bf, uint8_t *__restrict__ flag_all, double *__restrict__ ring_all)
 {
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	if (tid >= n_tasks) return;
 	const wm_sk_task T = tasks[tid];
-	const uint8_t *seq = codes + T.seq_off;
 	uint8_t *flag = flag_all + base_off[tid];
 	double *buf_ord = ring_all + (size_t)tid * 512; // order keys
 	double *buf_pos_ = buf_ord + 256;               // positions, stored as doubles (exact below 2^53)
@@ -196,7 +208,7 @@ __global__ void wm_sketch_seq_kernel(const uint8_t *__restrict__ codes, const wm
 	double min_ord = 2.0;
 	for (int j = 0; j < w; ++j) buf_ord[j] = 2.0, buf_pos_[j] = -1.0;
 	for (int i = 0; i < T.len; ++i) {
-		const int c = seq[i];
+		const int c = wm_pk_get(seq, T.seq_off + i);
 		double o = 2.0; int oi = -1;
 		if (c < 4) {
 			kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
@@ -237,7 +249,7 @@ __global__ void wm_sketch_count_kernel(const wm_sk_task *__restrict__ tasks, con
 	cnt[ch] = n;
 }
 
-__global__ void wm_sketch_emit_kernel(const uint8_t *__restrict__ codes, const wm_sk_task *__restrict__ tasks, const int64_t *__restrict__ chunk_off,
+__global__ void wm_sketch_emit_kernel(const wm_pkseq seq, const wm_sk_task *__restrict__ tasks, const int64_t *__restrict__ chunk_off,
                                       const int64_t *__restrict__ base_off, int n_tasks, int64_t n_chunks, int k,
                                       const uint8_t *__restrict__ flag_all, const int64_t *__restrict__ rank, wm128_dev *__restrict__ out,
                                       int64_t *__restrict__ mz_off)
@@ -249,7 +261,6 @@ __global__ void wm_sketch_emit_kernel(const uint8_t *__restrict__ codes, const w
 	while (hi - lo > 1) { int m = (lo + hi) >> 1; if (chunk_off[m] <= ch) lo = m; else hi = m; }
 	const wm_sk_task T = tasks[lo];
 	const uint8_t *flag = flag_all + base_off[lo];
-	const uint8_t *seq = codes + T.seq_off;
 	const int c0 = (int)(ch - chunk_off[lo]) * WM_SK_CH;
 	int c1 = c0 + WM_SK_CH; if (c1 > T.len) c1 = T.len;
 	if (c0 == 0) mz_off[lo] = rank[ch];
@@ -260,7 +271,7 @@ __global__ void wm_sketch_emit_kernel(const uint8_t *__restrict__ codes, const w
 	for (int i = c0; i < c1; ++i)
 		if (flag[i]) {
 			uint64_t f, r;
-			wm_kmer_at(seq + i - (k - 1), k, &f, &r);
+			wm_pk_kmer(wm_pk_window(seq.pk, T.seq_off + i - (k - 1)), k, &f, &r);
 			const int z = f < r ? 0 : 1; // src/sketch.c:167
 			wm128_dev m;
 			m.x = wm_hash64(z ? r : f, mask) << 8 | (uint64_t)k;   // :171 (span == k once l >= k)
@@ -269,33 +280,100 @@ __global__ void wm_sketch_emit_kernel(const uint8_t *__restrict__ codes, const w
 		}
 }
 
-__global__ void wm_ascii_to_code_kernel(const char *__restrict__ in, uint8_t *__restrict__ out, int64_t n)
+// ---- ASCII -> packed pool ----
+__device__ __forceinline__ uint8_t wm_nt4(unsigned c)
 { // seq_nt4_table (src/sketch.c:19-36): ACGT/acgt (and U/u) -> 0..3, everything else 4
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	unsigned char c = in[i];
-	uint8_t v = 4;
 	switch (c) {
-		case 'A': case 'a': v = 0; break;
-		case 'C': case 'c': v = 1; break;
-		case 'G': case 'g': v = 2; break;
-		case 'T': case 't': case 'U': case 'u': v = 3; break;
-		default: v = c < 4 ? c : 4; // the table maps bytes 0..3 to themselves
+		case 'A': case 'a': return 0;
+		case 'C': case 'c': return 1;
+		case 'G': case 'g': return 2;
+		case 'T': case 't': case 'U': case 'u': return 3;
+		default: return c < 4 ? (uint8_t)c : 4; // the table maps bytes 0..3 to themselves
 	}
-	out[i] = v;
 }
 
-void wm_ascii_to_code(const char *d_in, uint8_t *d_out, int64_t n, cudaStream_t st)
+// One thread packs 32 consecutive bases: two 128-bit loads in, 64 + 32 bits out.  `in` is 16-byte aligned.
+__global__ void __launch_bounds__(256)
+wm_pack_ascii_kernel(const char *__restrict__ in, int64_t n, uint32_t *__restrict__ pk, uint32_t *__restrict__ nm)
 {
+	__shared__ uint8_t lut[256];
+	lut[threadIdx.x] = wm_nt4(threadIdx.x);
+	__syncthreads();
+	const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x, b0 = g * 32;
+	if (b0 >= n) return;
+	uint32_t raw[8];
+	if (b0 + 32 <= n) {
+		const uint4 a = ((const uint4*)in)[2 * g], b = ((const uint4*)in)[2 * g + 1];
+		raw[0] = a.x, raw[1] = a.y, raw[2] = a.z, raw[3] = a.w, raw[4] = b.x, raw[5] = b.y, raw[6] = b.z, raw[7] = b.w;
+	} else { // the last group of the pool: the bases past the end read as ambiguous
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			uint32_t v = 0;
+			for (int b = 0; b < 4; ++b) { const int64_t i = b0 + 4 * j + b; v |= (uint32_t)(i < n ? (unsigned char)in[i] : 'N') << 8 * b; }
+			raw[j] = v;
+		}
+	}
+	uint64_t p; uint32_t m;
+	wm_pk_pack32(raw, lut, &p, &m);
+	((uint2*)pk)[g] = make_uint2((uint32_t)p, (uint32_t)(p >> 32));
+	nm[g] = m;
+}
+
+// the same for reads scattered over a device ASCII pool (read i: pool[src_off[i] ..), packed at dst_off[i] of the batch pool)
+__global__ void __launch_bounds__(256)
+wm_pack_gather_kernel(const char *__restrict__ pool, const int64_t *__restrict__ src_off, const int64_t *__restrict__ dst_off, int n_reads,
+                      int64_t n, uint32_t *__restrict__ pk, uint32_t *__restrict__ nm)
+{
+	__shared__ uint8_t lut[256];
+	lut[threadIdx.x] = wm_nt4(threadIdx.x);
+	__syncthreads();
+	const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x, b0 = g * 32;
+	if (b0 >= n) return;
+	int lo = 0, hi = n_reads;
+	while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (dst_off[m] <= b0) lo = m; else hi = m; }
+	uint64_t p = 0; uint32_t m = 0;
+	for (int j = 0; j < 32; ++j) {
+		const int64_t i = b0 + j;
+		uint32_t c = 4;
+		if (i < n) {
+			while (i >= dst_off[lo + 1]) ++lo;
+			c = lut[(unsigned char)pool[src_off[lo] + (i - dst_off[lo])]];
+		}
+		p |= (uint64_t)(c & 3) << 2 * j;
+		m |= (c >> 2) << j;
+	}
+	((uint2*)pk)[g] = make_uint2((uint32_t)p, (uint32_t)(p >> 32));
+	nm[g] = m;
+}
+
+// the look-ahead words past the last group (pkseq.cuh) are defined: ambiguous
+static void wm_pack_tail(int64_t n, uint32_t *d_pk, uint32_t *d_nm, cudaStream_t st)
+{
+	const int64_t g = (n + 31) / 32;
+	WM_CUDA_CHECK(cudaMemsetAsync(d_pk + 2 * g, 0, sizeof(uint32_t) * WM_PK_SLACK, st));
+	WM_CUDA_CHECK(cudaMemsetAsync(d_nm + g, 0xff, sizeof(uint32_t) * WM_PK_SLACK, st));
+}
+
+void wm_pack_ascii(const char *d_in, int64_t n, uint32_t *d_pk, uint32_t *d_nm, cudaStream_t st)
+{
+	wm_pack_tail(n, d_pk, d_nm, st);
 	if (n <= 0) return;
-	wm_count_launch(); wm_ascii_to_code_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, d_out, n);
+	wm_count_launch(); wm_pack_ascii_kernel<<<(unsigned)((n + 32 * 256 - 1) / (32 * 256)), 256, 0, st>>>(d_in, n, d_pk, d_nm);
+	WM_CUDA_CHECK(cudaGetLastError());
+}
+
+void wm_pack_gather(const char *d_pool, const int64_t *d_src_off, const int64_t *d_dst_off, int n_reads, int64_t n, uint32_t *d_pk, uint32_t *d_nm, cudaStream_t st)
+{
+	wm_pack_tail(n, d_pk, d_nm, st);
+	if (n <= 0) return;
+	wm_count_launch(); wm_pack_gather_kernel<<<(unsigned)((n + 32 * 256 - 1) / (32 * 256)), 256, 0, st>>>(d_pool, d_src_off, d_dst_off, n_reads, n, d_pk, d_nm);
 	WM_CUDA_CHECK(cudaGetLastError());
 }
 
 // ---- host-side launcher on device-resident code arrays ----
-// tasks (host copy) describe slices of d_codes.  On return *n_mz is the total number of minimizers,
+// tasks (host copy) describe slices of the packed pool `seq` (offsets in bases).  On return *n_mz is the total number of minimizers,
 // ws->mz holds them (device) and ws->mz_off (device, n_tasks+1) their per-task offsets.
-void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_codes, const wm_sk_task *h_tasks, int n_tasks,
+void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const wm_pkseq &seq, const wm_sk_task *h_tasks, int n_tasks,
                    int w, int k, int64_t *n_mz, cudaStream_t st)
 {
 	*n_mz = 0;
@@ -322,14 +400,13 @@ void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_co
 	if (k & 1) {
 		double *d_ord = (double*)ws->ord.need(sizeof(double) * n_bases);
 		uint8_t *d_elig = (uint8_t*)ws->elig.need(n_bases);
-		const size_t smem = (size_t)(WM_SK_TN + 256) * 8 + WM_SK_TN + 256 + 32;
-		wm_count_launch(); wm_sketch_order_kernel<<<(unsigned)n_tiles, WM_SK_THREADS, smem, st>>>(d_codes, d_tasks, d_tile_off, d_base_off, n_tasks, w, k, bf, d_ord, d_elig);
+		wm_count_launch(); wm_sketch_order_kernel<<<(unsigned)n_tiles, WM_SK_THREADS, WM_SK_SMEM, st>>>(seq, d_tasks, d_tile_off, d_base_off, n_tasks, w, k, bf, d_ord, d_elig);
 		WM_CUDA_CHECK(cudaGetLastError());
 		wm_count_launch(); wm_sketch_winnow_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, st>>>(d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, w, d_ord, d_elig, d_flag);
 		WM_CUDA_CHECK(cudaGetLastError());
 	} else {
 		double *d_ring = (double*)ws->ord.need(sizeof(double) * 512 * (size_t)n_tasks);
-		wm_count_launch(); wm_sketch_seq_kernel<<<(n_tasks + 63) / 64, 64, 0, st>>>(d_codes, d_tasks, d_base_off, n_tasks, w, k, bf, d_flag, d_ring);
+		wm_count_launch(); wm_sketch_seq_kernel<<<(n_tasks + 63) / 64, 64, 0, st>>>(seq, d_tasks, d_base_off, n_tasks, w, k, bf, d_flag, d_ring);
 		WM_CUDA_CHECK(cudaGetLastError());
 	}
 	int32_t *d_cnt = (int32_t*)ws->cnt.need(sizeof(int32_t) * (n_chunks + 1));
@@ -347,7 +424,7 @@ void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_co
 		std::vector<int64_t> fill(n_tasks + 1, total);
 		WM_CUDA_CHECK(wm_memcpy_async(d_mz_off, fill.data(), sizeof(int64_t) * (n_tasks + 1), cudaMemcpyHostToDevice, st));
 	}
-	wm_count_launch(); wm_sketch_emit_kernel<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, st>>>(d_codes, d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, k,
+	wm_count_launch(); wm_sketch_emit_kernel<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, st>>>(seq, d_tasks, d_chunk_off, d_base_off, n_tasks, n_chunks, k,
 	                                                                               d_flag, d_rank, d_mz, d_mz_off);
 	WM_CUDA_CHECK(cudaGetLastError());
 	*n_mz = total;
@@ -429,9 +506,10 @@ extern "C" int wm_sketch_batch(const wm_bloom_s *bloom, int n, const char *seq, 
 	if (n <= 0) return 0;
 	const int64_t tot = off[n];
 	char *d_ascii = wm_dev_alloc<char>(tot + 1);
-	uint8_t *d_codes = wm_dev_alloc<uint8_t>(tot + 1);
+	uint32_t *d_pk = wm_dev_alloc<uint32_t>(wm_pk_words(tot)), *d_nm = wm_dev_alloc<uint32_t>(wm_nm_words(tot));
 	WM_CUDA_CHECK(cudaMemcpy(d_ascii, seq, tot, cudaMemcpyHostToDevice));
-	wm_ascii_to_code(d_ascii, d_codes, tot, 0);
+	wm_pack_ascii(d_ascii, tot, d_pk, d_nm, 0);
+	wm_pkseq pks; pks.pk = d_pk, pks.nm = d_nm;
 	uint8_t *d_table = wm_dev_alloc<uint8_t>(bloom->table.size());
 	WM_CUDA_CHECK(cudaMemcpy(d_table, bloom->table.data(), bloom->table.size(), cudaMemcpyHostToDevice));
 	wm_bloom_dev bf; wm_bloom_dev_from_table(&bf, d_table, bloom->bits);
@@ -440,12 +518,12 @@ extern "C" int wm_sketch_batch(const wm_bloom_s *bloom, int n, const char *seq, 
 	for (int i = 0; i < n; ++i) tasks[i].seq_off = off[i], tasks[i].len = (int32_t)(off[i + 1] - off[i]), tasks[i].rid = rid ? rid[i] : 0;
 	wm_sketch_ws ws;
 	int64_t n_mz = 0;
-	wm_sketch_run(&ws, bf, d_codes, tasks.data(), n, w, k, &n_mz, 0);
+	wm_sketch_run(&ws, bf, pks, tasks.data(), n, w, k, &n_mz, 0);
 	WM_CUDA_CHECK(cudaDeviceSynchronize());
 	*out = (wm128_dev*)malloc(sizeof(wm128_dev) * (n_mz > 0 ? n_mz : 1));
 	if (n_mz > 0) WM_CUDA_CHECK(cudaMemcpy(*out, ws.mz.p, sizeof(wm128_dev) * n_mz, cudaMemcpyDeviceToHost));
 	WM_CUDA_CHECK(cudaMemcpy(*out_off, ws.mz_off.p, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost));
 	ws.release();
-	cudaFree(d_ascii); cudaFree(d_codes); cudaFree(d_table);
+	cudaFree(d_ascii); cudaFree(d_pk); cudaFree(d_nm); cudaFree(d_table);
 	return 0;
 }

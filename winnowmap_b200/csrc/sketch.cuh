@@ -1,5 +1,6 @@
 #pragma once
 #include "wm_common.cuh"
+#include "pkseq.cuh"
 
 struct wm128_dev { uint64_t x, y; };
 
@@ -11,7 +12,7 @@ struct wm_bloom_dev {
 	int n_salt;
 };
 
-// one sequence to sketch: a slice of a device code array (0..3 = ACGT, 4 = ambiguous)
+// one sequence to sketch: a slice of the packed pool (pkseq.cuh), seq_off in bases
 struct wm_sk_task {
 	int64_t seq_off;
 	int32_t len;
@@ -24,8 +25,13 @@ struct wm_sketch_ws {
 };
 
 struct wm_bloom_s;
-void wm_ascii_to_code(const char *d_in, uint8_t *d_out, int64_t n, cudaStream_t st);
-void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const uint8_t *d_codes, const wm_sk_task *h_tasks, int n_tasks,
+// sizes (in 32-bit words) of the two arrays of a packed pool of n bases, look-ahead included
+static inline size_t wm_pk_words(int64_t n) { return (size_t)((n + 31) / 32) * 2 + WM_PK_SLACK + 4; }
+static inline size_t wm_nm_words(int64_t n) { return (size_t)((n + 31) / 32) + WM_PK_SLACK + 4; }
+// ASCII (16-byte aligned device buffer) -> packed pool; the second form gathers reads scattered over a device ASCII pool
+void wm_pack_ascii(const char *d_in, int64_t n, uint32_t *d_pk, uint32_t *d_nm, cudaStream_t st);
+void wm_pack_gather(const char *d_pool, const int64_t *d_src_off, const int64_t *d_dst_off, int n_reads, int64_t n, uint32_t *d_pk, uint32_t *d_nm, cudaStream_t st);
+void wm_sketch_run(wm_sketch_ws *ws, const wm_bloom_dev &bf, const wm_pkseq &seq, const wm_sk_task *h_tasks, int n_tasks,
                    int w, int k, int64_t *n_mz, cudaStream_t st);
 void wm_bloom_dev_from_table(wm_bloom_dev *d, const uint8_t *d_table, uint64_t bits);
 void wm_bloom_params(const wm_bloom_s *b, uint64_t *bits, uint32_t *salt, int *n_salt);
