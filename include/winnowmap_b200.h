@@ -63,6 +63,15 @@ int wm_ksw_extd2_batch(int n, const uint8_t *qseq, const int64_t *qoff, const ui
                        const int32_t *w, const int32_t *zdrop, const int32_t *end_bonus, const int32_t *flag,
                        wm_extz_t *ez, uint32_t *cigar, const int64_t *cigar_off);
 
+/* Batched ksw_exts2_sse (src/ksw2_exts2_sse.c:26; prototype src/ksw2.h:63-64), the splice-aware extension mm_align_pair
+ * calls when MM_F_SPLICE is set (src/align.c:326-327): m = 5, no band, no end bonus.  flag: the KSW_EZ_* bits of
+ * src/ksw2.h:7-17, including SPLICE_FOR 0x100 / SPLICE_REV 0x200 / SPLICE_FLANK 0x400.  junc: one annotation byte per
+ * target base (mm_idx_bed_junc, src/index.c:780), same offsets as tseq, or NULL.  The kernel is complete and parity-
+ * tested; the mapper itself still refuses -x splice (the splice branches of mm_align1 are not built). */
+int wm_ksw_exts2_batch(int n, const uint8_t *qseq, const int64_t *qoff, const uint8_t *tseq, const int64_t *toff, const uint8_t *junc,
+                       const int8_t *mat, int q, int e, int q2, int noncan, int junc_bonus,
+                       const int32_t *zdrop, const int32_t *flag, wm_extz_t *ez, uint32_t *cigar, const int64_t *cigar_off);
+
 /* Batched ksw_ll_qinit + ksw_ll_i16 (src/ksw2_ll_sse.c:32,80): score, query end, target end. */
 int wm_ksw_ll_batch(int n, const uint8_t *qseq, const int64_t *qoff, const uint8_t *tseq, const int64_t *toff,
                     const int8_t *mat, int gapo, int gape, int32_t *score, int32_t *qe, int32_t *te);

@@ -14,7 +14,7 @@
 
 extern "C" {
 
-// ---- ksw2 (src/ksw2_extd2_sse.c:26, src/ksw2_extz2_sse.c:23) ----
+// ---- ksw2 (src/ksw2_extd2_sse.c:26, src/ksw2_extz2_sse.c:23, src/ksw2_exts2_sse.c:26) ----
 // out_ez: max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, reach_end, n_cigar
 int ref_ksw_extd2(int qlen, const uint8_t *q, int tlen, const uint8_t *t, const int8_t *mat,
                   int gapo, int gape, int gapo2, int gape2, int w, int zdrop, int end_bonus, int flag,
@@ -37,6 +37,22 @@ int ref_ksw_extz2(int qlen, const uint8_t *q, int tlen, const uint8_t *t, const 
 {
 	ksw_extz_t ez; memset(&ez, 0, sizeof(ez));
 	ksw_extz2_sse(0, qlen, q, tlen, t, 5, mat, gapo, gape, w, zdrop, end_bonus, flag, &ez);
+	out_ez[0] = ez.max; out_ez[1] = ez.zdropped; out_ez[2] = ez.max_q; out_ez[3] = ez.max_t;
+	out_ez[4] = ez.mqe; out_ez[5] = ez.mqe_t; out_ez[6] = ez.mte; out_ez[7] = ez.mte_q;
+	out_ez[8] = ez.score; out_ez[9] = ez.reach_end; out_ez[10] = ez.n_cigar;
+	int n = ez.n_cigar < max_cigar ? ez.n_cigar : max_cigar;
+	if (n > 0) memcpy(cigar, ez.cigar, n * 4);
+	kfree(0, ez.cigar);
+	return ez.n_cigar;
+}
+
+// splice-aware extension (src/ksw2_exts2_sse.c:26); junc may be null
+int ref_ksw_exts2(int qlen, const uint8_t *q, int tlen, const uint8_t *t, const int8_t *mat,
+                  int gapo, int gape, int gapo2, int noncan, int zdrop, int junc_bonus, int flag, const uint8_t *junc,
+                  int *out_ez, uint32_t *cigar, int max_cigar)
+{
+	ksw_extz_t ez; memset(&ez, 0, sizeof(ez));
+	ksw_exts2_sse(0, qlen, q, tlen, t, 5, mat, gapo, gape, gapo2, noncan, zdrop, junc_bonus, flag, junc, &ez);
 	out_ez[0] = ez.max; out_ez[1] = ez.zdropped; out_ez[2] = ez.max_q; out_ez[3] = ez.max_t;
 	out_ez[4] = ez.mqe; out_ez[5] = ez.mqe_t; out_ez[6] = ez.mte; out_ez[7] = ez.mte_q;
 	out_ez[8] = ez.score; out_ez[9] = ez.reach_end; out_ez[10] = ez.n_cigar;

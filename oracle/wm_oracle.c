@@ -463,6 +463,10 @@ int wmo_chain_dp(int max_dist_x, int min_dist_x, int max_dist_y, int bw, int max
  * ---------------------------------------------------------------------------------- */
 #define WMO_NEG_INF (-0x40000000)
 #define WMO_EZ_RIGHT      0x02
+#define WMO_EZ_GENERIC_SC 0x04
+#define WMO_EZ_SPLICE_FOR 0x100
+#define WMO_EZ_SPLICE_REV 0x200
+#define WMO_EZ_SPLICE_FLANK 0x400
 #define WMO_EZ_APPROX_MAX 0x08
 #define WMO_EZ_APPROX_DROP 0x10
 #define WMO_EZ_EXTZ_ONLY  0x40
@@ -868,6 +872,250 @@ int wmo_ksw_extz2(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 		} else if (ez->max_t >= 0 && ez->max_q >= 0) {
 			wmo_backtrack(rev_cigar, p, off, off_end, n_col_ * 16, ez->max_t, ez->max_q, &cig);
 		}
+	}
+	free(p); free(off);
+	ez->n_cigar = cig.n;
+	if (cigar_out) memcpy(cigar_out, cig.a, (size_t)(cig.n < max_cigar ? cig.n : max_cigar) * 4);
+	free(cig.a);
+	return ez->n_cigar;
+}
+
+/* ------------------------------------------------------------------------------------
+ * ksw_exts2_sse: src/ksw2_exts2_sse.c:26-408, the splice-aware extension (reached from mm_align_pair when
+ * MM_F_SPLICE is set, src/align.c:326-327).  One affine gap (q, e) plus a long deletion state x2 that opens at q2,
+ * extends for free and is entered / left through the donor[] / acceptor[] site costs (:100-165); no band, no
+ * end bonus, H as in the dual-affine code (signed bytes).  Restated cell by cell over whole 16-cell blocks
+ * with the reference's 8-bit wrap-around arithmetic (SSE4.1 branch).  junc may be null (:113,:126).
+ * ---------------------------------------------------------------------------------- */
+static void wmo_backtrack_intron(int is_rev, int min_intron_len, const uint8_t *p, const int *off, const int *off_end, int n_col, int i0, int j0, wmo_cig_t *c)
+{ /* ksw2.h:119-151, is_rot = 1, min_intron_len > 0: the long-gap state reads as N_SKIP (3) */
+	int i = i0, j = j0, r, state = 0;
+	uint32_t tmp;
+	c->n = 0;
+	while (i >= 0 && j >= 0) {
+		int force_state = -1;
+		r = i + j;
+		if (i < off[r]) force_state = 2;
+		if (i > off_end[r]) force_state = 1;
+		tmp = force_state < 0 ? p[(size_t)r * n_col + i - off[r]] : 0;
+		if (state == 0) state = tmp & 7;
+		else if (!(tmp >> (state + 2) & 1)) state = 0;
+		if (state == 0) state = tmp & 7;
+		if (force_state >= 0) state = force_state;
+		if (state == 0) wmo_push_cigar(c, 0, 1), --i, --j;
+		else if (state == 1 || (state == 3 && min_intron_len <= 0)) wmo_push_cigar(c, 2, 1), --i;
+		else if (state == 3 && min_intron_len > 0) wmo_push_cigar(c, 3, 1), --i;
+		else wmo_push_cigar(c, 1, 1), --j;
+	}
+	if (i >= 0) wmo_push_cigar(c, min_intron_len > 0 && i >= min_intron_len ? 3 : 2, i + 1);
+	if (j >= 0) wmo_push_cigar(c, 1, j + 1);
+	if (!is_rev)
+		for (i = 0; i < c->n >> 1; ++i) tmp = c->a[i], c->a[i] = c->a[c->n - 1 - i], c->a[c->n - 1 - i] = tmp;
+}
+
+int wmo_ksw_exts2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat,
+                  int q, int e, int q2, int noncan, int zdrop, int junc_bonus, int flag, const uint8_t *junc,
+                  wmo_ez_t *ez, uint32_t *cigar_out, int max_cigar)
+{
+	const int m = 5;
+	int r, t, qe = q + e, n_col_, *off, *off_end, tlen_, qlen_, last_st, last_en, max_sc, min_sc, long_thres, long_diff;
+	int approx_max = !!(flag & WMO_EZ_APPROX_MAX), right = !!(flag & WMO_EZ_RIGHT);
+	int32_t *H = 0, H0 = 0, last_H0_t = 0;
+	int8_t *mem, *u, *v, *x, *y, *x2, *donor, *acceptor, *s, sc_N;
+	uint8_t *sf, *qr, *p;
+	wmo_cig_t cig = {0, 0, 0};
+
+	wmo_reset_ez(ez);
+	if (qlen <= 0 || tlen <= 0 || q2 <= q + e) return 0; /* :61 */
+	sc_N = mat[m*m-1] == 0 ? -e : mat[m*m-1]; /* :69 */
+	tlen_ = (tlen + 15) / 16;
+	n_col_ = ((qlen < tlen ? qlen : tlen) + 15) / 16 + 1;
+	qlen_ = (qlen + 15) / 16;
+	for (t = 1, max_sc = mat[0], min_sc = mat[1]; t < m * m; ++t) {
+		max_sc = max_sc > mat[t] ? max_sc : mat[t];
+		min_sc = min_sc < mat[t] ? min_sc : mat[t];
+	}
+	if (-min_sc > 2 * (q + e)) return 0; /* :79 */
+	long_thres = (q2 - q) / e - 1; /* :81-84 */
+	if (q2 > q + e + long_thres * e) ++long_thres;
+	long_diff = long_thres * e - (q2 - q);
+
+	mem = (int8_t*)calloc((size_t)tlen_ * 9 + qlen_ + 1, 16); /* :86-90 */
+	u = mem; v = u + tlen_ * 16; x = v + tlen_ * 16; y = x + tlen_ * 16; x2 = y + tlen_ * 16;
+	donor = x2 + tlen_ * 16; acceptor = donor + tlen_ * 16;
+	s = acceptor + tlen_ * 16; sf = (uint8_t*)(s + tlen_ * 16); qr = sf + tlen_ * 16;
+	memset(u, -q - e, (size_t)tlen_ * 16 * 4);
+	memset(x2, -q2, (size_t)tlen_ * 16);
+	if (!approx_max) {
+		H = (int32_t*)malloc((size_t)tlen_ * 16 * 4);
+		for (t = 0; t < tlen_ * 16; ++t) H[t] = WMO_NEG_INF;
+	}
+	p = (uint8_t*)malloc(((size_t)(qlen + tlen - 1) * n_col_ + 1) * 16);
+	off = (int*)malloc((size_t)(qlen + tlen - 1) * sizeof(int) * 2);
+	off_end = off + qlen + tlen - 1;
+	for (t = 0; t < qlen; ++t) qr[t] = query[qlen - 1 - t];
+	memcpy(sf, target, tlen);
+
+	if (flag & (WMO_EZ_SPLICE_FOR | WMO_EZ_SPLICE_REV)) { /* :106-165 */
+		int semi_cost = flag & WMO_EZ_SPLICE_FLANK ? -noncan / 2 : 0;
+		int fw = !!(flag & WMO_EZ_SPLICE_FOR), rv = !!(flag & WMO_EZ_SPLICE_REV);
+		memset(donor, -noncan, (size_t)tlen_ * 16);
+		memset(acceptor, -noncan, (size_t)tlen_ * 16);
+		if (!(flag & WMO_EZ_REV_CIGAR)) {
+			for (t = 0; t < tlen - 4; ++t) {
+				int can_type = 0;
+				if (fw && target[t+1] == 2 && target[t+2] == 3) can_type = 1;
+				if (rv && target[t+1] == 1 && target[t+2] == 3) can_type = 1;
+				if (can_type && (target[t+3] == 0 || target[t+3] == 2)) can_type = 2;
+				if (can_type) donor[t] = can_type == 2 ? 0 : semi_cost;
+			}
+			if (junc)
+				for (t = 0; t < tlen - 1; ++t)
+					if ((fw && (junc[t+1] & 1)) || (rv && (junc[t+1] & 8))) donor[t] += junc_bonus;
+			for (t = 2; t < tlen; ++t) {
+				int can_type = 0;
+				if (fw && target[t-1] == 0 && target[t] == 2) can_type = 1;
+				if (rv && target[t-1] == 0 && target[t] == 1) can_type = 1;
+				if (can_type && (target[t-2] == 1 || target[t-2] == 3)) can_type = 2;
+				if (can_type) acceptor[t] = can_type == 2 ? 0 : semi_cost;
+			}
+			if (junc)
+				for (t = 0; t < tlen; ++t)
+					if ((fw && (junc[t] & 2)) || (rv && (junc[t] & 4))) acceptor[t] += junc_bonus;
+		} else {
+			for (t = 0; t < tlen - 4; ++t) {
+				int can_type = 0;
+				if (fw && target[t+1] == 2 && target[t+2] == 0) can_type = 1;
+				if (rv && target[t+1] == 1 && target[t+2] == 0) can_type = 1;
+				if (can_type && (target[t+3] == 1 || target[t+3] == 3)) can_type = 2;
+				if (can_type) donor[t] = can_type == 2 ? 0 : semi_cost;
+			}
+			if (junc)
+				for (t = 0; t < tlen - 1; ++t)
+					if ((fw && (junc[t+1] & 2)) || (rv && (junc[t+1] & 4))) donor[t] += junc_bonus;
+			for (t = 2; t < tlen; ++t) {
+				int can_type = 0;
+				if (fw && target[t-1] == 3 && target[t] == 2) can_type = 1;
+				if (rv && target[t-1] == 3 && target[t] == 1) can_type = 1;
+				if (can_type && (target[t-2] == 0 || target[t-2] == 2)) can_type = 2;
+				if (can_type) acceptor[t] = can_type == 2 ? 0 : semi_cost;
+			}
+			if (junc)
+				for (t = 0; t < tlen; ++t)
+					if ((fw && (junc[t] & 1)) || (rv && (junc[t] & 8))) acceptor[t] += junc_bonus;
+		}
+	}
+
+	for (r = 0, last_st = last_en = -1; r < qlen + tlen - 1; ++r) {
+		int st = 0, en = tlen - 1, st0, en0;
+		int8_t x1, x21, v1;
+		uint8_t *qrr = qr + (qlen - 1 - r);
+		if (st < r - qlen + 1) st = r - qlen + 1;
+		if (en > r) en = r;
+		st0 = st, en0 = en;
+		st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;
+		if (st > 0) { /* :178-186 */
+			if (st - 1 >= last_st && st - 1 <= last_en) x1 = x[st - 1], x21 = x2[st - 1], v1 = v[st - 1];
+			else x1 = -q - e, x21 = -q2, v1 = -q - e;
+		} else {
+			x1 = -q - e, x21 = -q2;
+			v1 = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : 0;
+		}
+		if (en >= r) {
+			y[r] = -q - e;
+			u[r] = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : 0;
+		}
+		if (!(flag & WMO_EZ_GENERIC_SC)) { /* :192-211 */
+			for (t = st0; t <= en0; t += 16) {
+				int kk;
+				for (kk = 0; kk < 16; ++kk) {
+					uint8_t sq = sf[t + kk], sq2 = qrr[t + kk];
+					s[t + kk] = (sq == m - 1 || sq2 == m - 1) ? sc_N : (sq == sq2 ? mat[0] : mat[1]);
+				}
+			}
+		} else {
+			for (t = st0; t <= en0; ++t) s[t] = mat[sf[t] * m + qrr[t]];
+		}
+		off[r] = st, off_end[r] = en;
+		{
+			int8_t cx = x1, cx2 = x21, cv = v1; /* cells t - 1 of the previous diagonal (the casts at :214-216 are to uint8_t) */
+			uint8_t *pr = p + (size_t)r * n_col_ * 16;
+			for (t = st; t <= en; ++t) {
+				int8_t xo = x[t], x2o = x2[t], vo = v[t], ut = u[t], z = s[t], a, b, a2, a2a, tmp, dn = donor[t];
+				uint8_t d;
+				a = (int8_t)(cx + cv); b = (int8_t)(y[t] + ut); a2 = (int8_t)(cx2 + cv); a2a = (int8_t)(a2 + acceptor[t]);
+				if (!right) { /* :252-259 */
+					d = a > z ? 1 : 0;    z = z > a ? z : a;
+					d = b > z ? 2 : d;    z = z > b ? z : b;
+					d = a2a > z ? 3 : d;  z = z > a2a ? z : a2a;
+				} else { /* :300-307 */
+					d = z > a ? 0 : 1;    z = z > a ? z : a;
+					d = z > b ? d : 2;    z = z > b ? z : b;
+					d = z > a2a ? d : 3;  z = z > a2a ? z : a2a;
+				}
+				u[t] = (int8_t)(z - cv); v[t] = (int8_t)(z - ut); /* :51-56 */
+				tmp = (int8_t)(z - q); a = (int8_t)(a - tmp); b = (int8_t)(b - tmp);
+				a2 = (int8_t)(a2 - (int8_t)(z - q2));
+				if (!right) { /* :272-290 */
+					x[t] = (int8_t)((a > 0 ? a : 0) - qe); d |= a > 0 ? 0x08 : 0;
+					y[t] = (int8_t)((b > 0 ? b : 0) - qe); d |= b > 0 ? 0x10 : 0;
+					x2[t] = (int8_t)((a2 > dn ? a2 : dn) - q2); d |= a2 > dn ? 0x20 : 0;
+				} else { /* :320-338 */
+					x[t] = (int8_t)((0 > a ? 0 : a) - qe); d |= 0 > a ? 0 : 0x08;
+					y[t] = (int8_t)((0 > b ? 0 : b) - qe); d |= 0 > b ? 0 : 0x10;
+					x2[t] = (int8_t)((dn > a2 ? dn : a2) - q2); d |= dn > a2 ? 0 : 0x20;
+				}
+				pr[t - st] = d;
+				cx = xo, cx2 = x2o, cv = vo;
+			}
+		}
+		if (!approx_max) { /* :341-389 */
+			int32_t max_H, max_t;
+			if (r > 0) {
+				int32_t HH[4], tt[4], en1 = st0 + (en0 - st0) / 4 * 4, i;
+				max_H = H[en0] = en0 > 0 ? H[en0 - 1] + u[en0] : H[en0] + v[en0];
+				max_t = en0;
+				for (i = 0; i < 4; ++i) HH[i] = max_H, tt[i] = max_t;
+				for (t = st0; t < en1; t += 4)
+					for (i = 0; i < 4; ++i) {
+						H[t + i] += (int32_t)v[t + i];
+						if (H[t + i] > HH[i]) HH[i] = H[t + i], tt[i] = t;
+					}
+				for (i = 0; i < 4; ++i)
+					if (max_H < HH[i]) max_H = HH[i], max_t = tt[i] + i;
+				for (; t < en0; ++t) {
+					H[t] += (int32_t)v[t];
+					if (H[t] > max_H) max_H = H[t], max_t = t;
+				}
+			} else H[0] = v[0] - qe, max_H = H[0], max_t = 0;
+			if (en0 == tlen - 1 && H[en0] > ez->mte) ez->mte = H[en0], ez->mte_q = r - en;
+			if (r - st0 == qlen - 1 && H[st0] > ez->mqe) ez->mqe = H[st0], ez->mqe_t = st0;
+			if (wmo_apply_zdrop(ez, max_H, r, max_t, zdrop, 0)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez->score = H[tlen - 1];
+		} else { /* :390-406 */
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					int32_t d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
+					H0 += v[last_H0_t];
+				} else {
+					++last_H0_t, H0 += u[last_H0_t];
+				}
+			} else H0 = v[0] - qe, last_H0_t = 0;
+			if ((flag & WMO_EZ_APPROX_DROP) && wmo_apply_zdrop(ez, H0, r, last_H0_t, zdrop, 0)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez->score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+	free(mem); free(H);
+	{ /* :411-419: no end-bonus clause here */
+		int rev_cigar = !!(flag & WMO_EZ_REV_CIGAR);
+		if (!ez->zdropped && !(flag & WMO_EZ_EXTZ_ONLY))
+			wmo_backtrack_intron(rev_cigar, long_thres, p, off, off_end, n_col_ * 16, tlen - 1, qlen - 1, &cig);
+		else if (ez->max_t >= 0 && ez->max_q >= 0)
+			wmo_backtrack_intron(rev_cigar, long_thres, p, off, off_end, n_col_ * 16, ez->max_t, ez->max_q, &cig);
 	}
 	free(p); free(off);
 	ez->n_cigar = cig.n;

@@ -10,6 +10,7 @@
 #include "../../winnowmap_b200/csrc/ksw_extd2_common.cuh"
 #include "../../winnowmap_b200/csrc/ksw_extd2_v2.cuh"
 #include "../../winnowmap_b200/csrc/ksw_extz2.cuh"
+#include "../../winnowmap_b200/csrc/ksw_exts2.cuh"
 #include "../../winnowmap_b200/csrc/chain_dev.cuh"
 #include "../../winnowmap_b200/csrc/rsort.cuh"
 #include "../../winnowmap_b200/csrc/pkseq.cuh"
@@ -137,6 +138,42 @@ extern "C" int wmt_emul_extz2(const uint8_t *query, int qlen, const uint8_t *tar
 	wm_zd_params Z; memset(&Z, 0, sizeof(Z));
 	Z.q = q, Z.e = e; memcpy(Z.mat, mat, 25);
 	wm_extd2_backtrack_job(J, &ez, bt.data(), cigar, seq.data(), Z, zd_out);
+	memcpy(ez_out, &ez, sizeof(ez));
+	return 0;
+}
+
+// one ksw_exts2 call (splice-aware extension) through the product's sweep (csrc/ksw_exts2.cuh) + the shared traceback
+extern "C" int wmt_emul_exts2(const uint8_t *query, int qlen, const uint8_t *target, int tlen, const uint8_t *junc, const int8_t *mat, int q, int e, int q2,
+                              int noncan, int junc_bonus, int zdrop, int flag, int32_t *ez_out, uint32_t *cigar, int cig_cap)
+{
+	wm_dp_params P; memset(&P, 0, sizeof(P)); // (wm_dp_params_init_splice of ksw_extd2.cu restated: src/ksw2_exts2_sse.c:61-84)
+	P.splice = 1, P.noncan = noncan, P.junc_bonus = junc_bonus; memcpy(P.mat, mat, 25);
+	P.q = q, P.e = e, P.q2 = q2, P.qe_h = q + e, P.sc_mch = mat[0], P.sc_mis = mat[1], P.sc_N = mat[24] == 0 ? -e : mat[24];
+	int min_sc = mat[1];
+	for (int t = 1; t < 25; ++t) min_sc = min_sc < mat[t] ? min_sc : mat[t];
+	P.early_out = q2 <= q + e || -min_sc > 2 * (q + e) || e <= 0;
+	if (!P.early_out) {
+		P.long_thres = (q2 - q) / e - 1;
+		if (q2 > q + e + P.long_thres * e) ++P.long_thres;
+		P.long_diff = P.long_thres * e - (q2 - q);
+	}
+	std::vector<uint8_t> seq((size_t)qlen + tlen + 64, 0);
+	if (qlen > 0) memcpy(seq.data(), query, qlen);
+	if (tlen > 0) memcpy(seq.data() + qlen, target, tlen);
+	wm_dp_job J; memset(&J, 0, sizeof(J));
+	J.q_off = 0, J.t_off = qlen, J.p_off = 0, J.cig_off = 0;
+	J.qlen = qlen, J.tlen = tlen, J.w = -1, J.zdrop = zdrop, J.end_bonus = -1, J.flag = flag, J.cig_cap = cig_cap, J.pad = -1;
+	wm_extz_dev ez; memset(&ez, 0, sizeof(ez));
+	const int tlen16 = (tlen + 15) / 16 * 16;
+	const int ww = tlen > qlen ? tlen : qlen;
+	const size_t bt_bytes = (qlen > 0 && tlen > 0) ? ((size_t)(qlen + tlen - 1) * (size_t)(wm_ncol16(qlen, tlen, ww) / 16) + 1) * 16 : 16;
+	std::vector<uint8_t> bt(bt_bytes + 64, 0);
+	std::vector<uint64_t> state((size_t)tlen16 * WM_EXTS2_CELL_BYTES / 8 + 16, 0);
+	struct Args { const wm_dp_job *J; const uint8_t *seq, *junc; uint8_t *bt; wm_extz_dev *ez; const wm_dp_params *P; int8_t *state; }
+		A = { &J, seq.data(), junc, bt.data(), &ez, &P, (int8_t*)state.data() };
+	wm_emul::run_warp([](int l, void *p) { Args &a = *(Args*)p; wm_exts2_fill_job(*a.J, a.seq, a.junc, a.bt, a.ez, *a.P, a.state, l, 0); }, &A);
+	wm_zd_params Z; memset(&Z, 0, sizeof(Z));
+	wm_extd2_backtrack_job(J, &ez, bt.data(), cigar, seq.data(), Z, 0, 1, P.long_thres, P.early_out);
 	memcpy(ez_out, &ez, sizeof(ez));
 	return 0;
 }

@@ -60,6 +60,7 @@ def oracle():
         L.wmo_chain_dp.argtypes = [C.c_int] * 8 + [C.c_float, C.c_long, _u64p, _u64p, _u64p, C.POINTER(C.c_long)]
         L.wmo_ksw_extd2.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p] + [C.c_int] * 8 + [_i32p, _u32p, C.c_int]
         L.wmo_ksw_extz2.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p] + [C.c_int] * 6 + [_i32p, _u32p, C.c_int]
+        L.wmo_ksw_exts2.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p] + [C.c_int] * 7 + [_u8p, _i32p, _u32p, C.c_int]
         L.wmo_ksw_ll.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p, C.c_int, C.c_int, _i32p, _i32p]
         L.wmo_counters_get.argtypes = [_u64p]
         _oracle = L
@@ -76,6 +77,7 @@ def ref():
         L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libref_harness.so"))
         L.ref_ksw_extd2.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p] + [C.c_int] * 8 + [_i32p, _u32p, C.c_int]
         L.ref_ksw_extz2.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p] + [C.c_int] * 6 + [_i32p, _u32p, C.c_int]
+        L.ref_ksw_exts2.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p] + [C.c_int] * 7 + [_u8p, _i32p, _u32p, C.c_int]
         L.ref_ksw_ll.argtypes = [C.c_int, _u8p, C.c_int, _u8p, _i8p, C.c_int, C.c_int, _i32p, _i32p]
         L.ref_radix_sort_128x.argtypes = [_u64p, C.c_long]
         L.ref_radix_sort_64.argtypes = [_u64p, C.c_long]
@@ -123,6 +125,27 @@ def _extz2(fn, q, t, mat, go, ge, w, zdrop, end_bonus, flag):
     n = fn(len(q), _ptr(q, _u8p), len(t), _ptr(t, _u8p), _ptr(mat, _i8p), go, ge, w, zdrop, end_bonus, flag,
            _ptr(ez, _i32p), _ptr(cig, _u32p), cap)
     return ez, cig[:n].copy()
+
+
+def _exts2(fn, q, t, mat, go, ge, go2, noncan, zdrop, junc_bonus, flag, junc=None):
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    ez = np.zeros(11, dtype=np.int32)
+    cap = len(q) + len(t) + 8
+    cig = np.zeros(cap, dtype=np.uint32)
+    if junc is not None:
+        junc = np.ascontiguousarray(junc, dtype=np.uint8)
+    n = fn(len(q), _ptr(q, _u8p), len(t), _ptr(t, _u8p), _ptr(mat, _i8p), go, ge, go2, noncan, zdrop, junc_bonus, flag,
+           _ptr(junc, _u8p) if junc is not None else None, _ptr(ez, _i32p), _ptr(cig, _u32p), cap)
+    return ez, cig[:n].copy()
+
+
+def oracle_exts2(*a, **k):
+    return _exts2(oracle().wmo_ksw_exts2, *a, **k)
+
+
+def ref_exts2(*a, **k):
+    return _exts2(ref().ref_ksw_exts2, *a, **k)
 
 
 def oracle_extz2(*a):

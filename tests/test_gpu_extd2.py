@@ -88,3 +88,34 @@ def test_extz2_single_gap_pair_batch(seed):
             e0, c0 = ol.oracle_extz2(Q[i], T[i], mat, go, ge, W[i], Z[i], E[i], F[i])
             assert np.array_equal(e0, ez[i]), (i, (a, b, go, ge), len(Q[i]), len(T[i]), W[i], hex(F[i]), e0, ez[i])
             assert np.array_equal(c0, cigs[i]), (i, (a, b, go, ge), len(Q[i]), len(T[i]), W[i], hex(F[i]))
+
+
+def test_exts2_splice_batch():
+    """The splice-aware extension kernel (csrc/ksw_exts2.cuh = ksw_exts2_sse, src/ksw2_exts2_sse.c:26) through the C ABI against the
+    oracle's restatement (pinned to the reference's function by tests/test_oracle_vs_ref.py): the splice presets' scorings, both
+    transcript strands, flank bonus, junction annotation, reversed inputs, Z-drop, generic scoring, a target whose state rows
+    live in the global slice, empty inputs and a scoring the reference refuses (q2 <= q + e)."""
+    from winnowmap_b200 import kernels
+    from test_kernel_emulation import _splice_cases
+    from test_oracle_vs_ref import spliced_pair
+    rng = np.random.default_rng(990)
+    cases = _splice_cases(rng, 200)
+    n_intron = 0
+    for k in range(5):
+        sub = [c for i, c in enumerate(cases) if i % 5 == k]
+        a, b, go, ge, go2, noncan, jb = sub[0][4]
+        if k == 0:  # a long one (global state slice) and empty inputs
+            q, t = spliced_pair(rng, 12, err=0.05)
+            sub.append((q, np.concatenate([t, rng.integers(0, 4, size=1500, dtype=np.uint8)]), 0x100 | 0x400 | 0x40, 200, sub[0][4], None))
+            sub.append((np.zeros(0, np.uint8), t[:10].copy(), 0x100, 200, sub[0][4], None))
+            sub.append((q[:30].copy(), np.zeros(0, np.uint8), 0x100, 200, sub[0][4], None))
+        mat = ol.simple_mat(a, b, 1)
+        any_junc = any(c[5] is not None for c in sub)
+        ez, cigs = kernels.ksw_exts2_batch([c[0] for c in sub], [c[1] for c in sub], mat, go, ge, go2, noncan, jb, np.array([c[3] for c in sub]),
+                                           np.array([c[2] for c in sub]), juncs=[c[5] for c in sub] if any_junc else None)
+        for i, (qq, tt, flag, zdrop, _, junc) in enumerate(sub):
+            e0, c0 = ol.oracle_exts2(qq, tt, mat, go, ge, go2, noncan, zdrop, jb, flag, junc=junc)
+            assert np.array_equal(e0, ez[i]), (k, i, len(qq), len(tt), hex(flag), e0, ez[i])
+            assert np.array_equal(c0, cigs[i]), (k, i, len(qq), len(tt), hex(flag))
+            n_intron += int((c0 & 0xf == 3).any())
+    assert n_intron > 20

@@ -78,6 +78,48 @@ def test_single_affine_sweep_matches_oracle(emul):
         assert np.array_equal(c0, cig[:max(0, ez[10])]), (it, len(qq), len(tt), w, hex(flag))
 
 
+def _splice_cases(rng, n):
+    """(q, t, flag, zdrop, scoring, junc) cases of the splice-aware extension, shared by the emulation test and the GPU test."""
+    from test_oracle_vs_ref import spliced_pair
+    out = []
+    for it in range(n):
+        if it % 5 == 4:
+            q, t = rand_pair(rng, int(rng.choice([1, 5, 17, 33, 100, 300])), err=0.1, drift=int(rng.choice([0, 30])), n_runs=int(rng.integers(0, 2)))
+        else:
+            q, t = spliced_pair(rng, int(rng.integers(1, 6)), err=float(rng.choice([0.0, 0.05, 0.2])), rev_sites=bool(it & 1), n_runs=int(rng.integers(0, 2)))
+        if it % 7 == 3:
+            q, t = q[::-1].copy(), t[::-1].copy()
+        flag = FLAGS[int(rng.integers(0, len(FLAGS)))] | (0x10 if rng.random() < 0.3 else 0) | (0x04 if rng.random() < 0.15 else 0)
+        flag |= [0x100, 0x200, 0x300, 0][int(rng.integers(0, 4))] | (0x400 if rng.random() < 0.7 else 0)
+        if it % 7 == 3:
+            flag |= 0x80 | 0x02
+        zdrop = int(rng.choice([200, 100, 30, -1]))
+        sc = [(1, 2, 2, 1, 32, 9, 9), (1, 4, 6, 1, 24, 9, 5), (2, 4, 4, 2, 24, 5, 3), (1, 2, 2, 1, 3, 9, 9), (1, 2, 2, 1, 60, 0, 0)][it % 5]
+        junc = None
+        if rng.random() < 0.4:
+            junc = np.where(rng.random(len(t)) < 0.05, rng.integers(1, 16, size=len(t)), 0).astype(np.uint8)
+        out.append((np.ascontiguousarray(q, dtype=np.uint8), np.ascontiguousarray(t, dtype=np.uint8), flag, zdrop, sc, junc))
+    return out
+
+
+def test_splice_sweep_matches_oracle(emul):
+    """csrc/ksw_exts2.cuh (ksw_exts2_sse: long-deletion state with donor / acceptor costs, N_SKIP traceback) on the software warp
+    against the oracle's restatement, which tests/test_oracle_vs_ref.py pins to the reference's function."""
+    emul.wmt_emul_exts2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p, C.c_int]
+    n_intron = 0
+    for it, (qq, tt, flag, zdrop, (a, b, go, ge, go2, noncan, jb), junc) in enumerate(_splice_cases(np.random.default_rng(4400), 60)):
+        mat = np.ascontiguousarray(ol.simple_mat(a, b, 1), dtype=np.int8)
+        cap = len(qq) + len(tt) + 2
+        ez = np.zeros(12, np.int32); cig = np.zeros(cap, np.uint32)
+        assert emul.wmt_emul_exts2(qq.ctypes.data, len(qq), tt.ctypes.data, len(tt), junc.ctypes.data if junc is not None else None, mat.ctypes.data,
+                                   go, ge, go2, noncan, jb, zdrop, flag, ez.ctypes.data, cig.ctypes.data, cap) == 0
+        e0, c0 = ol.oracle_exts2(qq, tt, mat, go, ge, go2, noncan, zdrop, jb, flag, junc=junc)
+        assert np.array_equal(e0[:11], ez[:11]), (it, len(qq), len(tt), hex(flag), (a, b, go, ge, go2), e0, ez)
+        assert np.array_equal(c0, cig[:max(0, ez[10])]), (it, len(qq), len(tt), hex(flag))
+        n_intron += int((c0 & 0xf == 3).any())
+    assert n_intron > 5
+
+
 def test_other_scorings_and_a_long_target(emul):
     rng = np.random.default_rng(4200)
     for a, b, q_, e_, q2, e2 in [(1, 4, 6, 2, 26, 1), (2, 4, 24, 1, 4, 2)]:  # asm-like scoring; gap pair given in swapped order

@@ -89,6 +89,61 @@ def test_extz2_matches_reference(seed):
     assert n == 70
 
 
+def spliced_pair(rng, n_exons, err=0.05, rev_sites=False, n_runs=0):
+    """(query, target): exons joined in the query, introns with GT..AG (or CT..AC) ends in the target; some sites left non-canonical."""
+    q, t = [], []
+    for i in range(n_exons):
+        ex = rng.integers(0, 4, size=int(rng.integers(8, 120)), dtype=np.uint8)
+        t.append(ex)
+        qq, _ = rand_pair(rng, 1, err=0.0)
+        ex_q = np.array([(c if rng.random() > err else (c + 1) & 3) for c in ex], dtype=np.uint8)
+        q.append(ex_q)
+        if i + 1 < n_exons:
+            intron = rng.integers(0, 4, size=int(rng.integers(30, 400)), dtype=np.uint8)
+            if rng.random() < 0.8:
+                intron[:3] = [1, 3, 0] if rev_sites else [2, 3, 0]      # GTA / CTA
+                intron[-3:] = [1, 0, 1] if rev_sites else [1, 0, 2]     # CAC / CAG
+            t.append(intron)
+    q = np.concatenate(q); t = np.concatenate(t)
+    for _ in range(n_runs):
+        if len(t) > 20:
+            p0 = int(rng.integers(0, len(t) - 10)); t[p0:p0 + int(rng.integers(1, 6))] = 4
+    return q, t
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_exts2_matches_reference(seed):
+    """The splice-aware restatement (oracle wmo_ksw_exts2) against the reference's ksw_exts2_sse (src/ksw2_exts2_sse.c:26): the
+    splice presets' scoring (src/options.c:116-128), both strands' signals, flank bonus, junction annotation, both gap
+    alignments, reversed CIGAR, extension-only, approximate maximum, generic scoring."""
+    rng = np.random.default_rng(900 + seed)
+    n = 0
+    for it in range(90):
+        rev_sites = bool(it & 1)
+        if it % 5 == 4:
+            q, t = rand_pair(rng, int(rng.choice([1, 5, 17, 33, 100, 300])), err=0.1, drift=int(rng.choice([0, 30])), n_runs=int(rng.integers(0, 2)))
+        else:
+            q, t = spliced_pair(rng, int(rng.integers(1, 6)), err=float(rng.choice([0.0, 0.05, 0.2])), rev_sites=rev_sites, n_runs=int(rng.integers(0, 2)))
+        if it % 7 == 3:  # reversed inputs, as the left extension passes them (src/align.c:696-697)
+            q, t = q[::-1].copy(), t[::-1].copy()
+        flag = FLAGS[int(rng.integers(0, len(FLAGS)))] | (0x10 if rng.random() < 0.3 else 0) | (0x04 if rng.random() < 0.15 else 0)
+        flag |= [0x100, 0x200, 0x300, 0][int(rng.integers(0, 4))] | (0x400 if rng.random() < 0.7 else 0)
+        if it % 7 == 3:
+            flag |= 0x80 | 0x02
+        zdrop = int(rng.choice([200, 100, 30, -1]))
+        a, b, go, ge, go2, noncan, jb = [(1, 2, 2, 1, 32, 9, 9), (1, 4, 6, 1, 24, 9, 5), (2, 4, 4, 2, 24, 5, 3), (1, 2, 2, 1, 3, 9, 9), (1, 2, 2, 1, 60, 0, 0)][int(rng.integers(0, 5))]
+        mat = ol.simple_mat(a, b, 1)
+        junc = None
+        if rng.random() < 0.4:
+            junc = np.where(rng.random(len(t)) < 0.05, rng.integers(1, 16, size=len(t)), 0).astype(np.uint8)
+        e1, c1 = ol.ref_exts2(q, t, mat, go, ge, go2, noncan, zdrop, jb, flag, junc=junc)
+        e2, c2 = ol.oracle_exts2(q, t, mat, go, ge, go2, noncan, zdrop, jb, flag, junc=junc)
+        assert np.array_equal(e1, e2), (it, len(t), len(q), hex(flag), zdrop, (a, b, go, ge, go2), e1, e2)
+        assert np.array_equal(c1, c2), (it, len(t), len(q), hex(flag))
+        n += (c1 & 0xf == 3).any()
+    assert n > 10  # introns were found
+
+
 def test_extd2_swapped_gap_and_asm_scoring():
     rng = np.random.default_rng(7)
     for a, b, q, e, q2, e2 in [(1, 4, 6, 2, 26, 1), (1, 9, 16, 2, 41, 1), (2, 4, 24, 1, 4, 2)]:

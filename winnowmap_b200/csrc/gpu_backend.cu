@@ -61,6 +61,14 @@ __global__ void wm_compact_chain_kernel(const int64_t *__restrict__ src_off, con
 	for (int64_t i = lane; i < nu; i += 32) u_out[uo + i] = u[so + i];
 }
 
+__global__ void wm_ncigar_kernel(const wm_dp_job *__restrict__ jobs, const wm_extz_dev *__restrict__ ez, int n_jobs, int32_t *__restrict__ nc)
+{ // CIGAR length of every job (what fits its buffer: an overflow is reported by the host from ez.n_cigar)
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_jobs) return;
+	const int n = ez[i].n_cigar;
+	nc[i] = n < jobs[i].cig_cap ? n : jobs[i].cig_cap;
+}
+
 __global__ void wm_compact_cigar_kernel(const wm_dp_job *__restrict__ jobs, const wm_extz_dev *__restrict__ ez, const int64_t *__restrict__ out_off, int n_jobs,
                                         const uint32_t *__restrict__ cig, uint32_t *__restrict__ out)
 {
@@ -87,11 +95,11 @@ struct GpuBackendImpl {
 	// workspaces
 	wm_sketch_ws sk; wm_seed_ws sd, sd2; wm_chain_ws ch; wm_extd2_ws dpws;
 	wm_dbuf masked_pk, masked_nm, mask_tasks, mask_toff, mask_pool, qlen_buf, pre_buf, cat_tasks, cat_toff, cat_a, set_id, off_buf, nb_off, nu_off, b_out, u_out;
-	wm_dbuf coop_ids, g_jobs, g_joff, seq_pool, dp_jobs, bt, ez, cig, cig_off, cig_out, ll_jobs, ll_scr, ll_out, mat;
+	wm_dbuf nc_buf, scan_tmp, coop_ids, g_jobs, g_joff, seq_pool, dp_jobs, bt, ez, cig, cig_off, cig_out, ll_jobs, ll_scr, ll_out, mat;
 	// host result pools
 	std::vector<uint32_t> h_mzpos; std::vector<int64_t> h_mz_off; std::vector<int32_t> h_rep;
-	std::vector<uint64_t> h_u; std::vector<wm_pair_t> h_b; std::vector<int32_t> h_nu; std::vector<int64_t> h_nb;
-	std::vector<uint32_t> h_cig; std::vector<wm_extz_dev> h_ez; std::vector<int32_t> h_zd; wm_dbuf zd;
+	wm_hbuf<uint64_t> h_u; wm_hbuf<wm_pair_t> h_b; std::vector<int32_t> h_nu; std::vector<int64_t> h_nb; // (the big ones: page-locked)
+	wm_hbuf<uint32_t> h_cig; wm_hbuf<wm_extz_dev> h_ez; wm_hbuf<int32_t> h_zd; wm_dbuf zd;
 	size_t bt_budget;
 	bool owns_index = false; // the lane that uploaded the index frees it; clones only borrow the pointers
 };
@@ -519,23 +527,26 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 			WM_CUDA_CHECK(wm_memcpy_async(d_coop, coop.data(), sizeof(int32_t) * coop.size(), cudaMemcpyHostToDevice, st));
 		}
 		wm_extd2_launch(&g.dpws, d_dj, m, plan, d_pool, d_bt, d_ez, d_cig, P, st, &zp, d_zd, d_coop, (int)coop.size());
+		// CIGAR lengths -> offsets -> compacted CIGARs, all behind the traceback on the stream: the host then only copies
+		int32_t *d_nc = (int32_t*)g.nc_buf.need(sizeof(int32_t) * (m + 1));
+		int64_t *d_ooff = (int64_t*)g.cig_off.need(sizeof(int64_t) * (m + 2));
+		int64_t *d_stmp = (int64_t*)g.scan_tmp.need(sizeof(int64_t) * (wm_scan_tmp_elems(m) + 1));
+		uint32_t *d_cout = (uint32_t*)g.cig_out.need(sizeof(uint32_t) * (c_off + 1));
+		wm_count_launch(); wm_ncigar_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_dj, d_ez, m, d_nc);
+		wm_exclusive_scan(d_nc, m, d_ooff, d_stmp, st);
+		wm_count_launch(); wm_compact_cigar_kernel<<<(unsigned)(((int64_t)m * 32 + 127) / 128), 128, 0, st>>>(d_dj, d_ez, d_ooff, m, d_cig, d_cout);
+		WM_CUDA_CHECK(cudaGetLastError());
+		std::vector<int64_t> o_off(m + 1, 0);
 		WM_CUDA_CHECK(wm_memcpy_async(g.h_ez.data() + done, d_ez, sizeof(wm_extz_dev) * m, cudaMemcpyDeviceToHost, st));
 		WM_CUDA_CHECK(wm_memcpy_async(g.h_zd.data() + 5 * (size_t)done, d_zd, sizeof(int32_t) * 5 * m, cudaMemcpyDeviceToHost, st));
+		WM_CUDA_CHECK(wm_memcpy_async(o_off.data(), d_ooff, sizeof(int64_t) * (m + 1), cudaMemcpyDeviceToHost, st));
 		wm_stream_sync(st);
 		g_timers.add("dp.gpu_fill_bt", Timers::now() - tq0);
 		double tr0 = Timers::now();
-		// compact the CIGARs on the device, then one copy
-		std::vector<int64_t> o_off(m + 1, 0);
 		for (int i = 0; i < m; ++i) {
 			int nc = g.h_ez[done + i].n_cigar;
 			if (nc > dj[i].cig_cap) { fprintf(stderr, "[ERROR] winnowmap-b200: CIGAR buffer overflow (%d > %d)\n", nc, dj[i].cig_cap); exit(1); }
-			o_off[i + 1] = o_off[i] + nc;
 		}
-		int64_t *d_ooff = (int64_t*)g.cig_off.need(sizeof(int64_t) * (m + 1));
-		uint32_t *d_cout = (uint32_t*)g.cig_out.need(sizeof(uint32_t) * (o_off[m] + 1));
-		WM_CUDA_CHECK(wm_memcpy_async(d_ooff, o_off.data(), sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
-		wm_count_launch(); wm_compact_cigar_kernel<<<(unsigned)(((int64_t)m * 32 + 127) / 128), 128, 0, st>>>(d_dj, d_ez, d_ooff, m, d_cig, d_cout);
-		WM_CUDA_CHECK(cudaGetLastError());
 		const size_t base = g.h_cig.size();
 		g.h_cig.resize(base + o_off[m] + 1);
 		if (o_off[m] > 0) WM_CUDA_CHECK(wm_memcpy_async(g.h_cig.data() + base, d_cout, sizeof(uint32_t) * o_off[m], cudaMemcpyDeviceToHost, st));

@@ -199,11 +199,12 @@ __device__ void wm_extd2_fill_job(const wm_dp_job &J, const uint8_t *__restrict_
 
 #include "ksw_extd2_v2.cuh"
 #include "ksw_extz2.cuh"
+#include "ksw_exts2.cuh"
 
 __global__ void __launch_bounds__(WM_FILL_WARPS * 32, 4)
 wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ seq, uint8_t *__restrict__ bt,
                      wm_extz_dev *__restrict__ ez, wm_dp_params P, int8_t *gscratch, size_t gscratch_stride, int g_tcap, int g_qcap, int use_v2,
-                     unsigned long long *cell_ctr)
+                     unsigned long long *cell_ctr, const uint8_t *__restrict__ junc_pool)
 {
 	// One job per warp, four consecutive jobs per CTA: jobs come largest first, so the four are of similar size and the
 	// CTA leaves its SM as soon as they are done (a persistent grid would hold every SM for the whole launch and keep
@@ -217,7 +218,8 @@ wm_extd2_fill_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8
 	if (J.flag & WM_DP_COOP) return; // swept by a whole CTA in wm_extd2_fill_coop_kernel
 	int8_t *my_g = J.pad >= 0 ? gscratch + (size_t)J.pad * gscratch_stride : (int8_t*)0;
 	const int tlen16 = (J.tlen + 15) / 16 * 16;
-	if (P.single) wm_extz2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane, cell_ctr);
+	if (P.splice) wm_exts2_fill_job(J, seq, junc_pool ? junc_pool + J.t_off : 0, bt, ez + j, P, J.pad < 0 ? my_smem : my_g, lane, cell_ctr);
+	else if (P.single) wm_extz2_fill_job(J, seq, bt, ez + j, P, tlen16 <= WM_SMEM_CELLS ? my_smem : my_g, lane, cell_ctr);
 	else if (use_v2 && J.qlen > 0 && J.tlen > 0 && !P.early_out) {
 		if (J.pad < 0) wm_extd2_fill_job_v2<true>(J, seq, bt, ez + j, P, (uint8_t*)my_smem, 0, 0, lane, cell_ctr ? cell_ctr + 1 : 0);
 		else wm_extd2_fill_job_v2<false>(J, seq, bt, ez + j, P, (uint8_t*)my_g, g_tcap, g_qcap, lane, cell_ctr ? cell_ctr + 1 : 0);
@@ -241,12 +243,12 @@ wm_extd2_fill_coop_kernel(const wm_dp_job *__restrict__ jobs, const int32_t *__r
 
 __global__ void wm_extd2_backtrack_kernel(const wm_dp_job *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ bt,
                                           wm_extz_dev *__restrict__ ezs, uint32_t *__restrict__ cigar_pool,
-                                          const uint8_t *__restrict__ seq, wm_zd_params Z, int32_t *__restrict__ zd)
+                                          const uint8_t *__restrict__ seq, wm_zd_params Z, int32_t *__restrict__ zd, int splice, int min_intron_len, int early_out)
 {
 	const int jid = blockIdx.x * blockDim.x + threadIdx.x;
 	if (jid >= n_jobs) return;
 	const wm_dp_job J = jobs[jid];
-	wm_extd2_backtrack_job(J, ezs + jid, bt, cigar_pool, seq, Z, zd ? zd + 5 * (size_t)jid : 0);
+	wm_extd2_backtrack_job(J, ezs + jid, bt, cigar_pool, seq, Z, zd ? zd + 5 * (size_t)jid : 0, splice, min_intron_len, early_out);
 }
 
 // ---- host-side launcher on device-resident jobs ----
@@ -254,6 +256,7 @@ __global__ void wm_extd2_backtrack_kernel(const wm_dp_job *__restrict__ jobs, in
 void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2)
 { // src/ksw2_extd2_sse.c:61-97
 	P->single = q == q2 && e == e2; // src/align.c:328-331: ksw_extz2_sse(q, e) instead
+	P->splice = 0, P->noncan = P->junc_bonus = 0; memcpy(P->mat, mat, 25);
 	P->qe_h = q + e;
 	if (q2 + e2 < q + e) { int t = q; q = q2; q2 = t; t = e; e = e2; e2 = t; }
 	P->q = q, P->e = e, P->q2 = q2, P->e2 = e2;
@@ -266,6 +269,23 @@ void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2,
 	if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
 	P->long_thres = long_thres;
 	P->long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+}
+
+void wm_dp_params_init_splice(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int noncan, int junc_bonus)
+{ // src/ksw2_exts2_sse.c:61-84
+	memset(P, 0, sizeof(*P));
+	P->splice = 1, P->noncan = noncan, P->junc_bonus = junc_bonus; memcpy(P->mat, mat, 25);
+	P->q = q, P->e = e, P->q2 = q2, P->e2 = 0, P->qe_h = q + e;
+	P->sc_mch = mat[0], P->sc_mis = mat[1];
+	P->sc_N = mat[24] == 0 ? -e : mat[24];
+	int min_sc = mat[1];
+	for (int t = 1; t < 25; ++t) min_sc = min_sc < mat[t] ? min_sc : mat[t];
+	P->early_out = q2 <= q + e || -min_sc > 2 * (q + e);
+	if (e <= 0) { P->early_out = 1; return; } // (the reference divides by e)
+	int long_thres = (q2 - q) / e - 1;
+	if (q2 > q + e + long_thres * e) ++long_thres;
+	P->long_thres = long_thres;
+	P->long_diff = long_thres * e - (q2 - q);
 }
 
 size_t wm_extd2_bt_bytes(int qlen, int tlen, int w)
@@ -284,14 +304,14 @@ static int wm_use_v2(void)
 	return use_v2;
 }
 
-wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n, bool single)
+wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n, bool single, bool splice)
 {
 	wm_extd2_plan_t pl; pl.n_slots = 0, pl.max_tlen = 0, pl.max_qlen = 0;
-	const int use_v2 = single ? 0 : wm_use_v2();
+	const int use_v2 = single || splice ? 0 : wm_use_v2();
 	for (int i = 0; i < n; ++i) {
 		wm_dp_job &J = h_jobs[i];
 		const int tlen16 = (J.tlen + 15) / 16 * 16;
-		const bool fits = use_v2 ? (tlen16 <= WM_V2_T && J.qlen <= WM_V2_Q) : tlen16 <= WM_SMEM_CELLS;
+		const bool fits = splice ? (size_t)tlen16 * WM_EXTS2_CELL_BYTES <= WM_FILL_SLICE : use_v2 ? (tlen16 <= WM_V2_T && J.qlen <= WM_V2_Q) : tlen16 <= WM_SMEM_CELLS;
 		J.pad = fits ? -1 : pl.n_slots++;
 		if (!fits) { if (J.tlen > pl.max_tlen) pl.max_tlen = J.tlen; if (J.qlen > pl.max_qlen) pl.max_qlen = J.qlen; }
 	}
@@ -309,15 +329,15 @@ cudaStream_t wm_stream_create_high_priority(void)
 
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream, const wm_zd_params *zp, int32_t *d_zd,
-                     const int32_t *d_coop_ids, int n_coop)
+                     const int32_t *d_coop_ids, int n_coop, const uint8_t *d_junc)
 {
 	if (n_jobs <= 0) return;
 	const size_t smem = (size_t)WM_FILL_WARPS * WM_FILL_SLICE;
-	const int use_v2 = P.single ? 0 : wm_use_v2();
+	const int use_v2 = P.single || P.splice ? 0 : wm_use_v2();
 	const int grid = (n_jobs + WM_FILL_WARPS - 1) / WM_FILL_WARPS;
 	// global state slices of the jobs that do not fit the shared-memory slice (wm_extd2_plan gave them slots)
 	const int tcap = (plan.max_tlen + 15) / 16 * 16;
-	const size_t stride = plan.n_slots == 0 ? 0 : use_v2 ? wm_v2_slice_bytes(tcap, plan.max_qlen) : (size_t)tcap * 11;
+	const size_t stride = plan.n_slots == 0 ? 0 : P.splice ? (size_t)tcap * WM_EXTS2_CELL_BYTES : use_v2 ? wm_v2_slice_bytes(tcap, plan.max_qlen) : (size_t)tcap * 11;
 	int8_t *gs = (int8_t*)ws->scratch.need(stride * (size_t)plan.n_slots + 16);
 	if (!ws->fill_st) {
 		int lo = 0, hi = 0;
@@ -347,7 +367,7 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const
 		WM_CUDA_CHECK(cudaGetLastError());
 		WM_CUDA_CHECK(cudaEventRecord(ws->ev_coop, ws->coop_st));
 	}
-	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, ws->fill_st>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, tcap, plan.max_qlen, use_v2, cell_ctr);
+	wm_count_launch(); wm_extd2_fill_kernel<<<grid, WM_FILL_WARPS * 32, smem, ws->fill_st>>>(d_jobs, n_jobs, d_seq, d_bt, d_ez, P, gs, stride, tcap, plan.max_qlen, use_v2, cell_ctr, d_junc);
 	WM_CUDA_CHECK(cudaGetLastError());
 	if (n_coop > 0 && use_v2) WM_CUDA_CHECK(cudaStreamWaitEvent(ws->fill_st, ws->ev_coop, 0));
 	wm_prof_launch_end(pslot, ws->fill_st);
@@ -355,7 +375,7 @@ void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const
 	WM_CUDA_CHECK(cudaStreamWaitEvent(stream, ws->ev_done, 0));
 	wm_zd_params Z; memset(&Z, 0, sizeof(Z));
 	if (zp && d_zd) Z = *zp;
-	wm_count_launch(); wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar, d_seq, Z, zp ? d_zd : 0);
+	wm_count_launch(); wm_extd2_backtrack_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(d_jobs, n_jobs, d_bt, d_ez, d_cigar, d_seq, Z, zp ? d_zd : 0, P.splice, P.splice ? P.long_thres : 0, P.early_out);
 	WM_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -39,7 +39,7 @@ __device__ __forceinline__ bool wm_apply_zdrop(wm_extz_dev &ez, int32_t H, int r
 	return false;
 }
 
-// ksw_backtrack (src/ksw2.h:119-151, is_rot = 1, min_intron_len = 0) + the start-cell choice of
+// ksw_backtrack (src/ksw2.h:119-151, is_rot = 1) + the start-cell choice of
 // src/ksw2_extd2_sse.c:379-391.  One thread per job; the band bounds off[]/off_end[] the
 // reference stores per diagonal are recomputed from r.
 // CIGAR run-length accumulator with ksw_push_cigar semantics (src/ksw2.h:103-113); the pending
@@ -85,18 +85,18 @@ __device__ void wm_zdrop_scan(const wm_zd_params &Z, const uint8_t *__restrict__
 
 // One job of the traceback kernel: *ez_io is the job's fill result (updated: reach_end, n_cigar), zd its five Z-drop words or null.
 __device__ __forceinline__ void wm_extd2_backtrack_job(const wm_dp_job &J, wm_extz_dev *ez_io, const uint8_t *__restrict__ bt, uint32_t *__restrict__ cigar_pool,
-                                              const uint8_t *__restrict__ seq, const wm_zd_params &Z, int32_t *zd)
-{
+                                              const uint8_t *__restrict__ seq, const wm_zd_params &Z, int32_t *zd, int splice = 0, int min_intron_len = 0, int early_out = 0)
+{ // early_out: the scoring made the reference return before the sweep (wm_dp_params::early_out): no CIGAR.  splice: the job came from ksw_exts2 (no end-bonus clause, src/ksw2_exts2_sse.c:411-419; the long-gap state reads as N_SKIP)
 	wm_extz_dev ez = *ez_io;
 	const int qlen = J.qlen, tlen = J.tlen;
 	int w = J.w;
 	const bool scan = zd != 0 && (J.flag & WM_DP_SCAN_ZDROP) != 0;
 	if (scan) zd[0] = -1; // "no result": the host falls back to its own walk
-	if (qlen <= 0 || tlen <= 0) return;
+	if (qlen <= 0 || tlen <= 0 || early_out) return;
 	if (w < 0) w = tlen > qlen ? tlen : qlen;
 	int i0 = -1, j0 = -1;
 	if (!ez.zdropped && !(J.flag & 0x40)) i0 = tlen - 1, j0 = qlen - 1;
-	else if (!ez.zdropped && (J.flag & 0x40) && ez.mqe + J.end_bonus > ez.max) ez.reach_end = 1, i0 = ez.mqe_t, j0 = qlen - 1;
+	else if (!splice && !ez.zdropped && (J.flag & 0x40) && ez.mqe + J.end_bonus > ez.max) ez.reach_end = 1, i0 = ez.mqe_t, j0 = qlen - 1;
 	else if (ez.max_t >= 0 && ez.max_q >= 0) i0 = ez.max_t, j0 = ez.max_q;
 	int n = 0;
 	if (i0 >= 0 && j0 >= 0) {
@@ -117,10 +117,11 @@ __device__ __forceinline__ void wm_extd2_backtrack_job(const wm_dp_job &J, wm_ex
 			if (state == 0) state = tmp & 7;
 			if (force_state >= 0) state = force_state;
 			if (state == 0) acc.push(0, 1), --i, --j;
-			else if (state == 1 || state == 3) acc.push(2, 1), --i;
+			else if (state == 1 || (state == 3 && min_intron_len <= 0)) acc.push(2, 1), --i;
+			else if (state == 3) acc.push(3, 1), --i; // intron (src/ksw2.h:142)
 			else acc.push(1, 1), --j;
 		}
-		if (i >= 0) acc.push(2, i + 1);
+		if (i >= 0) acc.push(min_intron_len > 0 && i >= min_intron_len ? 3u : 2u, i + 1);
 		if (j >= 0) acc.push(1, j + 1);
 		acc.flush();
 		n = acc.n;

@@ -62,6 +62,9 @@ struct wm_dp_params {
 	int32_t long_thres, long_diff;
 	int32_t early_out;         // -min_sc > 2*(q+e) (:92)
 	int32_t single;            // q == q2 && e == e2: the call is ksw_extz2_sse (src/align.c:328-331), csrc/ksw_extz2.cuh
+	int32_t splice;            // the call is ksw_exts2_sse (src/align.c:326-327), csrc/ksw_exts2.cuh: q, e, q2 as given, e2 unused
+	int32_t noncan, junc_bonus;
+	int8_t mat[25];            // for KSW_EZ_GENERIC_SC (splice path only)
 };
 
 struct wm_extz_dev {
@@ -110,6 +113,36 @@ struct wm_dbuf {
 	void release() { if (p) { if (async) cudaFreeAsync(p, st); else cudaFree(p); } p = 0; cap = 0; }
 };
 
+// Host result pool in page-locked memory, grow-only, with the small slice of std::vector's interface the backend uses.
+// Device-to-host copies into pageable memory are staged by the driver through a bounce buffer, a few GB/s and one lane at
+// a time; the chains and CIGARs of a wave are hundreds of MB.  Falls back to pageable memory if page-locking fails.
+template <typename T> struct wm_hbuf {
+	T *p; size_t n, cap; bool pinned;
+	wm_hbuf() : p(0), n(0), cap(0), pinned(false) {}
+	wm_hbuf(const wm_hbuf&) = delete;
+	wm_hbuf &operator=(const wm_hbuf&) = delete;
+	~wm_hbuf() { drop(p, pinned); }
+	static void drop(T *q, bool pin) { if (q) { if (pin) cudaFreeHost(q); else free(q); } }
+	T *data() { return p; }
+	const T *data() const { return p; }
+	size_t size() const { return n; }
+	void clear() { n = 0; }
+	void resize(size_t m) { // keeps the first min(n, m) elements
+		if (m > cap) {
+			const size_t nc = 2 * m + (1u << 16); // page-locking is slow (and serialises the lanes): grow rarely
+			T *q = 0; bool pin = true;
+			if (cudaMallocHost((void**)&q, nc * sizeof(T)) != cudaSuccess) { cudaGetLastError(); pin = false; q = (T*)malloc(nc * sizeof(T)); }
+			if (!q) { fprintf(stderr, "[ERROR] winnowmap-b200: out of host memory (%zu bytes)\n", nc * sizeof(T)); exit(1); }
+			if (n) memcpy(q, p, n * sizeof(T));
+			drop(p, pinned);
+			p = q, cap = nc, pinned = pin;
+		}
+		n = m;
+	}
+	void push_back(const T &v) { resize(n + 1); p[n - 1] = v; }
+	T &operator[](size_t i) { return p[i]; }
+};
+
 // ---- batched ksw_extd2 on device-resident jobs (ksw_extd2.cu) ----
 // The fill kernel runs on its own lowest-priority stream, ordered against the caller's stream by two events: its
 // CTAs leave the SMs job group by job group, and the short kernels of the other orchestration lanes (created with
@@ -122,10 +155,11 @@ struct wm_extd2_ws {
 };
 struct wm_extd2_plan_t { int n_slots, max_tlen, max_qlen; };
 void wm_dp_params_init(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int e2);
+void wm_dp_params_init_splice(wm_dp_params *P, const int8_t *mat, int q, int e, int q2, int noncan, int junc_bonus); // src/ksw2_exts2_sse.c:61-84
 size_t wm_extd2_bt_bytes(int qlen, int tlen, int w);
 // sets h_jobs[i].pad (global-scratch slot or -1) for the n jobs of one launch, in launch order; single: the jobs run the
 // single-affine sweep (wm_dp_params::single), whose state slice is 9 bytes per target cell
-wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n, bool single = false);
+wm_extd2_plan_t wm_extd2_plan(wm_dp_job *h_jobs, int n, bool single = false, bool splice = false); // splice: ksw_exts2.cuh, 12 bytes per cell
 // Jobs flagged WM_DP_SCAN_ZDROP also get the score walk of mm_test_zdrop (src/align.c:32-70) over their CIGAR: five
 // int32 per job in d_zd (max_zdrop, t0, t1, q0, q1; max_zdrop = -1: no result).  zp / d_zd may be null.
 #define WM_DP_SCAN_ZDROP 0x10000
@@ -144,7 +178,8 @@ static inline bool wm_dp_is_coop(int qlen, int tlen, int w)
 struct wm_zd_params { int32_t q, e; int8_t mat[25]; int8_t pad[3]; };
 void wm_extd2_launch(wm_extd2_ws *ws, const wm_dp_job *d_jobs, int n_jobs, const wm_extd2_plan_t &plan, const uint8_t *d_seq, uint8_t *d_bt,
                      wm_extz_dev *d_ez, uint32_t *d_cigar, const wm_dp_params &P, cudaStream_t stream,
-                     const wm_zd_params *zp = 0, int32_t *d_zd = 0, const int32_t *d_coop_ids = 0, int n_coop = 0);
+                     const wm_zd_params *zp = 0, int32_t *d_zd = 0, const int32_t *d_coop_ids = 0, int n_coop = 0,
+                     const uint8_t *d_junc = 0); // d_junc: junction annotation parallel to d_seq (splice jobs), or null
 cudaStream_t wm_stream_create_high_priority(void);
 
 // Wait for a stream without burning a core: an orchestration lane spends most of its time waiting for the GPU, and

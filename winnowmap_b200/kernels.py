@@ -47,6 +47,38 @@ def ksw_extd2_batch(queries, targets, mat, q, e, q2, e2, w, zdrop, end_bonus, fl
     return out, cigs
 
 
+def ksw_exts2_batch(queries, targets, mat, q, e, q2, noncan, junc_bonus, zdrop, flag, juncs=None):
+    """Batched ksw_exts2 (reference src/ksw2_exts2_sse.c:26), the splice-aware extension.  juncs: per-target annotation bytes
+    (arrays as long as the targets) or None.  Returns (ez[n,11] int32, [cigar arrays])."""
+    n = len(queries)
+    qb, qoff = _concat(queries)
+    tb, toff = _concat(targets)
+    as32 = lambda v: np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.int32), (n,)))
+    zdrop, flag = as32(zdrop), as32(flag)
+    cap = np.array([len(a) + len(b) + 2 for a, b in zip(queries, targets)], dtype=np.int64)
+    coff = np.zeros(n + 1, dtype=np.int64)
+    coff[1:] = np.cumsum(cap)
+    ez = (ExtZ * max(n, 1))()
+    cig = np.zeros(max(int(coff[-1]), 1), dtype=np.uint32)
+    mat = np.ascontiguousarray(mat, dtype=np.int8)
+    jb = None
+    if juncs is not None:
+        jb, _ = _concat([j if j is not None else np.zeros(len(t), np.uint8) for j, t in zip(juncs, targets)])
+        if len(jb) == 0:
+            jb = np.zeros(1, np.uint8)
+    if len(qb) == 0:
+        qb = np.zeros(1, np.uint8)
+    if len(tb) == 0:
+        tb = np.zeros(1, np.uint8)
+    L = lib()
+    L.wm_ksw_exts2_batch.argtypes = [C.c_int, u8p, i64p, u8p, i64p, u8p, i8p] + [C.c_int] * 5 + [i32p, i32p, C.c_void_p, u32p, i64p]
+    L.wm_ksw_exts2_batch(n, _p(qb, u8p), _p(qoff, i64p), _p(tb, u8p), _p(toff, i64p), _p(jb, u8p) if jb is not None else None, _p(mat, i8p),
+                         q, e, q2, noncan, junc_bonus, _p(zdrop, i32p), _p(flag, i32p), C.cast(ez, C.c_void_p), _p(cig, u32p), _p(coff, i64p))
+    out = np.array([[getattr(ez[i], f) for f in EZ_FIELDS] for i in range(n)], dtype=np.int32).reshape(n, len(EZ_FIELDS))
+    cigs = [cig[coff[i]: coff[i] + min(out[i, 10], cap[i])].copy() for i in range(n)]
+    return out, cigs
+
+
 def ksw_ll_batch(queries, targets, mat, gapo, gape):
     """Batched ksw_ll_qinit + ksw_ll_i16 (reference src/ksw2_ll_sse.c:32,80).  Returns (n,3) int32: score, query end, target end."""
     n = len(queries)
