@@ -73,6 +73,28 @@ def test_sort_matches_oracle_with_ties():
         assert np.array_equal(ol.oracle_sort128(a), g), len(a)
 
 
+def test_sort_two_bucket_passes_match_oracle():
+    """Passes with exactly two non-empty buckets take a closed form in the walker kernels (csrc/seed.cu: wm_gs_two_bucket_pass)
+    instead of the serial walk of src/ksort.h:126-138: anchor-like arrays with a strand bit (from one stray element to an even
+    split), positions that straddle a 64 kb / 16 Mb boundary, heavy ties, sizes on both sides of the kernel's size classes."""
+    from winnowmap_b200 import kernels
+    rng = np.random.default_rng(31)
+    arrays = []
+    for n in [600, 2049, 2500, 9000, 40000, 150000]:
+        for frac in [0.0, 0.0005, 0.03, 0.5, 0.97]:
+            base = int(rng.choice([(1 << 16) * 37 - 700, (1 << 24) * 3 - 5000, 123456789]))
+            span = int(rng.choice([1500, 40000, 140000]))
+            pos = base + rng.integers(0, span, size=n)
+            if rng.random() < 0.5:  # tandem-like: few distinct positions, many ties
+                pos = base + (rng.integers(0, max(2, n // 40), size=n) * 171) % span
+            x = pos.astype(np.uint64) | (np.uint64(rng.integers(0, 3)) << np.uint64(32))
+            x = x | ((rng.random(n) < frac).astype(np.uint64) << np.uint64(63))
+            arrays.append(np.stack([x, np.arange(n, dtype=np.uint64)], axis=1))
+    got = kernels.radix_sort_128x_batch(arrays)
+    for a, g in zip(arrays, got):
+        assert np.array_equal(ol.oracle_sort128(a), g), len(a)
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_chain_matches_oracle(seed):
     from winnowmap_b200 import kernels

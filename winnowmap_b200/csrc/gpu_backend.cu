@@ -346,6 +346,7 @@ void GpuBackend::seed_chain(const std::vector<SeedTask> &tasks, const int32_t *m
 	uint64_t *d_uo = (uint64_t*)g.u_out.need(sizeof(uint64_t) * (nu_off[n] + 1));
 	wm_count_launch(); wm_compact_chain_kernel<<<(unsigned)(((int64_t)n * 32 + 127) / 128), 128, 0, st>>>(d_foff, d_nb, d_nu, n, d_A, (const uint64_t*)g.ch.u2.p, d_bo, d_uo);
 	WM_CUDA_CHECK(cudaGetLastError());
+	g.h_b.clear(); g.h_u.clear(); // (nothing to carry over if the pools have to grow)
 	g.h_b.resize(nb_off[n] + 1); g.h_u.resize(nu_off[n] + 1);
 	if (nb_off[n] > 0) WM_CUDA_CHECK(wm_memcpy_async(g.h_b.data(), d_bo, sizeof(wm128_dev) * nb_off[n], cudaMemcpyDeviceToHost, st));
 	if (nu_off[n] > 0) WM_CUDA_CHECK(wm_memcpy_async(g.h_u.data(), d_uo, sizeof(uint64_t) * nu_off[n], cudaMemcpyDeviceToHost, st));
@@ -417,6 +418,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 	if (coop_on < 0) { const char *e = getenv("WM_DP_COOP"); coop_on = (e && *e == '0') ? 0 : 1; if (getenv("WM_DP_V1") && *getenv("WM_DP_V1") == '1') coop_on = 0; }
 	std::vector<int64_t> cig_base(n + 1, 0); // offsets into h_cig, by execution slot
 	std::vector<int> slot_of(n, 0);           // job -> execution slot (jobs of a chunk run sorted by size)
+	g.h_ez.clear(); g.h_zd.clear();
 	g.h_ez.resize(n); g.h_zd.resize(5 * (size_t)n);
 	std::vector<uint32_t> chunk_cig;
 	int done = 0;

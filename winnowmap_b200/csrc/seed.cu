@@ -205,11 +205,82 @@ __device__ __forceinline__ wm128_dev wm_gs_fifo_read(const wm128_dev *p)
 	return r;
 }
 
+// ---- a pass with exactly two non-empty buckets, in closed form ----
+// The walk of ksort.h:126-138 over two buckets A (lower digit, region [beg, mid)) and B ([mid, end)) does this: let
+// p_1 < .. < p_m be the positions of A's region that hold B-elements and q_1 < .. < q_m those of B's region that hold
+// A-elements.  Cycle j picks up the element at p_j, drops it at B's write pointer and pushes the B-elements it finds there
+// one slot to the right until it kicks out the A-element at q_j, which lands at p_j.  Hence, with q_0 = mid - 1:
+//   A's region: position p_j receives the element of q_j, everything else stays;
+//   B's region: position q_{j-1} + 1 receives the element of p_j, the positions up to q_j the element of their left
+//               neighbour; everything after q_m stays.
+// Both are prefix sums over "is misplaced" flags -- no serial walk.  The strand byte of an anchor array always splits it two
+// ways, and the 64 kb byte of the position often does.  tmp / idx: scratch of the array (elements / int32), same indexing as a.
+__device__ __forceinline__ int wm_gs_block_excl(bool flag, int *warp_tot, int tid, int *total)
+{ // exclusive rank of `flag` among the CTA's 128 threads (4 warps); *total = number of flags set
+	const unsigned w = __ballot_sync(0xffffffffu, flag);
+	const int lane = tid & 31, wid = tid >> 5;
+	if (lane == 0) warp_tot[wid] = __popc(w);
+	__syncthreads();
+	const int t0 = warp_tot[0], t1 = warp_tot[1], t2 = warp_tot[2], t3 = warp_tot[3];
+	__syncthreads();
+	*total = t0 + t1 + t2 + t3;
+	return __popc(w & ((1u << lane) - 1u)) + (wid > 0 ? t0 : 0) + (wid > 1 ? t1 : 0) + (wid > 2 ? t2 : 0);
+}
+
+__device__ void wm_gs_two_bucket_pass(wm128_dev *a, wm128_dev *tmp, int32_t *idx, int beg, int mid, int end, int s, int lo, int *warp_tot, int tid)
+{
+	int carry = 0, tot;
+	for (int base = beg; base < mid; base += WM_GS_THREADS) { // the list p_j (idx[beg ..))
+		const int t = base + tid;
+		const bool flag = t < mid && (int)(a[t].x >> s & 255) != lo;
+		const int r = carry + wm_gs_block_excl(flag, warp_tot, tid, &tot);
+		if (flag) idx[beg + r] = t;
+		carry += tot;
+	}
+	const int m = carry;
+	__syncthreads();
+	carry = 0;
+	for (int base = mid; base < end; base += WM_GS_THREADS) { // the list q_j (idx[mid ..)) and B's region
+		const int t = base + tid;
+		wm128_dev e; e.x = e.y = 0;
+		if (t < end) e = a[t];
+		const bool flag = t < end && (int)(e.x >> s & 255) == lo;
+		const int c = carry + wm_gs_block_excl(flag, warp_tot, tid, &tot); // A-elements in [mid, t)
+		if (flag) idx[mid + c] = t;
+		if (t < end) {
+			wm128_dev v = e;
+			if (c < m) {
+				wm128_dev left; left.x = left.y = 0;
+				if (t > mid) left = a[t - 1];
+				v = (t == mid || (int)(left.x >> s & 255) == lo) ? a[idx[beg + c]] : left;
+			}
+			tmp[t] = v;
+		}
+		carry += tot;
+	}
+	__syncthreads();
+	carry = 0;
+	for (int base = beg; base < mid; base += WM_GS_THREADS) { // A's region
+		const int t = base + tid;
+		wm128_dev e; e.x = e.y = 0;
+		if (t < mid) e = a[t];
+		const bool flag = t < mid && (int)(e.x >> s & 255) != lo;
+		const int j = carry + wm_gs_block_excl(flag, warp_tot, tid, &tot);
+		if (t < mid) tmp[t] = flag ? a[idx[mid + j]] : e;
+		carry += tot;
+	}
+	__syncthreads();
+	for (int t = beg + tid; t < end; t += WM_GS_THREADS) a[t] = tmp[t];
+	__syncthreads();
+}
+
 template <int WM_GS_F, int WM_GS_STAGE, bool WM_GS_DBG>
 __global__ void __launch_bounds__(WM_GS_THREADS)
 wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__restrict__ off, const int32_t *__restrict__ ids, int n_arr,
-                            wm_rs_range *__restrict__ wl_all, unsigned long long *dbg)
+                            wm_rs_range *__restrict__ wl_all, unsigned long long *dbg, wm128_dev *__restrict__ tmp_all, int32_t *__restrict__ idx_all, int two_min)
 {
+	// tmp_all / idx_all: scratch of the closed-form pass (wm_gs_two_bucket_pass), indexed like a_all; two_min: ranges of at least this many
+	// elements take it when their pass has two non-empty buckets (0: never)
 	// dbg (tuning aid, WM_SORT_DEBUG=1): clocks spent by thread 0 in [0] histograms, [1] the walk, [2] sub-bucket dispatch + tiny sorts,
 	// [3] phase 2, [4] walker steps, [5] walker waits (polls of an empty FIFO)
 	long long t_dbg = dbg ? clock64() : 0;
@@ -241,14 +312,18 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 			__syncthreads();
 			if (tid == 0) --S->n_big;
 			int beg = R.beg, end = R.end, s = R.s;
-			bool single;
+			bool single; int n_nz = 0, lo_digit = 0;
 			for (;;) { // histogram of byte s >> 3; identity passes (one bucket holds everything) are skipped (ksort.h:121-125)
 				for (int k = tid; k < 256; k += WM_GS_THREADS) S->hist[k] = 0;
 				__syncthreads();
 				for (int i = beg + tid; i < end; i += WM_GS_THREADS) atomicAdd(&S->hist[a[i].x >> s & 255], 1);
 				__syncthreads();
-				single = false;
-				for (int k = 0; k < 256; ++k) if (S->hist[k] == end - beg) single = true; // (uniform: every thread scans the same table)
+				single = false; n_nz = 0; lo_digit = -1;
+				for (int k = 0; k < 256; ++k) { // (uniform: every thread scans the same table)
+					const int h = S->hist[k];
+					if (h == end - beg) single = true;
+					if (h > 0) { ++n_nz; if (lo_digit < 0) lo_digit = k; }
+				}
 				if (!single || s == 0) break;
 				s = s > 8 ? s - 8 : 0;
 				__syncthreads();
@@ -268,6 +343,10 @@ wm_anchor_sort_giant_kernel(wm128_dev *__restrict__ a_all, const int64_t *__rest
 				if (lane == 0) S->walk_done = 0;
 			}
 			__syncthreads();
+			if (n_nz == 2 && two_min > 0 && end - beg >= two_min) { // two buckets: the pass in closed form, by all threads
+				wm_gs_two_bucket_pass(a, tmp_all + base, idx_all + base, beg, S->E[lo_digit], end, s, lo_digit, S->hist, tid);
+				if (WM_GS_DBG && tid == 0) atomicAdd(dbg + 6, (unsigned long long)(end - beg));
+			} else
 			if (tid == 0) { // the walker (ksort.h:126-138); b[] are its pointers, filled[] the feeders'
 				volatile int *filled = S->filled; int *b = S->b; const int *E = S->E;
 				for (int k = 0; k < 256;) {
@@ -408,6 +487,14 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 		int32_t *d_big = (int32_t*)ws->big_ids.need(sizeof(int32_t) * big.size());
 		wm_rs_range *d_wl = (wm_rs_range*)ws->rs_stacks.need(sizeof(wm_rs_range) * (size_t)((h_off[n_arr] >> 6) + n_arr + 2));
 		WM_CUDA_CHECK(wm_memcpy_async(d_big, big.data(), sizeof(int32_t) * big.size(), cudaMemcpyHostToDevice, st));
+		// scratch of the closed-form two-bucket passes of the walker kernels (one element + one int32 per anchor)
+		static int two_min = -1; // WM_SORT_TWO_MIN: ranges of at least this many anchors take the closed form (0: always walk)
+		if (two_min < 0) { const char *e = getenv("WM_SORT_TWO_MIN"); two_min = e ? atoi(e) : 512; }
+		wm128_dev *d_tmp = 0; int32_t *d_idx = 0;
+		if (two_min > 0 && (n_l || n_m)) {
+			d_tmp = (wm128_dev*)ws->sort_tmp.need(sizeof(wm128_dev) * (size_t)(h_off[n_arr] + 1));
+			d_idx = (int32_t*)ws->sort_idx.need(sizeof(int32_t) * (size_t)(h_off[n_arr] + 1));
+		}
 		if (n_l) {
 			wm_count_launch();
 			if (giant) {
@@ -423,13 +510,13 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 				static int giant_ctas = -1; // WM_SORT_GIANT_CTAS
 				if (giant_ctas < 0) { const char *e = getenv("WM_SORT_GIANT_CTAS"); giant_ctas = e && atoi(e) > 0 ? atoi(e) : 148; }
 				const unsigned g_l = (unsigned)(n_l < (size_t)giant_ctas ? n_l : (size_t)giant_ctas);
-				if (dbg) wm_anchor_sort_giant_kernel<16, 2048, true><<<g_l, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, dbg);
-				else wm_anchor_sort_giant_kernel<16, 2048, false><<<g_l, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, 0);
+				if (dbg) wm_anchor_sort_giant_kernel<16, 2048, true><<<g_l, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, dbg, d_tmp, d_idx, two_min);
+				else wm_anchor_sort_giant_kernel<16, 2048, false><<<g_l, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big, (int)n_l, d_wl, 0, d_tmp, d_idx, two_min);
 				if (dbg) {
 					unsigned long long h[8];
 					WM_CUDA_CHECK(cudaStreamSynchronize(st));
 					WM_CUDA_CHECK(cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost));
-					fprintf(stderr, "[sort-debug] arrays=%d clocks: hist %llu walk %llu dispatch %llu phase2 %llu | walker steps %llu wait polls %llu\n", (int)n_l, h[0], h[1], h[2], h[3], h[4], h[5]);
+					fprintf(stderr, "[sort-debug] arrays=%d clocks: hist %llu walk %llu dispatch %llu phase2 %llu | walker steps %llu wait polls %llu | elements in closed-form passes %llu\n", (int)n_l, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
 					cudaFree(dbg);
 				}
 			} else wm_anchor_sort_big_kernel<<<(unsigned)n_l, 32, 0, st>>>(d_a, d_off, d_big, (int)n_l, d_wl, 0);
@@ -450,13 +537,13 @@ void wm_anchor_sort_run(wm_seed_ws *ws, wm128_dev *d_a, const int64_t *d_off, co
 				if (med_ctas < 0) { const char *e = getenv("WM_SORT_MEDIUM_CTAS"); med_ctas = e && atoi(e) > 0 ? atoi(e) : 592; }
 				const unsigned g_m = (unsigned)(n_m < (size_t)med_ctas ? n_m : (size_t)med_ctas);
 				if (dbg) {
-					wm_anchor_sort_giant_kernel<8, 512, true><<<g_m, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, dbg);
+					wm_anchor_sort_giant_kernel<8, 512, true><<<g_m, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, dbg, d_tmp, d_idx, two_min);
 					unsigned long long h[8];
 					WM_CUDA_CHECK(cudaStreamSynchronize(st));
 					WM_CUDA_CHECK(cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost));
-					fprintf(stderr, "[sort-debug] arrays=%d clocks: hist %llu walk %llu dispatch %llu phase2 %llu | walker steps %llu wait polls %llu\n", (int)n_m, h[0], h[1], h[2], h[3], h[4], h[5]);
+					fprintf(stderr, "[sort-debug] arrays=%d clocks: hist %llu walk %llu dispatch %llu phase2 %llu | walker steps %llu wait polls %llu | elements in closed-form passes %llu\n", (int)n_m, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
 					cudaFree(dbg);
-				} else wm_anchor_sort_giant_kernel<8, 512, false><<<g_m, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, 0);
+				} else wm_anchor_sort_giant_kernel<8, 512, false><<<g_m, WM_GS_THREADS, sizeof(sm_t), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, 0, d_tmp, d_idx, two_min);
 			} else wm_anchor_sort_big_kernel<<<(unsigned)n_m, 32, cap_m * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l, (int)n_m, d_wl, cap_m);
 		}
 		if (n_s) { wm_count_launch(); wm_anchor_sort_big_kernel<<<(unsigned)n_s, 32, cap_s * sizeof(wm128_dev), st>>>(d_a, d_off, d_big + n_l + n_m, (int)n_s, d_wl, cap_s); }
