@@ -471,6 +471,10 @@ def main():
             r["limiter"] = ("integer ALU issue, not HBM: ncu --set full of the kernel alone shows ALU pipe 66 %, issue slots 68 %, DRAM 6 % of "
                             "peak at 333 G cells/s (profiles/r02_ncu_wm_extd2_fill_kernel_summary.txt); in the bench its launches share the SMs "
                             "with the other lanes' kernels")
+            # DRAM traffic: one ncu --set full capture of this kernel (profiles/r02_ncu_wm_extd2_fill_kernel_summary.txt) moved 16.8 GB for a
+            # launch of 14.1 GB algorithmic bytes; that ratio applied to this run's average launch
+            # (kept out of `traffic`, which stays null: it is a property of that capture, not a measurement of this run)
+            r["traffic_per_algorithmic_byte_ncu"] = 1.19
             r.update({"block_cells": units, "jobs": int(units2), "block_cells_per_s": units / (k_ms * 1e-3) if k_ms > 0 else 0.0})
         else:
             r.update({"anchors": units, "anchors_per_s": units / (k_ms * 1e-3) if k_ms > 0 else 0.0})
