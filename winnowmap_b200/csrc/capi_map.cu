@@ -117,6 +117,7 @@ static void map_lanes(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const std::vector
 		return;
 	}
 	std::vector<MapStats> st(L);
+	std::vector<double> lane_end(L, 0.0);
 	std::vector<std::thread> th;
 	std::atomic<int> next(0);
 	const int thr = n_threads / L > 0 ? n_threads / L : 1;
@@ -128,12 +129,19 @@ static void map_lanes(wm_gpu_ctx_s *c, const wm_mapopt_t *opt, const std::vector
 				if (j >= n_chunks) break;
 				std::vector<const wm_read*> sub(reads.begin() + cb[j], reads.begin() + cb[j + 1]);
 				std::vector<std::vector<wm_reg1_t>> r2; std::vector<int> rl2, fg2;
+				const double tb0 = wmh::Timers::now();
 				map_batch(c->lanes[l], &c->hidx, opt, sub, r2, rl2, fg2, thr, &st[l]);
+				wmh::g_timers.add("lane.map_batch", wmh::Timers::now() - tb0);
 				for (size_t k = 0; k < sub.size(); ++k) { const int i = cb[j] + (int)k; regs[i].swap(r2[k]); rl[i] = rl2[k]; fg[i] = fg2[k]; }
 			}
+			lane_end[l] = wmh::Timers::now();
 		});
 	}
 	for (auto &t : th) t.join();
+	{ // what the lanes that finished early waited for the last one (tuning aid)
+		const double t_end = wmh::Timers::now();
+		for (int l = 0; l < L; ++l) wmh::g_timers.add("lane.idle_tail", t_end - lane_end[l]);
+	}
 	for (int l = 0; l < L; ++l) {
 		MapStats &a = c->stats; const MapStats &b = st[l];
 		a.n_reads += b.n_reads, a.n_bases += b.n_bases, a.n_minimaps += b.n_minimaps, a.n_chained += b.n_chained, a.n_dp_jobs += b.n_dp_jobs;

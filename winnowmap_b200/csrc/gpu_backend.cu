@@ -409,6 +409,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 	wm_dbuf_use_stream(g.st);
 	cudaStream_t st = g.st;
 	const int n = (int)jobs.size();
+	const double t_setup0 = Timers::now();
 	res.assign(n, DpRes());
 	g.h_cig.clear();
 	if (n == 0) return;
@@ -421,6 +422,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 	g.h_ez.clear(); g.h_zd.clear();
 	g.h_ez.resize(n); g.h_zd.resize(5 * (size_t)n);
 	std::vector<uint32_t> chunk_cig;
+	g_timers.add("dp.setup", Timers::now() - t_setup0);
 	int done = 0;
 	while (done < n) {
 		// a chunk of jobs whose backtrack matrices fit the budget
@@ -560,6 +562,8 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		done = end;
 	}
 	g.h_cig.push_back(0);
+	const double t_res0 = Timers::now();
+	#pragma omp parallel for schedule(static) num_threads(8)
 	for (int i = 0; i < n; ++i) {
 		const int s = slot_of[i]; // where job i ran
 		const wm_extz_dev &e = g.h_ez[s];
@@ -571,6 +575,7 @@ void GpuBackend::run_dp(const std::vector<DpJob> &jobs, const std::vector<MapWin
 		r.has_zd = (jobs[i].flag & WM_DP_SCAN_ZDROP) && z[0] >= 0;
 		if (r.has_zd) r.zd_max = z[0], r.zd_pos[0] = z[1], r.zd_pos[1] = z[2], r.zd_pos[2] = z[3], r.zd_pos[3] = z[4];
 	}
+	g_timers.add("dp.results", Timers::now() - t_res0);
 }
 
 void GpuBackend::run_ll(const std::vector<LlJob> &jobs, const std::vector<MapWin> &wins, const DpScoring &sc, std::vector<LlRes> &res)

@@ -120,7 +120,10 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 		fprintf(stderr, "[ERROR] winnowmap-b200: mid_occ_frac (-f) is not implemented: set mid_occ itself\n");
 		exit(1);
 	}
+	const double t_batch0 = Timers::now();
 	be->begin_batch(reads);
+	g_timers.add("batch.begin_upload", Timers::now() - t_batch0);
+	const double t_enc0 = Timers::now();
 	// 0..4 codes of every read, both strands, once per batch: the alignment tasks of all windows of a read slice them
 	std::vector<int64_t> code_off(n_reads + 1, 0);
 	for (int i = 0; i < n_reads; ++i) code_off[i + 1] = code_off[i] + (int64_t)reads[i]->seq.size();
@@ -128,6 +131,7 @@ void map_batch(Backend *be, const wm_host_idx *mi, const wm_mapopt_t *opt, const
 	#pragma omp parallel for schedule(dynamic, 8) num_threads(n_threads)
 	for (int i = 0; i < n_reads; ++i)
 		encode_strands(reads[i]->seq.data(), (int)reads[i]->seq.size(), codes_fwd.data() + code_off[i], codes_rev.data() + code_off[i]);
+	g_timers.add("batch.encode_strands", Timers::now() - t_enc0);
 
 	// the three option sets of mm_map_frag: stage 1 (src/map.c:300-302), stage 2 (:711-717), fallback (= user options, :857)
 	wm_mapopt_t opt2 = *opt, opt3 = *opt;
