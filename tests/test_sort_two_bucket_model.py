@@ -4,7 +4,11 @@ A radix pass of the reference (rs_sort, src/ksort.h:116-146) whose keys fall int
 a closed form: the misplaced elements of the lower bucket's region swap, in order, with the misplaced ones of the upper region, and the
 upper region shifts its own elements one slot to the right up to the last misplaced one.  Here the whole sort is restated in Python --
 serial cycle-leader walk for the other passes, the closed form for the two-bucket ones -- and compared with ref_radix_sort_128x
-(oracle/_ref, the reference's compiled code).  The CUDA implementation itself is checked on the GPU (tests/test_gpu_stages.py)."""
+(oracle/_ref, the reference's compiled code).  The CUDA implementation itself is checked on the GPU (tests/test_gpu_stages.py).
+
+The second test checks the general form of the same observation (not built as a kernel yet): the j-th element to
+arrive in a bucket ejects that bucket's j-th misplaced element, so the serial part of ANY pass is a token walk over the destination
+digits of the misplaced elements with one arrival counter per bucket; where each element lands follows from its arrival index."""
 import ctypes as C
 
 import numpy as np
@@ -108,3 +112,68 @@ def test_two_bucket_closed_form_equals_the_reference_walk():
             _rs(got, 0, n, 56, used)
         assert np.array_equal(got, ref), (it, n)
     assert used[0] >= 10
+
+
+def _token_pass(a, beg, end, s, steps):
+    orig = a[beg:end].copy()
+    d = ((orig[:, 0] >> np.uint64(s)) & np.uint64(255)).astype(np.int64)
+    cnt = np.bincount(d, minlength=256)
+    B = np.zeros(257, np.int64); B[1:] = np.cumsum(cnt)
+    own = np.repeat(np.arange(256), cnt)                 # the bucket every slot belongs to
+    mis = np.nonzero(d != own)[0]
+    E = [mis[own[mis] == k] for k in range(256)]         # misplaced slots of every bucket, ascending
+    D = [d[E[k]] for k in range(256)]                    # ... and where their elements want to go
+    arrivals, A, land = [0] * 256, [0] * 256, {}
+    for k in range(256):                                 # the serial part: digits and counters only
+        A[k] = arrivals[k]                               # elements of k ejected by arrivals before its own turn
+        for c in range(A[k], len(E[k])):                 # the others open a cycle each (src/ksort.h:129-136)
+            cur, t = (k, c), int(D[k][c])
+            while True:
+                steps[0] += 1
+                j = arrivals[t]; arrivals[t] += 1
+                land[int(E[cur[0]][cur[1]])] = (0, t, j)  # lands at the start of run j of bucket t
+                cur, t2 = (t, j), int(D[t][j])
+                if t2 == k:
+                    land[int(E[t][j])] = (1, k, c)        # closes the cycle: lands where it was opened
+                    break
+                t = t2
+    new = orig.copy()                                    # the parallel part: pure index arithmetic
+    for t in range(256):
+        for r in range(A[t]):                            # the bucket's own elements of run r move one slot to the right
+            start = int(B[t]) if r == 0 else int(E[t][r - 1]) + 1
+            new[start + 1:int(E[t][r]) + 1] = orig[start:int(E[t][r])]
+    for src, (closing, t, j) in land.items():
+        if closing:
+            new[int(E[t][j])] = orig[src]
+        else:
+            new[int(B[t]) if j == 0 else int(E[t][j - 1]) + 1] = orig[src]
+    a[beg:end] = new
+    return [beg + int(B[k]) for k in range(256)], [beg + int(B[k + 1]) for k in range(256)]
+
+
+def _rs_token(a, beg, end, s, steps):
+    b, e = _token_pass(a, beg, end, s, steps)
+    if s:
+        for k in range(256):
+            if e[k] - b[k] > 64:
+                _rs_token(a, b[k], e[k], s - 8, steps)
+            elif e[k] - b[k] > 1:
+                _insertion(a, b[k], e[k])
+
+
+def test_token_walk_formulation_equals_the_reference_sort():
+    rng = np.random.default_rng(11)
+    for it in range(10):
+        n = int(rng.choice([100, 400, 1500, 4000]))
+        pos = rng.integers(1000, 1000 + int(rng.choice([300, 5000, 70000, 900000])), size=n).astype(np.uint64)
+        if it % 3 == 0:
+            pos = pos[rng.integers(0, max(2, n // 25), size=n)]
+        strand = (rng.random(n) < [0.0, 0.02, 0.5][it % 3]).astype(np.uint64)
+        x = (strand << np.uint64(63)) | (np.uint64(rng.integers(0, 3)) << np.uint64(32)) | pos
+        a = np.ascontiguousarray(np.stack([x, np.arange(n, dtype=np.uint64)], axis=1))
+        ref = a.copy()
+        ol.ref().ref_radix_sort_128x(ref.ctypes.data_as(C.POINTER(C.c_uint64)), n)
+        got, steps = a.copy(), [0]
+        _rs_token(got, 0, n, 56, steps)
+        assert np.array_equal(got, ref), (it, n)
+        assert steps[0] <= 2 * n  # serial steps of the whole sort: about 1.3 per element, against 2-3 walker steps per element today
